@@ -1,0 +1,153 @@
+/*
+ * uml_b200.h - C ABI of the B200-native UML hot path (libuml_b200.so).
+ *
+ * The reference (OEmiliatanO/Unpaired-Multimodal-Learning) has no FFI of its own: its hot path is
+ * Python calling PyTorch library ops.  Each entry point below replaces one of those call sites
+ * (cited as file:line relative to the reference root) with a hand-written sm_100a kernel.  The
+ * boundary rules are those of SURVEY.md section 8(b): plain pointers and sizes, a cudaStream_t passed
+ * as void*, int status (0 = ok, else call uml_last_error()), no allocation, no host sync and no
+ * exceptions inside the library.  All pointers are DEVICE pointers unless a comment says "host".
+ *
+ * Two arithmetic families:
+ *   *_f32   exact-path SIMT kernels (fp32 FFMA, like the reference which never enables TF32/AMP);
+ *           used at the reference's own batch sizes (8..64 rows) where the step is latency bound.
+ *   *_bf16  tcgen05/TMEM tensor-core kernels (bf16 operands, fp32 accumulate) fed by TMA; used at
+ *           throughput batch sizes.  Tolerance vs the fp32 path is stated in tests/.
+ */
+#ifndef UML_B200_H_
+#define UML_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UML_B200_ABI_VERSION 1
+#define UML_MAX_SEGMENTS 2
+
+/* A run of rows fed through the shared head in one step.  The reference builds two such runs per
+ * step - the image batch and the unpaired text batch (vision_language/finetune.py:165-178) - and
+ * pushes both through the same nn.Linear (engine/models/head.py:80-82,133-135). */
+typedef struct {
+  const void*    rows;        /* feature matrix base: fp32 for *_f32, bf16 for *_bf16 entry points   */
+  const int64_t* idx;         /* optional gather indices into `rows`/`labels` (NULL = dense 0..n-1)   */
+  const int64_t* labels;      /* class labels (bank labels when idx != NULL, else dense per row)      */
+  int64_t        n;           /* rows in this run for this step (the last batch of an epoch is short) */
+  int64_t        ld;          /* leading dimension of `rows`, in elements                             */
+  float          scale;       /* logit scale: exp(logit_scale) (UMLClip) or img_scale / txt_scale     */
+  float          loss_weight; /* 1.0 for the image run, alpha for the text run (finetune.py:188)      */
+} uml_segment;
+
+/* Per-run results written by the forward kernels (device memory, one per segment). */
+typedef struct {
+  float   loss_mean;   /* mean cross entropy over the run (F.cross_entropy default reduction)        */
+  float   dscale;      /* d loss_mean / d scale  (used when the scales are learnable, head.py:69-70)  */
+  int32_t correct;     /* rows whose argmax equals the label (finetune.py:197-198)                    */
+  int32_t n;           /* rows counted                                                                */
+} uml_seg_stats;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* uml_last_error(void);            /* host string, valid until the next failing call     */
+int         uml_abi_version(void);
+int         uml_device_ok(int device);        /* 0 when `device` is an sm_100 part                  */
+
+/* ---- K1  index-driven gather (replaces Dataset.__getitem__ + default_collate + .to(device),
+ *          finetune.py:165-172, engine/datasets/utils.py:100-101) ---------------------------------- */
+int uml_gather_rows_f32(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx,
+                        int64_t n, float* out, void* stream);
+int uml_gather_rows_bf16(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx,
+                         int64_t n, uint16_t* out, int64_t ld_out, void* stream);
+int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out,
+                          void* stream);
+int uml_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
+
+/* ---- K2+K3  head forward + logit scale + softmax cross entropy (head.py:80-82,133-135;
+ *             finetune.py:186-188).  Writes G = loss_weight * scale / n * (softmax - onehot), the
+ *             gradient of the weighted loss w.r.t. the raw (unscaled) logits, for the dW kernel.   */
+int uml_head_fwd_ce_f32(const uml_segment* segs /*host*/, int32_t nseg, int32_t dim,
+                        const float* W, int32_t n_classes, float* G, int64_t ldg,
+                        float* row_loss, int32_t* row_correct, float* row_dscale,
+                        uml_seg_stats* stats, void* stream);
+
+/* ---- K4  dW = G^T X (autograd of the above; finetune.py:190-193), optionally fused with the
+ *          optimizer update so the gradient never round-trips HBM -------------------------------- */
+typedef struct {
+  int32_t kind;        /* 0 = write dW only, 1 = AdamW, 2 = Adam (L2), 3 = SGD momentum (L2)        */
+  float   lr, beta1, beta2, eps, weight_decay, momentum;
+  int64_t step;        /* 1-based step count for the bias corrections                               */
+  float*  m;           /* exp_avg   | momentum buffer                                               */
+  float*  v;           /* exp_avg_sq| unused                                                        */
+} uml_update;
+
+int uml_head_bwd_dw_f32(const uml_segment* segs /*host*/, int32_t nseg, int32_t dim,
+                        const float* G, int64_t ldg, int32_t n_classes,
+                        float* W, float* dW /*may be NULL when fused*/, const uml_update* upd /*host*/,
+                        void* stream);
+
+/* ---- K5  adapter GEMMs in fp32 (head.py:65,79 and their autograd) ---------------------------- */
+/* C[m,n] = alpha * sum_k A[m,k] * B[n,k]        (both operands K-contiguous: nn.Linear forward)   */
+int uml_gemm_nt_f32(const float* A, int64_t lda, const int64_t* a_row_idx, const float* B, int64_t ldb,
+                    float* C, int64_t ldc, int64_t m, int64_t n, int64_t k, float alpha, void* stream);
+/* C[m,n] = alpha * sum_k A[m,k] * B[k,n]        (dZ = G W)                                         */
+int uml_gemm_nn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                    int64_t m, int64_t n, int64_t k, float alpha, void* stream);
+/* C[m,n] = alpha * sum_k A[k,m] * B[k,n] (+ optimizer update of P when upd->kind != 0)            */
+int uml_gemm_tn_f32(const float* A, int64_t lda, const float* B, int64_t ldb, const int64_t* b_row_idx,
+                    float* C, int64_t ldc, int64_t m, int64_t n, int64_t k, float alpha,
+                    float* P, const uml_update* upd /*host, may be NULL*/, void* stream);
+
+/* ---- K6  fused optimizer updates (engine/optimizer/optim.py:15-71 -> torch.optim rules) ------ */
+int uml_adamw_step(float* p, const float* g, const float* g2, float g2_weight, float* m, float* v,
+                   int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                   int64_t step, int32_t decoupled, uint16_t* p_bf16 /*optional shadow*/, void* stream);
+int uml_sgd_step(float* p, const float* g, const float* g2, float g2_weight, float* buf, int64_t n,
+                 double lr, double momentum, double weight_decay, int64_t step,
+                 uint16_t* p_bf16, void* stream);
+
+/* ---- K7  evaluation: logits + argmax + per-row CE over a bank (finetune.py:291-315) ---------- */
+int uml_eval_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t n_rows, int32_t dim,
+                 const float* W, int32_t n_classes, float scale,
+                 float* row_loss, int32_t* row_pred, void* stream);
+/* mean over reference batches of the batch-mean loss + hit count (finetune.py:310-312)           */
+int uml_eval_reduce(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
+                    int64_t batch_size, float* out_loss /*[1]*/, int32_t* out_correct /*[1]*/, void* stream);
+
+/* ---- K8  gradient diagnostics (finetune.py:200-206): out = {dot, |a|^2, |b|^2, sign agreement} */
+#define UML_DIAG_BLOCKS 296
+int uml_grad_diag(const float* a, const float* b, int64_t n, float* workspace /* >= 4*UML_DIAG_BLOCKS floats */,
+                  float* out4, void* stream);
+
+/* ---- tensor-core path (tcgen05 + TMEM + TMA) --------------------------------------------------- */
+/* X: [n_rows, dim] bf16 dense (ld = dim), W: [n_classes, dim] bf16.  Row r belongs to segment
+ * 0 when r < seg0_rows, else 1.  G: [n_rows, ldg] bf16, ldg a multiple of 64 and >= n_classes.     */
+typedef struct {
+  int64_t seg_rows[UML_MAX_SEGMENTS];
+  float   scale[UML_MAX_SEGMENTS];
+  float   loss_weight[UML_MAX_SEGMENTS];
+  int32_t nseg;
+} uml_tc_segments;
+
+int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W,
+                         int32_t n_classes, const int32_t* labels, const uml_tc_segments* segs /*host*/,
+                         uint16_t* G /*may be NULL: eval mode*/, int64_t ldg,
+                         float* row_loss, int32_t* row_pred /*optional: argmax class*/,
+                         int32_t* row_correct /*optional: argmax == label*/, float* row_dscale /*optional*/,
+                         void* stream);
+/* dW_partial[s] = (G^T X) over the s-th K split; partials: [n_splits, n_classes, dim] fp32.       */
+int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
+                         int32_t n_classes, float* partials, int32_t n_splits, void* stream);
+int uml_tc_dw_splits(int64_t n_rows, int32_t dim, int32_t n_classes);   /* suggested n_splits      */
+/* p -= update(sum_s partials[s]); also refreshes the bf16 shadow of p                             */
+int uml_adamw_step_partials(float* p, const float* partials, int32_t n_splits, int64_t split_stride,
+                            float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                            double eps, double weight_decay, int64_t step, int32_t decoupled,
+                            uint16_t* p_bf16, float* g_out /*optional: reduced gradient*/, void* stream);
+int uml_reduce_seg_stats(const float* row_loss, const int32_t* row_correct, const float* row_dscale,
+                         const int64_t* seg_rows /*host [nseg]*/, int32_t nseg, uml_seg_stats* stats,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UML_B200_H_ */

@@ -1,0 +1,337 @@
+"""Parity of every CUDA kernel with the CPU oracle, called through the C ABI (ctypes).
+
+Run on the B200 box:  python -m pytest tests -m gpu
+Tolerances: the *_f32 kernels compute in fp32 like the reference (differences are summation order
+only); the *_bf16 tensor-core kernels are compared (a) tightly against the oracle evaluated on the
+same bf16-rounded operands - this isolates kernel correctness - and (b) against the fp32 oracle
+within the stated 1e-3 relative tolerance on the loss.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uml_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import uml_b200  # noqa: F401
+    from uml_b200 import ops
+
+DEV = "cuda:0"
+
+
+def _mk(seed, n_img, n_txt, dv, d, c):
+    g = torch.Generator().manual_seed(seed)
+    xi = torch.randn(n_img, dv, generator=g)
+    yi = torch.randint(0, c, (n_img,), generator=g)
+    xt = torch.randn(n_txt, d, generator=g)
+    yt = torch.randint(0, c, (n_txt,), generator=g)
+    w = torch.randn(c, d, generator=g)
+    w = w / w.norm(dim=1, keepdim=True)
+    return xi, yi, xt, yt, w, g
+
+
+# ------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize("n_bank,dim,n", [(1000, 512, 32), (5000, 768, 1000), (300, 3200, 77), (64, 100, 9), (50, 30, 5),
+                                          (128, 768, 0), (20000, 768, 16384)])
+def test_gather_rows(n_bank, dim, n):
+    g = torch.Generator().manual_seed(n_bank + dim + n)
+    bank = torch.randn(n_bank, dim, generator=g)
+    idx = torch.randint(0, n_bank, (n,), generator=g)
+    bank_d, idx_d = bank.to(DEV), idx.to(DEV)
+    out = ops.gather_rows(bank_d, idx_d)
+    assert torch.equal(out.cpu(), bank[idx])  # byte-exact copy
+    if dim % 8 == 0:
+        out16 = ops.gather_rows(bank_d, idx_d, dtype=torch.bfloat16)
+        assert torch.equal(out16.cpu(), bank[idx].to(torch.bfloat16))
+    labels = torch.randint(0, 1000, (n_bank,), generator=g)
+    lab32 = torch.empty(max(n, 1), dtype=torch.int32, device=DEV)
+    ops.gather_labels(labels.to(DEV), idx_d, n, lab32)
+    assert torch.equal(lab32[:n].cpu().long(), labels[idx])
+
+
+def test_cast_bf16():
+    x = torch.randn(1000 * 768 + 3)
+    assert torch.equal(ops.cast_bf16(x.to(DEV)).cpu(), x.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------ K6
+@pytest.mark.parametrize("name,wd", [("adamw", 0.01), ("adamw", 0.0), ("adam", 0.01), ("sgd", 0.01)])
+@pytest.mark.parametrize("n", [1000 * 512, 12345])
+def test_optimizer_steps(name, wd, n):
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    ref = {"p": p0.clone()}
+    opt = O.OracleOptimizer(ref, name, 1e-3, wd)
+    p = p0.to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    for step in range(1, 6):
+        grad = torch.randn(n, generator=g) * (0.01 * step)
+        lr = 1e-3 * step / 5
+        opt.step({"p": grad}, lr)
+        if name == "sgd":
+            ops.sgd_step(p, grad.to(DEV), m, lr=lr, step=step, weight_decay=wd, shadow=shadow)
+        else:
+            ops.adamw_step(p, grad.to(DEV), m, v, lr=lr, step=step, weight_decay=wd, decoupled=(name == "adamw"),
+                           shadow=shadow)
+        np.testing.assert_allclose(p.cpu().numpy(), ref["p"].numpy(), rtol=2e-6, atol=2e-7)
+    assert torch.equal(shadow.cpu(), p.cpu().to(torch.bfloat16))
+
+
+def test_adamw_two_gradients_and_partials():
+    n = 1000 * 64
+    g = torch.Generator().manual_seed(3)
+    p0, g1, g2 = (torch.randn(n, generator=g) for _ in range(3))
+    ref = {"p": p0.clone()}
+    O.OracleOptimizer(ref, "adamw", 1e-3, 0.01).step({"p": g1 + 0.5 * g2})
+    p = p0.to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ops.adamw_step(p, g1.to(DEV), m, v, lr=1e-3, step=1, weight_decay=0.01, g2=g2.to(DEV), g2_weight=0.5)
+    np.testing.assert_allclose(p.cpu().numpy(), ref["p"].numpy(), rtol=2e-6, atol=2e-7)
+    parts = torch.randn(5, n, generator=g)
+    ref = {"p": p0.clone()}
+    O.OracleOptimizer(ref, "adamw", 1e-3, 0.01).step({"p": parts.sum(0)})
+    p = p0.to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    gout = torch.empty_like(p)
+    ops.adamw_step_partials(p, parts.to(DEV), 5, m, v, lr=1e-3, step=1, weight_decay=0.01, g_out=gout)
+    np.testing.assert_allclose(gout.cpu().numpy(), parts.sum(0).numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(p.cpu().numpy(), ref["p"].numpy(), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ fp32 head
+HEAD_CASES = [
+    # n_img_bank, n_txt_bank, D, C, B_img, B_txt, scale, alpha
+    (16000, 2994, 512, 1000, 32, 32, 100.0, 0.5),     # cfg2 step
+    (500, 300, 768, 1000, 5, 32, 100.0, 1.0),         # ragged image batch (epoch tail)
+    (400, 200, 512, 397, 32, 0, 1.0, 0.0),            # image only (SUN397 classes)
+    (300, 303, 512, 101, 64, 64, 100.0, 1.5),         # Food101 classes
+    (200, 100, 3200, 100, 8, 8, 1.0, 0.7),            # OpenLLaMA width, tiny batch
+    (3000, 3000, 96, 10, 300, 200, 10.0, 0.2),        # wide batch, narrow head
+]
+
+
+def _runs(xi, yi, xt, yt, ii, it, s_i, s_t, alpha):
+    runs = []
+    if ii is not None and ii.numel():
+        runs.append(ops.Run(xi, yi, ii, ii.numel(), s_i, 1.0))
+    if it is not None and it.numel():
+        runs.append(ops.Run(xt, yt, it, it.numel(), s_t, alpha))
+    return runs
+
+
+@pytest.mark.parametrize("case", HEAD_CASES)
+def test_head_step_f32_matches_oracle(case):
+    nib, ntb, d, c, bi, bt, scale, alpha = case
+    xi, yi, xt, yt, w, g = _mk(sum(case[:6]), nib, ntb, d, d, c)
+    ii = torch.randint(0, nib, (bi,), generator=g)
+    it = torch.randint(0, ntb, (bt,), generator=g)
+    st = O.HeadState(head=w.clone(), img_scale=scale, txt_scale=scale * 0.5)
+    stats, grads = O.uml_step_grads(st, xi[ii] if bi else None, yi[ii] if bi else None, xt[it] if bt else None,
+                                    yt[it] if bt else None, alpha)
+    dev = [t.to(DEV) for t in (xi, yi, xt, yt, ii, it)]
+    runs = _runs(*dev, scale, scale * 0.5, alpha)
+    ws = ops.HeadWorkspace(bi + bt, c, DEV)
+    Wd = w.to(DEV)
+    ops.head_fwd_ce_f32(runs, Wd, ws)
+    got = ws.read_stats()
+    k = 0
+    if bi:
+        assert math.isclose(got[k]["loss_mean"], stats["image_loss"], rel_tol=2e-5, abs_tol=1e-5)
+        assert got[k]["correct"] == round(stats["img_acc"] * bi) and got[k]["n"] == bi
+        k += 1
+    if bt:
+        assert math.isclose(got[k]["loss_mean"], stats["text_loss"], rel_tol=2e-5, abs_tol=1e-5)
+        assert got[k]["correct"] == round(stats["text_acc"] * bt) and got[k]["n"] == bt
+    dW = torch.empty_like(Wd)
+    ops.head_bwd_dw_f32(runs, Wd, ws, dW=dW)
+    want = grads["head.weight"]
+    err = (dW.cpu() - want).abs().max().item()
+    assert err <= 2e-5 * max(1.0, want.abs().max().item()), err
+    # fused AdamW epilogue == oracle optimizer step on the same gradient
+    ref = {"head.weight": w.clone()}
+    O.OracleOptimizer(ref, "adamw", 1e-3, 0.01).step({"head.weight": want}, 2e-4)
+    m, v = torch.zeros_like(Wd), torch.zeros_like(Wd)
+    upd = ops.make_update("adamw", 2e-4, 1, m, v, weight_decay=0.01)
+    ops.head_bwd_dw_f32(runs, Wd, ws, update=upd)
+    # AdamW's first step is lr*sign(g): elements whose gradient is ~0 may flip, so compare robustly
+    diff = (Wd.cpu() - ref["head.weight"]).abs()
+    assert diff.max().item() <= 2 * 2e-4 + 1e-7
+    assert (diff > 1e-6).float().mean().item() < 1e-3
+
+
+def test_learnable_scale_gradient_f32():
+    nib, ntb, d, c, bi, bt = 200, 120, 64, 20, 16, 24
+    xi, yi, xt, yt, w, g = _mk(77, nib, ntb, d, d, c)
+    ii = torch.randint(0, nib, (bi,), generator=g)
+    it = torch.randint(0, ntb, (bt,), generator=g)
+    st = O.HeadState(head=w.clone(), img_scale=3.0, txt_scale=2.0, learnable_temp=True)
+    _, grads = O.uml_step_grads(st, xi[ii], yi[ii], xt[it], yt[it], 0.7)
+    dev = [t.to(DEV) for t in (xi, yi, xt, yt, ii, it)]
+    ws = ops.HeadWorkspace(bi + bt, c, DEV)
+    ops.head_fwd_ce_f32(_runs(*dev, 3.0, 2.0, 0.7), w.to(DEV), ws)
+    got = ws.read_stats()
+    assert math.isclose(got[0]["dscale"], float(grads["img_scale"]), rel_tol=1e-4, abs_tol=1e-6)
+    assert math.isclose(got[1]["dscale"], float(grads["txt_scale"]), rel_tol=1e-4, abs_tol=1e-6)
+
+
+def test_adapter_gemms_f32():
+    g = torch.Generator().manual_seed(5)
+    b, dv, d, c = 37, 96, 160, 50
+    bank = torch.randn(100, dv, generator=g)
+    idx = torch.randint(0, 100, (b,), generator=g)
+    wp = torch.randn(d, dv, generator=g) * 0.1
+    w = torch.randn(c, d, generator=g) * 0.1
+    gm = torch.randn(b, c, generator=g)
+    z = torch.empty(b, d, device=DEV)
+    ops.gemm_nt(bank.to(DEV), wp.to(DEV), z, a_row_idx=idx.to(DEV))
+    np.testing.assert_allclose(z.cpu().numpy(), (bank[idx] @ wp.t()).numpy(), rtol=1e-4, atol=1e-5)
+    dz = torch.empty(b, d, device=DEV)
+    ops.gemm_nn(gm.to(DEV), w.to(DEV), dz, alpha=2.0)
+    np.testing.assert_allclose(dz.cpu().numpy(), (2.0 * gm @ w).numpy(), rtol=1e-4, atol=1e-5)
+    dwp = torch.empty(d, dv, device=DEV)
+    ops.gemm_tn(dz, bank.to(DEV), dwp, k=b, m=d, n=dv, b_row_idx=idx.to(DEV))
+    np.testing.assert_allclose(dwp.cpu().numpy(), ((2.0 * gm @ w).t() @ bank[idx]).numpy(), rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------ K7
+@pytest.mark.parametrize("n,d,c,bs", [(4000, 512, 1000, 32), (333, 768, 397, 32), (11, 64, 7, 4), (1000, 100, 101, 64)])
+def test_eval_matches_oracle_validate(n, d, c, bs):
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.randn(n, d, generator=g)
+    y = torch.randint(0, c, (n,), generator=g)
+    w = torch.randn(c, d, generator=g) / math.sqrt(d)
+    st = O.HeadState(head=w, img_scale=30.0)
+    vloss, vacc = O.validate(st, x, y, bs, loader_protocol=False)
+    xd, yd, wd = x.to(DEV), y.to(DEV), w.to(DEV)
+    rl = torch.empty(n, device=DEV)
+    rp = torch.empty(n, dtype=torch.int32, device=DEV)
+    ops.eval_f32(xd, yd, wd, 30.0, rl, rp)
+    out_l = torch.empty(1, device=DEV)
+    out_c = torch.empty(1, dtype=torch.int32, device=DEV)
+    ops.eval_reduce(rl, rp, yd, bs, out_l, out_c)
+    assert math.isclose(out_l.item(), vloss, rel_tol=2e-5)
+    assert out_c.item() == round(vacc * n)
+
+
+def test_grad_diag():
+    g = torch.Generator().manual_seed(8)
+    a, b = torch.randn(1000 * 512, generator=g), torch.randn(1000 * 512, generator=g)
+    out = torch.empty(4, device=DEV)
+    ops.grad_diag(a.to(DEV), b.to(DEV), torch.empty(4 * 296, device=DEV), out)
+    o = out.cpu()
+    assert math.isclose(o[0].item(), float(torch.dot(a, b)), rel_tol=1e-3, abs_tol=0.5)
+    assert math.isclose(o[1].item(), float(a.pow(2).sum()), rel_tol=1e-4)
+    assert math.isclose(o[2].item(), float(b.pow(2).sum()), rel_tol=1e-4)
+    assert o[3].item() == float((torch.sign(a) == torch.sign(b)).sum())
+
+
+# ------------------------------------------------------------------------------------------ tensor cores
+TC_CASES = [
+    # rows_img, rows_txt, D, C
+    (128, 128, 64, 256),      # one k-block, one chunk
+    (256, 0, 512, 1000),      # ViT-B/16 head, single run
+    (300, 212, 768, 1000),    # ViT-L/14 head, ragged rows
+    (1000, 1048, 768, 1000),
+    (64, 70, 128, 101),       # Food101
+    (200, 56, 3200, 397),     # OpenLLaMA width
+]
+
+
+def _tc_reference(x16, w16, labels, n0, n1, scales, weights):
+    """fp32 math on the bf16-rounded operands."""
+    x, w = x16.float(), w16.float()
+    raw = x @ w.t()
+    outs = []
+    G = torch.zeros_like(raw)
+    loss = torch.zeros(raw.shape[0])
+    for (lo, hi, s, wt) in ((0, n0, scales[0], weights[0]), (n0, n0 + n1, scales[1], weights[1])):
+        if hi == lo:
+            continue
+        lg = raw[lo:hi] * s
+        lse = torch.logsumexp(lg, 1)
+        loss[lo:hi] = lse - lg.gather(1, labels[lo:hi].view(-1, 1).long()).squeeze(1)
+        p = torch.softmax(lg, 1)
+        p[torch.arange(hi - lo), labels[lo:hi].long()] -= 1.0
+        G[lo:hi] = p * (wt * s / (hi - lo))
+    return raw, loss, G
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_tc_forward_and_dw(case):
+    n0, n1, d, c = case
+    n = n0 + n1
+    g = torch.Generator().manual_seed(n + d + c)
+    x = torch.randn(n, d, generator=g)
+    w = torch.randn(c, d, generator=g)
+    w = w / w.norm(dim=1, keepdim=True)
+    labels = torch.randint(0, c, (n,), generator=g, dtype=torch.int32)
+    scales, weights = (100.0, 50.0), (1.0, 0.5)
+    x16, w16 = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    raw, loss_ref, G_ref = _tc_reference(x16, w16, labels, n0, n1, scales, weights)
+    ws = ops.HeadWorkspace(n, c, DEV, bf16=True)
+    ws.G.fill_(float("nan"))
+    rp = torch.empty(n, dtype=torch.int32, device=DEV)
+    rows = [r for r in (n0, n1) if r]
+    segs = ops.tc_segments(rows, scales[:len(rows)] if n0 else scales[1:], weights[:len(rows)] if n0 else weights[1:])
+    xd, wd = x16.to(DEV), w16.to(DEV)
+    ops.head_fwd_ce_bf16(xd, wd, labels.to(DEV), segs, ws, ws.row_loss, row_pred=rp, row_correct=ws.row_correct,
+                         row_dscale=ws.row_dscale)
+    torch.cuda.synchronize()
+    loss = ws.row_loss[:n].cpu()
+    np.testing.assert_allclose(loss.numpy(), loss_ref.numpy(), rtol=2e-4, atol=2e-3)
+    lg = raw.clone()
+    lg[:n0] *= scales[0]
+    lg[n0:] *= scales[1]
+    top2 = lg.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-2  # rows whose argmax is not a numerical near-tie
+    assert torch.equal(rp.cpu()[clear].long(), lg.argmax(1)[clear])
+    G = ws.G[:n].float().cpu()
+    assert torch.isfinite(G).all()
+    assert float(G[:, c:].abs().max()) == 0.0 if ws.ldg > c else True
+    scale_ref = G_ref.abs().max().item()
+    assert (G[:, :c] - G_ref).abs().max().item() <= 1.2e-2 * scale_ref  # two bf16 roundings of values <= scale_ref
+    # dscale
+    ds_ref = torch.zeros(n)
+    for (lo, hi, s, wt) in ((0, n0, scales[0], weights[0]), (n0, n, scales[1], weights[1])):
+        if hi > lo:
+            ds_ref[lo:hi] = (G_ref[lo:hi] / s * raw[lo:hi]).sum(1)
+    np.testing.assert_allclose(ws.row_dscale[:n].cpu().numpy(), ds_ref.numpy(), rtol=2e-2, atol=2e-4)
+    # dW from the kernel's own G (isolates the MN-major GEMM) ------------------------------------
+    splits = ops.tc_dw_splits(n, d, c)
+    parts = torch.full((splits, c, d), float("nan"), device=DEV)
+    ops.head_bwd_dw_bf16(ws.G, ws.ldg, xd, n, c, parts, splits)
+    torch.cuda.synchronize()
+    dW = parts.sum(0).cpu()
+    dW_ref = G[:, :c].t() @ x16.float()
+    assert torch.isfinite(dW).all()
+    assert (dW - dW_ref).abs().max().item() <= 1e-3 * max(1e-6, dW_ref.abs().max().item())
+    # and against the full-precision gradient: bf16 operand noise only
+    full = G_ref.t() @ x16.float()
+    rel = (dW - full).norm().item() / full.norm().item()
+    assert rel < 1e-2, rel
+
+
+def test_tc_loss_within_stated_tolerance_of_fp32():
+    """bf16 tensor-core forward vs the fp32 oracle on the SAME fp32 inputs: mean loss within 1e-3 rel."""
+    n0 = n1 = 512
+    d, c = 768, 1000
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n0 + n1, d, generator=g)
+    w = torch.randn(c, d, generator=g)
+    w = w / w.norm(dim=1, keepdim=True)
+    y = torch.randint(0, c, (n0 + n1,), generator=g)
+    st = O.HeadState(head=w, img_scale=100.0, txt_scale=100.0)
+    stats, _ = O.uml_step_grads(st, x[:n0], y[:n0], x[n0:], y[n0:], 1.0)
+    ws = ops.HeadWorkspace(n0 + n1, c, DEV, bf16=True)
+    segs = ops.tc_segments([n0, n1], [100.0, 100.0], [1.0, 1.0])
+    ops.head_fwd_ce_bf16(ops.cast_bf16(x.to(DEV)), ops.cast_bf16(w.to(DEV)), y.to(torch.int32).to(DEV), segs, ws,
+                         ws.row_loss, row_correct=ws.row_correct)
+    ops.reduce_seg_stats(ws.row_loss, ws.row_correct, None, [n0, n1], ws.stats)
+    got = ws.read_stats()
+    assert abs(got[0]["loss_mean"] - stats["image_loss"]) <= 1e-3 * abs(stats["image_loss"])
+    assert abs(got[1]["loss_mean"] - stats["text_loss"]) <= 1e-3 * abs(stats["text_loss"])

@@ -1,0 +1,99 @@
+"""ctypes binding of the C ABI declared in include/uml_b200.h.
+
+The library is looked up in-tree (``lib/libuml_b200.so``, built by ``build.py``).  A missing
+library is a hard error - the product path never falls back to PyTorch or the CPU."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libuml_b200.so")
+
+c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+class Segment(C.Structure):
+    """uml_segment"""
+    _fields_ = [("rows", c_vp), ("idx", c_vp), ("labels", c_vp), ("n", c_i64), ("ld", c_i64),
+                ("scale", c_f32), ("loss_weight", c_f32)]
+
+
+class SegStats(C.Structure):
+    """uml_seg_stats"""
+    _fields_ = [("loss_mean", c_f32), ("dscale", c_f32), ("correct", c_i32), ("n", c_i32)]
+
+
+class Update(C.Structure):
+    """uml_update"""
+    _fields_ = [("kind", c_i32), ("lr", c_f32), ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32),
+                ("weight_decay", c_f32), ("momentum", c_f32), ("step", c_i64), ("m", c_vp), ("v", c_vp)]
+
+
+class TcSegments(C.Structure):
+    """uml_tc_segments"""
+    _fields_ = [("seg_rows", c_i64 * 2), ("scale", c_f32 * 2), ("loss_weight", c_f32 * 2), ("nseg", c_i32)]
+
+
+# name -> argtypes; every function returns int except uml_last_error
+PROTOTYPES = {
+    "uml_abi_version": [],
+    "uml_device_ok": [c_i32],
+    "uml_gather_rows_f32": [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
+    "uml_gather_rows_bf16": [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp],
+    "uml_gather_labels_i32": [c_vp, c_vp, c_i64, c_vp, c_vp],
+    "uml_cast_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],
+    "uml_head_fwd_ce_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "uml_head_bwd_dw_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, C.POINTER(Update), c_vp],
+    "uml_gemm_nt_f32": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp],
+    "uml_gemm_nn_f32": [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp],
+    "uml_gemm_tn_f32": [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp,
+                        C.POINTER(Update), c_vp],
+    "uml_adamw_step": [c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32,
+                       c_vp, c_vp],
+    "uml_sgd_step": [c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp],
+    "uml_eval_f32": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp],
+    "uml_eval_reduce": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "uml_grad_diag": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "uml_head_fwd_ce_bf16": [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, C.POINTER(TcSegments), c_vp, c_i64, c_vp, c_vp,
+                             c_vp, c_vp, c_vp],
+    "uml_head_bwd_dw_bf16": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp],
+    "uml_tc_dw_splits": [c_i64, c_i32, c_i32],
+    "uml_adamw_step_partials": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64,
+                                c_i32, c_vp, c_vp, c_vp],
+    "uml_reduce_seg_stats": [c_vp, c_vp, c_vp, C.POINTER(c_i64), c_i32, c_vp, c_vp],
+}
+
+_lib = None
+
+
+class UmlLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libuml_b200.so once and attach prototypes.  Raises if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UmlLibraryError(
+            f"{LIB_PATH} not found - build it with `python unpaired-multimodal-learning_b200/build.py` "
+            "(or __graft_entry__.build()).  There is no CPU/PyTorch fallback for the UML hot path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.uml_last_error.restype = C.c_char_p
+    lib.uml_last_error.argtypes = []
+    for name, args in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = c_i32
+        fn.argtypes = args
+    if lib.uml_abi_version() != 1:
+        raise UmlLibraryError("libuml_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load().uml_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libuml_b200: {msg} (status {status})")

@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI (include/uml_b200.h).
+
+PyTorch is used for device memory and streams only; every function launches hand-written sm_100a
+kernels from libuml_b200.so on ``torch.cuda.current_stream()`` and never synchronises the host.
+Inputs must live on a CUDA device - there is deliberately no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import Segment, SegStats, TcSegments, Update, check
+
+UPDATE_KINDS = {"none": 0, "adamw": 1, "adam": 2, "sgd": 3}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype, name: str, contiguous: bool = True):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (uml_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t
+
+
+@dataclass
+class Run:
+    """One run of rows pushed through the shared head in a step (image batch or text batch)."""
+    rows: torch.Tensor                 # [N, D] fp32 feature bank (or dense batch when idx is None)
+    labels: torch.Tensor               # [N] int64
+    idx: Optional[torch.Tensor]        # [n] int64 indices into rows/labels, or None
+    n: int
+    scale: float = 1.0
+    loss_weight: float = 1.0
+
+    def c_segment(self) -> Segment:
+        _need(self.rows, torch.float32, "run.rows")
+        _need(self.labels, torch.int64, "run.labels")
+        if self.idx is not None:
+            _need(self.idx, torch.int64, "run.idx")
+            if self.idx.numel() < self.n:
+                raise ValueError("run.idx shorter than run.n")
+        elif self.rows.shape[0] < self.n:
+            raise ValueError("run.rows shorter than run.n")
+        return Segment(self.rows.data_ptr(), _ptr(self.idx), self.labels.data_ptr(), int(self.n),
+                       int(self.rows.stride(0)), float(self.scale), float(self.loss_weight))
+
+
+def _segs(runs: Sequence[Run]):
+    if not 1 <= len(runs) <= 2:
+        raise ValueError("1 or 2 runs per step")
+    arr = (Segment * len(runs))(*[r.c_segment() for r in runs])
+    return arr, len(runs)
+
+
+def make_update(kind: str, lr: float, step: int, m: Optional[torch.Tensor], v: Optional[torch.Tensor],
+                weight_decay: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8, momentum: float = 0.9) -> Update:
+    return Update(UPDATE_KINDS[kind], float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+                  float(momentum), int(step), _ptr(m), _ptr(v))
+
+
+# ------------------------------------------------------------------------------------------ K1
+
+def gather_rows(bank: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None,
+                dtype=torch.float32) -> torch.Tensor:
+    _need(bank, torch.float32, "bank")
+    _need(idx, torch.int64, "idx")
+    n, d = idx.numel(), bank.shape[1]
+    if out is None:
+        out = torch.empty((n, d), device=bank.device, dtype=dtype)
+    lib = _lib.load()
+    if out.dtype == torch.float32:
+        check(lib.uml_gather_rows_f32(bank.data_ptr(), bank.shape[0], d, idx.data_ptr(), n, out.data_ptr(), _stream()))
+    elif out.dtype == torch.bfloat16:
+        check(lib.uml_gather_rows_bf16(bank.data_ptr(), bank.shape[0], d, idx.data_ptr(), n, out.data_ptr(),
+                                       out.stride(0), _stream()))
+    else:
+        raise TypeError("gather_rows: out must be float32 or bfloat16")
+    return out
+
+
+def gather_labels(labels: torch.Tensor, idx: Optional[torch.Tensor], n: int, out: torch.Tensor) -> torch.Tensor:
+    _need(labels, torch.int64, "labels")
+    _need(out, torch.int32, "out")
+    check(_lib.load().uml_gather_labels_i32(labels.data_ptr(), _ptr(idx), n, out.data_ptr(), _stream()))
+    return out
+
+
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need(src, torch.float32, "src")
+    if dst is None:
+        dst = torch.empty(src.shape, device=src.device, dtype=torch.bfloat16)
+    check(_lib.load().uml_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()))
+    return dst
+
+
+# ------------------------------------------------------------------------------------------ fp32 head
+
+class HeadWorkspace:
+    """Caller-owned scratch for one head step (the library never allocates)."""
+
+    def __init__(self, max_rows: int, n_classes: int, device, bf16: bool = False):
+        self.max_rows, self.n_classes = int(max_rows), int(n_classes)
+        self.ldg = ((n_classes + 63) // 64) * 64
+        self.G = torch.empty((max_rows, self.ldg), device=device, dtype=torch.bfloat16 if bf16 else torch.float32)
+        self.row_loss = torch.empty(max_rows, device=device, dtype=torch.float32)
+        self.row_correct = torch.empty(max_rows, device=device, dtype=torch.int32)
+        self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
+        self.stats = torch.zeros((2, 4), device=device, dtype=torch.float32)  # 2 x uml_seg_stats (16 B each)
+
+    def read_stats(self):
+        """Host copy of the two uml_seg_stats records (synchronises)."""
+        raw = self.stats.cpu()
+        ints = raw.view(torch.int32)
+        return [dict(loss_mean=float(raw[i, 0]), dscale=float(raw[i, 1]), correct=int(ints[i, 2]), n=int(ints[i, 3]))
+                for i in range(2)]
+
+
+def head_fwd_ce_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace):
+    """logits -> softmax CE -> G (in ws.G), per-run stats in ws.stats.  finetune.py:181-188."""
+    _need(W, torch.float32, "W")
+    arr, n = _segs(runs)
+    total = sum(r.n for r in runs)
+    if total > ws.max_rows:
+        raise ValueError("workspace too small")
+    check(_lib.load().uml_head_fwd_ce_f32(arr, n, W.shape[1], W.data_ptr(), W.shape[0], ws.G.data_ptr(), ws.ldg,
+                                          ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr(),
+                                          ws.stats.data_ptr(), _stream()))
+
+
+def head_bwd_dw_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, dW: Optional[torch.Tensor] = None,
+                    update: Optional[Update] = None):
+    """dW = G^T X; with ``update`` the optimizer step is applied to W in the GEMM epilogue."""
+    _need(W, torch.float32, "W")
+    arr, n = _segs(runs)
+    check(_lib.load().uml_head_bwd_dw_f32(arr, n, W.shape[1], ws.G.data_ptr(), ws.ldg, W.shape[0], W.data_ptr(),
+                                          _ptr(dW), C.byref(update) if update is not None else None, _stream()))
+
+
+def gemm_nt(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, alpha: float = 1.0,
+            a_row_idx: Optional[torch.Tensor] = None, m: Optional[int] = None):
+    """out[m,n] = alpha * sum_k A[row(m),k] B[n,k]"""
+    m = out.shape[0] if m is None else m
+    check(_lib.load().uml_gemm_nt_f32(A.data_ptr(), A.stride(0), _ptr(a_row_idx), B.data_ptr(), B.stride(0),
+                                      out.data_ptr(), out.stride(0), m, B.shape[0], B.shape[1], alpha, _stream()))
+
+
+def gemm_nn(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, alpha: float = 1.0, m: Optional[int] = None,
+            k: Optional[int] = None):
+    """out[m,n] = alpha * sum_k A[m,k] B[k,n]"""
+    m = out.shape[0] if m is None else m
+    k = B.shape[0] if k is None else k
+    check(_lib.load().uml_gemm_nn_f32(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), out.data_ptr(),
+                                      out.stride(0), m, B.shape[1], k, alpha, _stream()))
+
+
+def gemm_tn(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor], k: int, m: int, n: int, alpha: float = 1.0,
+            b_row_idx: Optional[torch.Tensor] = None, P: Optional[torch.Tensor] = None,
+            update: Optional[Update] = None, ldc: Optional[int] = None):
+    """out[m,n] = alpha * sum_k A[k,m] B[row(k),n]  (+ fused optimizer update of P)"""
+    ldc = (out.stride(0) if out is not None else P.stride(0)) if ldc is None else ldc
+    check(_lib.load().uml_gemm_tn_f32(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), _ptr(b_row_idx), _ptr(out),
+                                      ldc, m, n, k, alpha, _ptr(P), C.byref(update) if update is not None else None,
+                                      _stream()))
+
+
+# ------------------------------------------------------------------------------------------ K6
+
+def adamw_step(p, g, m, v, *, lr, step, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, decoupled=True,
+               g2=None, g2_weight=0.0, shadow=None):
+    for t, nm in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _need(t, torch.float32, nm)
+    check(_lib.load().uml_adamw_step(p.data_ptr(), g.data_ptr(), _ptr(g2), float(g2_weight), m.data_ptr(), v.data_ptr(),
+                                     p.numel(), lr, betas[0], betas[1], eps, weight_decay, step, int(decoupled),
+                                     _ptr(shadow), _stream()))
+
+
+def adamw_step_partials(p, partials, n_splits, m, v, *, lr, step, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
+                        decoupled=True, shadow=None, g_out=None):
+    _need(p, torch.float32, "p")
+    _need(partials, torch.float32, "partials")
+    check(_lib.load().uml_adamw_step_partials(p.data_ptr(), partials.data_ptr(), n_splits, p.numel(), m.data_ptr(),
+                                              v.data_ptr(), p.numel(), lr, betas[0], betas[1], eps, weight_decay, step,
+                                              int(decoupled), _ptr(shadow), _ptr(g_out), _stream()))
+
+
+def sgd_step(p, g, buf, *, lr, step, momentum=0.9, weight_decay=0.0, g2=None, g2_weight=0.0, shadow=None):
+    for t, nm in ((p, "p"), (g, "g"), (buf, "buf")):
+        _need(t, torch.float32, nm)
+    check(_lib.load().uml_sgd_step(p.data_ptr(), g.data_ptr(), _ptr(g2), float(g2_weight), buf.data_ptr(), p.numel(),
+                                   lr, momentum, weight_decay, step, _ptr(shadow), _stream()))
+
+
+# ------------------------------------------------------------------------------------------ K7 / K8
+
+def eval_f32(feats, labels, W, scale, row_loss, row_pred):
+    _need(feats, torch.float32, "feats")
+    _need(labels, torch.int64, "labels")
+    _need(W, torch.float32, "W")
+    check(_lib.load().uml_eval_f32(feats.data_ptr(), feats.stride(0), labels.data_ptr(), feats.shape[0], feats.shape[1],
+                                   W.data_ptr(), W.shape[0], float(scale), row_loss.data_ptr(), row_pred.data_ptr(),
+                                   _stream()))
+
+
+def eval_reduce(row_loss, row_pred, labels, batch_size, out_loss, out_correct):
+    check(_lib.load().uml_eval_reduce(row_loss.data_ptr(), row_pred.data_ptr(), labels.data_ptr(), labels.numel(),
+                                      int(batch_size), out_loss.data_ptr(), out_correct.data_ptr(), _stream()))
+
+
+def grad_diag(a, b, workspace, out4):
+    check(_lib.load().uml_grad_diag(a.data_ptr(), b.data_ptr(), a.numel(), workspace.data_ptr(), out4.data_ptr(),
+                                    _stream()))
+
+
+# ------------------------------------------------------------------------------------------ tensor-core head
+
+def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[float]) -> TcSegments:
+    s = TcSegments()
+    s.nseg = len(rows)
+    for i in range(len(rows)):
+        s.seg_rows[i], s.scale[i], s.loss_weight[i] = int(rows[i]), float(scales[i]), float(weights[i])
+    return s
+
+
+def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadWorkspace], row_loss, row_pred=None,
+                     row_correct=None, row_dscale=None, n_rows: Optional[int] = None):
+    _need(X, torch.bfloat16, "X")
+    _need(W_bf16, torch.bfloat16, "W")
+    _need(labels_i32, torch.int32, "labels")
+    n_rows = X.shape[0] if n_rows is None else n_rows
+    G, ldg = (ws.G.data_ptr(), ws.ldg) if ws is not None else (None, 0)
+    check(_lib.load().uml_head_fwd_ce_bf16(X.data_ptr(), n_rows, X.shape[1], W_bf16.data_ptr(), W_bf16.shape[0],
+                                           labels_i32.data_ptr(), C.byref(segs), G, ldg, row_loss.data_ptr(),
+                                           _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), _stream()))
+
+
+def tc_dw_splits(n_rows: int, dim: int, n_classes: int) -> int:
+    return int(_lib.load().uml_tc_dw_splits(n_rows, dim, n_classes))
+
+
+def head_bwd_dw_bf16(G, ldg, X, n_rows, n_classes, partials, n_splits):
+    _need(G, torch.bfloat16, "G")
+    _need(X, torch.bfloat16, "X")
+    _need(partials, torch.float32, "partials")
+    check(_lib.load().uml_head_bwd_dw_bf16(G.data_ptr(), ldg, X.data_ptr(), n_rows, X.shape[1], n_classes,
+                                           partials.data_ptr(), n_splits, _stream()))
+
+
+def reduce_seg_stats(row_loss, row_correct, row_dscale, seg_rows: Sequence[int], stats):
+    arr = (C.c_int64 * len(seg_rows))(*[int(x) for x in seg_rows])
+    check(_lib.load().uml_reduce_seg_stats(row_loss.data_ptr(), row_correct.data_ptr(), _ptr(row_dscale), arr,
+                                           len(seg_rows), stats.data_ptr(), _stream()))
