@@ -37,6 +37,10 @@ typedef struct {
   int64_t        ld;          /* leading dimension of `rows`, in elements                             */
   float          scale;       /* logit scale: exp(logit_scale) (UMLClip) or img_scale / txt_scale     */
   float          loss_weight; /* 1.0 for the image run, alpha for the text run (finetune.py:188)      */
+  const int64_t* label_idx;   /* optional: indices into `labels` when they differ from `idx` (adapter
+                                 output rows are dense but their labels still live in the bank)        */
+  const float*   scale_dev;   /* optional: device scalar overriding `scale` (learnable temperature,
+                                 head.py:69-70) so the step never reads it back to the host            */
 } uml_segment;
 
 /* Per-run results written by the forward kernels (device memory, one per segment). */
@@ -126,6 +130,7 @@ typedef struct {
   float   scale[UML_MAX_SEGMENTS];
   float   loss_weight[UML_MAX_SEGMENTS];
   int32_t nseg;
+  const float* scale_dev[UML_MAX_SEGMENTS];   /* optional device scalars overriding scale[]        */
 } uml_tc_segments;
 
 int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W,
@@ -143,6 +148,9 @@ int uml_adamw_step_partials(float* p, const float* partials, int32_t n_splits, i
                             float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                             double eps, double weight_decay, int64_t step, int32_t decoupled,
                             uint16_t* p_bf16, float* g_out /*optional: reduced gradient*/, void* stream);
+/* out = sum_s partials[s] in a fixed order (local split-K reduction before a data-parallel allreduce) */
+int uml_sum_partials(const float* partials, int32_t n_splits, int64_t split_stride, int64_t n, float* out,
+                     void* stream);
 int uml_reduce_seg_stats(const float* row_loss, const int32_t* row_correct, const float* row_dscale,
                          const int64_t* seg_rows /*host [nseg]*/, int32_t nseg, uml_seg_stats* stats,
                          void* stream);

@@ -16,7 +16,7 @@ c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, 
 class Segment(C.Structure):
     """uml_segment"""
     _fields_ = [("rows", c_vp), ("idx", c_vp), ("labels", c_vp), ("n", c_i64), ("ld", c_i64),
-                ("scale", c_f32), ("loss_weight", c_f32)]
+                ("scale", c_f32), ("loss_weight", c_f32), ("label_idx", c_vp), ("scale_dev", c_vp)]
 
 
 class SegStats(C.Structure):
@@ -32,7 +32,8 @@ class Update(C.Structure):
 
 class TcSegments(C.Structure):
     """uml_tc_segments"""
-    _fields_ = [("seg_rows", c_i64 * 2), ("scale", c_f32 * 2), ("loss_weight", c_f32 * 2), ("nseg", c_i32)]
+    _fields_ = [("seg_rows", c_i64 * 2), ("scale", c_f32 * 2), ("loss_weight", c_f32 * 2), ("nseg", c_i32),
+                ("scale_dev", c_vp * 2)]
 
 
 # name -> argtypes; every function returns int except uml_last_error
@@ -61,10 +62,33 @@ PROTOTYPES = {
     "uml_tc_dw_splits": [c_i64, c_i32, c_i32],
     "uml_adamw_step_partials": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64,
                                 c_i32, c_vp, c_vp, c_vp],
+    "uml_sum_partials": [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp],
     "uml_reduce_seg_stats": [c_vp, c_vp, c_vp, C.POINTER(c_i64), c_i32, c_vp, c_vp],
 }
 
 _lib = None
+
+# kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
+KERNELS_PER_CALL = {
+    "uml_gather_rows_f32": 1, "uml_gather_rows_bf16": 1, "uml_gather_labels_i32": 1, "uml_cast_f32_to_bf16": 1,
+    "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
+    "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
+    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 1, "uml_head_bwd_dw_bf16": 1, "uml_adamw_step_partials": 1,
+    "uml_sum_partials": 1, "uml_reduce_seg_stats": 1,
+}
+LAUNCH_COUNT = [0]
+
+
+class _Counted:
+    """Wraps a ctypes function so every successful call adds its kernel count to LAUNCH_COUNT."""
+
+    def __init__(self, fn, n):
+        self.fn, self.n = fn, n
+
+    def __call__(self, *a):
+        r = self.fn(*a)
+        LAUNCH_COUNT[0] += self.n
+        return r
 
 
 class UmlLibraryError(RuntimeError):
@@ -87,6 +111,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = c_i32
         fn.argtypes = args
+        if name in KERNELS_PER_CALL:
+            setattr(lib, name, _Counted(fn, KERNELS_PER_CALL[name]))
     if lib.uml_abi_version() != 1:
         raise UmlLibraryError("libuml_b200.so ABI version mismatch")
     _lib = lib

@@ -138,8 +138,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 template <bool kBf16>
 static int launch_gather(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx, int64_t n, void* out,
                          int64_t ld_out, cudaStream_t st) {
-  UML_REQUIRE(bank && out && dim > 0 && bank_rows > 0 && n >= 0, "gather: bad arguments");
   if (n == 0) return 0;
+  UML_REQUIRE(bank && out && dim > 0 && bank_rows > 0 && n > 0, "gather: bad arguments");
   const uint32_t row_bytes = static_cast<uint32_t>(dim) * 4u;
   const bool tma_ok = (row_bytes % 16 == 0) && (!kBf16 || dim % 8 == 0) && row_bytes <= kGatherStageBytes &&
                       (reinterpret_cast<uintptr_t>(bank) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
@@ -181,8 +181,8 @@ int uml_gather_rows_bf16(const float* bank, int64_t bank_rows, int32_t dim, cons
 }
 
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out, void* stream) {
-  UML_REQUIRE(bank_labels && out && n >= 0, "gather_labels: bad arguments");
   if (n == 0) return 0;
+  UML_REQUIRE(bank_labels && out && n > 0, "gather_labels: bad arguments");
   uml::gather_labels_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, uml::as_stream(stream)>>>(
       bank_labels, idx, n, out);
   UML_CUDA(cudaGetLastError());

@@ -116,6 +116,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+__global__ void __launch_bounds__(256)
+    sum_partials_kernel(const float* __restrict__ parts, int n_parts, int64_t stride, int64_t n4,
+                        float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 g = reinterpret_cast<const float4*>(parts)[i];
+    for (int s = 1; s < n_parts; ++s) {
+      const float4 q = reinterpret_cast<const float4*>(parts + s * stride)[i];
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = g;
+  }
+}
+
 static int launch_adam(float* p, const float* parts, int n_parts, int64_t stride, const float* g2, float w2, float* m,
                        float* v, int64_t n, const AdamArgs& a, uint16_t* shadow, float* g_out, cudaStream_t st) {
   if (n == 0) return 0;
@@ -156,6 +170,21 @@ int uml_adamw_step_partials(float* p, const float* partials, int32_t n_splits, i
               "adamw_step_partials: bad arguments");
   return launch_adam(p, partials, n_splits, split_stride, nullptr, 0.f, m, v, n,
                      make_adam(lr, beta1, beta2, eps, weight_decay, step, decoupled), p_bf16, g_out, as_stream(stream));
+}
+
+int uml_sum_partials(const float* partials, int32_t n_splits, int64_t split_stride, int64_t n, float* out,
+                     void* stream) {
+  using namespace uml;
+  UML_REQUIRE(partials && out && n_splits >= 1 && n >= 0 && split_stride >= n, "sum_partials: bad arguments");
+  UML_REQUIRE(n % 4 == 0 && split_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(partials) & 15u) == 0 &&
+                  (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+              "sum_partials: buffers must be 16B aligned and n a multiple of 4");
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  const int grid = static_cast<int>(std::min<int64_t>((n4 + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
+  sum_partials_kernel<<<grid, 256, 0, as_stream(stream)>>>(partials, n_splits, split_stride, n4, out);
+  UML_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int uml_sgd_step(float* p, const float* g, const float* g2, float g2_weight, float* buf, int64_t n, double lr,

@@ -196,6 +196,7 @@ struct SegInfo {
   int64_t n0, n1;
   const int64_t* idx[2];
   const int64_t* labels[2];
+  const float* scale_dev[2];
   float scale[2], weight[2];
 };
 
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(256)
   const int64_t* ix = s ? seg.idx[1] : seg.idx[0];
   const int64_t src = ix ? ix[l] : l;
   const int label = static_cast<int>((s ? seg.labels[1] : seg.labels[0])[src]);
-  const float scale = s ? seg.scale[1] : seg.scale[0];
+  const float* sdev = s ? seg.scale_dev[1] : seg.scale_dev[0];
+  const float scale = sdev ? *sdev : (s ? seg.scale[1] : seg.scale[0]);
   const float weight = s ? seg.weight[1] : seg.weight[0];
   float* row = L + r * ldl;
   const float label_raw = row[label];  // read before the row is overwritten with G
@@ -499,8 +501,9 @@ int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, cons
     si.n1 = n1;
     for (int i = 0; i < 2; ++i) {
       const uml_segment& s = segs[i < nseg ? i : 0];
-      si.idx[i] = s.idx;
+      si.idx[i] = s.label_idx ? s.label_idx : s.idx;
       si.labels[i] = s.labels;
+      si.scale_dev[i] = s.scale_dev;
       si.scale[i] = s.scale;
       si.weight[i] = s.loss_weight;
     }

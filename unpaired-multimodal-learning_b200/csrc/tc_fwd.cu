@@ -36,7 +36,8 @@ constexpr int kFwdSmemBytes = kFwdStages * kFwdStageBytes + 1024 /*align*/ + 256
 
 struct FwdSegs {
   int64_t n0;
-  float scale[2], gcoef[2], dcoef[2];  // gcoef = w*s/n ; dcoef = w/n
+  const float* scale_dev[2];
+  float scale[2], dcoef[2];  // dcoef = w/n ; the logit-gradient coefficient is dcoef * scale
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -143,9 +144,10 @@ __global__ void __launch_bounds__(256, 1)
       const int64_t row = tile * kFwdBlockM + q * 32 + lane;
       const bool valid = row < n_rows;
       const bool sg = valid && row >= segs.n0;
-      const float scale = sg ? segs.scale[1] : segs.scale[0];
-      const float gcoef = sg ? segs.gcoef[1] : segs.gcoef[0];
+      const float* sdev = sg ? segs.scale_dev[1] : segs.scale_dev[0];
+      const float scale = sdev ? __ldg(sdev) : (sg ? segs.scale[1] : segs.scale[0]);
       const float dcoef = sg ? segs.dcoef[1] : segs.dcoef[0];
+      const float gcoef = dcoef * scale;
       const int label = valid ? labels[row] : -1;
       __nv_bfloat16* grow = G ? G + row * ldg : nullptr;
       float run_max = -INFINITY, run_sum = 0.f, run_pr = 0.f, lab_logit = 0.f, lab_raw = 0.f;
@@ -293,7 +295,7 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
     const int j = i < segs->nseg ? i : 0;
     const double n = static_cast<double>(segs->seg_rows[j] > 0 ? segs->seg_rows[j] : 1);
     fs.scale[i] = segs->scale[j];
-    fs.gcoef[i] = static_cast<float>(static_cast<double>(segs->loss_weight[j]) * segs->scale[j] / n);
+    fs.scale_dev[i] = segs->scale_dev[j];
     fs.dcoef[i] = static_cast<float>(static_cast<double>(segs->loss_weight[j]) / n);
   }
   static bool attr_set = false;

@@ -1,0 +1,219 @@
+"""Feature-bank datasets and index loaders (L1 of the hot path).
+
+Replaces the reference's ``engine/datasets/utils.py`` (TextTensorDataset :48-107, DatasetWrapper
+:153-174) and the ``torch.utils.data.DataLoader`` objects built in ``finetune.py:370-383``.
+
+The reference loader fetches rows one by one on the host, stacks them and copies the batch to the
+device every step.  Here a bank lives in HBM for the whole run and a loader only produces *index
+batches*; the rows are gathered on the device by the CUDA kernels.  What is preserved bit-exactly is
+the ORDER in which rows are visited: ``BankLoader`` draws from the global torch CPU generator exactly
+when and how ``DataLoader(shuffle=True)`` + ``RandomSampler`` do (see ``BankLoader.__iter__``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+
+def get_few_shot_setup_name(train_shot, seed):
+    """``shot_{k}-seed_{s}`` - names few-shot splits and result directories (reference utils.py:9-12)."""
+    return "shot_{}-seed_{}".format(train_shot, seed)
+
+
+class TextTensorDataset(torch.utils.data.Dataset):
+    """Text feature rows with optional per-class subsampling / averaging.
+
+    Same contract as the reference class of this name (engine/datasets/utils.py:48-107):
+    ``n_shots=None`` keeps every row, an int keeps that many random rows per class (one global-RNG
+    ``randperm`` per class, classes in ``torch.unique`` order), ``'average'`` replaces each class by
+    its mean row.  Exposes ``input_tensor``, ``label_tensor``, ``eot_indices``."""
+
+    def __init__(self, input_tensor, label_tensor, eot_indices, n_shots=None):
+        if n_shots is None:
+            picked = (input_tensor, label_tensor, eot_indices)
+        elif isinstance(n_shots, int) and not isinstance(n_shots, bool):
+            picked = self._subsample(input_tensor, label_tensor, eot_indices, n_shots)
+            print(f"=> Using {n_shots} text shots per class, with total of {picked[1].shape[0]} samples")
+        elif isinstance(n_shots, str) and n_shots.lower() == "average":
+            picked = self._class_means(input_tensor, label_tensor, eot_indices)
+            print(f"=> Averaging text features per class, with total of {picked[1].shape[0]} samples")
+        else:
+            raise ValueError("n_shots must be an int, None, or 'average'")
+        self.input_tensor, self.label_tensor, self.eot_indices = picked
+
+    @staticmethod
+    def _subsample(feats, labels, eot, k):
+        chosen = []
+        for cls in torch.unique(labels):
+            members = torch.nonzero(labels == cls, as_tuple=True)[0]
+            order = torch.randperm(members.numel())  # global generator, like the reference
+            chosen.append(members[order[: min(k, members.numel())]])
+        chosen = torch.cat(chosen)
+        if isinstance(feats, list):
+            feats = [feats[i] for i in chosen.tolist()]
+        else:
+            feats = feats[chosen]
+        return feats, labels[chosen], eot[chosen]
+
+    @staticmethod
+    def _class_means(feats, labels, eot):
+        classes = torch.unique(labels)
+        # one sorted pass instead of a boolean mask per class
+        order = torch.argsort(labels, stable=True)
+        sorted_labels = labels[order]
+        counts = torch.bincount(sorted_labels, minlength=int(classes.max()) + 1)[classes]
+        sums = torch.zeros(int(classes.max()) + 1, feats.shape[1], dtype=feats.dtype).index_add_(0, labels, feats)
+        means = sums[classes] / counts.unsqueeze(1).to(feats.dtype)
+        first = order[torch.cumsum(counts, 0) - counts]
+        return means, classes, eot[first]
+
+    def __getitem__(self, i):
+        return self.input_tensor[i], self.label_tensor[i], self.eot_indices[i]
+
+    def __len__(self):
+        t = self.input_tensor
+        return t.size(0) if isinstance(t, torch.Tensor) else len(t)
+
+
+class FeatureBank:
+    """An ``[N, D]`` fp32 feature matrix plus ``[N]`` int64 labels resident in HBM.
+
+    ``features.py`` of the reference writes exactly these two tensors per split
+    (features.py:152-184, 225-248); nothing in the reference's finetune.py reads the image ones back -
+    this class is what does."""
+
+    def __init__(self, features: torch.Tensor, labels: torch.Tensor, device="cuda"):
+        if features.dim() != 2 or labels.dim() != 1 or features.shape[0] != labels.shape[0]:
+            raise ValueError("FeatureBank: expected features [N, D] and labels [N]")
+        self.features = features.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.labels = labels.detach().to(device=device, dtype=torch.int64).contiguous()
+
+    @classmethod
+    def from_text_dataset(cls, ds: TextTensorDataset, device="cuda"):
+        return cls(ds.input_tensor, ds.label_tensor, device)
+
+    def __len__(self):
+        return self.features.shape[0]
+
+    def bf16(self):
+        """bf16 copy of the rows (tensor-core eval operand), converted once on the device and cached."""
+        if getattr(self, "_bf16", None) is None:
+            from ... import ops
+            self._bf16 = ops.cast_bf16(self.features)
+        return self._bf16
+
+    def labels32(self):
+        if getattr(self, "_labels32", None) is None:
+            self._labels32 = self.labels.to(torch.int32)
+        return self._labels32
+
+    @property
+    def dim(self):
+        return self.features.shape[1]
+
+    @property
+    def device(self):
+        return self.features.device
+
+
+@dataclass
+class IndexBatch:
+    """What a BankLoader yields: ``n`` row indices into ``bank`` (a device int64 view), or
+    ``idx=None`` meaning the dense range ``[start, start+n)`` for sequential (eval) loaders."""
+    bank: FeatureBank
+    idx: Optional[torch.Tensor]
+    n: int
+    start: int = 0
+    host_idx: Optional[torch.Tensor] = None  # the same indices on the host (tests / tracing)
+
+
+def _draw_int64(generator=None) -> int:
+    return int(torch.empty((), dtype=torch.int64).random_(generator=generator).item())
+
+
+class BankLoader:
+    """``DataLoader(dataset, batch_size, shuffle, drop_last, num_workers, generator)`` over a bank.
+
+    RNG protocol (what makes the sampler order bit-exact with the reference):
+      * ``iter(loader)`` draws one int64 "base seed" from ``generator`` (global CPU generator when
+        None) - every DataLoader iterator does, shuffled or not (so ``validate`` consumes RNG too);
+      * a shuffled loader then draws the sampler seed and a ``torch.randperm(n)`` from a fresh
+        generator seeded with it - lazily at the first ``next()`` when ``num_workers == 0``, but
+        already inside ``iter()`` when ``num_workers > 0`` (worker loaders prefetch in their
+        constructor).  With an explicit ``generator`` the permutation is drawn from it directly and a
+        second, discarded permutation is drawn when the epoch ends (``RandomSampler.__iter__`` tail).
+    ``num_workers`` therefore only selects the protocol; no worker processes exist.
+
+    ``upload`` chooses how index batches reach the device: "epoch" copies the whole permutation once
+    per epoch and yields views of it; "step" copies each batch from pinned host memory when it is
+    fetched."""
+
+    def __init__(self, bank: FeatureBank, batch_size: int, shuffle: bool = False, drop_last: bool = False,
+                 num_workers: int = 0, generator: Optional[torch.Generator] = None, upload: str = "epoch",
+                 pin_memory: bool = True):
+        if upload not in ("epoch", "step"):
+            raise ValueError("upload must be 'epoch' or 'step'")
+        self.bank, self.batch_size, self.shuffle = bank, int(batch_size), bool(shuffle)
+        self.drop_last, self.num_workers, self.generator = bool(drop_last), int(num_workers), generator
+        self.upload = upload
+        self.dataset = bank
+
+    def __len__(self):
+        n = len(self.bank)
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        return _BankIter(self)
+
+
+class _BankIter:
+    def __init__(self, loader: BankLoader):
+        self.l = loader
+        self.n = len(loader.bank)
+        self.pos = 0
+        self.perm_host = None
+        self.perm_dev = None
+        self.tail_drawn = False
+        _draw_int64(loader.generator)  # base seed
+        if loader.shuffle and loader.num_workers > 0:
+            self._draw()
+
+    def _draw(self):
+        l = self.l
+        if l.generator is None:
+            g = torch.Generator()
+            g.manual_seed(_draw_int64(None))
+            self.perm_host = torch.randperm(self.n, generator=g)
+        else:
+            self.perm_host = torch.randperm(self.n, generator=l.generator)
+        if l.upload == "epoch":
+            self.perm_dev = self.perm_host.to(l.bank.device, non_blocking=False)
+        else:
+            self.perm_host = self.perm_host.pin_memory() if torch.cuda.is_available() else self.perm_host
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> IndexBatch:
+        l = self.l
+        if l.shuffle and self.perm_host is None:
+            self._draw()
+        left = self.n - self.pos
+        if left <= 0 or (l.drop_last and left < l.batch_size):
+            if l.shuffle and l.generator is not None and not self.tail_drawn:
+                torch.randperm(self.n, generator=l.generator)  # RandomSampler's trailing empty slice
+                self.tail_drawn = True
+            raise StopIteration
+        take = min(l.batch_size, left)
+        start = self.pos
+        self.pos += take
+        if not l.shuffle:
+            return IndexBatch(l.bank, None, take, start)
+        host = self.perm_host[start:start + take]
+        if l.upload == "epoch":
+            dev = self.perm_dev[start:start + take]
+        else:
+            dev = host.to(l.bank.device, non_blocking=True)
+        return IndexBatch(l.bank, dev, take, start, host)

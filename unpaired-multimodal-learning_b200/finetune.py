@@ -1,0 +1,451 @@
+"""UML fine-tuning over HBM-resident feature banks - drop-in for the hot path of the reference's
+``vision_language/finetune.py``.
+
+Same entry points and argument meaning: ``train`` (:120), ``validate`` (:291), ``setup`` (:323),
+``sweep`` (:406), ``main`` (:451), ``hparam_str`` (:58), ``savedir`` (:67), ``fetch_next`` (:33), the
+``-c/-s/-d/-f/-o`` CLI (:513-555), the YAML sweep files, ``test_result.pth`` / ``results.pth`` outputs.
+
+What differs, by design: the reference decodes JPEGs and runs the frozen backbone
+inside every step; here image AND text features come from banks written by ``features.py`` and stay in
+HBM, loaders yield index batches (bit-exact sampler order), and one step is a handful of hand-written
+CUDA kernels (``engine/trainer.py``) instead of an autograd graph with three backward sweeps.
+Per-step diagnostics that cost a device sync each (grad cosine, CKA on re-encoded images, finetune.py
+:197-244) are opt-in and evaluated at eval cadence.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from itertools import product
+
+import torch
+
+from . import ops
+from .engine.config import parser
+from .engine.datasets.utils import (BankLoader, FeatureBank, IndexBatch, TextTensorDataset,
+                                    get_few_shot_setup_name)
+from .engine.models.head import (CLIP_EMBED_DIM, LANGUAGE_HIDDEN, UML, VISION_NUM_FEATURES, UMLClip, _width)
+from .engine.optimizer.default import HYPER_DICT
+from .engine.optimizer.optim import build_optimizer
+from .engine.optimizer.scheduler import build_lr_scheduler
+from .engine.tools.utils import Tee, makedirs, set_random_seed
+from .engine.trainer import StepEngine
+from .features import img_outdir, load_image_bank, load_text_bank, text_outdir
+
+EVAL_FREQ = 100  # evaluate on the val bank every 100 iterations (early stopping)
+FLAG = 0         # 1: run although the experiment directory already holds a result
+
+
+def fetch_next(loader, loader_iter):
+    """Next batch; when the epoch is exhausted build a fresh iterator (new permutation) first."""
+    try:
+        return next(loader_iter), loader_iter
+    except StopIteration:
+        loader_iter = iter(loader)
+        return next(loader_iter), loader_iter
+
+
+def clip_outdim(model_name):
+    return _width(model_name, CLIP_EMBED_DIM, "CLIP encoder")
+
+
+def vision_model_outdim(model_name):
+    return _width(model_name, VISION_NUM_FEATURES, "vision model")
+
+
+def language_model_outdim(model_name):
+    return _width(model_name, LANGUAGE_HIDDEN, "language model")
+
+
+def hparam_str(optim, lr, wd, batch_size, iters, dropout, learnable_temp):
+    parts = [f"optim_{optim}", f"lr_{lr}", f"wd_{wd}", f"bs_{batch_size}", f"iters_{iters}"]
+    if dropout is not None:
+        parts.append(f"dropout_{dropout}")
+    if learnable_temp is True:
+        parts.append("learnable_temp")
+    return "-".join(parts)
+
+
+def savedir(outdir, dataset, encoder, train_shot, seed, text_type, text_shots, image_augmentation, mode,
+            init_mode="zeroshot", alpha=0.0, text_bs=0, custom_name="", args=None):
+    bench = f"{dataset}-{get_few_shot_setup_name(train_shot, seed)}"
+    text_name = f"text_{text_type}" + (f"_n_{text_shots}" if text_shots is not None else "")
+    image_name = f"image_{image_augmentation}_{custom_name}"
+    if mode == "crossmodal":
+        mod = f"finetune-{text_name}-{image_name}-alpha_{alpha}"
+    elif mode == "image":
+        mod = f"finetune-{image_name}"
+    else:
+        mod = text_name
+    if text_bs > 0:
+        mod += f"-text_bs_{text_bs}"
+    if args is not None and mode != "crossmodal":
+        mod += f"-common_dim_{args.common_dim}"
+    return os.path.join(outdir, bench, encoder.replace("/", "-"), mod, init_mode)
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation
+# ------------------------------------------------------------------------------------------------
+
+def _dist():
+    d = torch.distributed
+    if d.is_available() and d.is_initialized() and d.get_world_size() > 1:
+        return d.get_rank(), d.get_world_size()
+    return 0, 1
+
+
+def validate(model, val_loader, device="cuda"):
+    """(val_loss, val_acc) over the loader's bank: accuracy over all rows, loss = mean over the
+    loader's batches of the batch-mean CE (the reference's weighting, finetune.py:310-312).  One logit +
+    argmax kernel streams the bank; logits never reach the host."""
+    iter(val_loader)  # a DataLoader iterator draws a base seed from the global RNG; keep the stream aligned
+    bank, bs = val_loader.bank, val_loader.batch_size
+    n = len(bank)
+    dev = bank.device
+    feats = bank.features
+    if model.img_proj is not None:
+        feats = model.extract_features(feats)
+    s_img = float(model.scales()[0])
+    row_loss = torch.empty(n, device=dev)
+    row_pred = torch.empty(n, device=dev, dtype=torch.int32)
+    W = model.head.weight.data
+    use_tc = getattr(model, "precision", "auto") != "fp32" and n >= 4096 and W.shape[1] % 8 == 0 and W.shape[0] <= 2048
+    if use_tc:
+        x16 = bank.bf16() if model.img_proj is None and hasattr(bank, "bf16") else ops.cast_bf16(feats.contiguous())
+        labels32 = bank.labels32() if hasattr(bank, "labels32") else bank.labels.to(torch.int32)
+        segs = ops.tc_segments([n], [s_img], [1.0])
+        ops.head_fwd_ce_bf16(x16, ops.cast_bf16(W), labels32, segs, None, row_loss, row_pred=row_pred)
+    else:
+        ops.eval_f32(feats, bank.labels, W, s_img, row_loss, row_pred)
+    out_loss = torch.empty(1, device=dev)
+    out_hits = torch.empty(1, device=dev, dtype=torch.int32)
+    ops.eval_reduce(row_loss, row_pred, bank.labels, bs, out_loss, out_hits)
+    return float(out_loss.item()), int(out_hits.item()) / n
+
+
+# ------------------------------------------------------------------------------------------------
+# training
+# ------------------------------------------------------------------------------------------------
+
+def _local_slice(batch: IndexBatch, rank: int, world: int) -> IndexBatch:
+    """This rank's contiguous share of a global batch (sizes differ by at most one row)."""
+    if world == 1:
+        return batch
+    lo, hi = (batch.n * rank) // world, (batch.n * (rank + 1)) // world
+    idx = batch.idx[lo:hi] if batch.idx is not None else None
+    host = batch.host_idx[lo:hi] if batch.host_idx is not None else None
+    return IndexBatch(batch.bank, idx, hi - lo, batch.start + lo, host)
+
+
+def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, scheduler, device="cuda",
+          max_iters=1000, alpha=1.0, eval_freq=EVAL_FREQ, patience=5, capture_features_during_training=False,
+          features_pth="./", args=None, logger=None, trace=None, stats_to_host="eval"):
+    """The UML loop (reference finetune.py:120-288).  ``trace`` (optional dict) receives the host-side
+    index batches and per-step stats - used by the parity tests.  ``stats_to_host``: "eval" reads the
+    per-step losses back once per evaluation; "step" pushes each step's record to pinned host memory
+    with an asynchronous copy (what a per-step logger needs), still without stalling the stream."""
+    if stats_to_host not in ("eval", "step"):
+        raise ValueError("stats_to_host must be 'eval' or 'step'")
+    out = {"iter": None, "val_acc": None, "model": None, "val_classwise": None, "val_loss": None, "model_records": []}
+    if trace is not None:
+        trace["engine"] = None
+    assert image_loader is not None or text_loader is not None, "At least one of the loaders should be provided"
+    if capture_features_during_training:
+        print("=> capture_features_during_training is a per-step diagnostic outside the hot path; ignored")
+    model.train()
+    rank, world = _dist()
+    bs_i = image_loader.batch_size if image_loader is not None else 0
+    bs_t = text_loader.batch_size if text_loader is not None else 0
+    precision = getattr(args, "precision", None) or getattr(model, "precision", "auto")
+    engine = StepEngine(model, optimizer, device, -(-bs_i // world), -(-bs_t // world),
+                        log_slots=min(max(int(eval_freq), 1), int(max_iters)) + 1, precision=precision,
+                        dist_group=None, world_size=world)
+    if trace is not None:
+        trace["engine"] = engine
+        if trace.get("profile"):
+            engine.profile = {}
+    image_iter = iter(image_loader) if image_loader is not None else None
+    text_iter = iter(text_loader) if text_loader is not None else None
+    no_improve = 0
+    pending = []  # steps whose stats have not been read back yet
+    last = {"image_loss": 0.0, "text_loss": 0.0, "img_acc": 0.0, "text_acc": 0.0}
+
+    def flush():
+        nonlocal last
+        if not pending:
+            return
+        recs = engine.read_log([s for s, _ in pending], from_host_ring=(stats_to_host == "step"))
+        for (slot, lr), rec in zip(pending, recs):
+            if trace is not None:
+                trace.setdefault("stats", []).append(dict(rec, lr=lr))
+            if logger is not None:
+                logger.log({"train/image_loss": rec["image_loss"], "train/text_loss": rec["text_loss"],
+                            "train/image_acc": rec["img_acc"], "train/text_acc": rec["text_acc"], "train/lr": lr})
+        last = recs[-1]
+        pending.clear()
+
+    for i in range(max_iters):
+        img = txt = None
+        if image_iter is not None:
+            img, image_iter = fetch_next(image_loader, image_iter)
+        if text_iter is not None:
+            txt, text_iter = fetch_next(text_loader, text_iter)
+        if trace is not None:
+            if img is not None:
+                trace.setdefault("img_idx", []).append(img.host_idx.clone())
+            if txt is not None:
+                trace.setdefault("txt_idx", []).append(txt.host_idx.clone())
+        lr = scheduler.get_last_lr()[0]
+        engine.step(_local_slice(img, rank, world) if img is not None else None,
+                    _local_slice(txt, rank, world) if txt is not None else None, alpha, slot=i,
+                    global_img_rows=img.n if (img is not None and world > 1) else None,
+                    global_txt_rows=txt.n if (txt is not None and world > 1) else None)
+        scheduler.step()
+        if stats_to_host == "step":
+            engine.copy_slot_to_host(i)
+        pending.append((i, lr))
+        if trace is not None and trace.get("record_weights"):
+            trace.setdefault("weights", []).append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
+
+        if i % eval_freq == 0:
+            flush()
+            snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            val_loss, val_acc = validate(model, val_loader, device=device)
+            testlog = ""
+            if test_loader is not None:
+                _, test_acc = validate(model, test_loader, device=device)
+                testlog = f" | Test Acc: {test_acc:.4f}"
+            if out["val_acc"] is None or val_acc > out["val_acc"]:
+                out.update(iter=i, val_acc=val_acc, val_loss=val_loss,
+                           model={k: v.cpu() for k, v in snapshot.items()})
+                no_improve = 0
+            else:
+                no_improve += 1
+            if trace is not None:
+                trace.setdefault("evals", []).append((i, val_loss, val_acc))
+            if logger is not None:
+                logger.log({"val/val_loss": val_loss, "val/val_acc": val_acc, "iter": i})
+            if rank == 0:
+                print(f"Iter {i} | Img Loss: {last['image_loss']:.4f} | Text Loss: {last['text_loss']:.4f} | "
+                      f"Img Acc: {last['img_acc']:.4f} | Text Acc: {last['text_acc']:.4f} | Val Loss: {val_loss:.4f} | "
+                      f"Val Acc {val_acc:.4f}{testlog} | Count {no_improve}/{patience}")
+            if no_improve >= patience:
+                print(f"=> Early stopping at Iter {i}")
+                break
+    flush()
+    print(f"{torch.cuda.memory_allocated(0) / (1024 ** 3):.4f} GB allocated after training")
+    model.load_state_dict(out["model"])
+    engine.invalidate_shadow()
+    val_loss, val_acc = validate(model, val_loader, device=device)
+    if logger is not None:
+        logger.log({"val/best_val_loss": val_loss, "val/best_val_acc": val_acc, "iter": out["iter"]})
+    print(f"=> Best Val Loss {val_loss:.4f}, Val Acc {val_acc:.4f} at Iter {out['iter']}")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# orchestration
+# ------------------------------------------------------------------------------------------------
+
+class _NullLogger:
+    def log(self, *_a, **_k):
+        pass
+
+
+def setup_wandb_logger(hparams, args):
+    """wandb when it is importable and not disabled, else a no-op (the reference calls wandb.init
+    unconditionally, finetune.py:318-321, which needs network access)."""
+    if os.environ.get("WANDB_MODE", "disabled") in ("disabled", "offline") and not os.environ.get("UML_WANDB"):
+        return _NullLogger()
+    import wandb
+    return wandb.init(entity="unpaired_multimodal", project="unpaired_multimodal",
+                      tags=[args.dataset, args.modality, args.hyperparams], config={**vars(args), **dict(hparams)},
+                      reinit="finish_previous")
+
+
+def setup(datasets, hparams, args):
+    logger = setup_wandb_logger(hparams, args)
+    device = args.device
+    ckpt_dir = os.path.join(args.savepath, hparam_str(hparams["optim"], hparams["lr"], hparams["weight_decay"],
+                                                      hparams["batch_size"], hparams["max_iter"], hparams["dropout"],
+                                                      hparams["learnable_temp"]))
+    makedirs(ckpt_dir)
+    test_path = os.path.join(ckpt_dir, "test_result.pth")
+    if os.path.exists(test_path) and not FLAG:
+        print(f"=> Skipping {ckpt_dir} as it already exists!")
+        return torch.load(test_path, map_location=device)
+    print(f"=> Setting up {ckpt_dir}")
+    freeze = args.hyperparams == "linear"
+    if args.use_clip:
+        model = UMLClip(f"{args.clip_encoder}:{args.img_indim}", args.nclasses, logit_scale_init=args.logit, bias=False,
+                        learnable_temp=hparams["learnable_temp"], freeze_backbone=freeze)
+    else:
+        shared = args.text_indim if args.modality == "crossmodal" else args.common_dim
+        model = UML(f"{args.vision_model}:{args.img_indim}", shared, args.nclasses, bias=False,
+                    learnable_temp=hparams["learnable_temp"], freeze_backbone=freeze)
+    model.precision = getattr(args, "precision", "auto")
+    model.to(device)
+    print(f"=> UML trainable parameters: {sum(p.numel() for p in model.parameters())}")
+    if args.classifier_init == "zeroshot" and (args.modality == "crossmodal" or
+                                               (args.modality == "image" and args.common_dim == args.text_indim)):
+        model.zero_shot_init(datasets["text_ds"])
+    model.to(device)
+
+    optimizer = build_optimizer(model.parameters(), hparams["optim"], hparams["lr"], hparams["weight_decay"])
+    scheduler = build_lr_scheduler(optimizer, hparams["lr_scheduler"], hparams["warmup_iter"], hparams["max_iter"],
+                                   warmup_type=hparams["warmup_type"], warmup_lr=hparams["warmup_min_lr"])
+    bs, nw = hparams["batch_size"], args.num_workers
+    image_loader = BankLoader(datasets["img_tr_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
+    text_loader = BankLoader(datasets["text_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
+    if args.modality == "image":
+        text_loader = None
+        print("=> Running Unimodal: Image Only Model")
+    elif args.modality == "text":
+        image_loader = None
+        print("=> Running Unimodal: Text Only Model")
+    val_loader = BankLoader(datasets["img_val_bank"], bs, shuffle=False, num_workers=nw)
+    test_loader = BankLoader(datasets["img_te_bank"], bs, shuffle=False, num_workers=nw)
+
+    result = train(model, image_loader, text_loader, val_loader, test_loader if args.eval_test else None, optimizer,
+                   scheduler, device=device, max_iters=hparams["max_iter"], alpha=args.alpha, eval_freq=EVAL_FREQ,
+                   patience=hparams["patience"], capture_features_during_training=False, features_pth=ckpt_dir,
+                   args=args, logger=logger)
+    test_loss, test_acc = validate(model, test_loader, device=device)
+    del model
+    logger.log({"test/test_loss": test_loss, "test/test_acc": test_acc})
+    test_dict = {"test_acc": test_acc, "val_acc": result["val_acc"], "model": result["model"], "iter": result["iter"]}
+    print(f"=> Test Acc: {test_acc:.4f}")
+    if not FLAG or getattr(args, "overwrite", False):
+        print(f"=> Saving Test Results for hparams to {test_path}")
+        torch.save(test_dict, test_path)
+    return test_dict
+
+
+def sweep(datasets, hyperparams, args):
+    grid = {k: (v if isinstance(v, list) else [v]) for k, v in hyperparams.items()}
+    keys = list(grid)
+    combos = list(product(*[grid[k] for k in keys]))
+    results = {"test_acc": [], "val_acc": [], "hparams": [], "model_records": []}
+    best_val = best_test = 0
+    best_hp = None
+    for n, combo in enumerate(combos):
+        hp = dict(zip(keys, combo))
+        print(f"=> Running {n + 1}/{len(combos)}: {hp}")
+        res = setup(datasets, hp, args)
+        results["test_acc"].append(res["test_acc"])
+        results["val_acc"].append(res["val_acc"])
+        results["hparams"].append(hp)
+        if res["val_acc"] > best_val:
+            best_val, best_test, best_hp = res["val_acc"], res["test_acc"], hp
+            print(f"=> New Best Val Acc: {best_val:.4f} | Test Acc: {best_test:.4f}")
+        print(f"=> Best Val Acc (so far): {best_val:.4f} | Test Acc (corresponding): {best_test:.4f}")
+        print(f"=> Best Hyperparameters (so far): {best_hp}")
+        print("--------------------------------------------------------\n")
+    if not FLAG or getattr(args, "overwrite", False):
+        print(f"=> Saving results across all hparams to {args.savepath}")
+        torch.save(results, os.path.join(args.savepath, "results.pth"))
+    k = int(torch.argmax(torch.tensor(results["val_acc"])))
+    print(f"=> [FINAL] Best Val Acc: {results['val_acc'][k]:.4f} | Best Test Acc: {results['test_acc'][k]:.4f}")
+    print(f"=> [FINAL] Mean Val Acc: {torch.tensor(results['val_acc']).mean():.4f} | "
+          f"Mean Test Acc: {torch.tensor(results['test_acc']).mean():.4f}")
+    print(f"=> [FINAL] Best Hyperparameters: {results['hparams'][k]}")
+    return results, results["val_acc"][k], results["test_acc"][k]
+
+
+def main(args):
+    if args.seed >= 0:
+        print("=> Setting fixed seed: {}".format(args.seed))
+        set_random_seed(args.seed)
+    if not torch.cuda.is_available():
+        raise RuntimeError("uml_b200.finetune needs a CUDA device: the hot path has no CPU implementation")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.device = f"cuda:{local_rank}"
+    torch.cuda.set_device(local_rank)
+    args.use_clip = args.vision_model == "" and args.language_model == ""
+    encoder_name = args.clip_encoder if args.use_clip else f"{args.vision_model}-{args.language_model}"
+    args.savepath = savedir(args.result_dir, args.dataset, encoder_name, args.train_shot, args.seed, args.text_type,
+                            args.text_shot, args.image_augmentation, args.modality, args.classifier_init, args.alpha,
+                            getattr(args, "text_batch_size", 0), args.custom_name, args)
+    makedirs(args.savepath)
+    logfile = open(os.path.join(args.savepath, "log.txt"), "w")
+    sys.stdout = Tee(sys.__stdout__, logfile)
+    try:
+        print("=> Arguments:", args)
+        text_encoder = args.clip_encoder if args.use_clip else args.language_model
+        text_path = text_outdir(args.feature_dir, text_encoder, args.dataset, args.text_type)
+        print(f"=> Loading text features from: {text_path}")
+        tf = load_text_bank(text_path)
+        shots = args.text_shot
+        if shots is not None and shots != "average":
+            shots = int(shots)
+        text_ds = TextTensorDataset(tf["features"], tf["labels"], tf["eot_indices"], n_shots=shots)
+
+        image_encoder = args.clip_encoder if args.use_clip else args.vision_model
+        tr_path = img_outdir(args.feature_dir, image_encoder, args.dataset, args.image_augmentation, args.train_shot,
+                             args.seed, "train")
+        te_path = img_outdir(args.feature_dir, image_encoder, args.dataset, args.image_augmentation, args.train_shot,
+                             args.seed, "test")
+        print(f"=> Loading image features from: {tr_path} and {te_path}")
+        tr, te = load_image_bank(tr_path), load_image_bank(te_path)
+        lab2cname = tr.get("lab2cname") or te.get("lab2cname") or tf.get("lab2cname")
+        args.img_indim = int(tr["train"]["features"].shape[1])
+        args.text_indim = int(tf["features"].shape[1])
+        if args.use_clip and args.img_indim != args.text_indim:
+            raise ValueError("CLIP image and text features must share a width")
+        args.nclasses = len(lab2cname) if lab2cname else int(max(tr["train"]["labels"].max(), te["labels"].max())) + 1
+        dev = args.device
+        datasets = {
+            "text_ds": text_ds, "text_bank": FeatureBank.from_text_dataset(text_ds, dev),
+            "img_tr_bank": FeatureBank(tr["train"]["features"], tr["train"]["labels"], dev),
+            "img_val_bank": FeatureBank(tr["val"]["features"], tr["val"]["labels"], dev),
+            "img_te_bank": FeatureBank(te["features"], te["labels"], dev),
+        }
+        results, best_val, best_test = sweep(datasets, HYPER_DICT[args.hyperparams], args)
+        del datasets
+        print("Done!")
+    finally:
+        sys.stdout = sys.__stdout__
+        logfile.close()
+    return results, best_val, best_test
+
+
+def cli(argv=None):
+    import yaml
+
+    outer = argparse.ArgumentParser(description="UML fine-tuning over feature banks")
+    outer.add_argument("-c", "--config", type=str, default="config.yaml", help="Configuration file")
+    outer.add_argument("-s", "--slurm", action="store_true", help="Launched with slurm")
+    outer.add_argument("-d", "--debug", action="store_true", help="Debug mode")
+    outer.add_argument("-f", "--flag", action="store_true", help="Run despite existing experiments directory")
+    outer.add_argument("-o", "--overwrite", action="store_true", help="Overwrite existing experiments directory")
+    outer_args, rest = outer.parse_known_args(argv)
+    global FLAG
+    FLAG = int(outer_args.flag)
+    if outer_args.debug:
+        args = parser.parse_args(rest)
+        args.overwrite = outer_args.overwrite
+        return main(args)
+    with open(outer_args.config) as f:
+        sweep_args = yaml.load(f, Loader=yaml.FullLoader)
+    keys = list(sweep_args)
+    combos = [dict(zip(keys, v)) for v in product(*[(v if isinstance(v, list) else [v]) for v in sweep_args.values()])]
+    print("Total combinations:", len(combos))
+    for i, c in enumerate(combos):
+        print(f"Combination {i}: {c}")
+    if outer_args.slurm:
+        job = int(os.getenv("SLURM_ARRAY_TASK_ID", "-1"))
+        if not 0 <= job < len(combos):
+            print("Invalid SLURM_ARRAY_TASK_ID")
+            sys.exit(1)
+        combos = [combos[job]]
+    for i, c in enumerate(combos):
+        print(f"=> Running job {i}")
+        args = parser.parse_args([], argparse.Namespace(**c))
+        args.overwrite = outer_args.overwrite
+        main(args)
+
+
+if __name__ == "__main__":
+    cli()

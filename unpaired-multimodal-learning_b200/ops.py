@@ -45,6 +45,8 @@ class Run:
     n: int
     scale: float = 1.0
     loss_weight: float = 1.0
+    label_idx: Optional[torch.Tensor] = None   # indices into labels when rows are dense (adapter output)
+    scale_dev: Optional[torch.Tensor] = None   # 0-dim fp32 CUDA tensor overriding `scale` (learnable temperature)
 
     def c_segment(self) -> Segment:
         _need(self.rows, torch.float32, "run.rows")
@@ -55,8 +57,11 @@ class Run:
                 raise ValueError("run.idx shorter than run.n")
         elif self.rows.shape[0] < self.n:
             raise ValueError("run.rows shorter than run.n")
+        if self.scale_dev is not None:
+            _need(self.scale_dev, torch.float32, "run.scale_dev")
         return Segment(self.rows.data_ptr(), _ptr(self.idx), self.labels.data_ptr(), int(self.n),
-                       int(self.rows.stride(0)), float(self.scale), float(self.loss_weight))
+                       int(self.rows.stride(0)), float(self.scale), float(self.loss_weight), _ptr(self.label_idx),
+                       _ptr(self.scale_dev))
 
 
 def _segs(runs: Sequence[Run]):
@@ -129,16 +134,17 @@ class HeadWorkspace:
                 for i in range(2)]
 
 
-def head_fwd_ce_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace):
-    """logits -> softmax CE -> G (in ws.G), per-run stats in ws.stats.  finetune.py:181-188."""
+def head_fwd_ce_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, stats: Optional[torch.Tensor] = None):
+    """logits -> softmax CE -> G (in ws.G), per-run stats in ``stats`` (default ws.stats).  finetune.py:181-188."""
     _need(W, torch.float32, "W")
     arr, n = _segs(runs)
     total = sum(r.n for r in runs)
     if total > ws.max_rows:
         raise ValueError("workspace too small")
+    stats = ws.stats if stats is None else stats
     check(_lib.load().uml_head_fwd_ce_f32(arr, n, W.shape[1], W.data_ptr(), W.shape[0], ws.G.data_ptr(), ws.ldg,
                                           ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr(),
-                                          ws.stats.data_ptr(), _stream()))
+                                          stats.data_ptr(), _stream()))
 
 
 def head_bwd_dw_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, dW: Optional[torch.Tensor] = None,
@@ -227,11 +233,13 @@ def grad_diag(a, b, workspace, out4):
 
 # ------------------------------------------------------------------------------------------ tensor-core head
 
-def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[float]) -> TcSegments:
+def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[float],
+                scale_dev: Optional[Sequence[Optional[torch.Tensor]]] = None) -> TcSegments:
     s = TcSegments()
     s.nseg = len(rows)
     for i in range(len(rows)):
         s.seg_rows[i], s.scale[i], s.loss_weight[i] = int(rows[i]), float(scales[i]), float(weights[i])
+        s.scale_dev[i] = _ptr(scale_dev[i]) if scale_dev is not None else None
     return s
 
 
@@ -257,6 +265,10 @@ def head_bwd_dw_bf16(G, ldg, X, n_rows, n_classes, partials, n_splits):
     _need(partials, torch.float32, "partials")
     check(_lib.load().uml_head_bwd_dw_bf16(G.data_ptr(), ldg, X.data_ptr(), n_rows, X.shape[1], n_classes,
                                            partials.data_ptr(), n_splits, _stream()))
+
+
+def sum_partials(partials, n_splits, n, out):
+    check(_lib.load().uml_sum_partials(partials.data_ptr(), n_splits, n, n, out.data_ptr(), _stream()))
 
 
 def reduce_seg_stats(row_loss, row_correct, row_dscale, seg_rows: Sequence[int], stats):
