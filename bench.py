@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the UML training step on B200 (contract in the task statement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3]
+
+Metric (BASELINE.json): UML train samples/sec (image + text rows consumed per second).
+Workload at N=1 (``config.workload``): cfg3 = ImageNet full-data shapes, "ViT-L/14" 768-d features,
+1000-class shared linear head + unpaired text bank, preset ``clip_linear`` arithmetic (logit scale
+exp(4.60517), AdamW) at the THROUGHPUT batch of 16384 rows per modality per GPU (SURVEY.md section 8d;
+the reference's own batch of 32 is a latency-bound regime reported separately by --workload cfg2).
+Synthetic seeded banks, random-init/zero-shot-init head.  One "step" = one full UML iteration:
+gather(img) + gather(txt) -> shared head forward -> logit scale + softmax CE -> dW -> AdamW.
+
+``value``  device-resident: banks and index permutations already in HBM, K steps timed with CUDA events.
+``e2e``    the same K steps through the public ``uml_b200.finetune.train`` call with index batches copied
+           from pinned host memory every step and every step's loss record copied back to the host.
+``roofline`` dominant kernel (head forward/CE/G, tcgen05) timed with CUDA events inside the run.
+``cpu_baseline`` / ``--impl reference``: the oracle port of the reference step on the host cores.
+Multi-GPU (torchrun): data-parallel, fixed per-GPU batch (weak scaling), one NCCL all-reduce of dW per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_img_bank, n_txt_bank, dim, classes, batch_per_modality_per_gpu, n_val, logit)
+    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=16384, n_val=4096,
+                 desc="ImageNet full-data CLIP ViT-L/14 768-d features + CUPL text, linear head, throughput batch"),
+    "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, n_val=4000,
+                 desc="ImageNet 16-shot CLIP ViT-B/16 512-d features + CUPL text, linear head, reference batch 32"),
+    "cfg3_refB": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=32, n_val=4096,
+                      desc="cfg3 banks at the reference batch of 32"),
+}
+ALPHA, LR, WD, LOGIT = 0.5, 1e-3, 0.01, 4.60517
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference step on the host cores
+# -----------------------------------------------------------------------------------------------
+
+def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
+    """Times the reference's step algorithm (oracle port: per-sample fetch + collate, F.linear,
+    F.cross_entropy, two autograd.grad sweeps + backward, AdamW - finetune.py:163-195) on all host
+    threads.  The image bank is a seeded sample of ``bank_rows`` rows of the workload's shape."""
+    from oracle import uml_oracle as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(1)
+    D, C, B = wl["dim"], wl["classes"], wl["batch"]
+    n_img = min(wl["n_img"], bank_rows)
+    xi = torch.randn(n_img, D, generator=g)
+    yi = torch.randint(0, C, (n_img,), generator=g)
+    xt = torch.randn(wl["n_txt"], D, generator=g)
+    yt = torch.arange(wl["n_txt"]) % C
+    st = O.HeadState(head=O.zero_shot_weights(xt, yt, C), img_scale=math.exp(LOGIT), txt_scale=math.exp(LOGIT))
+    opt = O.OracleOptimizer(st.param_dict(), "adamw", LR, WD)
+    il, tl = O.OracleLoader(n_img, B), O.OracleLoader(wl["n_txt"], B)
+    torch.manual_seed(2)
+    il.iter(); tl.iter()
+
+    def one(i):
+        ii, it = O.fetch_next_indices(il), O.fetch_next_indices(tl)
+        # default_collate over a map-style dataset: one row at a time, then stack
+        xb = torch.stack([xi[int(j)] for j in ii]); yb = torch.stack([yi[int(j)] for j in ii])
+        tb = torch.stack([xt[int(j)] for j in it]); ub = torch.stack([yt[int(j)] for j in it])
+        _, grads = O.uml_step_grads_autograd(st, xb, yb, tb, ub, ALPHA)
+        opt.step(grads, O.lr_at(i, LR, "cosine", 50, 12800))
+        return ii.numel() + it.numel()
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    rows = 0
+    done = 0
+    for i in range(steps):
+        rows += one(warmup + i)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=rows / dt, ms_per_step=1e3 * dt / done, steps=done, cores=cores,
+                sample=f"{done} steps of B={B}/modality on a {n_img}-row sample of the image bank, {cores} threads")
+
+
+# -----------------------------------------------------------------------------------------------
+# our arm
+# -----------------------------------------------------------------------------------------------
+
+def build_banks(wl, dev):
+    from uml_b200.engine.datasets.utils import FeatureBank
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    D, C = wl["dim"], wl["classes"]
+    img = torch.randn(wl["n_img"], D, device=dev, generator=g)
+    img_y = torch.randint(0, C, (wl["n_img"],), device=dev, generator=g)
+    txt = torch.randn(wl["n_txt"], D, device=dev, generator=g)
+    txt_y = (torch.arange(wl["n_txt"], device=dev) % C)
+    val = torch.randn(wl["n_val"], D, device=dev, generator=g)
+    val_y = torch.randint(0, C, (wl["n_val"],), device=dev, generator=g)
+    return FeatureBank(img, img_y, dev), FeatureBank(txt, txt_y, dev), FeatureBank(val, val_y, dev)
+
+
+def make_model(wl, dev, txt_bank):
+    from uml_b200.engine.models.head import UMLClip
+    from uml_b200.engine.optimizer.optim import build_optimizer
+    from uml_b200.engine.optimizer.scheduler import build_lr_scheduler
+
+    torch.manual_seed(1)
+    model = UMLClip(f"synthetic:{wl['dim']}", wl["classes"], logit_scale_init=LOGIT)
+    model.to(dev)
+    model.zero_shot_init(txt_bank)
+    model.to(dev)
+    opt = build_optimizer(model.parameters(), "adamw", LR, WD)
+    sch = build_lr_scheduler(opt, "cosine", 50, 12800, warmup_type="linear", warmup_lr=1e-5)
+    return model, opt, sch
+
+
+def run_ours(args, wl, rank, world, dev):
+    import uml_b200  # noqa: F401
+    from uml_b200 import _lib, finetune as ft
+    from uml_b200.engine.datasets.utils import BankLoader
+    from uml_b200.engine.trainer import StepEngine
+
+    dist = torch.distributed if world > 1 else None
+    img_bank, txt_bank, val_bank = build_banks(wl, dev)
+    B = wl["batch"]
+    GB = B * world  # global batch per modality (weak scaling: per-GPU rows fixed)
+    K, W = args.steps, args.warmup
+
+    # ---------------- device-resident arm: CUDA events around K steps ----------------------------
+    model, opt, sch = make_model(wl, dev, txt_bank)
+    engine = StepEngine(model, opt, dev, B, B, log_slots=64, precision=args.precision, world_size=world)
+    il = BankLoader(img_bank, GB, shuffle=True, upload="epoch")
+    tl = BankLoader(txt_bank, GB, shuffle=True, upload="epoch")
+    torch.manual_seed(2)
+    ii, ti = iter(il), iter(tl)
+
+    def step(i):
+        nonlocal ii, ti
+        img, ii = ft.fetch_next(il, ii)
+        txt, ti = ft.fetch_next(tl, ti)
+        engine.step(ft._local_slice(img, rank, world), ft._local_slice(txt, rank, world), ALPHA, slot=i,
+                    global_img_rows=img.n if world > 1 else None, global_txt_rows=txt.n if world > 1 else None)
+        sch.step()
+        return img.n + txt.n
+
+    for i in range(W):
+        step(i)
+    engine.profile = {}
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.LAUNCH_COUNT[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rows = 0
+    e0.record()
+    for i in range(K):
+        rows += step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches = _lib.LAUNCH_COUNT[0] - n0
+    ms = e0.elapsed_time(e1)
+    if dist:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ktimes = engine.kernel_times_ms()
+    loss_tail = engine.read_log([W + K - 1])[0]
+    del engine
+
+    # ---------------- end-to-end arm: public train() call, per-step H2D indices + D2H loss ---------
+    def e2e_once(iters):
+        m2, o2, s2 = make_model(wl, dev, txt_bank)
+        m2.precision = args.precision
+        il2 = BankLoader(img_bank, GB, shuffle=True, upload="step")
+        tl2 = BankLoader(txt_bank, GB, shuffle=True, upload="step")
+        vl2 = BankLoader(val_bank, 512, shuffle=False)
+        torch.manual_seed(2)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ft.train(m2, il2, tl2, vl2, None, o2, s2, device=dev, max_iters=iters, alpha=ALPHA, eval_freq=10 ** 9,
+                 patience=5, stats_to_host="step")
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        return time.perf_counter() - t0
+
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        e2e_once(max(W, 3))
+        dt = e2e_once(K)
+    if dist:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = K * 2 * GB / dt
+    return dict(ms=ms, rows=rows, launches=launches, clocks=clocks, ktimes=ktimes, e2e_value=e2e_value,
+                h2d=2 * B * 8, d2h=2 * 4 * 4, loss_tail=loss_tail, GB=GB)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", type=str, default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    peaks = measured_peaks()
+    D, C, B = wl["dim"], wl["classes"], wl["batch"]
+    config = {"workload": f"{args.workload}: {wl['desc']}", "dim": D, "classes": C, "img_bank_rows": wl["n_img"],
+              "txt_bank_rows": wl["n_txt"], "batch_per_modality_per_gpu": B, "global_batch": 2 * B * world,
+              "optimizer": "adamw", "alpha": ALPHA, "parallelism": f"dp{world}",
+              "l2_policy": "inputs larger than L2: every step gathers fresh rows from a 3.9 GB bank and rewrites a "
+                           "67 MB gradient-logit matrix" if args.workload != "cfg2" else "working set fits L2 (few-shot)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(wl, args.steps, args.warmup, budget_s=150.0)
+        line = {"impl": "reference", "metric": "UML train samples/sec (img+text)", "value": r["value"], "unit": "samples/s",
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the UML hot path has no CPU implementation "
+                         "(use --impl reference for the CPU arm)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    res = run_ours(args, wl, rank, world, dev)
+    if rank == 0:
+        K = args.steps
+        value = res["rows"] / (res["ms"] * 1e-3)
+        used_bf16 = "head_fwd_ce_bf16" in res["ktimes"]
+        rows_per_gpu = 2 * B
+        if used_bf16:
+            kname = "head_fwd_ce_bf16"
+            kms = res["ktimes"][kname]
+            flops = 2.0 * rows_per_gpu * D * C  # algorithmic: the forward contraction only (4*D*C/sample is fwd+dW)
+            roof = {"bound": "tensor", "kernel": kname, "achieved": flops / (kms * 1e-3) / 1e12,
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "traffic": None,
+                    "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)"}
+        else:
+            kname = "head_bwd_dw_f32"
+            kms = res["ktimes"].get(kname, float("nan"))
+            bytes_ = 28.0 * C * D  # AdamW pass fused in the dW epilogue: p,g,m,v read + p,m,v written
+            roof = {"bound": "hbm", "kernel": kname, "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
+                    "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy"}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["kernel_ms"] = {k: round(v, 5) for k, v in res["ktimes"].items()}
+        step_flops = 4.0 * D * C * rows_per_gpu
+        line = {"metric": "UML train samples/sec (img+text)", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": K, "warmup": args.warmup, "ms_per_step": res["ms"] / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if used_bf16 else "f32", "data": "synthetic",
+                "config": config, "clocks": res["clocks"],
+                "e2e": {"value": res["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": res["h2d"],
+                        "d2h_bytes_per_step": res["d2h"]},
+                "gpu_launches": res["launches"], "roofline": roof,
+                "step_tensor_frac": {"achieved_tflops_per_gpu": step_flops / (res["ms"] / K * 1e-3) / 1e12,
+                                     "of_sustained_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_sustained"],
+                                     "of_burst_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_burst"],
+                                     "algorithmic_flops_per_sample": 4.0 * D * C},
+                "final_losses": res["loss_tail"]}
+        if world == 1:
+            try:
+                r = cpu_reference_run(wl, 10 ** 6, 1, budget_s=args.cpu_seconds)
+                line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                        "sample": r["sample"]}
+            except Exception as e:  # the baseline is a reported extra; never lose the measurement over it
+                line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

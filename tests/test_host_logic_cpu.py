@@ -1,0 +1,176 @@
+"""Host-side logic of the product against the golden vectors recorded from the reference - runs
+without a GPU: sampler RNG protocol, text-bank selection, LR schedule, presets, path layout."""
+import ast
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import uml_b200  # noqa: F401
+from uml_b200 import finetune as ft
+from uml_b200.engine.datasets.utils import BankLoader, FeatureBank, TextTensorDataset
+from uml_b200.engine.optimizer.default import HYPER_DICT
+from uml_b200.engine.optimizer.optim import build_optimizer
+from uml_b200.engine.optimizer.scheduler import build_lr_scheduler
+from uml_b200 import features as F
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+M = np.load(os.path.join(GOLDEN, "misc.npz"), allow_pickle=False)
+
+
+def _bank(n):
+    return FeatureBank(torch.zeros(n, 4), torch.zeros(n, dtype=torch.int64), device="cpu")
+
+
+@pytest.mark.parametrize("nw", [0, 2])
+def test_bankloader_matches_dataloader_index_stream(nw):
+    torch.manual_seed(123)
+    a, b = BankLoader(_bank(23), 5, shuffle=True, num_workers=nw), BankLoader(_bank(17), 5, shuffle=True, num_workers=nw)
+    ia, ib = iter(a), iter(b)
+    for s in range(12):
+        x, ia = ft.fetch_next(a, ia)
+        y, ib = ft.fetch_next(b, ib)
+        ga, gb = M[f"nw{nw}_a"][s], M[f"nw{nw}_b"][s]
+        assert np.array_equal(x.host_idx.numpy(), ga[ga >= 0]) and x.n == (ga >= 0).sum()
+        assert np.array_equal(y.host_idx.numpy(), gb[gb >= 0])
+        assert torch.equal(x.idx.cpu(), x.host_idx)
+
+
+def test_sequential_loader_draws_one_base_seed_and_covers_the_bank():
+    torch.manual_seed(9)
+    want = int(torch.empty((), dtype=torch.int64).random_().item())
+    second = int(torch.empty((), dtype=torch.int64).random_().item())
+    torch.manual_seed(9)
+    l = BankLoader(_bank(11), 4, shuffle=False)
+    batches = list(iter(l))
+    assert [(b.start, b.n) for b in batches] == [(0, 4), (4, 4), (8, 3)] and len(l) == 3
+    assert int(torch.empty((), dtype=torch.int64).random_().item()) == second and want != second
+
+
+def test_explicit_generator_protocol_matches_gaussian_loader():
+    """DataLoader(..., shuffle=True, drop_last=True, generator=g): permutations come from g itself and a
+    discarded permutation is drawn at each epoch end (checked against torch's own DataLoader)."""
+    from torch.utils.data import DataLoader, TensorDataset
+    g1, g2 = torch.Generator().manual_seed(42), torch.Generator().manual_seed(42)
+    ref = DataLoader(TensorDataset(torch.arange(40)), batch_size=16, shuffle=True, drop_last=True, generator=g1)
+    ours = BankLoader(_bank(40), 16, shuffle=True, drop_last=True, generator=g2)
+    ri, oi = iter(ref), iter(ours)
+    for _ in range(7):
+        try:
+            r = next(ri)[0]
+        except StopIteration:
+            ri = iter(ref)
+            r = next(ri)[0]
+        o, oi = ft.fetch_next(ours, oi)
+        assert torch.equal(r, o.host_idx)
+
+
+def test_text_dataset_selection_matches_reference():
+    feats, labels, eot = (torch.from_numpy(M["text/" + k]) for k in ("feats", "labels", "eot"))
+    for shots in (2, 4):
+        torch.manual_seed(31)
+        ds = TextTensorDataset(feats, labels, eot, n_shots=shots)
+        assert np.array_equal(ds.eot_indices.numpy(), M[f"text/shot{shots}/eot"])
+        assert int(torch.empty((), dtype=torch.int64).random_().item()) == int(M[f"text/shot{shots}/after_draw"])
+    ds = TextTensorDataset(feats, labels, eot, n_shots="average")
+    np.testing.assert_allclose(ds.input_tensor.numpy(), M["text/avg/feats"], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(ds.label_tensor.numpy(), M["text/avg/labels"])
+    assert np.array_equal(ds.eot_indices.numpy(), M["text/avg/eot"])
+    assert len(TextTensorDataset(feats, labels, eot)) == feats.shape[0]
+    with pytest.raises(ValueError):
+        TextTensorDataset(feats, labels, eot, n_shots=1.5)
+
+
+def test_zero_shot_weights_cpu_path():
+    from uml_b200.engine.models.head import get_zero_shot_weights
+    feats, labels, eot = (torch.from_numpy(M["text/" + k]) for k in ("feats", "labels", "eot"))
+    w = get_zero_shot_weights(TextTensorDataset(feats, labels, eot), 7, feats.shape[1], device="cpu")
+    np.testing.assert_allclose(w.numpy(), M["text/zeroshot_w"], rtol=1e-5, atol=1e-6)
+    assert float(w[2].abs().sum()) == 0.0
+
+
+def test_lr_schedule_matches_reference_scheduler():
+    for key in [k for k in M.files if k.startswith("sched/") and not k.endswith("/cfg")]:
+        kw = ast.literal_eval(str(M[key + "/cfg"]))
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = build_optimizer([p], "adamw", kw["base"], 0.0)
+        sch = build_lr_scheduler(opt, kw["s"], kw["w"], kw["T"], warmup_type=kw["wt"], warmup_lr=kw["wl"])
+        got = []
+        for _ in range(len(M[key])):
+            got.append(opt.param_groups[0]["lr"])
+            assert sch.get_last_lr()[0] == opt.param_groups[0]["lr"]
+            sch.step()
+        np.testing.assert_allclose(got, M[key], rtol=1e-9, atol=1e-18, err_msg=key)
+    with pytest.raises(ValueError):
+        build_lr_scheduler(opt, "step", 0, 10)
+    with pytest.raises(ValueError):
+        build_lr_scheduler(opt, "cosine", 5, 10, warmup_type="exp")
+    with pytest.raises(AssertionError):
+        build_optimizer([p], "lion", 1e-3, 0.0)
+
+
+def test_paths_and_names_match_reference():
+    assert F.img_outdir("F", "ViT-B/16", "imagenet", "crop", 16, 1, "train") == str(M["path/img_train"])
+    assert F.img_outdir("F", "ViT-B/16", "imagenet", "crop", 16, 1, "test") == str(M["path/img_test"])
+    assert F.text_outdir("F", "ViT-B/16", "imagenet", "gpt3_cupl") == str(M["path/text"])
+    assert ft.hparam_str("adamw", 0.001, 0.01, 32, 12800, 0.0, True) == str(M["path/hparam"])
+    import argparse
+    a = argparse.Namespace(common_dim=0)
+    assert ft.savedir("E", "imagenet", "ViT-B/16", 16, 1, "gpt3_cupl", "average", "crop", "crossmodal", "zeroshot", 0.5,
+                      0, "", a) == str(M["path/savedir_x"])
+    assert ft.savedir("E", "sun397", "a-b", 4, 2, "gpt3_cupl", None, "flip", "image", "random", 0.0, 0, "tag",
+                      a) == str(M["path/savedir_i"])
+
+
+def test_presets_equal_reference_when_available():
+    from oracle import ref_harness as rh
+    assert set(HYPER_DICT) == {"full_ds_full_model_finetune", "clip_linear", "linear", "audio"}
+    assert HYPER_DICT["clip_linear"]["batch_size"] == [32] and HYPER_DICT["linear"]["learnable_temp"] == [True]
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    assert rh.load_vision_language().default.HYPER_DICT == HYPER_DICT
+
+
+def test_bank_files_round_trip(tmp_path):
+    g = torch.Generator().manual_seed(0)
+    feats, labels = torch.randn(12, 8, generator=g), torch.arange(12) % 3
+    tp = F.text_outdir(str(tmp_path), "ViT-B/16", "toy", "gpt3_cupl")
+    F.write_text_bank(tp, feats, labels, lab2cname={0: "a", 1: "b", 2: "c"})
+    d = F.load_text_bank(tp)
+    assert torch.equal(d["features"], feats) and torch.equal(d["labels"], labels) and d["eot_indices"].shape == (12,)
+    ip = F.img_outdir(str(tmp_path), "ViT-B/16", "toy", "crop", 4, 1, "train")
+    F.write_image_bank(ip, train=(feats, labels), val=(feats[:6], labels[:6]), lab2cname={0: "a", 1: "b", 2: "c"})
+    d = F.load_image_bank(ip)
+    assert set(d) == {"train", "val", "lab2cname"} and set(d["train"]) == {"features", "labels", "paths"}
+    tep = F.img_outdir(str(tmp_path), "ViT-B/16", "toy", "crop", 4, 1, "test")
+    F.write_image_bank(tep, test=(feats, labels))
+    assert torch.equal(F.load_image_bank(tep)["features"], feats)
+    with pytest.raises(KeyError):
+        torch.save({"features": feats, "labels": labels}, tp)
+        F.load_text_bank(tp)
+
+
+def test_config_parser_defaults_match_reference_when_available():
+    from uml_b200.engine.config import parser
+    ours = vars(parser.parse_args([]))
+    assert ours["logit"] == 4.60517 and ours["num_workers"] == 4 and ours["modality"] == "image"
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip("reference tree not present")
+    rh.load_vision_language()
+    from engine.config import parser as ref_parser  # the reference's, via the harness' sys.path
+    ref = vars(ref_parser.parse_args([]))
+    for k, v in ref.items():
+        assert ours[k] == v, k
+
+
+def test_local_slice_partitions_a_global_batch():
+    from uml_b200.engine.datasets.utils import IndexBatch
+    bank = _bank(100)
+    idx = torch.arange(37)
+    b = IndexBatch(bank, idx, 37, 0, idx.clone())
+    for world in (2, 3, 8):
+        parts = [ft._local_slice(b, r, world) for r in range(world)]
+        assert sum(p.n for p in parts) == 37 and max(p.n for p in parts) - min(p.n for p in parts) <= 1
+        assert torch.equal(torch.cat([p.idx for p in parts]), idx)

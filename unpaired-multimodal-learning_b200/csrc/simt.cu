@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(256)
   }
   const float dsum = block_reduce_sum(ds, sh);
   if (threadIdx.x == 0) {
-    row_loss[r] = (bmax + logf(sum)) - label_raw * scale;
+    row_loss[r] = logf(sum) - (label_raw * scale - bmax);  // log_softmax form: exact 0 for a dominant label
     row_correct[r] = (sh_arg == label) ? 1 : 0;
     row_dscale[r] = dsum * weight / static_cast<float>(n_seg);
   }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256)
     }
     const int64_t m = m0 + ty * TM + i;
     if (tx == 0 && m < n_rows) {
-      row_loss[m] = (st[i].m + logf(st[i].l)) - st[i].lab;
+      row_loss[m] = logf(st[i].l) - (st[i].lab - st[i].m);
       row_pred[m] = st[i].arg;
     }
   }

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256, 1)
 
       if (valid) {
         const float inv_sum = 1.f / run_sum;
-        row_loss[row] = (run_max + logf(run_sum)) - lab_logit;
+        row_loss[row] = logf(run_sum) - (lab_logit - run_max);
         if (row_pred) row_pred[row] = arg;
         if (row_correct) row_correct[row] = (arg == label) ? 1 : 0;
         if (row_dscale) row_dscale[row] = (run_pr * inv_sum - lab_raw) * dcoef;
