@@ -62,6 +62,9 @@ int uml_gather_rows_f32(const float* bank, int64_t bank_rows, int32_t dim, const
                         int64_t n, float* out, void* stream);
 int uml_gather_rows_bf16(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx,
                          int64_t n, uint16_t* out, int64_t ld_out, void* stream);
+/* bf16 gather that also gathers the int64 bank labels of the same rows into int32 (one launch)         */
+int uml_gather_rows_labels_bf16(const float* bank, const int64_t* bank_labels, int32_t dim, const int64_t* idx,
+                                int64_t n, uint16_t* out, int64_t ld_out, int32_t* out_labels, void* stream);
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out,
                           void* stream);
 int uml_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
@@ -125,6 +128,7 @@ int uml_grad_diag(const float* a, const float* b, int64_t n, float* workspace /*
 /* ---- tensor-core path (tcgen05 + TMEM + TMA) --------------------------------------------------- */
 /* X: [n_rows, dim] bf16 dense (ld = dim), W: [n_classes, dim] bf16.  Row r belongs to segment
  * 0 when r < seg0_rows, else 1.  G: [n_rows, ldg] bf16, ldg a multiple of 64 and >= n_classes.     */
+#define UML_FAC_STRIDE 9
 typedef struct {
   int64_t seg_rows[UML_MAX_SEGMENTS];
   float   scale[UML_MAX_SEGMENTS];
@@ -138,6 +142,7 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          uint16_t* G /*may be NULL: eval mode*/, int64_t ldg,
                          float* row_loss, int32_t* row_pred /*optional: argmax class*/,
                          int32_t* row_correct /*optional: argmax == label*/, float* row_dscale /*optional*/,
+                         float* fac_ws /* [n_rows * UML_FAC_STRIDE] scratch, required when G != NULL */,
                          void* stream);
 /* dW_partial[s] = (G^T X) over the s-th K split; partials: [n_splits, n_classes, dim] fp32.       */
 int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
@@ -154,6 +159,34 @@ int uml_sum_partials(const float* partials, int32_t n_splits, int64_t split_stri
 int uml_reduce_seg_stats(const float* row_loss, const int32_t* row_correct, const float* row_dscale,
                          const int64_t* seg_rows /*host [nseg]*/, int32_t nseg, uml_seg_stats* stats,
                          void* stream);
+
+/* ---- one whole UML iteration (finetune.py:163-195) enqueued by a single call --------------------
+ * precision 0: fp32 SIMT path (rows gathered inside the GEMMs, update fused in the dW epilogue);
+ * precision 1: bf16 tcgen05 path (TMA gather+cast -> fwd/CE/G -> split-K dW -> update + split reduce).
+ * When dW_out != NULL the summed gradient is written there and W is left untouched (data parallel:
+ * the caller all-reduces dW_out and then calls uml_adamw_step / uml_sgd_step).                      */
+typedef struct {
+  int32_t       dim, n_classes, nseg, precision;
+  uml_segment   seg[UML_MAX_SEGMENTS];      /* fp32 banks + indices + labels + scale + loss weight     */
+  float*        W;                          /* [n_classes, dim] shared head                            */
+  uml_update    upd;                        /* optimizer kind, hyper-parameters, step, m, v for W      */
+  void*         G;                          /* [rows, ldg] workspace: fp32 (precision 0) / bf16 (1)    */
+  int64_t       ldg;
+  float*        row_loss;  int32_t* row_correct;  float* row_dscale;   /* [rows] workspaces            */
+  uml_seg_stats* stats;                     /* [nseg] per-run results of THIS step                     */
+  uint16_t*     X16;  uint16_t* W16;  int32_t* labels32;  float* partials;   /* bf16 path workspaces   */
+  float*        fac_ws;                     /* [rows * UML_FAC_STRIDE], bf16 path                      */
+  int32_t       max_splits;  int32_t w16_valid;
+  float*        dW_out;                     /* optional, see above                                     */
+  float*        dW_scratch;                 /* [n_classes*dim], only for SGD on the bf16 path          */
+  float*        scale_param[UML_MAX_SEGMENTS];  /* learnable temperatures (device scalars) or NULL     */
+  float*        scale_m[UML_MAX_SEGMENTS];  float* scale_v[UML_MAX_SEGMENTS];
+  int64_t       scale_step[UML_MAX_SEGMENTS];
+  /* optional cudaEvent_t pairs recorded around {gather, forward, dW, update} on `stream` (bench.py) */
+  void*         ev[8];
+} uml_linear_step_args;
+
+int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -71,6 +71,31 @@ def main():
     res["torch_matmul_fwd_bf16"] = dict(ms=med, TFs=2.0 * N * D * C / med / 1e9)
     med, best = timeit(lambda: torch.matmul(ws.G[:, :C].t(), a))
     res["torch_matmul_dw_bf16"] = dict(ms=med, TFs=2.0 * N * D * C / med / 1e9)
+    # whole step through the single C call (host dispatch cost included)
+    from uml_b200.engine.datasets.utils import BankLoader, FeatureBank
+    from uml_b200.engine.models.head import UMLClip
+    from uml_b200.engine.optimizer.optim import build_optimizer
+    from uml_b200.engine.trainer import StepEngine
+    from uml_b200 import finetune as ft
+    import time
+    fb = FeatureBank.__new__(FeatureBank); fb.features = bank; fb.labels = torch.randint(0, C, (bank.shape[0],), device=DEV)
+    model = UMLClip(f"s:{D}", C, logit_scale_init=4.60517).to(DEV)
+    opt = build_optimizer(model.parameters(), "adamw", 1e-3, 0.01)
+    eng = StepEngine(model, opt, DEV, B, B, precision="auto")
+    il, tl = BankLoader(fb, B, shuffle=True), BankLoader(fb, B, shuffle=True)
+    ii, ti = iter(il), iter(tl)
+    def one(i):
+        nonlocal ii, ti
+        a, ii = ft.fetch_next(il, ii); b, ti = ft.fetch_next(tl, ti)
+        eng.step(a, b, 0.5, slot=i)
+    for i in range(5): one(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(50): one(i)
+    host = (time.perf_counter() - t0) / 50 * 1e3
+    e1.record(); torch.cuda.synchronize()
+    res["step_single_call"] = dict(ms=e0.elapsed_time(e1) / 50, host_ms=host, TFs=4.0 * N * D * C / (e0.elapsed_time(e1) / 50) / 1e9)
     for k, val in res.items():
         print(k, json.dumps({a: (round(b, 4) if isinstance(b, float) else b) for a, b in val.items()}))
 

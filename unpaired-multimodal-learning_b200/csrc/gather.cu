@@ -22,7 +22,8 @@ constexpr int kGatherMaxRows = 32;  // one lane issues one row
 template <bool kBf16>
 __global__ void __launch_bounds__(kBf16 ? 128 : 32)
     gather_rows_kernel(const float* __restrict__ bank, const int64_t* __restrict__ idx, int64_t n, int dim,
-                       int rows_per_stage, void* __restrict__ out_v, int64_t ld_out) {
+                       int rows_per_stage, void* __restrict__ out_v, int64_t ld_out,
+                       const int64_t* __restrict__ bank_labels, int32_t* __restrict__ out_labels) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kGatherStages];
   const uint32_t row_bytes = static_cast<uint32_t>(dim) * 4u;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(kBf16 ? 128 : 32)
     if (lane < rows) {
       const int64_t src = idx ? idx[r0 + lane] : (r0 + lane);
       bulk_load_1d(smem + s * stage_bytes + lane * row_bytes, bank + src * dim, row_bytes, &full_bar[s]);
+      if (out_labels) out_labels[r0 + lane] = static_cast<int32_t>(bank_labels[src]);  // label rides along
     }
   };
 
@@ -93,6 +95,9 @@ __global__ void __launch_bounds__(kBf16 ? 128 : 32)
   if (!kBf16) bulk_wait<0>();
 }
 
+__global__ void gather_labels_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ idx, int64_t n,
+                                     int32_t* __restrict__ out);
+
 // Fallback for rows that are not a multiple of 16 bytes (dim % 4 != 0; bf16 needs dim % 8 == 0).
 template <bool kBf16>
 __global__ void gather_rows_plain(const float* __restrict__ bank, const int64_t* __restrict__ idx, int64_t n, int dim,
@@ -137,7 +142,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 template <bool kBf16>
 static int launch_gather(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx, int64_t n, void* out,
-                         int64_t ld_out, cudaStream_t st) {
+                         int64_t ld_out, cudaStream_t st, const int64_t* bank_labels = nullptr,
+                         int32_t* out_labels = nullptr) {
   if (n == 0) return 0;
   UML_REQUIRE(bank && out && dim > 0 && bank_rows > 0 && n > 0, "gather: bad arguments");
   const uint32_t row_bytes = static_cast<uint32_t>(dim) * 4u;
@@ -148,6 +154,10 @@ static int launch_gather(const float* bank, int64_t bank_rows, int32_t dim, cons
     const int grid = static_cast<int>(std::min<int64_t>(n, 148 * 8));
     gather_rows_plain<kBf16><<<grid, 256, 0, st>>>(bank, idx, n, dim, out, ld_out);
     UML_CUDA(cudaGetLastError());
+    if (out_labels) {
+      gather_labels_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(bank_labels, idx, n, out_labels);
+      UML_CUDA(cudaGetLastError());
+    }
     return 0;
   }
   int rows = kGatherStageBytes / row_bytes;
@@ -161,7 +171,8 @@ static int launch_gather(const float* bank, int64_t bank_rows, int32_t dim, cons
   }
   const int64_t groups = (n + rows - 1) / rows;
   const int grid = static_cast<int>(std::min<int64_t>(groups, sm_count()));
-  gather_rows_kernel<kBf16><<<grid, kBf16 ? 128 : 32, smem, st>>>(bank, idx, n, dim, rows, out, ld_out);
+  gather_rows_kernel<kBf16><<<grid, kBf16 ? 128 : 32, smem, st>>>(bank, idx, n, dim, rows, out, ld_out, bank_labels,
+                                                                  out_labels);
   UML_CUDA(cudaGetLastError());
   return 0;
 }
@@ -178,6 +189,13 @@ int uml_gather_rows_f32(const float* bank, int64_t bank_rows, int32_t dim, const
 int uml_gather_rows_bf16(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx, int64_t n,
                          uint16_t* out, int64_t ld_out, void* stream) {
   return uml::launch_gather<true>(bank, bank_rows, dim, idx, n, out, ld_out, uml::as_stream(stream));
+}
+
+int uml_gather_rows_labels_bf16(const float* bank, const int64_t* bank_labels, int32_t dim, const int64_t* idx,
+                                int64_t n, uint16_t* out, int64_t ld_out, int32_t* out_labels, void* stream) {
+  UML_REQUIRE(bank_labels && out_labels, "gather_rows_labels_bf16: null labels");
+  return uml::launch_gather<true>(bank, INT64_MAX / 2, dim, idx, n, out, ld_out, uml::as_stream(stream), bank_labels,
+                                  out_labels);
 }
 
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out, void* stream) {

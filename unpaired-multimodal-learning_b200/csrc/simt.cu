@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // deterministic per-run reduction of the per-row results (fixed summation order)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
     seg_stats_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_correct,
                      const float* __restrict__ row_dscale, int64_t n0, int64_t n1, uml_seg_stats* __restrict__ out) {
-  __shared__ float sh[8];
+  __shared__ float sh[32];
   const int s = blockIdx.x;
   const int64_t beg = s ? n0 : 0, n = s ? n1 : n0;
   float ls = 0.f, ds = 0.f;
@@ -511,7 +511,7 @@ int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, cons
                                                                         row_dscale);
     UML_CUDA(cudaGetLastError());
   }
-  seg_stats_kernel<<<nseg, 256, 0, st>>>(row_loss, row_correct, row_dscale, n0, n1, stats);
+  seg_stats_kernel<<<nseg, 1024, 0, st>>>(row_loss, row_correct, row_dscale, n0, n1, stats);
   UML_CUDA(cudaGetLastError());
   return 0;
 }
@@ -589,7 +589,7 @@ int uml_reduce_seg_stats(const float* row_loss, const int32_t* row_correct, cons
   using namespace uml;
   UML_REQUIRE(row_loss && row_correct && seg_rows && stats && nseg >= 1 && nseg <= UML_MAX_SEGMENTS,
               "reduce_seg_stats: bad arguments");
-  seg_stats_kernel<<<nseg, 256, 0, as_stream(stream)>>>(row_loss, row_correct, row_dscale, seg_rows[0],
+  seg_stats_kernel<<<nseg, 1024, 0, as_stream(stream)>>>(row_loss, row_correct, row_dscale, seg_rows[0],
                                                         nseg > 1 ? seg_rows[1] : 0, stats);
   UML_CUDA(cudaGetLastError());
   return 0;

@@ -1,0 +1,134 @@
+// One UML iteration behind ONE C-ABI call: the host enqueues every kernel of the step
+// (reference loop body, vision_language/finetune.py:163-195) without returning to Python in between.
+// At the reference's batch sizes the step is launch-latency bound, at throughput batch sizes the host
+// must stay ahead of a ~150 us GPU step - either way per-kernel Python dispatch is what limits it.
+#include "common.cuh"
+
+namespace {
+inline void rec(void* ev, void* stream) {
+  if (ev) cudaEventRecord(static_cast<cudaEvent_t>(ev), uml::as_stream(stream));
+}
+}  // namespace
+
+extern "C" {
+
+int uml_linear_step(const uml_linear_step_args* a, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(a != nullptr, "linear_step: null args");
+  UML_REQUIRE(a->nseg >= 1 && a->nseg <= UML_MAX_SEGMENTS, "linear_step: 1..2 segments");
+  UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
+  const int64_t n0 = a->seg[0].n, n1 = a->nseg > 1 ? a->seg[1].n : 0, total = n0 + n1;
+  const bool fused = a->dW_out == nullptr;
+  const bool learn = a->scale_param[0] != nullptr || a->scale_param[1] != nullptr;
+  int rc;
+
+  if (a->precision == 0) {
+    // ------------------------------------------------------------------ fp32 exact path (3 launches)
+    UML_REQUIRE(a->row_dscale, "linear_step: fp32 path needs row_dscale");
+    rec(a->ev[2], stream);
+    rc = uml_head_fwd_ce_f32(a->seg, a->nseg, a->dim, a->W, a->n_classes, static_cast<float*>(a->G), a->ldg,
+                             a->row_loss, a->row_correct, a->row_dscale, a->stats, stream);
+    if (rc) return rc;
+    rec(a->ev[3], stream);
+  } else {
+    // ------------------------------------------------------------------ bf16 tensor-core path
+    UML_REQUIRE(a->X16 && a->W16 && a->labels32 && a->partials && a->fac_ws && a->max_splits >= 1,
+                "linear_step: bf16 buffers");
+    if (!a->w16_valid) {
+      rc = uml_cast_f32_to_bf16(a->W, a->W16, static_cast<int64_t>(a->n_classes) * a->dim, stream);
+      if (rc) return rc;
+    }
+    uml_tc_segments ts;
+    memset(&ts, 0, sizeof(ts));
+    ts.nseg = 0;
+    int64_t off = 0;
+    rec(a->ev[0], stream);
+    for (int i = 0; i < a->nseg; ++i) {
+      const uml_segment& s = a->seg[i];
+      if (s.n == 0) continue;
+      const float* rows = static_cast<const float*>(s.rows);
+      UML_REQUIRE(s.ld == a->dim, "linear_step: bf16 path needs dense bank rows (ld == dim)");
+      if (s.idx && !s.label_idx) {
+        rc = uml_gather_rows_labels_bf16(rows, s.labels, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim,
+                                         a->labels32 + off, stream);
+        if (rc) return rc;
+      } else {
+        if (s.idx)
+          rc = uml_gather_rows_bf16(rows, INT64_MAX / 2, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim, stream);
+        else
+          rc = uml_cast_f32_to_bf16(rows, a->X16 + off * a->dim, s.n * a->dim, stream);
+        if (rc) return rc;
+        rc = uml_gather_labels_i32(s.labels, s.label_idx ? s.label_idx : s.idx, s.n, a->labels32 + off, stream);
+        if (rc) return rc;
+      }
+      ts.seg_rows[ts.nseg] = s.n;
+      ts.scale[ts.nseg] = s.scale;
+      ts.loss_weight[ts.nseg] = s.loss_weight;
+      ts.scale_dev[ts.nseg] = s.scale_dev;
+      ts.nseg++;
+      off += s.n;
+    }
+    rec(a->ev[1], stream);
+    if (total > 0) {
+      rec(a->ev[2], stream);
+      rc = uml_head_fwd_ce_bf16(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
+                                static_cast<uint16_t*>(a->G), a->ldg, a->row_loss, nullptr, a->row_correct,
+                                learn ? a->row_dscale : nullptr, a->fac_ws, stream);
+      if (rc) return rc;
+      rec(a->ev[3], stream);
+    }
+    int64_t rows2[2] = {n0, n1};
+    rc = uml_reduce_seg_stats(a->row_loss, a->row_correct, learn ? a->row_dscale : nullptr, rows2, a->nseg, a->stats,
+                              stream);
+    if (rc) return rc;
+  }
+
+  // learnable temperatures: scalar Adam(W) steps fed straight from the stats record on the device
+  for (int i = 0; i < a->nseg; ++i) {
+    if (!a->scale_param[i]) continue;
+    const float* g = &a->stats[i].dscale;
+    if (a->upd.kind == 3)
+      rc = uml_sgd_step(a->scale_param[i], g, nullptr, 0.f, a->scale_m[i], 1, a->upd.lr, a->upd.momentum,
+                        a->upd.weight_decay, a->scale_step[i], nullptr, stream);
+    else
+      rc = uml_adamw_step(a->scale_param[i], g, nullptr, 0.f, a->scale_m[i], a->scale_v[i], 1, a->upd.lr, a->upd.beta1,
+                          a->upd.beta2, a->upd.eps, a->upd.weight_decay, a->scale_step[i], a->upd.kind == 1, nullptr,
+                          stream);
+    if (rc) return rc;
+  }
+
+  if (total == 0) return 0;
+  if (a->precision == 0) {
+    uml_update none;
+    memset(&none, 0, sizeof(none));
+    rec(a->ev[4], stream);
+    rc = uml_head_bwd_dw_f32(a->seg, a->nseg, a->dim, static_cast<const float*>(a->G), a->ldg, a->n_classes, a->W,
+                             a->dW_out, fused ? &a->upd : &none, stream);
+    rec(a->ev[5], stream);
+    return rc;
+  }
+  int splits = uml_tc_dw_splits(total, a->dim, a->n_classes);
+  if (splits > a->max_splits) splits = a->max_splits;
+  rec(a->ev[4], stream);
+  rc = uml_head_bwd_dw_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes, a->partials,
+                            splits, stream);
+  if (rc) return rc;
+  rec(a->ev[5], stream);
+  const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
+  if (!fused) return uml_sum_partials(a->partials, splits, np, np, a->dW_out, stream);
+  if (a->upd.kind == 3) {
+    UML_REQUIRE(a->dW_scratch, "linear_step: SGD on the bf16 path needs dW_scratch");
+    rc = uml_sum_partials(a->partials, splits, np, np, a->dW_scratch, stream);
+    if (rc) return rc;
+    return uml_sgd_step(a->W, a->dW_scratch, nullptr, 0.f, a->upd.m, np, a->upd.lr, a->upd.momentum, a->upd.weight_decay,
+                        a->upd.step, a->W16, stream);
+  }
+  rec(a->ev[6], stream);
+  rc = uml_adamw_step_partials(a->W, a->partials, splits, np, a->upd.m, a->upd.v, np, a->upd.lr, a->upd.beta1,
+                               a->upd.beta2, a->upd.eps, a->upd.weight_decay, a->upd.step, a->upd.kind == 1, a->W16,
+                               nullptr, stream);
+  rec(a->ev[7], stream);
+  return rc;
+}
+
+}  // extern "C"

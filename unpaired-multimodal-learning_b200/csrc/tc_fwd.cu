@@ -32,7 +32,10 @@ constexpr int kFwdABytes = kFwdBlockM * kFwdBlockK * 2;
 constexpr int kFwdBBytes = kFwdBlockN * kFwdBlockK * 2;
 constexpr int kFwdStageBytes = kFwdABytes + kFwdBBytes;
 constexpr int kFwdMaxChunks = 8;  // up to 2048 classes
-constexpr int kFwdSmemBytes = kFwdStages * kFwdStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kFacStride = kFwdMaxChunks + 1;  // per row: one factor per class chunk + the onehot coefficient
+constexpr int kFwdStoreBox = 32 * 128;          // 32 rows x 64 bf16 columns, SWIZZLE_128B
+constexpr int kFwdStoreBytes = 4 * 2 * kFwdStoreBox;  // 4 epilogue warps x double buffer
+constexpr int kFwdSmemBytes = kFwdStages * kFwdStageBytes + kFwdStoreBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 struct FwdSegs {
   int64_t n0;
@@ -48,13 +51,14 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 __global__ void __launch_bounds__(256, 1)
     head_fwd_ce_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                          int64_t n_rows, int dim, int n_classes, const int32_t* __restrict__ labels, FwdSegs segs,
+                          const __grid_constant__ CUtensorMap tmap_g, int64_t n_rows, int dim, int n_classes, const int32_t* __restrict__ labels, FwdSegs segs,
                           __nv_bfloat16* __restrict__ G, int64_t ldg, float* __restrict__ row_loss,
                           int32_t* __restrict__ row_pred, int32_t* __restrict__ row_correct,
-                          float* __restrict__ row_dscale) {
+                          float* __restrict__ row_dscale, float* __restrict__ fac) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kFwdStages * kFwdStageBytes);
+  unsigned char* store_smem = smem + kFwdStages * kFwdStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(store_smem + kFwdStoreBytes);
   uint64_t* empty_bar = full_bar + kFwdStages;
   uint64_t* tfull_bar = empty_bar + kFwdStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -139,7 +143,8 @@ __global__ void __launch_bounds__(256, 1)
     // ------------------------------------------------ epilogue ----------------------------------
     const int q = warp - 4;  // TMEM lane quarter this warp may access
     constexpr float kLog2e = 1.4426950408889634f;
-    uint32_t acc_it = 0;
+    uint32_t acc_it = 0, store_it = 0;
+    if (lane == 0 && warp == 4) tma_prefetch_desc(&tmap_g);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t row = tile * kFwdBlockM + q * 32 + lane;
       const bool valid = row < n_rows;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(256, 1)
       const float dcoef = sg ? segs.dcoef[1] : segs.dcoef[0];
       const float gcoef = dcoef * scale;
       const int label = valid ? labels[row] : -1;
-      __nv_bfloat16* grow = G ? G + row * ldg : nullptr;
+      const bool grow = G != nullptr;
       float run_max = -INFINITY, run_sum = 0.f, run_pr = 0.f, lab_logit = 0.f, lab_raw = 0.f;
       int arg = 0;
       float chunk_max[kFwdMaxChunks];
@@ -205,17 +210,33 @@ __global__ void __launch_bounds__(256, 1)
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
             packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
           }
-          if (grow && valid) {
-            const int c = col0 + cb * 32;
-            if (c + 32 <= ldg) {
-              uint4* dst = reinterpret_cast<uint4*>(grow + c);
-              dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-              dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-              dst[2] = make_uint4(packed[8], packed[9], packed[10], packed[11]);
-              dst[3] = make_uint4(packed[12], packed[13], packed[14], packed[15]);
-            } else {
-              for (int i = 0; i < 16; ++i)
-                if (c + 2 * i + 2 <= ldg) reinterpret_cast<uint32_t*>(grow + c)[i] = packed[i];
+          if (G) {
+            // stage the 32-row x 32-column piece in shared memory in the TMA 128B-swizzled layout
+            // (16-byte chunk j of row r lives at chunk j ^ (r & 7)); every second column block the
+            // warp's 32 x 64 tile goes out as ONE coalesced TMA store.
+            unsigned char* sbuf = store_smem + (q * 2 + (store_it & 1)) * kFwdStoreBox;
+            if ((cb & 1) == 0) {
+              if (lane == 0) bulk_wait_read<1>();  // the store that last read this buffer has drained it
+              __syncwarp();
+            }
+            unsigned char* srow = sbuf + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = ((cb & 1) * 4 + j) ^ (lane & 7);
+              *reinterpret_cast<uint4*>(srow + chunk * 16) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            if (cb & 1) {
+              fence_proxy_async();
+              __syncwarp();
+              const int c = col0 + (cb - 1) * 32;
+              if (lane == 0 && c < ldg) {
+                tma_store_2d(&tmap_g, sbuf, c, static_cast<int32_t>(tile * kFwdBlockM + q * 32));
+                bulk_commit();
+              } else if (lane == 0) {
+                bulk_commit();  // keep one group per buffer use so wait_group.read<1> stays exact
+              }
+              ++store_it;
             }
           }
         }
@@ -231,36 +252,62 @@ __global__ void __launch_bounds__(256, 1)
         if (row_correct) row_correct[row] = (arg == label) ? 1 : 0;
         if (row_dscale) row_dscale[row] = (run_pr * inv_sum - lab_raw) * dcoef;
         if (grow) {
-          // deferred normalisation: p = exp(x - m_j) * exp(m_j - m_final) / sum ; then G = gcoef*(p - onehot)
-          for (int ch = 0; ch < n_chunks; ++ch) {
-            const float f = fast_exp2((chunk_max[ch] - run_max) * kLog2e) * inv_sum * gcoef;
-            const int col0 = ch * kFwdBlockN;
-#pragma unroll 4
-            for (int c = col0; c < col0 + kFwdBlockN && c < ldg; c += 8) {
-              uint4 u = *reinterpret_cast<uint4*>(grow + c);
-              uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&w[i]);
-                float2 p = __bfloat1622float2(h);
-                p.x *= f;
-                p.y *= f;
-                if (c + 2 * i == label) p.x -= gcoef;
-                if (c + 2 * i + 1 == label) p.y -= gcoef;
-                h = __floats2bfloat162_rn(p.x, p.y);
-                w[i] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(grow + c) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-          }
+          // deferred normalisation, finished by g_fixup_kernel:
+          //   p = exp(x - m_j) * exp(m_j - m_final) / sum ;  G = gcoef * (p - onehot)
+          float* f = fac + row * kFacStride;
+          for (int ch = 0; ch < n_chunks; ++ch)
+            f[ch] = fast_exp2((chunk_max[ch] - run_max) * kLog2e) * inv_sum * gcoef;
+          f[kFwdMaxChunks] = gcoef;
         }
       }
     }
   }
 
+  if (warp >= 4 && lane == 0) bulk_wait<0>();  // outstanding TMA stores read shared memory: drain before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Second half of the deferred softmax normalisation: one warp per row, 16-byte vectors, every load
+// of a row in flight at once.  The rows were written moments ago by the forward kernel, so at
+// training batch sizes this pass runs out of L2.
+__global__ void __launch_bounds__(256)
+    g_fixup_kernel(__nv_bfloat16* __restrict__ G, int64_t ldg, int64_t n_rows, const int32_t* __restrict__ labels,
+                   const float* __restrict__ fac) {
+  const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int label = labels[row];
+  const float* f = fac + row * kFacStride;
+  const float gcoef = f[kFwdMaxChunks];
+  __nv_bfloat16* g = G + row * ldg;
+  uint4 v[kFwdMaxChunks];
+  const int iters = static_cast<int>((ldg + 255) / 256);
+#pragma unroll
+  for (int j = 0; j < kFwdMaxChunks; ++j) {
+    const int c = j * 256 + lane * 8;
+    if (j < iters && c < ldg) v[j] = *reinterpret_cast<const uint4*>(g + c);
+  }
+#pragma unroll
+  for (int j = 0; j < kFwdMaxChunks; ++j) {
+    const int c = j * 256 + lane * 8;
+    if (j < iters && c < ldg) {
+      const float fj = f[j];
+      uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 p = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[i]));
+        p.x *= fj;
+        p.y *= fj;
+        if (c + 2 * i == label) p.x -= gcoef;
+        if (c + 2 * i + 1 == label) p.y -= gcoef;
+        __nv_bfloat162 h = __floats2bfloat162_rn(p.x, p.y);
+        w[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(g + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
 }
 
 }  // namespace uml
@@ -270,13 +317,14 @@ extern "C" {
 int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                          const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg,
                          float* row_loss, int32_t* row_pred, int32_t* row_correct, float* row_dscale,
-                         void* stream) {
+                         float* fac_ws, void* stream) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && row_loss && n_rows >= 0 && dim > 0 && n_classes > 0,
               "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
   UML_REQUIRE(n_classes <= kFwdMaxChunks * kFwdBlockN, "head_fwd_ce_bf16: at most %d classes", kFwdMaxChunks * kFwdBlockN);
   UML_REQUIRE(!G || (ldg % 64 == 0 && ldg >= n_classes), "head_fwd_ce_bf16: ldg must be a multiple of 64 and >= n_classes");
+  UML_REQUIRE(!G || fac_ws, "head_fwd_ce_bf16: fac_ws (n_rows * UML_FAC_STRIDE floats) is required when G is written");
   UML_REQUIRE(segs->nseg >= 1 && segs->nseg <= UML_MAX_SEGMENTS, "head_fwd_ce_bf16: 1..2 segments");
   if (n_rows == 0) return 0;
   const int64_t n0 = segs->seg_rows[0], n1 = segs->nseg > 1 ? segs->seg_rows[1] : 0;
@@ -289,6 +337,13 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   if (make_tmap_2d(&tw, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim, n_classes, static_cast<uint64_t>(dim) * 2,
                    kFwdBlockK, kFwdBlockN, CU_TENSOR_MAP_SWIZZLE_128B))
     return 1;
+  CUtensorMap tg;
+  memset(&tg, 0, sizeof(tg));
+  if (G) {
+    if (make_tmap_2d(&tg, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, static_cast<uint64_t>(ldg), n_rows,
+                     static_cast<uint64_t>(ldg) * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
+      return 1;
+  }
   FwdSegs fs;
   fs.n0 = segs->nseg > 1 ? n0 : INT64_MAX;
   for (int i = 0; i < 2; ++i) {
@@ -306,9 +361,14 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   const int64_t tiles = (n_rows + kFwdBlockM - 1) / kFwdBlockM;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   head_fwd_ce_tc_kernel<<<grid, 256, kFwdSmemBytes, as_stream(stream)>>>(
-      tx, tw, n_rows, dim, n_classes, labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg, row_loss, row_pred,
-      row_correct, row_dscale);
+      tx, tw, tg, n_rows, dim, n_classes, labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg, row_loss, row_pred,
+      row_correct, row_dscale, fac_ws);
   UML_CUDA(cudaGetLastError());
+  if (G) {
+    g_fixup_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels, fac_ws);
+    UML_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -26,6 +26,18 @@ from .datasets.utils import IndexBatch
 BF16_MIN_ROWS = 1024  # below this the step is launch-bound and the exact fp32 path is used
 
 
+def dp_loss_weights(n_img_local, n_txt_local, alpha, n_img_global=None, n_txt_global=None):
+    """Per-run loss weights of one rank in a data-parallel step.
+
+    The kernels divide a run's gradient by the LOCAL row count; the loss is a mean over the GLOBAL
+    batch (finetune.py:186-188), so a rank holding n_local of n_global rows scales its run by
+    n_local / n_global.  Summing the ranks' gradients (all-reduce) then gives exactly the single-process
+    gradient; the text run also carries alpha."""
+    wi = 1.0 if not n_img_global or not n_img_local else n_img_local / float(n_img_global)
+    wt = alpha if not n_txt_global or not n_txt_local else alpha * n_txt_local / float(n_txt_global)
+    return wi, wt
+
+
 class StepEngine:
     def __init__(self, model, optimizer, device, max_img_rows: int, max_txt_rows: int, log_slots: int = 128,
                  precision: str = "auto", dist_group=None, world_size: int = 1):
@@ -52,6 +64,8 @@ class StepEngine:
         self.X16 = self.W16 = self.labels32 = self.partials = None
         self._w16_valid = False
         self.host_log = None
+        self._args = None
+        self.single_call = True  # False: dispatch every kernel from Python (debugging)
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
 
     # ------------------------------------------------------------------------------------ helpers
@@ -67,7 +81,13 @@ class StepEngine:
 
     def kernel_times_ms(self):
         """Mean device time per launch of every profiled kernel (call after a synchronize)."""
-        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in (self.profile or {}).items()}
+        out = {}
+        for k, v in (self.profile or {}).items():
+            ts = [a.elapsed_time(b) for a, b in v]
+            ts = [t for t in ts if t > 1e-4]  # pairs the launcher did not use stay at ~0
+            if ts:
+                out[k] = sum(ts) / len(ts)
+        return out
 
     def _scales(self):
         si, st = self.model.scales()
@@ -104,13 +124,86 @@ class StepEngine:
         n_i, n_t = (img.n if img else 0), (txt.n if txt else 0)
         slot %= self.log_slots
         self.slot_modalities[slot] = (img is not None, txt is not None)
-        # data parallel: the loss is a mean over the GLOBAL batch, so rescale the local 1/n
-        wi = 1.0 if global_img_rows is None or n_i == 0 else n_i / float(global_img_rows)
-        wt = alpha if global_txt_rows is None or n_t == 0 else alpha * n_t / float(global_txt_rows)
-        if self._use_bf16(n_i + n_t):
-            self._step_bf16(img, txt, n_i, n_t, wi, wt, slot)
+        wi, wt = dp_loss_weights(n_i, n_t, alpha, global_img_rows, global_txt_rows)
+        bf16 = self._use_bf16(n_i + n_t)
+        if self.adapter or not self.single_call:
+            # per-kernel dispatch: adapter variant, and the profiling mode that brackets each kernel
+            (self._step_bf16 if bf16 else self._step_fp32)(img, txt, n_i, n_t, wi, wt, slot)
         else:
-            self._step_fp32(img, txt, n_i, n_t, wi, wt, slot)
+            self._step_single_call(img, txt, n_i, n_t, wi, wt, slot, bf16)
+
+    # ------------------------------------------------------------------------------------ one C call
+    def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):
+        """The whole iteration enqueued by uml_linear_step (csrc/step.cu): Python only fills a struct."""
+        import ctypes as C
+        from .._lib import LAUNCH_COUNT, LinearStepArgs, check, load
+        a = self._args
+        if a is None:
+            a = self._args = LinearStepArgs()
+            a.dim, a.n_classes = self.D, self.C
+        if bf16 and self.ws16 is None:
+            self._alloc_bf16()
+        if not bf16 and self.ws32 is None:
+            self.ws32 = ops.HeadWorkspace(self.max_rows, self.C, self.device)
+        ws = self.ws16 if bf16 else self.ws32
+        s_i, s_t, sd_i, sd_t = self._scales()
+        k = 0
+        for b, cnt, s, w, sd, prm in ((img, n_i, s_i, wi, sd_i, getattr(self.model, "img_scale", None)),
+                                      (txt, n_t, s_t, wt, sd_t, getattr(self.model, "txt_scale", None))):
+            if b is None or cnt == 0:
+                continue
+            rows, labels, idx = self._view(b)
+            seg = a.seg[k]
+            seg.rows, seg.labels, seg.idx = rows.data_ptr(), labels.data_ptr(), (idx.data_ptr() if idx is not None else None)
+            seg.n, seg.ld, seg.scale, seg.loss_weight = cnt, rows.stride(0), s, w
+            seg.label_idx, seg.scale_dev = None, (sd.data_ptr() if sd is not None else None)
+            if self.learnable:
+                st = self.opt.slot(prm)
+                st["step"] += 1
+                a.scale_param[k], a.scale_m[k] = prm.data.data_ptr(), st["m"].data_ptr()
+                a.scale_v[k] = st["v"].data_ptr() if st["v"] is not None else None
+                a.scale_step[k] = st["step"]
+            else:
+                a.scale_param[k] = None
+            k += 1
+        a.nseg, a.precision = k, int(bf16)
+        W = self.W.data
+        a.W, a.upd = W.data_ptr(), self.opt.update_struct(self.W)
+        a.G, a.ldg = ws.G.data_ptr(), ws.ldg
+        a.row_loss, a.row_correct, a.row_dscale = ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr()
+        a.stats = self.stats_log[slot].data_ptr()
+        if bf16:
+            a.X16, a.W16, a.labels32 = self.X16.data_ptr(), self.W16.data_ptr(), self.labels32.data_ptr()
+            a.partials, a.max_splits, a.w16_valid = self.partials.data_ptr(), self.max_splits, int(self._w16_valid)
+            a.fac_ws = ws.fac.data_ptr()
+        need_dw = self.world > 1 or (bf16 and self.opt.name == "sgd")
+        if need_dw and self.dW is None:
+            self.dW = torch.empty_like(W)
+        a.dW_out = self.dW.data_ptr() if self.world > 1 else None
+        a.dW_scratch = self.dW.data_ptr() if (bf16 and self.opt.name == "sgd" and self.world == 1) else None
+        if self.profile is not None:
+            # cudaEvent pairs recorded by the C launcher around gather / forward / dW / update
+            names = ("gather_bf16", "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32",
+                     "head_bwd_dw_bf16" if bf16 else "head_bwd_dw_f32", "adamw_step_partials")
+            for j, nm in enumerate(names):
+                if not bf16 and j in (0, 3):  # the fp32 path gathers inside its GEMMs and updates in the dW epilogue
+                    a.ev[2 * j] = a.ev[2 * j + 1] = None
+                    continue
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); e1.record()  # forces creation of the underlying cudaEvent_t
+                a.ev[2 * j], a.ev[2 * j + 1] = e0.cuda_event, e1.cuda_event
+                self.profile.setdefault(nm, []).append((e0, e1))
+        else:
+            for j in range(8):
+                a.ev[j] = None
+        check(load().uml_linear_step(C.byref(a), torch.cuda.current_stream().cuda_stream))
+        LAUNCH_COUNT[0] += (k + 5 + (0 if self._w16_valid else 1) if bf16 else 4) + (k if self.learnable else 0)
+        if self.world > 1:
+            # undo the step count taken by update_struct: apply() counts the step itself
+            self.opt.slot(self.W)["step"] -= 1
+            torch.distributed.all_reduce(self.dW, group=self.dist_group)
+            self.opt.apply(self.W, self.dW, shadow=self.W16 if bf16 else None)
+        self._w16_valid = bf16
 
     # ------------------------------------------------------------------------------------ fp32
     def _step_fp32(self, img, txt, n_i, n_t, wi, wt, slot):

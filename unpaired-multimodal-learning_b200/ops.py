@@ -125,6 +125,7 @@ class HeadWorkspace:
         self.row_correct = torch.empty(max_rows, device=device, dtype=torch.int32)
         self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
         self.stats = torch.zeros((2, 4), device=device, dtype=torch.float32)  # 2 x uml_seg_stats (16 B each)
+        self.fac = torch.empty((max_rows, 9), device=device, dtype=torch.float32) if bf16 else None  # UML_FAC_STRIDE
 
     def read_stats(self):
         """Host copy of the two uml_seg_stats records (synchronises)."""
@@ -249,10 +250,10 @@ def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadW
     _need(W_bf16, torch.bfloat16, "W")
     _need(labels_i32, torch.int32, "labels")
     n_rows = X.shape[0] if n_rows is None else n_rows
-    G, ldg = (ws.G.data_ptr(), ws.ldg) if ws is not None else (None, 0)
+    G, ldg, fac = (ws.G.data_ptr(), ws.ldg, ws.fac.data_ptr()) if ws is not None else (None, 0, None)
     check(_lib.load().uml_head_fwd_ce_bf16(X.data_ptr(), n_rows, X.shape[1], W_bf16.data_ptr(), W_bf16.shape[0],
                                            labels_i32.data_ptr(), C.byref(segs), G, ldg, row_loss.data_ptr(),
-                                           _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), _stream()))
+                                           _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), fac, _stream()))
 
 
 def tc_dw_splits(n_rows: int, dim: int, n_classes: int) -> int:
