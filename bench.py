@@ -207,7 +207,7 @@ def run_ours(args, wl, rank, world, dev):
 
     for i in range(W):
         step(i)
-    engine.profile = {}
+    engine.prepare_profile(K)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()

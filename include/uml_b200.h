@@ -128,7 +128,6 @@ int uml_grad_diag(const float* a, const float* b, int64_t n, float* workspace /*
 /* ---- tensor-core path (tcgen05 + TMEM + TMA) --------------------------------------------------- */
 /* X: [n_rows, dim] bf16 dense (ld = dim), W: [n_classes, dim] bf16.  Row r belongs to segment
  * 0 when r < seg0_rows, else 1.  G: [n_rows, ldg] bf16, ldg a multiple of 64 and >= n_classes.     */
-#define UML_FAC_STRIDE 9
 typedef struct {
   int64_t seg_rows[UML_MAX_SEGMENTS];
   float   scale[UML_MAX_SEGMENTS];
@@ -142,8 +141,12 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          uint16_t* G /*may be NULL: eval mode*/, int64_t ldg,
                          float* row_loss, int32_t* row_pred /*optional: argmax class*/,
                          int32_t* row_correct /*optional: argmax == label*/, float* row_dscale /*optional*/,
-                         float* fac_ws /* [n_rows * UML_FAC_STRIDE] scratch, required when G != NULL */,
+                         float* tile_ws /* optional [UML_TILE_WS_FLOATS(n_rows)]: per-tile partial sums of the
+                                           per-run statistics, reduced by uml_reduce_tile_stats            */,
                          void* stream);
+#define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 127) / 128) * 32)
+/* per-run {mean loss, dscale, hits, rows} from the forward kernel's per-tile partials (fixed order)     */
+int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream);
 /* dW_partial[s] = (G^T X) over the s-th K split; partials: [n_splits, n_classes, dim] fp32.       */
 int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
                          int32_t n_classes, float* partials, int32_t n_splits, void* stream);
@@ -175,7 +178,7 @@ typedef struct {
   float*        row_loss;  int32_t* row_correct;  float* row_dscale;   /* [rows] workspaces            */
   uml_seg_stats* stats;                     /* [nseg] per-run results of THIS step                     */
   uint16_t*     X16;  uint16_t* W16;  int32_t* labels32;  float* partials;   /* bf16 path workspaces   */
-  float*        fac_ws;                     /* [rows * UML_FAC_STRIDE], bf16 path                      */
+  float*        tile_ws;                    /* [UML_TILE_WS_FLOATS(rows)], bf16 path                   */
   int32_t       max_splits;  int32_t w16_valid;
   float*        dW_out;                     /* optional, see above                                     */
   float*        dW_scratch;                 /* [n_classes*dim], only for SGD on the bf16 path          */

@@ -41,7 +41,7 @@ class LinearStepArgs(C.Structure):
     _fields_ = [("dim", c_i32), ("n_classes", c_i32), ("nseg", c_i32), ("precision", c_i32),
                 ("seg", Segment * 2), ("W", c_vp), ("upd", Update), ("G", c_vp), ("ldg", c_i64),
                 ("row_loss", c_vp), ("row_correct", c_vp), ("row_dscale", c_vp), ("stats", c_vp),
-                ("X16", c_vp), ("W16", c_vp), ("labels32", c_vp), ("partials", c_vp), ("fac_ws", c_vp),
+                ("X16", c_vp), ("W16", c_vp), ("labels32", c_vp), ("partials", c_vp), ("tile_ws", c_vp),
                 ("max_splits", c_i32), ("w16_valid", c_i32), ("dW_out", c_vp), ("dW_scratch", c_vp),
                 ("scale_param", c_vp * 2), ("scale_m", c_vp * 2), ("scale_v", c_vp * 2), ("scale_step", c_i64 * 2),
                 ("ev", c_vp * 8)]
@@ -76,6 +76,7 @@ PROTOTYPES = {
                                 c_i32, c_vp, c_vp, c_vp],
     "uml_sum_partials": [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp],
     "uml_reduce_seg_stats": [c_vp, c_vp, c_vp, C.POINTER(c_i64), c_i32, c_vp, c_vp],
+    "uml_reduce_tile_stats": [c_vp, c_i64, c_i32, c_vp, c_vp],
     "uml_linear_step": [C.POINTER(LinearStepArgs), c_vp],
 }
 
@@ -87,7 +88,7 @@ KERNELS_PER_CALL = {
     "uml_gather_rows_labels_bf16": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
-    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_head_bwd_dw_bf16": 1, "uml_adamw_step_partials": 1,
+    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 1, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_adamw_step_partials": 1,
     "uml_sum_partials": 1, "uml_reduce_seg_stats": 1,
 }  # uml_linear_step is counted by the caller (its kernel count depends on the path)
 LAUNCH_COUNT = [0]

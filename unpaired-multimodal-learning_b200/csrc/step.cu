@@ -32,7 +32,7 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     rec(a->ev[3], stream);
   } else {
     // ------------------------------------------------------------------ bf16 tensor-core path
-    UML_REQUIRE(a->X16 && a->W16 && a->labels32 && a->partials && a->fac_ws && a->max_splits >= 1,
+    UML_REQUIRE(a->X16 && a->W16 && a->labels32 && a->partials && a->tile_ws && a->max_splits >= 1,
                 "linear_step: bf16 buffers");
     if (!a->w16_valid) {
       rc = uml_cast_f32_to_bf16(a->W, a->W16, static_cast<int64_t>(a->n_classes) * a->dim, stream);
@@ -72,14 +72,12 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     if (total > 0) {
       rec(a->ev[2], stream);
       rc = uml_head_fwd_ce_bf16(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
-                                static_cast<uint16_t*>(a->G), a->ldg, a->row_loss, nullptr, a->row_correct,
-                                learn ? a->row_dscale : nullptr, a->fac_ws, stream);
+                                static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
+                                stream);
       if (rc) return rc;
       rec(a->ev[3], stream);
     }
-    int64_t rows2[2] = {n0, n1};
-    rc = uml_reduce_seg_stats(a->row_loss, a->row_correct, learn ? a->row_dscale : nullptr, rows2, a->nseg, a->stats,
-                              stream);
+    rc = uml_reduce_tile_stats(a->tile_ws, total, a->nseg, a->stats, stream);
     if (rc) return rc;
   }
 

@@ -64,6 +64,7 @@ class StepEngine:
         self.X16 = self.W16 = self.labels32 = self.partials = None
         self._w16_valid = False
         self.host_log = None
+        self._event_pool = []
         self._args = None
         self.single_call = True  # False: dispatch every kernel from Python (debugging)
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
@@ -78,6 +79,18 @@ class StepEngine:
         e1.record()
         self.profile.setdefault(name, []).append((e0, e1))
         return r
+
+    @staticmethod
+    def _new_event_pair():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); e1.record()  # forces creation of the underlying cudaEvent_t
+        return e0, e1
+
+    def prepare_profile(self, n_steps):
+        """Pre-create the CUDA events a profiled run of n_steps needs, so that creating them does not
+        sit on the host's critical path inside the timed region."""
+        self._event_pool = [self._new_event_pair() for _ in range(4 * n_steps)]
+        self.profile = {}
 
     def kernel_times_ms(self):
         """Mean device time per launch of every profiled kernel (call after a synchronize)."""
@@ -175,7 +188,7 @@ class StepEngine:
         if bf16:
             a.X16, a.W16, a.labels32 = self.X16.data_ptr(), self.W16.data_ptr(), self.labels32.data_ptr()
             a.partials, a.max_splits, a.w16_valid = self.partials.data_ptr(), self.max_splits, int(self._w16_valid)
-            a.fac_ws = ws.fac.data_ptr()
+            a.tile_ws = ws.fac.data_ptr()
         need_dw = self.world > 1 or (bf16 and self.opt.name == "sgd")
         if need_dw and self.dW is None:
             self.dW = torch.empty_like(W)
@@ -189,8 +202,7 @@ class StepEngine:
                 if not bf16 and j in (0, 3):  # the fp32 path gathers inside its GEMMs and updates in the dW epilogue
                     a.ev[2 * j] = a.ev[2 * j + 1] = None
                     continue
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(); e1.record()  # forces creation of the underlying cudaEvent_t
+                e0, e1 = self._event_pool.pop() if self._event_pool else self._new_event_pair()
                 a.ev[2 * j], a.ev[2 * j + 1] = e0.cuda_event, e1.cuda_event
                 self.profile.setdefault(nm, []).append((e0, e1))
         else:
@@ -299,7 +311,7 @@ class StepEngine:
         self._timed("head_fwd_ce_bf16", ops.head_fwd_ce_bf16, self.X16, self.W16, self.labels32, segs, ws, ws.row_loss,
                     row_correct=ws.row_correct, row_dscale=ws.row_dscale if self.learnable else None, n_rows=n)
         stats = self.stats_log[slot]
-        ops.reduce_seg_stats(ws.row_loss, ws.row_correct, ws.row_dscale if self.learnable else None, rows_l, stats)
+        ops.reduce_tile_stats(ws.fac, n, len(rows_l), stats)
         if self.learnable:
             k = 0
             if n_i:

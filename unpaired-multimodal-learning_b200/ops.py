@@ -125,7 +125,8 @@ class HeadWorkspace:
         self.row_correct = torch.empty(max_rows, device=device, dtype=torch.int32)
         self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
         self.stats = torch.zeros((2, 4), device=device, dtype=torch.float32)  # 2 x uml_seg_stats (16 B each)
-        self.fac = torch.empty((max_rows, 9), device=device, dtype=torch.float32) if bf16 else None  # UML_FAC_STRIDE
+        # UML_TILE_WS_FLOATS(max_rows): per-tile partial sums written by the tensor-core forward
+        self.fac = torch.zeros(((max_rows + 127) // 128) * 32, device=device, dtype=torch.float32) if bf16 else None
 
     def read_stats(self):
         """Host copy of the two uml_seg_stats records (synchronises)."""
@@ -270,6 +271,10 @@ def head_bwd_dw_bf16(G, ldg, X, n_rows, n_classes, partials, n_splits):
 
 def sum_partials(partials, n_splits, n, out):
     check(_lib.load().uml_sum_partials(partials.data_ptr(), n_splits, n, n, out.data_ptr(), _stream()))
+
+
+def reduce_tile_stats(tile_ws, n_rows, nseg, stats):
+    check(_lib.load().uml_reduce_tile_stats(tile_ws.data_ptr(), int(n_rows), int(nseg), stats.data_ptr(), _stream()))
 
 
 def reduce_seg_stats(row_loss, row_correct, row_dscale, seg_rows: Sequence[int], stats):
