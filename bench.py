@@ -6,7 +6,7 @@
 Metric (BASELINE.json): UML train samples/sec (image + text rows consumed per second).
 Workload at N=1 (``config.workload``): cfg3 = ImageNet full-data shapes, "ViT-L/14" 768-d features,
 1000-class shared linear head + unpaired text bank, preset ``clip_linear`` arithmetic (logit scale
-exp(4.60517), AdamW) at the THROUGHPUT batch of 16384 rows per modality per GPU (SURVEY.md section 8d;
+exp(4.60517), AdamW) at the THROUGHPUT batch of 18944 (=148*128) rows per modality per GPU (SURVEY.md section 8d;
 the reference's own batch of 32 is a latency-bound regime reported separately by --workload cfg2).
 Synthetic seeded banks, random-init/zero-shot-init head.  One "step" = one full UML iteration:
 gather(img) + gather(txt) -> shared head forward -> logit scale + softmax CE -> dW -> AdamW.
@@ -36,8 +36,12 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (n_img_bank, n_txt_bank, dim, classes, batch_per_modality_per_gpu, n_val, logit)
-    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=16384, n_val=4096,
+    # throughput batch: 148 SMs x 128-row tiles = 18944 rows per modality -> 2 x 18944 rows per step are exactly
+    # two waves of forward tiles (16384 would leave 14% of the second wave idle)
+    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, n_val=4096,
                  desc="ImageNet full-data CLIP ViT-L/14 768-d features + CUPL text, linear head, throughput batch"),
+    "cfg3_b16k": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=16384, n_val=4096,
+                      desc="cfg3 at 16384 rows per modality per GPU"),
     "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, n_val=4000,
                  desc="ImageNet 16-shot CLIP ViT-B/16 512-d features + CUPL text, linear head, reference batch 32"),
     "cfg3_refB": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=32, n_val=4096,

@@ -151,6 +151,15 @@ int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, um
 int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
                          int32_t n_classes, float* partials, int32_t n_splits, void* stream);
 int uml_tc_dw_splits(int64_t n_rows, int32_t dim, int32_t n_classes);   /* suggested n_splits      */
+/* Generic bf16 tcgen05 GEMM  D[m,n] = sum_k A(m,k) B(k,n)  (adapter: head.py:65,79 and its autograd).
+ * a_mn_major = 0: A stored [M, K] (lda >= K);  1: A stored [K, M] (lda >= M).   Same for B with N.
+ * out_bf16 = 1: D written as bf16 [M, ldo] (n_splits must be 1);  0: fp32 split-K partials
+ * [n_splits, M, ldo].  Instantiated layouts: (1,1,fp32) (0,0,bf16) (0,1,bf16) (0,0,fp32).
+ * M > 128 runs the MMA across CTA pairs (cta_group::2); env UML_TC_CTA_GROUP=1|2 overrides.          */
+int uml_gemm_bf16(const uint16_t* A, int64_t lda, int32_t a_mn_major, const uint16_t* B, int64_t ldb,
+                  int32_t b_mn_major, int64_t M, int64_t N, int64_t K, void* out, int64_t ldo,
+                  int32_t out_bf16, int32_t n_splits, void* stream);
+int uml_gemm_bf16_splits(int64_t M, int64_t N, int64_t K);               /* suggested n_splits      */
 /* p -= update(sum_s partials[s]); also refreshes the bf16 shadow of p                             */
 int uml_adamw_step_partials(float* p, const float* partials, int32_t n_splits, int64_t split_stride,
                             float* m, float* v, int64_t n, double lr, double beta1, double beta2,

@@ -335,3 +335,43 @@ def test_tc_loss_within_stated_tolerance_of_fp32():
     got = ws.read_stats()
     assert abs(got[0]["loss_mean"] - stats["image_loss"]) <= 1e-3 * abs(stats["image_loss"])
     assert abs(got[1]["loss_mean"] - stats["text_loss"]) <= 1e-3 * abs(stats["text_loss"])
+
+
+# ------------------------------------------------------------------------------------------ generic tensor-core GEMM
+GEMM_CASES = [
+    # M, N, K, a_mn, b_mn, out_bf16, splits     (M > 128 runs on CTA pairs, cta_group::2)
+    (100, 520, 200, False, False, True, 1),
+    (300, 520, 200, False, False, True, 1),      # Z = X Wp^T
+    (1000, 768, 1536, False, False, False, 3),
+    (300, 520, 1000, False, True, True, 1),      # dZ = G W
+    (2048, 3200, 1000, False, True, True, 1),
+    (100, 96, 333, True, True, False, 2),        # dW, single-CTA tiles
+    (1000, 768, 4096, True, True, False, 6),     # dW, CTA pairs
+    (3200, 1536, 2048, True, True, False, 1),    # dW_proj
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES)
+def test_tc_gemm_layouts(case):
+    M, N, K, a_mn, b_mn, out_bf16, splits = case
+    g = torch.Generator().manual_seed(M + N + K)
+    pad = lambda x: (x + 7) // 8 * 8
+    A = torch.randn((K, pad(M)) if a_mn else (M, pad(K)), generator=g).to(torch.bfloat16)
+    B = torch.randn((K, pad(N)) if b_mn else (N, pad(K)), generator=g).to(torch.bfloat16)
+    a = (A[:, :M].t() if a_mn else A[:, :K]).float()
+    b = (B[:, :N] if b_mn else B[:, :K].t()).float()
+    ref = a @ b
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    if out_bf16:
+        out = torch.full((M, pad(N)), float("nan"), device=DEV, dtype=torch.bfloat16)
+        ops.gemm_bf16(Ad, Bd, out, M, N, K, a_mn=a_mn, b_mn=b_mn)
+        got = out[:, :N].float().cpu()
+        tol = 1e-2 * ref.abs().max().item()
+    else:
+        out = torch.full((splits, M, N), float("nan"), device=DEV)
+        ops.gemm_bf16(Ad, Bd, out, M, N, K, a_mn=a_mn, b_mn=b_mn, n_splits=splits)
+        got = out.sum(0).cpu()
+        tol = 2e-4 * ref.abs().max().item()
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= tol, (got - ref).abs().max().item()

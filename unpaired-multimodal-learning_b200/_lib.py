@@ -72,6 +72,8 @@ PROTOTYPES = {
                              c_vp, c_vp, c_vp, c_vp],
     "uml_head_bwd_dw_bf16": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp],
     "uml_tc_dw_splits": [c_i64, c_i32, c_i32],
+    "uml_gemm_bf16": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "uml_gemm_bf16_splits": [c_i64, c_i64, c_i64],
     "uml_adamw_step_partials": [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp, c_i64, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64,
                                 c_i32, c_vp, c_vp, c_vp],
     "uml_sum_partials": [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp],
@@ -88,7 +90,7 @@ KERNELS_PER_CALL = {
     "uml_gather_rows_labels_bf16": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
-    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 1, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_adamw_step_partials": 1,
+    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 1, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,
     "uml_sum_partials": 1, "uml_reduce_seg_stats": 1,
 }  # uml_linear_step is counted by the caller (its kernel count depends on the path)
 LAUNCH_COUNT = [0]

@@ -19,7 +19,6 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
   const int64_t n0 = a->seg[0].n, n1 = a->nseg > 1 ? a->seg[1].n : 0, total = n0 + n1;
   const bool fused = a->dW_out == nullptr;
-  const bool learn = a->scale_param[0] != nullptr || a->scale_param[1] != nullptr;
   int rc;
 
   if (a->precision == 0) {

@@ -5,7 +5,7 @@
 //   logits[b,c] = scale_b * sum_d X[b,d] W[c,d]         bf16 x bf16 -> fp32 in TMEM
 //   G[b,c]      = w_b * scale_b / n_b * (softmax(logits)[b,c] - [c == y_b])     written as bf16
 //
-// One persistent CTA per SM, 384 threads, warp-specialised:
+// One persistent CTA per SM, 512 threads, warp-specialised:
 //   warp 0     TMA producer : X tile 128x64 + W chunk 256x64 per stage, 4 stages, SWIZZLE_128B
 //   warp 1     MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in
 //                             TMEM; two 256-column accumulator buffers so the MMA of class chunk j+1
@@ -15,7 +15,7 @@
 //                             row max / sum (online softmax), argmax, label logit; the unnormalised
 //                             probabilities exp(l - m_running) are staged in shared memory in the
 //                             128B-swizzled layout and leave as coalesced TMA stores.
-//   warps 8-11 normaliser   : a 1000-class fp32 row needs 1000 TMEM columns and an SM has 512, so the
+//   warps 8-15 normaliser   : a 1000-class fp32 row needs 1000 TMEM columns and an SM has 512, so the
 //                             row cannot wait in TMEM for its final max/sum.  Instead, when a tile's
 //                             last chunk is done the epilogue hands the per-row, per-chunk factors
 //                             exp(m_chunk - m_final) / sum * coef to these warps through shared memory;
@@ -41,8 +41,8 @@ constexpr int kFwdStoreBytes = 4 * kFwdStoreBox;      // one staging box per epi
 constexpr int kFacFloats = kFwdMaxChunks + 2;         // per row: chunk factors, one-hot coefficient, label
 constexpr int kFacBytes = 2 * kFwdBlockM * kFacFloats * 4;
 constexpr int kFwdSmemBytes = kFwdStages * kFwdStageBytes + kFwdStoreBytes + kFacBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kFwdThreads = 384;
-constexpr int kTilePartFloats = 4 * 2 * 4;            // per tile: 4 warps x 2 segments x {loss, dscale, correct, rows}
+constexpr int kFwdThreads = 512;
+constexpr int kNormWarps = 8;  // warps 8-15
 
 struct FwdSegs {
   int64_t n0;
@@ -56,6 +56,8 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// kIters = 16-byte vectors per lane per G row (ceil(ldg / 256)) the normaliser is compiled for
+template <int kIters>
 __global__ void __launch_bounds__(kFwdThreads, 1)
     head_fwd_ce_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                           const __grid_constant__ CUtensorMap tmap_g, int64_t n_rows, int dim, int n_classes,
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 128);
       mbar_init(&fix_full[b], 4);   // one arrive per epilogue warp
-      mbar_init(&fix_empty[b], 4);  // one arrive per normaliser warp
+      mbar_init(&fix_empty[b], kNormWarps);  // one arrive per normaliser warp
     }
     fence_barrier_init();
   }
@@ -302,37 +304,36 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
       const uint32_t fb = tile_it & 1, fph = (tile_it >> 1) & 1;
       mbar_wait(&fix_full[fb], fph);
       const float* fbase = fac_smem + fb * kFwdBlockM * kFacFloats;
-      // rows w, w+4, ...; two rows per pass keeps 2 * iters (<= 16) independent loads in flight per lane
+      // rows w, w+8, ...; four rows per pass keep 4 * iters (16 for 1000 classes) independent 16-byte
+      // loads in flight per lane, which is what hides the L2 round trip
+      constexpr int kRowsPerPass = 16 / kIters;
 #pragma unroll 1
-      for (int r = w; r < kFwdBlockM; r += 8) {
-        const int64_t row0 = tile * kFwdBlockM + r, row1 = row0 + 4;
-        const bool ok0 = row0 < n_rows, ok1 = row1 < n_rows && (r + 4) < kFwdBlockM;
-        __nv_bfloat16* g0 = G + row0 * ldg;
-        __nv_bfloat16* g1 = G + row1 * ldg;
-        uint4 v0[kFwdMaxChunks], v1[kFwdMaxChunks];
+      for (int r = w; r < kFwdBlockM; r += kRowsPerPass * kNormWarps) {
+        uint4 v[kRowsPerPass][kIters];
 #pragma unroll
-        for (int j = 0; j < kFwdMaxChunks; ++j) {
-          const int c = j * 256 + lane * 8;
-          if (j < iters && c < ldg) {
-            if (ok0) v0[j] = __ldcg(reinterpret_cast<const uint4*>(g0 + c));
-            if (ok1) v1[j] = __ldcg(reinterpret_cast<const uint4*>(g1 + c));
+        for (int h = 0; h < kRowsPerPass; ++h) {
+          const int64_t row = tile * kFwdBlockM + r + h * kNormWarps;
+          const __nv_bfloat16* g = G + row * ldg;
+#pragma unroll
+          for (int j = 0; j < kIters; ++j) {
+            const int c = j * 256 + lane * 8;
+            if (j < iters && c < ldg && row < n_rows) v[h][j] = __ldcg(reinterpret_cast<const uint4*>(g + c));
           }
         }
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const bool ok = half ? ok1 : ok0;
-          if (!ok) continue;
-          const float* f = fbase + (r + 4 * half) * kFacFloats;
+        for (int h = 0; h < kRowsPerPass; ++h) {
+          const int64_t row = tile * kFwdBlockM + r + h * kNormWarps;
+          if (row >= n_rows) continue;
+          const float* f = fbase + (r + h * kNormWarps) * kFacFloats;
           const float gcoef = f[kFwdMaxChunks];
           const int label = __float_as_int(f[kFwdMaxChunks + 1]);
-          __nv_bfloat16* g = half ? g1 : g0;
+          __nv_bfloat16* g = G + row * ldg;
 #pragma unroll
-          for (int j = 0; j < kFwdMaxChunks; ++j) {
+          for (int j = 0; j < kIters; ++j) {
             const int c = j * 256 + lane * 8;
             if (j < iters && c < ldg) {
               const float fj = f[j];
-              const uint4 u = half ? v1[j] : v0[j];
-              uint32_t wds[4] = {u.x, u.y, u.z, u.w};
+              uint32_t wds[4] = {v[h][j].x, v[h][j].y, v[h][j].z, v[h][j].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float2 p = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&wds[i]));
@@ -340,8 +341,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
                 p.y *= fj;
                 if (c + 2 * i == label) p.x -= gcoef;
                 if (c + 2 * i + 1 == label) p.y -= gcoef;
-                __nv_bfloat162 h = __floats2bfloat162_rn(p.x, p.y);
-                wds[i] = *reinterpret_cast<uint32_t*>(&h);
+                __nv_bfloat162 hh = __floats2bfloat162_rn(p.x, p.y);
+                wds[i] = *reinterpret_cast<uint32_t*>(&hh);
               }
               *reinterpret_cast<uint4*>(g + c) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
             }
@@ -431,14 +432,16 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   }
   static bool attr_set = false;
   if (!attr_set) {
-    UML_CUDA(cudaFuncSetAttribute(head_fwd_ce_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    UML_CUDA(cudaFuncSetAttribute(head_fwd_ce_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    UML_CUDA(cudaFuncSetAttribute(head_fwd_ce_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
     attr_set = true;
   }
   const int64_t tiles = (n_rows + kFwdBlockM - 1) / kFwdBlockM;
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
-  head_fwd_ce_tc_kernel<<<grid, kFwdThreads, kFwdSmemBytes, as_stream(stream)>>>(
-      tx, tw, tg, n_rows, dim, n_classes, labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg, row_loss, row_pred,
-      row_correct, row_dscale, tile_ws);
+  auto kern = (!G || ldg <= 4 * 256) ? head_fwd_ce_tc_kernel<4> : head_fwd_ce_tc_kernel<8>;
+  kern<<<grid, kFwdThreads, kFwdSmemBytes, as_stream(stream)>>>(tx, tw, tg, n_rows, dim, n_classes, labels, fs,
+                                                               reinterpret_cast<__nv_bfloat16*>(G), ldg, row_loss,
+                                                               row_pred, row_correct, row_dscale, tile_ws);
   UML_CUDA(cudaGetLastError());
   return 0;
 }

@@ -269,6 +269,21 @@ def head_bwd_dw_bf16(G, ldg, X, n_rows, n_classes, partials, n_splits):
                                            partials.data_ptr(), n_splits, _stream()))
 
 
+def gemm_bf16(A, B, out, M, N, K, a_mn=False, b_mn=False, n_splits=1):
+    """D[m,n] = sum_k A(m,k) B(k,n) on the tensor cores.  A: [M,K] (or [K,M] when a_mn); B: [N,K] (or [K,N] when
+    b_mn); out: bf16 [M, ld] or fp32 partials [n_splits, M, N]."""
+    _need(A, torch.bfloat16, "A", contiguous=False)
+    _need(B, torch.bfloat16, "B", contiguous=False)
+    out_bf16 = out.dtype == torch.bfloat16
+    ldo = out.stride(0) if out_bf16 else out.stride(-2)
+    check(_lib.load().uml_gemm_bf16(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                                    out.data_ptr(), ldo, int(out_bf16), n_splits, _stream()))
+
+
+def gemm_bf16_splits(M, N, K):
+    return int(_lib.load().uml_gemm_bf16_splits(M, N, K))
+
+
 def sum_partials(partials, n_splits, n, out):
     check(_lib.load().uml_sum_partials(partials.data_ptr(), n_splits, n, n, out.data_ptr(), _stream()))
 
