@@ -144,3 +144,40 @@ def test_bf16_path_tracks_fp32_training():
     assert abs(o32["val_acc"] - o16["val_acc"]) <= 0.001 + 1e-9
     w32, w16 = o32["model"]["head.weight"], o16["model"]["head.weight"]
     assert (w32 - w16).norm() / w32.norm() < 1e-3
+
+
+def test_bf16_adapter_path_tracks_fp32_training():
+    """Adapter variant (img_proj + shared head + learnable temperatures, preset 'linear') on the
+    tensor-core path vs the exact path: same sampler order, losses within 1e-3 relative (+ small abs),
+    weights within 1e-2 relative after 40 steps (two chained bf16 GEMMs per direction)."""
+    C, Dv, D = 100, 128, 192
+    xi, yi, xt, yt, xv, yv = synth_banks(9, C, Dv, D, 5000, 12, 4096)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(4)
+        model = UML(f"synthetic:{Dv}", D, C, learnable_temp=True)
+        model.precision = prec
+        model.to(DEV)
+        opt = build_optimizer(model.parameters(), "adamw", 1e-3, 0.001)
+        sch = build_lr_scheduler(opt, "cosine", 5, 40, warmup_type="linear", warmup_lr=1e-5)
+        il = BankLoader(FeatureBank(xi, yi, DEV), 1024, shuffle=True)
+        tl = BankLoader(FeatureBank(xt, yt, DEV), 1024, shuffle=True)
+        vl = BankLoader(FeatureBank(xv, yv, DEV), 512, shuffle=False)
+        trace = {}
+        torch.manual_seed(78)
+        out = ft.train(model, il, tl, vl, None, opt, sch, device=DEV, max_iters=40, alpha=0.7, eval_freq=20,
+                       patience=5, trace=trace)
+        res[prec] = (out, trace)
+    (o32, t32), (o16, t16) = res["fp32"], res["bf16"]
+    for a, b in zip(t32["txt_idx"], t16["txt_idx"]):
+        assert torch.equal(a, b)
+    for key in ("image_loss", "text_loss"):
+        l32 = np.array([s[key] for s in t32["stats"]])
+        l16 = np.array([s[key] for s in t16["stats"]])
+        assert np.abs(l16 - l32).max() <= 2e-3 * np.abs(l32).max() + 2e-3, key
+    assert abs(o32["val_acc"] - o16["val_acc"]) <= 0.005
+    for k in ("head.weight", "img_proj.weight"):
+        a, b = o32["model"][k], o16["model"][k]
+        assert (a - b).norm() / a.norm() < 1e-2, k
+    for k in ("img_scale", "txt_scale"):
+        assert abs(float(o32["model"][k]) - float(o16["model"][k])) < 5e-3

@@ -109,9 +109,9 @@ class StepEngine:
         return float(si), float(st), None, None
 
     def _use_bf16(self, rows: int) -> bool:
-        if self.precision == "fp32" or self.adapter:
+        if self.precision == "fp32":
             return False
-        ok = self.D % 8 == 0 and self.C <= 2048
+        ok = self.D % 8 == 0 and self.C <= 2048 and (not self.adapter or self.Dv % 8 == 0)
         if self.precision == "bf16":
             if not ok:
                 raise RuntimeError("bf16 path needs dim % 8 == 0 and <= 2048 classes")
@@ -139,8 +139,10 @@ class StepEngine:
         self.slot_modalities[slot] = (img is not None, txt is not None)
         wi, wt = dp_loss_weights(n_i, n_t, alpha, global_img_rows, global_txt_rows)
         bf16 = self._use_bf16(n_i + n_t)
-        if self.adapter or not self.single_call:
-            # per-kernel dispatch: adapter variant, and the profiling mode that brackets each kernel
+        if self.adapter and bf16:
+            self._step_bf16_adapter(img, txt, n_i, n_t, wi, wt, slot)
+        elif self.adapter or not self.single_call:
+            # per-kernel dispatch: adapter variant on the exact path, or debugging
             (self._step_bf16 if bf16 else self._step_fp32)(img, txt, n_i, n_t, wi, wt, slot)
         else:
             self._step_single_call(img, txt, n_i, n_t, wi, wt, slot, bf16)
@@ -333,6 +335,84 @@ class StepEngine:
             self._timed("adamw_step_partials", ops.adamw_step_partials, W, self.partials, splits, st["m"], st["v"],
                         lr=g["lr"], step=st["step"], weight_decay=g["weight_decay"], betas=g["betas"], eps=g["eps"],
                         decoupled=(self.opt.name == "adamw"), shadow=self.W16)
+
+    # ------------------------------------------------------------------------------------ bf16 + adapter
+    def _step_bf16_adapter(self, img, txt, n_i, n_t, wi, wt, slot):
+        """Adapter variant (reference UML with img_proj, head.py:63-84) on the tensor cores:
+        Z = X_img Wp^T -> shared head on [Z ; T] -> dZ = G_img W -> dW = G^T [Z ; T], dWp = dZ^T X_img."""
+        dev, D, Dv, C = self.device, self.D, self.Dv, self.C
+        if self.ws16 is None:
+            self._alloc_bf16()  # ws16 (G), X16 -> [Z ; T] operand, W16, labels32, head partials
+            self.Xi16 = torch.empty((self.max_img, Dv), device=dev, dtype=torch.bfloat16)
+            self.dZ16 = torch.empty((self.max_img, D), device=dev, dtype=torch.bfloat16)
+            self.Wp16 = torch.empty((D, Dv), device=dev, dtype=torch.bfloat16)
+            self.proj_splits = max(1, ops.gemm_bf16_splits(D, Dv, self.max_img))
+            self.partials_p = torch.empty((self.proj_splits, D, Dv), device=dev)
+            self.dWp = None
+        ws, W, Wp, n = self.ws16, self.W.data, self.model.img_proj.weight, n_i + n_t
+        if not self._w16_valid:
+            ops.cast_bf16(W, self.W16)
+            ops.cast_bf16(Wp.data, self.Wp16)
+            self._w16_valid = True
+        s_i, s_t, sd_i, sd_t = self._scales()
+        rows_l, scales, weights, sdevs = [], [], [], []
+        if n_i:
+            feats, labels, idx = self._view(img)
+            if idx is None:
+                ops.cast_bf16(feats, self.Xi16[:n_i])
+                ops.gather_labels(labels, None, n_i, self.labels32[:n_i])
+            else:
+                ops.gather_rows_labels(feats, labels, idx, self.Xi16[:n_i], self.labels32[:n_i])
+            ops.gemm_bf16(self.Xi16, self.Wp16, self.X16, n_i, D, Dv)  # Z -> rows [0, n_i) of the head operand
+            rows_l.append(n_i); scales.append(s_i); weights.append(wi); sdevs.append(sd_i)
+        if n_t:
+            feats, labels, idx = self._view(txt)
+            if idx is None:
+                ops.cast_bf16(feats, self.X16[n_i:n])
+                ops.gather_labels(labels, None, n_t, self.labels32[n_i:n])
+            else:
+                ops.gather_rows_labels(feats, labels, idx, self.X16[n_i:n], self.labels32[n_i:n])
+            rows_l.append(n_t); scales.append(s_t); weights.append(wt); sdevs.append(sd_t)
+        segs = ops.tc_segments(rows_l, scales, weights, sdevs if self.learnable else None)
+        ops.head_fwd_ce_bf16(self.X16, self.W16, self.labels32, segs, ws, None, n_rows=n)
+        stats = self.stats_log[slot]
+        ops.reduce_tile_stats(ws.fac, n, len(rows_l), stats)
+        if self.learnable:
+            k = 0
+            if n_i:
+                self._apply_scalar(self.model.img_scale, stats[k, 1:2]); k += 1
+            if n_t:
+                self._apply_scalar(self.model.txt_scale, stats[k, 1:2])
+        if n_i:
+            # dZ = G_img W with the head BEFORE its update (W16 is refreshed by the optimizer kernel below)
+            ops.gemm_bf16(ws.G, self.W16, self.dZ16, n_i, D, C, b_mn=True)
+        splits = min(self.max_splits, max(1, ops.tc_dw_splits(n, D, C)))
+        ops.head_bwd_dw_bf16(ws.G, ws.ldg, self.X16, n, C, self.partials, splits)
+        self._apply_partials(self.W, self.partials, splits, self.W16, "dW")
+        if n_i:
+            ps = min(self.proj_splits, max(1, ops.gemm_bf16_splits(D, Dv, n_i)))
+            ops.gemm_bf16(self.dZ16, self.Xi16, self.partials_p, D, Dv, n_i, a_mn=True, b_mn=True, n_splits=ps)
+            self._apply_partials(Wp, self.partials_p, ps, self.Wp16, "dWp")
+
+    def _apply_partials(self, param, partials, splits, shadow, buf_name):
+        """Optimizer step of ``param`` from split-K partials (summed in the same kernel), with the
+        data-parallel all-reduce in between when there is more than one rank."""
+        g, st = self.opt.group_of(param), self.opt.slot(param)
+        data = param.data
+        if self.world > 1 or self.opt.name == "sgd":
+            buf = getattr(self, buf_name, None)
+            if buf is None:
+                buf = torch.empty_like(data)
+                setattr(self, buf_name, buf)
+            ops.sum_partials(partials, splits, data.numel(), buf)
+            if self.world > 1:
+                torch.distributed.all_reduce(buf, group=self.dist_group)
+            self.opt.apply(param, buf, shadow=shadow)
+        else:
+            st["step"] += 1
+            ops.adamw_step_partials(data, partials, splits, st["m"], st["v"], lr=g["lr"], step=st["step"],
+                                    weight_decay=g["weight_decay"], betas=g["betas"], eps=g["eps"],
+                                    decoupled=(self.opt.name == "adamw"), shadow=shadow)
 
     # ------------------------------------------------------------------------------------ readback
     def copy_slot_to_host(self, slot):

@@ -104,20 +104,23 @@ def validate(model, val_loader, device="cuda"):
     bank, bs = val_loader.bank, val_loader.batch_size
     n = len(bank)
     dev = bank.device
-    feats = bank.features
-    if model.img_proj is not None:
-        feats = model.extract_features(feats)
     s_img = float(model.scales()[0])
     row_loss = torch.empty(n, device=dev)
     row_pred = torch.empty(n, device=dev, dtype=torch.int32)
     W = model.head.weight.data
-    use_tc = getattr(model, "precision", "auto") != "fp32" and n >= 4096 and W.shape[1] % 8 == 0 and W.shape[0] <= 2048
+    adapter = model.img_proj is not None
+    use_tc = (getattr(model, "precision", "auto") != "fp32" and n >= 4096 and W.shape[1] % 8 == 0
+              and W.shape[0] <= 2048 and bank.dim % 8 == 0)
     if use_tc:
-        x16 = bank.bf16() if model.img_proj is None and hasattr(bank, "bf16") else ops.cast_bf16(feats.contiguous())
-        labels32 = bank.labels32() if hasattr(bank, "labels32") else bank.labels.to(torch.int32)
+        x16 = bank.bf16()
+        if adapter:  # Z = X Wp^T on the tensor cores
+            z16 = torch.empty((n, W.shape[1]), device=dev, dtype=torch.bfloat16)
+            ops.gemm_bf16(x16, ops.cast_bf16(model.img_proj.weight.data), z16, n, W.shape[1], bank.dim)
+            x16 = z16
         segs = ops.tc_segments([n], [s_img], [1.0])
-        ops.head_fwd_ce_bf16(x16, ops.cast_bf16(W), labels32, segs, None, row_loss, row_pred=row_pred)
+        ops.head_fwd_ce_bf16(x16, ops.cast_bf16(W), bank.labels32(), segs, None, row_loss, row_pred=row_pred)
     else:
+        feats = model.extract_features(bank.features) if adapter else bank.features
         ops.eval_f32(feats, bank.labels, W, s_img, row_loss, row_pred)
     out_loss = torch.empty(1, device=dev)
     out_hits = torch.empty(1, device=dev, dtype=torch.int32)

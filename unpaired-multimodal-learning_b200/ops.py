@@ -97,6 +97,16 @@ def gather_rows(bank: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tenso
     return out
 
 
+def gather_rows_labels(bank, labels, idx, out16, out_labels32):
+    """bf16 row gather that also gathers the rows' int64 bank labels into int32 (one launch)."""
+    _need(bank, torch.float32, "bank")
+    _need(labels, torch.int64, "labels")
+    _need(idx, torch.int64, "idx")
+    check(_lib.load().uml_gather_rows_labels_bf16(bank.data_ptr(), labels.data_ptr(), bank.shape[1], idx.data_ptr(),
+                                                  idx.numel(), out16.data_ptr(), out16.stride(0), out_labels32.data_ptr(),
+                                                  _stream()))
+
+
 def gather_labels(labels: torch.Tensor, idx: Optional[torch.Tensor], n: int, out: torch.Tensor) -> torch.Tensor:
     _need(labels, torch.int64, "labels")
     _need(out, torch.int32, "out")
@@ -245,7 +255,7 @@ def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[
     return s
 
 
-def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadWorkspace], row_loss, row_pred=None,
+def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadWorkspace], row_loss=None, row_pred=None,
                      row_correct=None, row_dscale=None, n_rows: Optional[int] = None):
     _need(X, torch.bfloat16, "X")
     _need(W_bf16, torch.bfloat16, "W")
@@ -253,7 +263,7 @@ def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadW
     n_rows = X.shape[0] if n_rows is None else n_rows
     G, ldg, fac = (ws.G.data_ptr(), ws.ldg, ws.fac.data_ptr()) if ws is not None else (None, 0, None)
     check(_lib.load().uml_head_fwd_ce_bf16(X.data_ptr(), n_rows, X.shape[1], W_bf16.data_ptr(), W_bf16.shape[0],
-                                           labels_i32.data_ptr(), C.byref(segs), G, ldg, row_loss.data_ptr(),
+                                           labels_i32.data_ptr(), C.byref(segs), G, ldg, _ptr(row_loss),
                                            _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), fac, _stream()))
 
 
