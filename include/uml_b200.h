@@ -116,7 +116,8 @@ int uml_sgd_step(float* p, const float* g, const float* g2, float g2_weight, flo
 int uml_eval_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t n_rows, int32_t dim,
                  const float* W, int32_t n_classes, float scale,
                  float* row_loss, int32_t* row_pred, void* stream);
-/* mean over reference batches of the batch-mean loss + hit count (finetune.py:310-312)           */
+/* mean over reference batches of the batch-mean loss + hit count (finetune.py:310-312).
+ * labels == NULL: row_pred already holds 0/1 hit flags (the tensor-core forward's row_correct).    */
 int uml_eval_reduce(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
                     int64_t batch_size, float* out_loss /*[1]*/, int32_t* out_correct /*[1]*/, void* stream);
 
@@ -141,10 +142,11 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          uint16_t* G /*may be NULL: eval mode*/, int64_t ldg,
                          float* row_loss, int32_t* row_pred /*optional: argmax class*/,
                          int32_t* row_correct /*optional: argmax == label*/, float* row_dscale /*optional*/,
-                         float* tile_ws /* optional [UML_TILE_WS_FLOATS(n_rows)]: per-tile partial sums of the
-                                           per-run statistics, reduced by uml_reduce_tile_stats            */,
+                         float* tile_ws /* [UML_TILE_WS_FLOATS(n_rows)] (required with G): per-tile partial sums
+                                           of the per-run statistics, reduced by uml_reduce_tile_stats, then
+                                           the per-row factors of the deferred softmax normalisation      */,
                          void* stream);
-#define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 127) / 128) * 32)
+#define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 255) / 256) * 64 + (n_rows) * 16)
 /* per-run {mean loss, dscale, hits, rows} from the forward kernel's per-tile partials (fixed order)     */
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream);
 /* dW_partial[s] = (G^T X) over the s-th K split; partials: [n_splits, n_classes, dim] fp32.       */

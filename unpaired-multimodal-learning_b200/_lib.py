@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libuml_b200.so")
+LIB_PATH = os.environ.get("UML_LIB_PATH") or os.path.join(_HERE, "lib", "libuml_b200.so")  # override: A/B builds
 
 c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
 
@@ -90,7 +90,7 @@ KERNELS_PER_CALL = {
     "uml_gather_rows_labels_bf16": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
-    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 1, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,
+    "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,
     "uml_sum_partials": 1, "uml_reduce_seg_stats": 1,
 }  # uml_linear_step is counted by the caller (its kernel count depends on the path)
 LAUNCH_COUNT = [0]

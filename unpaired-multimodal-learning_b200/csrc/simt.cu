@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(256)
     float s = 0.f;
     for (int64_t i = beg; i < end; ++i) {
       s += row_loss[i];
-      hits += (row_pred[i] == static_cast<int32_t>(labels[i]));
+      hits += labels ? (row_pred[i] == static_cast<int32_t>(labels[i])) : (row_pred[i] != 0);
     }
     acc += s / static_cast<float>(end - beg);
   }
@@ -576,7 +576,7 @@ int uml_eval_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t 
 int uml_eval_reduce(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
                     int64_t batch_size, float* out_loss, int32_t* out_correct, void* stream) {
   using namespace uml;
-  UML_REQUIRE(row_loss && row_pred && labels && out_loss && out_correct && n_rows > 0 && batch_size > 0,
+  UML_REQUIRE(row_loss && row_pred && out_loss && out_correct && n_rows > 0 && batch_size > 0,
               "eval_reduce: bad arguments");
   eval_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size, out_loss,
                                                        out_correct);

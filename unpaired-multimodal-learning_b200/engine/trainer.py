@@ -111,10 +111,10 @@ class StepEngine:
     def _use_bf16(self, rows: int) -> bool:
         if self.precision == "fp32":
             return False
-        ok = self.D % 8 == 0 and self.C <= 2048 and (not self.adapter or self.Dv % 8 == 0)
+        ok = self.D % 8 == 0 and self.C <= 1024 and (not self.adapter or self.Dv % 8 == 0)
         if self.precision == "bf16":
             if not ok:
-                raise RuntimeError("bf16 path needs dim % 8 == 0 and <= 2048 classes")
+                raise RuntimeError("bf16 path needs dim % 8 == 0 and <= 1024 classes")
             return True
         return ok and rows >= BF16_MIN_ROWS
 

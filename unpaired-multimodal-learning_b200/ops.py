@@ -136,7 +136,8 @@ class HeadWorkspace:
         self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
         self.stats = torch.zeros((2, 4), device=device, dtype=torch.float32)  # 2 x uml_seg_stats (16 B each)
         # UML_TILE_WS_FLOATS(max_rows): per-tile partial sums written by the tensor-core forward
-        self.fac = torch.zeros(((max_rows + 127) // 128) * 32, device=device, dtype=torch.float32) if bf16 else None
+        self.fac = (torch.zeros(((max_rows + 255) // 256) * 64 + max_rows * 16, device=device, dtype=torch.float32)
+                    if bf16 else None)
 
     def read_stats(self):
         """Host copy of the two uml_seg_stats records (synchronises)."""
@@ -234,7 +235,8 @@ def eval_f32(feats, labels, W, scale, row_loss, row_pred):
 
 
 def eval_reduce(row_loss, row_pred, labels, batch_size, out_loss, out_correct):
-    check(_lib.load().uml_eval_reduce(row_loss.data_ptr(), row_pred.data_ptr(), labels.data_ptr(), labels.numel(),
+    """labels=None: row_pred holds 0/1 hit flags instead of predicted classes."""
+    check(_lib.load().uml_eval_reduce(row_loss.data_ptr(), row_pred.data_ptr(), _ptr(labels), row_loss.numel(),
                                       int(batch_size), out_loss.data_ptr(), out_correct.data_ptr(), _stream()))
 
 
