@@ -59,43 +59,81 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region, through NVML inside this process.
 
-    def __init__(self, index=0):
-        self.index, self.proc, self.rows = index, None, []
+    (The first version spawned `nvidia-smi -lms` right before the timed region; its start-up - NVML/driver
+    initialisation of a second process - stalled this process's CUDA calls for tens of milliseconds at random
+    and the 50-step region is only ~10 ms long: values swung between 40 M and 116 M samples/s.)  NVML is
+    initialised before the warm-up; a thread then polls every ``period`` seconds while ``active``."""
 
-    def start(self):
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+
+    def __init__(self, index=0, period=0.004):
+        self.index, self.period, self.rows, self.active, self.thread, self.h = index, period, [], False, None, None
+        self.stop_flag = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self._sample()  # first query pays NVML's lazy set-up
+            self.rows.clear()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception as e:  # no NVML: report that instead of a number
+            self.err = f"NVML unavailable: {e}"
+            self.h = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                return int(vis.split(",")[index])
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return index
+
+    def _sample(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        self.rows.append((sm, mask))
+
+    def _loop(self):
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def start(self):
+        self.rows.clear()
+        self.active = True
+
+    def stop(self):
+        self.active = False
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [getattr(self, "err", "NVML unavailable")]}
+        if not self.rows:  # region shorter than one period: one sample right at its end (still under load)
+            try:
+                self._sample()
+            except Exception:
+                pass
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
+        for r in self.rows:
+            mask |= r[1]
+        reasons = [nm for nm, attr in self.REASONS if mask & getattr(self.nv, attr, 0)]
+        return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "samples": len(sm), "source": "NVML in-process, polled during the timed region"}
+
+    def close(self):
+        self.stop_flag = True
 
 
 # -----------------------------------------------------------------------------------------------
@@ -200,31 +238,63 @@ def run_ours(args, wl, rank, world, dev):
     torch.manual_seed(2)
     ii, ti = iter(il), iter(tl)
 
-    def step(i):
-        nonlocal ii, ti
-        img, ii = ft.fetch_next(il, ii)
-        txt, ti = ft.fetch_next(tl, ti)
-        engine.step(ft._local_slice(img, rank, world), ft._local_slice(txt, rank, world), ALPHA, slot=i,
-                    global_img_rows=img.n if world > 1 else None, global_txt_rows=txt.n if world > 1 else None)
-        sch.step()
-        return img.n + txt.n
+    host_split = [0.0, 0.0]  # seconds in the loaders / in engine.run (host-side enqueue cost, reported on stderr)
+    CHUNK = 10  # iterations enqueued per library call (uml_linear_run), as finetune.train does
 
+    def step(i, n=1):
+        """Enqueue iterations i .. i+n-1; returns the number of (global) rows they consume."""
+        nonlocal ii, ti
+        batches, lrs, rows_ = [], [], 0
+        t0 = time.perf_counter()
+        for _ in range(n):
+            img, ii = ft.fetch_next(il, ii)
+            txt, ti = ft.fetch_next(tl, ti)
+            batches.append((img, txt))
+            lrs.append(sch.get_last_lr()[0])
+            sch.step()
+            rows_ += img.n + txt.n
+        t1 = time.perf_counter()
+        engine.run(batches, ALPHA, lrs, slot0=i)
+        host_split[0] += t1 - t0
+        host_split[1] += time.perf_counter() - t1
+        return rows_
+
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None  # NVML set-up happens here, before the warm-up
     for i in range(W):
         step(i)
-    engine.prepare_profile(K)
+    bf16_path = engine._use_bf16(2 * B)
+    dominant = "head_fwd_ce_bf16" if bf16_path else "head_bwd_dw_f32"
+    engine.prepare_profile(K, only=[dominant])  # the roofline kernel is timed live inside the timed region
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
     n0 = _lib.LAUNCH_COUNT[0]
+    host_split[0] = host_split[1] = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rows = 0
+    prof = None
+    if os.environ.get("UML_BENCH_PROFILE"):
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
+    t_host0 = time.perf_counter()
     e0.record()
-    for i in range(K):
-        rows += step(W + i)
+    i = 0
+    while i < K:
+        n = min(CHUNK, K - i)
+        rows += step(W + i, n)
+        i += n
     e1.record()
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(14)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / K  # enqueue cost per step (the loop never syncs)
+    if rank == 0:
+        print(f"host per step: loaders {host_split[0] / K * 1e3:.4f} ms, engine.run {host_split[1] / K * 1e3:.4f} ms",
+              file=sys.stderr)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -235,41 +305,49 @@ def run_ours(args, wl, rank, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.close()
     ktimes = engine.kernel_times_ms()
     loss_tail = engine.read_log([W + K - 1])[0]
+    # per-kernel breakdown of the step from a few extra (untimed) steps with every kernel bracketed
+    engine.prepare_profile(8)
+    for i in range(8):
+        step(W + K + i)
+    torch.cuda.synchronize()
+    breakdown = engine.kernel_times_ms()
     del engine
 
     # ---------------- end-to-end arm: public train() call, per-step H2D indices + D2H loss ---------
-    def e2e_once(iters):
+    def e2e_run(warm, iters):
+        """ONE public train() call of warm + iters iterations; the timed region is iterations warm.. (wall clock,
+        stream-synchronised on both sides): per step it holds the H2D copy of the step's index batches from pinned
+        memory, the step, and the D2H copy of its loss record, read on the host before the clock stops."""
         m2, o2, s2 = make_model(wl, dev, txt_bank)
         m2.precision = args.precision
         il2 = BankLoader(img_bank, GB, shuffle=True, upload="step")
         tl2 = BankLoader(txt_bank, GB, shuffle=True, upload="step")
         vl2 = BankLoader(val_bank, 512, shuffle=False)
         torch.manual_seed(2)
-        torch.cuda.synchronize()
+        tr = {"timing": {"warmup": warm}}
         if dist:
             dist.barrier()
-        t0 = time.perf_counter()
-        ft.train(m2, il2, tl2, vl2, None, o2, s2, device=dev, max_iters=iters, alpha=ALPHA, eval_freq=10 ** 9,
-                 patience=5, stats_to_host="step")
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        return time.perf_counter() - t0
+        ft.train(m2, il2, tl2, vl2, None, o2, s2, device=dev, max_iters=warm + iters, alpha=ALPHA, eval_freq=10 ** 9,
+                 patience=5, stats_to_host="step", trace=tr)
+        assert tr["timing"]["iters"] == iters
+        return tr["timing"]["seconds"], tr["timing"]["rows"]
 
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
-        e2e_once(max(W, 3))
-        dt = e2e_once(K)
+        dt, e2e_rows = e2e_run(max(W, 3), K)
     if dist:
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    e2e_value = K * 2 * GB / dt
+    e2e_value = e2e_rows / dt  # global rows (every rank walks the same global batches) over the slowest rank's time
     return dict(ms=ms, rows=rows, launches=launches, clocks=clocks, ktimes=ktimes, e2e_value=e2e_value,
-                h2d=2 * B * 8, d2h=2 * 4 * 4, loss_tail=loss_tail, GB=GB)
+                host_ms=host_ms, breakdown=breakdown,
+                h2d=2 * GB * 8, d2h=2 * 4 * 4, loss_tail=loss_tail, GB=GB)
 
 
 def main():
@@ -338,6 +416,7 @@ def main():
                     "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy"}
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel_ms"] = {k: round(v, 5) for k, v in res["ktimes"].items()}
+        roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in res["breakdown"].items()}
         step_flops = 4.0 * D * C * rows_per_gpu
         line = {"metric": "UML train samples/sec (img+text)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": K, "warmup": args.warmup, "ms_per_step": res["ms"] / K, "higher_is_better": True,
@@ -345,7 +424,7 @@ def main():
                 "config": config, "clocks": res["clocks"],
                 "e2e": {"value": res["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": res["h2d"],
                         "d2h_bytes_per_step": res["d2h"]},
-                "gpu_launches": res["launches"], "roofline": roof,
+                "gpu_launches": res["launches"], "host_enqueue_ms_per_step": res["host_ms"], "roofline": roof,
                 "step_tensor_frac": {"achieved_tflops_per_gpu": step_flops / (res["ms"] / K * 1e-3) / 1e12,
                                      "of_sustained_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_sustained"],
                                      "of_burst_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_burst"],

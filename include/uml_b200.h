@@ -198,9 +198,42 @@ typedef struct {
   int64_t       scale_step[UML_MAX_SEGMENTS];
   /* optional cudaEvent_t pairs recorded around {gather, forward, dW, update} on `stream` (bench.py) */
   void*         ev[8];
+  int32_t       dp_allreduce;               /* != 0: all-reduce dW_out across the uml_dp_init ranks, then update W */
 } uml_linear_step_args;
 
 int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);
+
+/* Several consecutive iterations enqueued by one call (the host stays well ahead of the GPU: Python
+ * dispatch, not the kernels, limited throughput when every step was a separate call).  `base` describes
+ * the model/workspaces; `steps[i]` patches what changes from one iteration to the next.                */
+typedef struct {
+  const int64_t* idx[UML_MAX_SEGMENTS];          /* this step's index batches (views of the epoch permutation) */
+  int64_t        n[UML_MAX_SEGMENTS];            /* rows per run (the last batch of an epoch is short)        */
+  float          loss_weight[UML_MAX_SEGMENTS];
+  float          lr;                             /* learning rate of this step (scheduler output)             */
+  int64_t        opt_step;                       /* 1-based optimizer step of the head                        */
+  int64_t        scale_step[UML_MAX_SEGMENTS];
+  uml_seg_stats* stats;                          /* where this step's per-run results go                      */
+  void*          ev_fwd[2];                      /* optional cudaEvent_t pair around the forward kernel       */
+} uml_run_step;
+int uml_linear_run(const uml_linear_step_args* base /*host*/, const uml_run_step* steps /*host*/, int32_t n_steps,
+                   void* stream);
+
+/* ---- data parallel: NCCL all-reduce of the head gradient issued from inside the step --------------
+ * uml_dp_unique_id fills a 128-byte NCCL id on one rank; every rank then calls uml_dp_init with it.
+ * With args->dp_allreduce != 0 the step sums dW over the ranks (ncclAllReduce on `stream`) between the
+ * dW kernel and the optimizer update, so a data-parallel iteration is still a single host call.          */
+int uml_dp_unique_id(void* out_128_bytes /*host*/);
+int uml_dp_init(const void* id_128_bytes /*host*/, int32_t rank, int32_t world);
+int uml_dp_allreduce_f32(float* buf, int64_t n, void* stream);
+int uml_dp_shutdown(void);
+
+/* ---- sampler: the epoch permutation on the host, bit-exact with torch.randperm(n, generator=
+ * torch.Generator().manual_seed(seed)) on the CPU - what RandomSampler draws once per epoch for the
+ * DataLoaders of finetune.py:370-371 (MT19937 seeded with the low 32 bits of `seed`, Fisher-Yates
+ * `z = rand() % (n - i)`), with the swap targets prefetched a window ahead.  Pure host code; `out`
+ * (n int64, normally pinned memory) is then copied to the device asynchronously.  n < 2^32 / 20.      */
+int uml_randperm_i64(uint64_t seed, int64_t n, int64_t* out /*host*/);
 
 #ifdef __cplusplus
 }

@@ -174,3 +174,16 @@ def test_local_slice_partitions_a_global_batch():
         parts = [ft._local_slice(b, r, world) for r in range(world)]
         assert sum(p.n for p in parts) == 37 and max(p.n for p in parts) - min(p.n for p in parts) <= 1
         assert torch.equal(torch.cat([p.idx for p in parts]), idx)
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 63, 64, 65, 66, 1000, 29940, 300_007])
+def test_native_randperm_is_bit_exact_with_torch(n):
+    """uml_randperm_i64 (csrc/sampler.cu) == torch.randperm(n, generator=Generator().manual_seed(seed)), the call
+    RandomSampler makes once per epoch; seeds above 32 bits are truncated like at::mt19937 does."""
+    from uml_b200.engine.datasets.utils import _native_randperm
+    g = torch.Generator()
+    for seed in (0, 1, 5489, 2 ** 32 + 7, 2 ** 63 - 1, 0x5EADBEEFCAFEBABE):
+        g.manual_seed(seed)
+        want = torch.randperm(n, generator=g)
+        got = _native_randperm(seed, n, pin=False)
+        assert got.dtype == torch.int64 and torch.equal(got, want), (n, seed)

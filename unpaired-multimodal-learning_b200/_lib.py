@@ -44,7 +44,13 @@ class LinearStepArgs(C.Structure):
                 ("X16", c_vp), ("W16", c_vp), ("labels32", c_vp), ("partials", c_vp), ("tile_ws", c_vp),
                 ("max_splits", c_i32), ("w16_valid", c_i32), ("dW_out", c_vp), ("dW_scratch", c_vp),
                 ("scale_param", c_vp * 2), ("scale_m", c_vp * 2), ("scale_v", c_vp * 2), ("scale_step", c_i64 * 2),
-                ("ev", c_vp * 8)]
+                ("ev", c_vp * 8), ("dp_allreduce", c_i32)]
+
+
+class RunStep(C.Structure):
+    """uml_run_step"""
+    _fields_ = [("idx", c_vp * 2), ("n", c_i64 * 2), ("loss_weight", c_f32 * 2), ("lr", c_f32), ("opt_step", c_i64),
+                ("scale_step", c_i64 * 2), ("stats", c_vp), ("ev_fwd", c_vp * 2)]
 
 
 # name -> argtypes; every function returns int except uml_last_error
@@ -80,6 +86,12 @@ PROTOTYPES = {
     "uml_reduce_seg_stats": [c_vp, c_vp, c_vp, C.POINTER(c_i64), c_i32, c_vp, c_vp],
     "uml_reduce_tile_stats": [c_vp, c_i64, c_i32, c_vp, c_vp],
     "uml_linear_step": [C.POINTER(LinearStepArgs), c_vp],
+    "uml_linear_run": [C.POINTER(LinearStepArgs), C.POINTER(RunStep), c_i32, c_vp],
+    "uml_dp_unique_id": [c_vp],
+    "uml_dp_init": [c_vp, c_i32, c_i32],
+    "uml_dp_allreduce_f32": [c_vp, c_i64, c_vp],
+    "uml_dp_shutdown": [],
+    "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
 }
 
 _lib = None

@@ -10,7 +10,47 @@ inline void rec(void* ev, void* stream) {
 }
 }  // namespace
 
+// data parallel tail of a step: sum dW over the ranks, then the optimizer update on every rank
+static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void* stream) {
+  int rc = uml_dp_allreduce_f32(a->dW_out, np, stream);
+  if (rc) return rc;
+  uint16_t* shadow = a->precision == 1 ? a->W16 : nullptr;
+  rec(a->ev[6], stream);
+  if (a->upd.kind == 3)
+    rc = uml_sgd_step(a->W, a->dW_out, nullptr, 0.f, a->upd.m, np, a->upd.lr, a->upd.momentum, a->upd.weight_decay,
+                      a->upd.step, shadow, stream);
+  else
+    rc = uml_adamw_step(a->W, a->dW_out, nullptr, 0.f, a->upd.m, a->upd.v, np, a->upd.lr, a->upd.beta1, a->upd.beta2,
+                        a->upd.eps, a->upd.weight_decay, a->upd.step, a->upd.kind == 1, shadow, stream);
+  rec(a->ev[7], stream);
+  return rc;
+}
+
 extern "C" {
+
+int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, int32_t n_steps, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(base && steps && n_steps >= 0, "linear_run: bad arguments");
+  uml_linear_step_args a = *base;
+  for (int i = 0; i < n_steps; ++i) {
+    const uml_run_step& s = steps[i];
+    for (int k = 0; k < a.nseg; ++k) {
+      a.seg[k].idx = s.idx[k];
+      a.seg[k].n = s.n[k];
+      a.seg[k].loss_weight = s.loss_weight[k];
+      a.scale_step[k] = s.scale_step[k];
+    }
+    a.upd.lr = s.lr;
+    a.upd.step = s.opt_step;
+    a.stats = s.stats;
+    a.ev[2] = s.ev_fwd[0];
+    a.ev[3] = s.ev_fwd[1];
+    if (i > 0 && a.precision == 1) a.w16_valid = 1;  // the optimizer kernel of the previous step refreshed the shadow
+    const int rc = uml_linear_step(&a, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
 
 int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   using namespace uml;
@@ -18,6 +58,8 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   UML_REQUIRE(a->nseg >= 1 && a->nseg <= UML_MAX_SEGMENTS, "linear_step: 1..2 segments");
   UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
   const int64_t n0 = a->seg[0].n, n1 = a->nseg > 1 ? a->seg[1].n : 0, total = n0 + n1;
+  const bool dp = a->dp_allreduce != 0;
+  UML_REQUIRE(!dp || a->dW_out, "linear_step: data-parallel mode needs dW_out");
   const bool fused = a->dW_out == nullptr;
   int rc;
 
@@ -83,7 +125,11 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   // learnable temperatures: scalar Adam(W) steps fed straight from the stats record on the device
   for (int i = 0; i < a->nseg; ++i) {
     if (!a->scale_param[i]) continue;
-    const float* g = &a->stats[i].dscale;
+    float* g = &a->stats[i].dscale;
+    if (dp) {  // the temperature gradient is a sum over the global batch as well
+      rc = uml_dp_allreduce_f32(g, 1, stream);
+      if (rc) return rc;
+    }
     if (a->upd.kind == 3)
       rc = uml_sgd_step(a->scale_param[i], g, nullptr, 0.f, a->scale_m[i], 1, a->upd.lr, a->upd.momentum,
                         a->upd.weight_decay, a->scale_step[i], nullptr, stream);
@@ -94,7 +140,12 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     if (rc) return rc;
   }
 
-  if (total == 0) return 0;
+  const int64_t np_all = static_cast<int64_t>(a->n_classes) * a->dim;
+  if (total == 0 && !dp) return 0;
+  if (total == 0) {  // a rank without rows still takes part in the all-reduce, contributing zeros
+    UML_CUDA(cudaMemsetAsync(a->dW_out, 0, np_all * sizeof(float), as_stream(stream)));
+    return dp_reduce_and_update(a, np_all, stream);
+  }
   if (a->precision == 0) {
     uml_update none;
     memset(&none, 0, sizeof(none));
@@ -102,7 +153,8 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     rc = uml_head_bwd_dw_f32(a->seg, a->nseg, a->dim, static_cast<const float*>(a->G), a->ldg, a->n_classes, a->W,
                              a->dW_out, fused ? &a->upd : &none, stream);
     rec(a->ev[5], stream);
-    return rc;
+    if (rc || !dp) return rc;
+    return dp_reduce_and_update(a, np_all, stream);
   }
   int splits = uml_tc_dw_splits(total, a->dim, a->n_classes);
   if (splits > a->max_splits) splits = a->max_splits;
@@ -112,7 +164,11 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   if (rc) return rc;
   rec(a->ev[5], stream);
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
-  if (!fused) return uml_sum_partials(a->partials, splits, np, np, a->dW_out, stream);
+  if (!fused) {
+    rc = uml_sum_partials(a->partials, splits, np, np, a->dW_out, stream);
+    if (rc || !dp) return rc;
+    return dp_reduce_and_update(a, np, stream);
+  }
   if (a->upd.kind == 3) {
     UML_REQUIRE(a->dW_scratch, "linear_step: SGD on the bf16 path needs dW_scratch");
     rc = uml_sum_partials(a->partials, splits, np, np, a->dW_scratch, stream);

@@ -1,2 +1,2 @@
 from .utils import (BankLoader, FeatureBank, IndexBatch, TextTensorDataset,  # noqa: F401
-                    get_few_shot_setup_name)
+                    get_few_shot_setup_name, local_slice)

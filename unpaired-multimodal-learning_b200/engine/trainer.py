@@ -21,7 +21,7 @@ from typing import Optional
 import torch
 
 from .. import ops
-from .datasets.utils import IndexBatch
+from .datasets.utils import IndexBatch, local_slice as _local_slice
 
 BF16_MIN_ROWS = 1024  # below this the step is launch-bound and the exact fp32 path is used
 
@@ -36,6 +36,30 @@ def dp_loss_weights(n_img_local, n_txt_local, alpha, n_img_global=None, n_txt_gl
     wi = 1.0 if not n_img_global or not n_img_local else n_img_local / float(n_img_global)
     wt = alpha if not n_txt_global or not n_txt_local else alpha * n_txt_local / float(n_txt_global)
     return wi, wt
+
+
+_DP_READY = False
+
+
+def ensure_dp_comm():
+    """One NCCL communicator per process for the step launcher (csrc/dp.cu).  Rank 0 creates the NCCL id, it is
+    broadcast through torch.distributed, every rank joins."""
+    global _DP_READY
+    if _DP_READY:
+        return
+    import ctypes as C
+    from .._lib import check, load
+    dist = torch.distributed
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(load().uml_dp_unique_id(buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    raw = bytes(t.cpu().tolist())
+    check(load().uml_dp_init(C.c_char_p(raw), rank, world))
+    _DP_READY = True
 
 
 class StepEngine:
@@ -53,6 +77,8 @@ class StepEngine:
         self.W = model.head.weight
         if self.W.device.type != "cuda":
             raise RuntimeError("StepEngine: the model must live on a CUDA device (no CPU path)")
+        if self.world > 1:
+            ensure_dp_comm()
         self.learnable = bool(getattr(model, "learnable_temp", False))
         self.ws32: Optional[ops.HeadWorkspace] = None
         self.ws16: Optional[ops.HeadWorkspace] = None
@@ -65,6 +91,7 @@ class StepEngine:
         self._w16_valid = False
         self.host_log = None
         self._event_pool = []
+        self.profile_only = None
         self._args = None
         self.single_call = True  # False: dispatch every kernel from Python (debugging)
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
@@ -86,10 +113,11 @@ class StepEngine:
         e0.record(); e1.record()  # forces creation of the underlying cudaEvent_t
         return e0, e1
 
-    def prepare_profile(self, n_steps):
+    def prepare_profile(self, n_steps, only=None):
         """Pre-create the CUDA events a profiled run of n_steps needs, so that creating them does not
-        sit on the host's critical path inside the timed region."""
-        self._event_pool = [self._new_event_pair() for _ in range(4 * n_steps)]
+        sit on the host's critical path inside the timed region.  ``only``: kernel names to bracket."""
+        self.profile_only = set(only) if only else None
+        self._event_pool = [self._new_event_pair() for _ in range((len(only) if only else 4) * n_steps)]
         self.profile = {}
 
     def kernel_times_ms(self):
@@ -148,10 +176,9 @@ class StepEngine:
             self._step_single_call(img, txt, n_i, n_t, wi, wt, slot, bf16)
 
     # ------------------------------------------------------------------------------------ one C call
-    def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):
-        """The whole iteration enqueued by uml_linear_step (csrc/step.cu): Python only fills a struct."""
-        import ctypes as C
-        from .._lib import LAUNCH_COUNT, LinearStepArgs, check, load
+    def _fill_base(self, img, txt, n_i, n_t, wi, wt, bf16):
+        """Fill the uml_linear_step_args struct for one iteration; returns (args, k, params)."""
+        from .._lib import LinearStepArgs
         a = self._args
         if a is None:
             a = self._args = LinearStepArgs()
@@ -163,9 +190,10 @@ class StepEngine:
         ws = self.ws16 if bf16 else self.ws32
         s_i, s_t, sd_i, sd_t = self._scales()
         k = 0
+        scale_params = []
         for b, cnt, s, w, sd, prm in ((img, n_i, s_i, wi, sd_i, getattr(self.model, "img_scale", None)),
                                       (txt, n_t, s_t, wt, sd_t, getattr(self.model, "txt_scale", None))):
-            if b is None or cnt == 0:
+            if b is None:
                 continue
             rows, labels, idx = self._view(b)
             seg = a.seg[k]
@@ -174,19 +202,17 @@ class StepEngine:
             seg.label_idx, seg.scale_dev = None, (sd.data_ptr() if sd is not None else None)
             if self.learnable:
                 st = self.opt.slot(prm)
-                st["step"] += 1
                 a.scale_param[k], a.scale_m[k] = prm.data.data_ptr(), st["m"].data_ptr()
                 a.scale_v[k] = st["v"].data_ptr() if st["v"] is not None else None
-                a.scale_step[k] = st["step"]
+                scale_params.append(prm)
             else:
                 a.scale_param[k] = None
             k += 1
         a.nseg, a.precision = k, int(bf16)
         W = self.W.data
-        a.W, a.upd = W.data_ptr(), self.opt.update_struct(self.W)
+        a.W = W.data_ptr()
         a.G, a.ldg = ws.G.data_ptr(), ws.ldg
         a.row_loss, a.row_correct, a.row_dscale = ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr()
-        a.stats = self.stats_log[slot].data_ptr()
         if bf16:
             a.X16, a.W16, a.labels32 = self.X16.data_ptr(), self.W16.data_ptr(), self.labels32.data_ptr()
             a.partials, a.max_splits, a.w16_valid = self.partials.data_ptr(), self.max_splits, int(self._w16_valid)
@@ -196,28 +222,126 @@ class StepEngine:
             self.dW = torch.empty_like(W)
         a.dW_out = self.dW.data_ptr() if self.world > 1 else None
         a.dW_scratch = self.dW.data_ptr() if (bf16 and self.opt.name == "sgd" and self.world == 1) else None
+        a.dp_allreduce = int(self.world > 1)
+        for j in range(8):
+            a.ev[j] = None
+        return a, k, scale_params
+
+    def _kernels_per_step(self, k, bf16):
+        n = (k + 5 + (0 if self._w16_valid else 1)) if bf16 else 4
+        return n + (k if self.learnable else 0) + (1 if self.world > 1 else 0)
+
+    def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):
+        """The whole iteration enqueued by uml_linear_step (csrc/step.cu): Python only fills a struct."""
+        import ctypes as C
+        from .._lib import LAUNCH_COUNT, check, load
+        a, k, scale_params = self._fill_base(img if n_i else None, txt if n_t else None, n_i, n_t, wi, wt, bf16)
+        for j, prm in enumerate(scale_params):
+            st = self.opt.slot(prm)
+            st["step"] += 1
+            a.scale_step[j] = st["step"]
+        a.upd = self.opt.update_struct(self.W)
+        a.stats = self.stats_log[slot].data_ptr()
         if self.profile is not None:
             # cudaEvent pairs recorded by the C launcher around gather / forward / dW / update
             names = ("gather_bf16", "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32",
                      "head_bwd_dw_bf16" if bf16 else "head_bwd_dw_f32", "adamw_step_partials")
             for j, nm in enumerate(names):
-                if not bf16 and j in (0, 3):  # the fp32 path gathers inside its GEMMs and updates in the dW epilogue
-                    a.ev[2 * j] = a.ev[2 * j + 1] = None
+                if (not bf16 and j in (0, 3)) or (self.profile_only and nm not in self.profile_only):
+                    # the fp32 path gathers inside its GEMMs and updates in the dW epilogue; profile_only restricts
+                    # the bracketed kernels (every event pair costs host time and a small bubble on the stream)
                     continue
                 e0, e1 = self._event_pool.pop() if self._event_pool else self._new_event_pair()
                 a.ev[2 * j], a.ev[2 * j + 1] = e0.cuda_event, e1.cuda_event
                 self.profile.setdefault(nm, []).append((e0, e1))
-        else:
-            for j in range(8):
-                a.ev[j] = None
         check(load().uml_linear_step(C.byref(a), torch.cuda.current_stream().cuda_stream))
-        LAUNCH_COUNT[0] += (k + 5 + (0 if self._w16_valid else 1) if bf16 else 4) + (k if self.learnable else 0)
-        if self.world > 1:
-            # undo the step count taken by update_struct: apply() counts the step itself
-            self.opt.slot(self.W)["step"] -= 1
-            torch.distributed.all_reduce(self.dW, group=self.dist_group)
-            self.opt.apply(self.W, self.dW, shadow=self.W16 if bf16 else None)
+        LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16)
         self._w16_valid = bf16
+
+    def run(self, batches, alpha, lrs, slot0):
+        """Enqueue ``len(batches)`` consecutive iterations with as few host calls as possible.
+
+        ``batches[j] = (img_batch | None, txt_batch | None)`` are the GLOBAL index batches of step j (a
+        data-parallel rank takes its slice here), ``lrs[j]`` the learning rate the scheduler emitted for it
+        and ``slot0 + j`` its slot in the stats log.  Consecutive steps that take the same arithmetic path
+        go down in ONE uml_linear_run call."""
+        import ctypes as C
+        from .._lib import LAUNCH_COUNT, RunStep, check, load
+        rank = torch.distributed.get_rank() if self.world > 1 else 0
+        wgroup = self.opt.group_of(self.W)
+        j = 0
+        n_all = len(batches)
+        while j < n_all:
+            img_g, txt_g = batches[j]
+            img = _local_slice(img_g, rank, self.world) if img_g is not None else None
+            txt = _local_slice(txt_g, rank, self.world) if txt_g is not None else None
+            n_i, n_t = (img.n if img else 0), (txt.n if txt else 0)
+            bf16 = self._use_bf16(n_i + n_t)
+            if self.adapter or not self.single_call or n_i == 0 and img is not None or n_t == 0 and txt is not None:
+                wgroup["lr"] = lrs[j]
+                for g in self.opt.param_groups:
+                    g["lr"] = lrs[j]
+                self.step(img, txt, alpha, slot0 + j, img_g.n if (img_g is not None and self.world > 1) else None,
+                          txt_g.n if (txt_g is not None and self.world > 1) else None)
+                j += 1
+                continue
+            wi, wt = dp_loss_weights(n_i, n_t, alpha, img_g.n if (img_g is not None and self.world > 1) else None,
+                                     txt_g.n if (txt_g is not None and self.world > 1) else None)
+            a, k, scale_params = self._fill_base(img, txt, n_i, n_t, wi, wt, bf16)
+            a.upd = self.opt.update_struct(self.W)      # hyper-parameters; lr / step are patched per step below
+            wst = self.opt.slot(self.W)
+            wst["step"] -= 1
+            # how many following steps share this path (same modalities, same arithmetic)?
+            m = j
+            steps = []
+            while m < n_all:
+                ig, tg = batches[m]
+                if (ig is None) != (img_g is None) or (tg is None) != (txt_g is None):
+                    break
+                il = _local_slice(ig, rank, self.world) if ig is not None else None
+                tl = _local_slice(tg, rank, self.world) if tg is not None else None
+                ni, nt = (il.n if il else 0), (tl.n if tl else 0)
+                if self._use_bf16(ni + nt) != bf16 or (il is not None and (ni == 0 or il.idx is None)) or \
+                        (tl is not None and (nt == 0 or tl.idx is None)):
+                    break
+                w_i, w_t = dp_loss_weights(ni, nt, alpha, ig.n if (ig is not None and self.world > 1) else None,
+                                           tg.n if (tg is not None and self.world > 1) else None)
+                rs = RunStep()
+                kk = 0
+                for b_, cnt, w_ in ((il, ni, w_i), (tl, nt, w_t)):
+                    if b_ is None:
+                        continue
+                    rs.idx[kk], rs.n[kk], rs.loss_weight[kk] = b_.idx.data_ptr(), cnt, w_
+                    kk += 1
+                rs.lr = lrs[m]
+                wst["step"] += 1
+                rs.opt_step = wst["step"]
+                for jj, prm in enumerate(scale_params):
+                    st = self.opt.slot(prm)
+                    st["step"] += 1
+                    rs.scale_step[jj] = st["step"]
+                slot = (slot0 + m) % self.log_slots
+                self.slot_modalities[slot] = (ig is not None, tg is not None)
+                rs.stats = self.stats_log[slot].data_ptr()
+                if self.profile is not None:
+                    nm = "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32"
+                    if not self.profile_only or nm in self.profile_only:
+                        e0, e1 = self._event_pool.pop() if self._event_pool else self._new_event_pair()
+                        rs.ev_fwd[0], rs.ev_fwd[1] = e0.cuda_event, e1.cuda_event
+                        self.profile.setdefault(nm, []).append((e0, e1))
+                steps.append(rs)
+                m += 1
+            if not steps:  # the first step itself does not qualify (dense batch): fall back to the per-step path
+                wgroup["lr"] = lrs[j]
+                self.step(img, txt, alpha, slot0 + j, img_g.n if (img_g is not None and self.world > 1) else None,
+                          txt_g.n if (txt_g is not None and self.world > 1) else None)
+                j += 1
+                continue
+            arr = (RunStep * len(steps))(*steps)
+            check(load().uml_linear_run(C.byref(a), arr, len(steps), torch.cuda.current_stream().cuda_stream))
+            LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16) * len(steps) - (0 if self._w16_valid or not bf16 else len(steps) - 1)
+            self._w16_valid = bf16
+            j = m
 
     # ------------------------------------------------------------------------------------ fp32
     def _step_fp32(self, img, txt, n_i, n_t, wi, wt, slot):
