@@ -41,6 +41,8 @@ typedef struct {
                                  output rows are dense but their labels still live in the bank)        */
   const float*   scale_dev;   /* optional: device scalar overriding `scale` (learnable temperature,
                                  head.py:69-70) so the step never reads it back to the host            */
+  const uint16_t* rows16;     /* optional: bf16 shadow of `rows` (same shape, ld == dim); the tensor-core step
+                                 then gathers with plain TMA copies instead of converting fp32 rows     */
 } uml_segment;
 
 /* Per-run results written by the forward kernels (device memory, one per segment). */
@@ -65,6 +67,11 @@ int uml_gather_rows_bf16(const float* bank, int64_t bank_rows, int32_t dim, cons
 /* bf16 gather that also gathers the int64 bank labels of the same rows into int32 (one launch)         */
 int uml_gather_rows_labels_bf16(const float* bank, const int64_t* bank_labels, int32_t dim, const int64_t* idx,
                                 int64_t n, uint16_t* out, int64_t ld_out, int32_t* out_labels, void* stream);
+/* Both runs of a step (image rows, then text rows) copied from bf16 shadow banks into one [n0+n1, dim] operand
+ * in a single launch, with their labels (int64 bank labels -> int32).  Pure TMA data movement.            */
+int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const int64_t* idx0, int64_t n0,
+                          const uint16_t* bank1, const int64_t* labels1, const int64_t* idx1, int64_t n1, int32_t dim,
+                          uint16_t* out, int64_t ld_out, int32_t* out_labels /* nullable */, void* stream);
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out,
                           void* stream);
 int uml_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);

@@ -16,7 +16,7 @@ c_i32, c_i64, c_f32, c_f64, c_vp = C.c_int32, C.c_int64, C.c_float, C.c_double, 
 class Segment(C.Structure):
     """uml_segment"""
     _fields_ = [("rows", c_vp), ("idx", c_vp), ("labels", c_vp), ("n", c_i64), ("ld", c_i64),
-                ("scale", c_f32), ("loss_weight", c_f32), ("label_idx", c_vp), ("scale_dev", c_vp)]
+                ("scale", c_f32), ("loss_weight", c_f32), ("label_idx", c_vp), ("scale_dev", c_vp), ("rows16", c_vp)]
 
 
 class SegStats(C.Structure):
@@ -61,6 +61,7 @@ PROTOTYPES = {
     "uml_gather_rows_bf16": [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp],
     "uml_gather_rows_labels_bf16": [c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp],
     "uml_gather_labels_i32": [c_vp, c_vp, c_i64, c_vp, c_vp],
+    "uml_gather2_rows_bf16": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "uml_cast_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],
     "uml_head_fwd_ce_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "uml_head_bwd_dw_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, C.POINTER(Update), c_vp],
@@ -99,7 +100,7 @@ _lib = None
 # kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {
     "uml_gather_rows_f32": 1, "uml_gather_rows_bf16": 1, "uml_gather_labels_i32": 1, "uml_cast_f32_to_bf16": 1,
-    "uml_gather_rows_labels_bf16": 1,
+    "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
     "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,

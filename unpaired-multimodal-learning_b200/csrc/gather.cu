@@ -98,6 +98,70 @@ __global__ void __launch_bounds__(kBf16 ? 128 : 32)
 __global__ void gather_labels_kernel(const int64_t* __restrict__ labels, const int64_t* __restrict__ idx, int64_t n,
                                      int32_t* __restrict__ out);
 
+// Row copy for banks that already hold the operand type (the bf16 shadow of a feature bank): both runs of a
+// step - image rows then text rows - in ONE launch, bytes moved by the TMA engine only (bulk global->shared,
+// bulk shared->global), no thread ever touches the data.  4-stage ring: the stage refilled at iteration `it`
+// is the one whose stores were committed at `it - 1`, so one store group may stay in flight.
+constexpr int kCopyStages = 4;
+
+struct CopySeg {
+  const unsigned char* bank;   // row-major, row_bytes per row
+  const int64_t* idx;          // gather indices (required)
+  const int64_t* labels;       // bank labels (int64) or nullptr
+  int64_t n;
+};
+
+__global__ void __launch_bounds__(32)
+    gather_copy2_kernel(CopySeg s0, CopySeg s1, uint32_t row_bytes, int rows_per_stage, unsigned char* __restrict__ out,
+                        int64_t out_pitch, int32_t* __restrict__ out_labels) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[kCopyStages];
+  const int64_t n = s0.n + s1.n;
+  const uint32_t stage_bytes = rows_per_stage * row_bytes;
+  const int64_t n_groups = (n + rows_per_stage - 1) / rows_per_stage;
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    for (int s = 0; s < kCopyStages; ++s) mbar_init(&full_bar[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+
+  auto issue = [&](int64_t it) {
+    const int64_t g = blockIdx.x + it * gridDim.x;
+    if (g >= n_groups) return;
+    const int s = static_cast<int>(it % kCopyStages);
+    const int64_t r0 = g * rows_per_stage;
+    const int rows = static_cast<int>((n - r0) < rows_per_stage ? (n - r0) : rows_per_stage);
+    if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], rows * row_bytes);
+    __syncwarp();
+    if (lane < rows) {
+      const int64_t r = r0 + lane;
+      const bool second = r >= s0.n;
+      const CopySeg& sg = second ? s1 : s0;
+      const int64_t src = sg.idx[second ? r - s0.n : r];
+      bulk_load_1d(smem + s * stage_bytes + lane * row_bytes, sg.bank + src * row_bytes, row_bytes, &full_bar[s]);
+      if (out_labels) out_labels[r] = static_cast<int32_t>(sg.labels[src]);  // the label rides along
+    }
+  };
+
+  for (int p = 0; p < kCopyStages - 1; ++p) issue(p);
+  for (int64_t it = 0;; ++it) {
+    const int64_t g = blockIdx.x + it * gridDim.x;
+    if (g >= n_groups) break;
+    const int s = static_cast<int>(it % kCopyStages);
+    const int64_t r0 = g * rows_per_stage;
+    const int rows = static_cast<int>((n - r0) < rows_per_stage ? (n - r0) : rows_per_stage);
+    mbar_wait(&full_bar[s], static_cast<uint32_t>((it / kCopyStages) & 1));
+    if (lane < rows) bulk_store_1d(out + (r0 + lane) * out_pitch, smem + s * stage_bytes + lane * row_bytes, row_bytes);
+    bulk_commit();
+    bulk_wait_read<1>();  // the group committed one iteration ago has left its stage
+    __syncwarp();
+    issue(it + kCopyStages - 1);
+  }
+  bulk_wait<0>();
+}
+
+
 // Fallback for rows that are not a multiple of 16 bytes (dim % 4 != 0; bf16 needs dim % 8 == 0).
 template <bool kBf16>
 __global__ void gather_rows_plain(const float* __restrict__ bank, const int64_t* __restrict__ idx, int64_t n, int dim,
@@ -196,6 +260,36 @@ int uml_gather_rows_labels_bf16(const float* bank, const int64_t* bank_labels, i
   UML_REQUIRE(bank_labels && out_labels, "gather_rows_labels_bf16: null labels");
   return uml::launch_gather<true>(bank, INT64_MAX / 2, dim, idx, n, out, ld_out, uml::as_stream(stream), bank_labels,
                                   out_labels);
+}
+
+int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const int64_t* idx0, int64_t n0,
+                          const uint16_t* bank1, const int64_t* labels1, const int64_t* idx1, int64_t n1, int32_t dim,
+                          uint16_t* out, int64_t ld_out, int32_t* out_labels, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(n0 >= 0 && n1 >= 0 && dim > 0 && out, "gather2: bad arguments");
+  UML_REQUIRE((n0 == 0 || (bank0 && idx0)) && (n1 == 0 || (bank1 && idx1)), "gather2: null bank or index pointer");
+  UML_REQUIRE(!out_labels || ((n0 == 0 || labels0) && (n1 == 0 || labels1)), "gather2: labels requested but not given");
+  if (n0 + n1 == 0) return 0;
+  const uint32_t row_bytes = static_cast<uint32_t>(dim) * 2u;
+  UML_REQUIRE(row_bytes % 16 == 0 && (ld_out * 2) % 16 == 0 && row_bytes <= 48 * 1024, "gather2: rows must be 16B multiples");
+  UML_REQUIRE(((reinterpret_cast<uintptr_t>(bank0) | reinterpret_cast<uintptr_t>(bank1) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+              "gather2: pointers must be 16B aligned");
+  int rows = static_cast<int>(48 * 1024 / row_bytes);
+  if (rows > 32) rows = 32;
+  const size_t smem = static_cast<size_t>(kCopyStages) * rows * row_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    UML_CUDA(cudaFuncSetAttribute(gather_copy2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCopyStages * 48 * 1024));
+    attr_set = true;
+  }
+  const int64_t groups = (n0 + n1 + rows - 1) / rows;
+  const int grid = static_cast<int>(std::min<int64_t>(groups, sm_count()));
+  CopySeg a{reinterpret_cast<const unsigned char*>(bank0), idx0, labels0, n0};
+  CopySeg b{reinterpret_cast<const unsigned char*>(bank1), idx1, labels1, n1};
+  gather_copy2_kernel<<<grid, 32, smem, as_stream(stream)>>>(a, b, row_bytes, rows, reinterpret_cast<unsigned char*>(out),
+                                                             ld_out * 2, out_labels);
+  UML_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out, void* stream) {

@@ -84,23 +84,43 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     ts.nseg = 0;
     int64_t off = 0;
     rec(a->ev[0], stream);
+    bool shadow_gather = true;  // every non-empty run has a bf16 shadow bank and gather indices
+    for (int i = 0; i < a->nseg; ++i) {
+      const uml_segment& s = a->seg[i];
+      if (s.n > 0 && !(s.rows16 && s.idx && !s.label_idx)) shadow_gather = false;
+    }
+    if (shadow_gather) {
+      // one launch of the TMA copy kernel for both runs (rows + labels)
+      const uml_segment* g[2] = {nullptr, nullptr};
+      int ng = 0;
+      for (int i = 0; i < a->nseg; ++i)
+        if (a->seg[i].n > 0) g[ng++] = &a->seg[i];
+      if (ng > 0) {
+        rc = uml_gather2_rows_bf16(g[0]->rows16, g[0]->labels, g[0]->idx, g[0]->n, ng > 1 ? g[1]->rows16 : nullptr,
+                                   ng > 1 ? g[1]->labels : nullptr, ng > 1 ? g[1]->idx : nullptr, ng > 1 ? g[1]->n : 0,
+                                   a->dim, a->X16, a->dim, a->labels32, stream);
+        if (rc) return rc;
+      }
+    }
     for (int i = 0; i < a->nseg; ++i) {
       const uml_segment& s = a->seg[i];
       if (s.n == 0) continue;
-      const float* rows = static_cast<const float*>(s.rows);
-      UML_REQUIRE(s.ld == a->dim, "linear_step: bf16 path needs dense bank rows (ld == dim)");
-      if (s.idx && !s.label_idx) {
-        rc = uml_gather_rows_labels_bf16(rows, s.labels, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim,
-                                         a->labels32 + off, stream);
-        if (rc) return rc;
-      } else {
-        if (s.idx)
-          rc = uml_gather_rows_bf16(rows, INT64_MAX / 2, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim, stream);
-        else
-          rc = uml_cast_f32_to_bf16(rows, a->X16 + off * a->dim, s.n * a->dim, stream);
-        if (rc) return rc;
-        rc = uml_gather_labels_i32(s.labels, s.label_idx ? s.label_idx : s.idx, s.n, a->labels32 + off, stream);
-        if (rc) return rc;
+      if (!shadow_gather) {
+        const float* rows = static_cast<const float*>(s.rows);
+        UML_REQUIRE(s.ld == a->dim, "linear_step: bf16 path needs dense bank rows (ld == dim)");
+        if (s.idx && !s.label_idx) {
+          rc = uml_gather_rows_labels_bf16(rows, s.labels, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim,
+                                           a->labels32 + off, stream);
+          if (rc) return rc;
+        } else {
+          if (s.idx)
+            rc = uml_gather_rows_bf16(rows, INT64_MAX / 2, a->dim, s.idx, s.n, a->X16 + off * a->dim, a->dim, stream);
+          else
+            rc = uml_cast_f32_to_bf16(rows, a->X16 + off * a->dim, s.n * a->dim, stream);
+          if (rc) return rc;
+          rc = uml_gather_labels_i32(s.labels, s.label_idx ? s.label_idx : s.idx, s.n, a->labels32 + off, stream);
+          if (rc) return rc;
+        }
       }
       ts.seg_rows[ts.nseg] = s.n;
       ts.scale[ts.nseg] = s.scale;

@@ -92,6 +92,7 @@ class StepEngine:
         self.host_log = None
         self._event_pool = []
         self.profile_only = None
+        self.shadow_banks = True  # keep a bf16 copy of each bank in HBM (+50% bank memory) for the tensor-core path
         self._args = None
         self.single_call = True  # False: dispatch every kernel from Python (debugging)
         self.profile = None  # set to {} to collect (start, end) CUDA events per kernel name
@@ -200,6 +201,8 @@ class StepEngine:
             seg.rows, seg.labels, seg.idx = rows.data_ptr(), labels.data_ptr(), (idx.data_ptr() if idx is not None else None)
             seg.n, seg.ld, seg.scale, seg.loss_weight = cnt, rows.stride(0), s, w
             seg.label_idx, seg.scale_dev = None, (sd.data_ptr() if sd is not None else None)
+            # bf16 shadow bank (built once per bank): the step then gathers with plain TMA copies, one launch
+            seg.rows16 = b.bank.bf16().data_ptr() if (bf16 and idx is not None and self.shadow_banks) else None
             if self.learnable:
                 st = self.opt.slot(prm)
                 a.scale_param[k], a.scale_m[k] = prm.data.data_ptr(), st["m"].data_ptr()
@@ -228,7 +231,7 @@ class StepEngine:
         return a, k, scale_params
 
     def _kernels_per_step(self, k, bf16):
-        n = (k + 5 + (0 if self._w16_valid else 1)) if bf16 else 4
+        n = ((1 if self.shadow_banks else k) + 5 + (0 if self._w16_valid else 1)) if bf16 else 4
         return n + (k if self.learnable else 0) + (1 if self.world > 1 else 0)
 
     def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):

@@ -107,6 +107,29 @@ def gather_rows_labels(bank, labels, idx, out16, out_labels32):
                                                   _stream()))
 
 
+def gather2_rows_bf16(bank0, labels0, idx0, bank1, labels1, idx1, out16, out_labels32=None):
+    """Both runs of a step copied from bf16 shadow banks into one operand (rows of run 0, then run 1) with their
+    labels, in one launch of the TMA copy kernel.  Either run may be None."""
+    d = out16.shape[1]
+    args = []
+    for bank, labels, idx, nm in ((bank0, labels0, idx0, "0"), (bank1, labels1, idx1, "1")):
+        if bank is None:
+            args += [None, None, None, 0]
+            continue
+        _need(bank, torch.bfloat16, "bank" + nm)
+        _need(idx, torch.int64, "idx" + nm)
+        if labels is not None:
+            _need(labels, torch.int64, "labels" + nm)
+        if bank.shape[1] != d:
+            raise ValueError("gather2_rows_bf16: bank width differs from the output width")
+        args += [bank.data_ptr(), _ptr(labels), idx.data_ptr(), idx.numel()]
+    _need(out16, torch.bfloat16, "out16", contiguous=False)
+    if args[3] + args[7] > out16.shape[0]:
+        raise ValueError("gather2_rows_bf16: output too small")
+    check(_lib.load().uml_gather2_rows_bf16(*args, d, out16.data_ptr(), out16.stride(0), _ptr(out_labels32), _stream()))
+    return out16
+
+
 def gather_labels(labels: torch.Tensor, idx: Optional[torch.Tensor], n: int, out: torch.Tensor) -> torch.Tensor:
     _need(labels, torch.int64, "labels")
     _need(out, torch.int32, "out")
