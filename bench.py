@@ -218,6 +218,11 @@ def make_model(wl, dev, txt_bank):
     return model, opt, sch
 
 
+def _stage(msg):
+    if os.environ.get("UML_BENCH_VERBOSE"):
+        print(f"[bench] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args, wl, rank, world, dev):
     import uml_b200  # noqa: F401
     from uml_b200 import _lib, finetune as ft
@@ -304,6 +309,7 @@ def run_ours(args, wl, rank, world, dev):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    _stage("timed region done")
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         sampler.close()
@@ -316,6 +322,7 @@ def run_ours(args, wl, rank, world, dev):
     torch.cuda.synchronize()
     breakdown = engine.kernel_times_ms()
     del engine
+    _stage("breakdown done")
 
     # ---------------- end-to-end arm: public train() call, per-step H2D indices + D2H loss ---------
     def e2e_run(warm, iters):
@@ -331,6 +338,7 @@ def run_ours(args, wl, rank, world, dev):
         tr = {"timing": {"warmup": warm}}
         if dist:
             dist.barrier()
+        _stage("e2e train() starts")
         ft.train(m2, il2, tl2, vl2, None, o2, s2, device=dev, max_iters=warm + iters, alpha=ALPHA, eval_freq=10 ** 9,
                  patience=5, stats_to_host="step", trace=tr)
         assert tr["timing"]["iters"] == iters
@@ -344,6 +352,7 @@ def run_ours(args, wl, rank, world, dev):
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    _stage("e2e done")
     e2e_value = e2e_rows / dt  # global rows (every rank walks the same global batches) over the slowest rank's time
     return dict(ms=ms, rows=rows, launches=launches, clocks=clocks, ktimes=ktimes, e2e_value=e2e_value,
                 host_ms=host_ms, breakdown=breakdown,

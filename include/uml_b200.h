@@ -152,6 +152,8 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          float* tile_ws /* [UML_TILE_WS_FLOATS(n_rows)] (required with G): per-tile partial sums
                                            of the per-run statistics, reduced by uml_reduce_tile_stats, then
                                            the per-row factors of the deferred softmax normalisation      */,
+                         uml_seg_stats* stats /* optional, with G: per-run {mean loss, dscale, hits, rows} written by
+                                                 the fix-up launch (saves the uml_reduce_tile_stats launch)     */,
                          void* stream);
 #define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 255) / 256) * 64 + (n_rows) * 16)
 /* per-run {mean loss, dscale, hits, rows} from the forward kernel's per-tile partials (fixed order)     */

@@ -187,3 +187,41 @@ def test_native_randperm_is_bit_exact_with_torch(n):
         want = torch.randperm(n, generator=g)
         got = _native_randperm(seed, n, pin=False)
         assert got.dtype == torch.int64 and torch.equal(got, want), (n, seed)
+
+
+def test_speculative_epoch_permutations_hit_and_miss_without_changing_the_stream():
+    """The sampler thread precomputes the next epoch's permutation from a predicted seed; the index stream must be
+    the one torch's DataLoader produces whether the prediction holds (single loader) or not (another consumer of
+    the global generator draws in between)."""
+    def stream(n, bs, steps, speculate, disturb):
+        torch.manual_seed(77)
+        ld = BankLoader(_bank(n), bs, shuffle=True)
+        ld.speculate = speculate
+        it, out = iter(ld), []
+        for s in range(steps):
+            b, it = ft.fetch_next(ld, it)
+            out.append(b.host_idx.clone())
+            if disturb and s % 3 == 2:
+                torch.rand(1)  # someone else draws from the global generator
+        return torch.cat(out), ld
+
+    for disturb in (False, True):
+        ref, _ = stream(37, 10, 41, False, disturb)
+        got, ld = stream(37, 10, 41, True, disturb)
+        assert torch.equal(ref, got)
+        if disturb:
+            assert ld.spec_misses > 0
+        else:
+            assert ld.spec_hits >= 9 and ld.spec_misses == 0
+    # and against torch itself
+    torch.manual_seed(77)
+    dl = torch.utils.data.DataLoader(torch.arange(37), batch_size=10, shuffle=True)
+    want, it = [], iter(dl)
+    for s in range(41):
+        try:
+            b = next(it)
+        except StopIteration:
+            it = iter(dl)
+            b = next(it)
+        want.append(b)
+    assert torch.equal(torch.cat(want), stream(37, 10, 41, True, False)[0])

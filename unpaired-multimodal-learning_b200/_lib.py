@@ -76,7 +76,7 @@ PROTOTYPES = {
     "uml_eval_reduce": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
     "uml_grad_diag": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "uml_head_fwd_ce_bf16": [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, C.POINTER(TcSegments), c_vp, c_i64, c_vp, c_vp,
-                             c_vp, c_vp, c_vp, c_vp],
+                             c_vp, c_vp, c_vp, c_vp, c_vp],
     "uml_head_bwd_dw_bf16": [c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp, c_i32, c_vp],
     "uml_tc_dw_splits": [c_i64, c_i32, c_i32],
     "uml_gemm_bf16": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_i32, c_vp],

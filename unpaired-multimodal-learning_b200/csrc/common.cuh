@@ -45,6 +45,39 @@ void set_error(const char* fmt, ...);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached multiprocessor count of the current device
+bool pdl_enabled();  // programmatic dependent launch between the kernels of a step (env UML_PDL=0 disables)
+
+// Launch with optional thread-block cluster and programmatic stream serialization (PDL).  A kernel launched
+// with `pdl` MUST execute pdl_wait() before touching anything an earlier kernel on the stream produced (or
+// overwriting anything it reads) - and must execute it even if it needs nothing, so that completion stays
+// transitive along the stream.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                 bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl && pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // Encode a 2D row-major tensor map (inner dim contiguous).  Returns 0 on success.
 int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint32_t elem_bytes,
@@ -61,6 +94,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---- programmatic dependent launch --------------------------------------------------------------
+// pdl_trigger: the next kernel on the stream may start launching (its prologue overlaps our run / tail).
+// pdl_wait   : blocks until every kernel this one depends on has completed and its writes are visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;

@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(32)
     fence_barrier_init();
   }
   __syncwarp();
+  pdl_trigger();
+  pdl_wait();  // the previous step's dW still reads the operand buffer this kernel overwrites
 
   auto issue = [&](int64_t it) {
     const int64_t g = blockIdx.x + it * gridDim.x;
@@ -286,9 +288,8 @@ int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const i
   const int grid = static_cast<int>(std::min<int64_t>(groups, sm_count()));
   CopySeg a{reinterpret_cast<const unsigned char*>(bank0), idx0, labels0, n0};
   CopySeg b{reinterpret_cast<const unsigned char*>(bank1), idx1, labels1, n1};
-  gather_copy2_kernel<<<grid, 32, smem, as_stream(stream)>>>(a, b, row_bytes, rows, reinterpret_cast<unsigned char*>(out),
-                                                             ld_out * 2, out_labels);
-  UML_CUDA(cudaGetLastError());
+  UML_CUDA(launch_kernel(gather_copy2_kernel, dim3(grid), dim3(32), smem, as_stream(stream), 1, true, a, b, row_bytes, rows,
+                         reinterpret_cast<unsigned char*>(out), ld_out * 2, out_labels));
   return 0;
 }
 

@@ -1,6 +1,7 @@
 // Library plumbing: error string, device check, tensor-map encoding through the driver entry point
 // (so the .so links against libcudart only and loads on a host without libcuda).
 #include <cstdarg>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -25,6 +26,18 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    // OFF unless UML_PDL=1.  Measured on B200 (round 1): with every kernel of the step triggering its dependents
+    // at entry the 50-step bench got SLOWER (0.266 vs 0.214 ms/step - early-resident dependents compete with the
+    // running kernel) and the end-to-end arm (memcpys interleaved with the kernels) hung; kept for experiments.
+    const char* e = getenv("UML_PDL");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached != 0;
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

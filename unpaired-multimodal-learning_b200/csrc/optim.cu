@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(256)
                 AdamArgs a, __nv_bfloat16* __restrict__ shadow, float* __restrict__ g_out) {
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  pdl_trigger();
+  pdl_wait();
   if (kVec) {
     const int64_t nv = n >> 2;
     for (int64_t i = tid; i < nv; i += nthreads) {
@@ -142,10 +144,11 @@ static int launch_adam(float* p, const float* parts, int n_parts, int64_t stride
   const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
   __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
   if (vec)
-    adam_kernel<true><<<grid, 256, 0, st>>>(p, parts, n_parts, stride, g2, w2, m, v, n, a, sh, g_out);
+    UML_CUDA(launch_kernel(adam_kernel<true>, dim3(grid), dim3(256), 0, st, 1, true, p, parts, n_parts, stride, g2, w2, m, v, n,
+                           a, sh, g_out));
   else
-    adam_kernel<false><<<grid, 256, 0, st>>>(p, parts, n_parts, stride, g2, w2, m, v, n, a, sh, g_out);
-  UML_CUDA(cudaGetLastError());
+    UML_CUDA(launch_kernel(adam_kernel<false>, dim3(grid), dim3(256), 0, st, 1, true, p, parts, n_parts, stride, g2, w2, m, v, n,
+                           a, sh, g_out));
   return 0;
 }
 

@@ -134,12 +134,10 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
       rec(a->ev[2], stream);
       rc = uml_head_fwd_ce_bf16(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
                                 static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                stream);
+                                a->stats, stream);  // the fix-up launch also reduces the per-run statistics
       if (rc) return rc;
       rec(a->ev[3], stream);
     }
-    rc = uml_reduce_tile_stats(a->tile_ws, total, a->nseg, a->stats, stream);
-    if (rc) return rc;
   }
 
   // learnable temperatures: scalar Adam(W) steps fed straight from the stats record on the device

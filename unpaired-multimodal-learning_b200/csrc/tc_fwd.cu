@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // barriers, TMEM and descriptors were set up while the gather kernel was still draining
 
   if (warp == kWarpTma) {
     // ------------------------------------------------ TMA producer ------------------------------
@@ -488,11 +490,47 @@ __global__ void __launch_bounds__(kFwdThreads, 1)
   }
 }
 
+// per-run statistics from the per-tile partials, summed in a fixed order (deterministic); one CTA per run
+__device__ void tile_stats_block(const float* __restrict__ tile_part, int64_t n_tiles, int s, uml_seg_stats* __restrict__ out) {
+  __shared__ float sh[4][32];
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t n = n_tiles * 4;  // (tile, warp) partials of this run
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float* p = tile_part + (i * 2 + s) * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] += p[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4; ++k)
+      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot[k] += sh[k][w];
+    out[s].loss_mean = tot[3] > 0.f ? tot[0] / tot[3] : 0.f;
+    out[s].dscale = tot[1];
+    out[s].correct = static_cast<int32_t>(tot[2] + 0.5f);
+    out[s].n = static_cast<int32_t>(tot[3] + 0.5f);
+  }
+}
+
 // Second half of the deferred softmax normalisation: G[b,c] = G[b,c] * fac[b][c / 64] - [c == y_b] * coef_b.
-// One warp per row, 16-byte vectors, all loads of a row in flight at once; fully coalesced.
+// One warp per row, 16-byte vectors, all loads of a row in flight at once; fully coalesced.  The last `nseg`
+// CTAs of the grid reduce the forward kernel's per-tile partials into the per-run statistics instead (what
+// used to be a launch of its own).
 __global__ void __launch_bounds__(256)
     g_fixup_kernel(__nv_bfloat16* __restrict__ G, int64_t ldg, int64_t n_rows, const int32_t* __restrict__ labels,
-                   const float* __restrict__ fac, FwdSegs segs) {
+                   const float* __restrict__ fac, FwdSegs segs, const float* __restrict__ tile_part, int64_t n_tiles,
+                   int row_blocks, uml_seg_stats* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
+  if (static_cast<int>(blockIdx.x) >= row_blocks) {
+    tile_stats_block(tile_part, n_tiles, static_cast<int>(blockIdx.x) - row_blocks, stats);
+    return;
+  }
   const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
@@ -543,33 +581,12 @@ static int fwd_cta_group(int64_t n_rows) {
   return n_rows > kFwdBlockM ? 2 : 1;
 }
 
-// per-run statistics from the per-tile partials, summed in a fixed order (deterministic)
+// stand-alone version for forward passes that write no G (evaluation) and therefore launch no fix-up kernel
 __global__ void __launch_bounds__(1024)
     tile_stats_kernel(const float* __restrict__ tile_part, int64_t n_tiles, int nseg, uml_seg_stats* __restrict__ out) {
-  __shared__ float sh[4][32];
-  const int s = blockIdx.x;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int64_t n = n_tiles * 4;  // (tile, warp) partials of this run
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const float* p = tile_part + (i * 2 + s) * 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] += p[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float v = warp_sum(acc[k]);
-    if ((threadIdx.x & 31) == 0) sh[k][threadIdx.x >> 5] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float tot[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < 4; ++k)
-      for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) tot[k] += sh[k][w];
-    out[s].loss_mean = tot[3] > 0.f ? tot[0] / tot[3] : 0.f;
-    out[s].dscale = tot[1];
-    out[s].correct = static_cast<int32_t>(tot[2] + 0.5f);
-    out[s].n = static_cast<int32_t>(tot[3] + 0.5f);
-  }
+  pdl_trigger();
+  pdl_wait();
+  tile_stats_block(tile_part, n_tiles, blockIdx.x, out);
   (void)nseg;
 }
 
@@ -590,7 +607,7 @@ int uml_debug_fwd_timing(long long* host_out /* [148*16] */, int reset) {
 int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                          const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg,
                          float* row_loss, int32_t* row_pred, int32_t* row_correct, float* row_dscale,
-                         float* tile_ws, void* stream) {
+                         float* tile_ws, uml_seg_stats* stats, void* stream) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && n_rows >= 0 && dim > 0 && n_classes > 0, "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
@@ -640,26 +657,16 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   UML_REQUIRE(!G || tile_ws, "head_fwd_ce_bf16: tile_ws is required when G is written");
   // workspace layout: per-tile partial sums, then the per-row normalisation factors
   float* fac = tile_ws ? tile_ws + units * cg * 32 : nullptr;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>((units < max_clusters ? units : max_clusters) * cg));
-  cfg.blockDim = dim3(kFwdThreads);
-  cfg.dynamicSmemBytes = kFwdSmemBytes;
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cg;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  UML_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tw, tg, n_rows, static_cast<int>(dim), static_cast<int>(n_classes), labels,
-                              fs, reinterpret_cast<__nv_bfloat16*>(G), ldg, row_loss, row_pred, row_correct, row_dscale,
-                              tile_ws, fac));
+  const dim3 grid(static_cast<unsigned>((units < max_clusters ? units : max_clusters) * cg));
+  UML_CUDA(launch_kernel(kern, grid, dim3(kFwdThreads), kFwdSmemBytes, as_stream(stream), cg, true, tx, tw, tg, n_rows,
+                         static_cast<int>(dim), static_cast<int>(n_classes), labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg,
+                         row_loss, row_pred, row_correct, row_dscale, tile_ws, fac));
   if (G) {
-    g_fixup_kernel<<<static_cast<unsigned>((n_rows + 7) / 8), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels, fac, fs);
-    UML_CUDA(cudaGetLastError());
+    const int row_blocks = static_cast<int>((n_rows + 7) / 8);
+    const int stat_blocks = stats ? segs->nseg : 0;
+    UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks)), dim3(256), 0, as_stream(stream), 1,
+                           true, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels, static_cast<const float*>(fac), fs,
+                           static_cast<const float*>(tile_ws), units * cg, row_blocks, stats));
   }
   return 0;
 }
@@ -669,8 +676,8 @@ int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, um
   UML_REQUIRE(tile_ws && stats && nseg >= 1 && nseg <= UML_MAX_SEGMENTS && n_rows >= 0, "reduce_tile_stats: bad arguments");
   const int cg = fwd_cta_group(n_rows);
   const int64_t tiles = ((n_rows + kFwdBlockM * cg - 1) / (kFwdBlockM * cg)) * cg;  // tiles the forward kernel wrote
-  tile_stats_kernel<<<nseg, 1024, 0, as_stream(stream)>>>(tile_ws, tiles, nseg, stats);
-  UML_CUDA(cudaGetLastError());
+  UML_CUDA(launch_kernel(tile_stats_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, true, tile_ws, tiles,
+                         static_cast<int>(nseg), stats));
   return 0;
 }
 

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256, 1)
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (every CTA) -------------------
@@ -254,21 +256,9 @@ static int launch_tc_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int64_t 
     UML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(static_cast<unsigned>((M + Cfg::kTileM - 1) / Cfg::kTileM) * kCG,
-                     static_cast<unsigned>((N + Cfg::kTileN - 1) / Cfg::kTileN), static_cast<unsigned>(n_splits));
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  UML_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, M, N, K, n_splits, out, ldo));
+  const dim3 grid(static_cast<unsigned>((M + Cfg::kTileM - 1) / Cfg::kTileM) * kCG,
+                  static_cast<unsigned>((N + Cfg::kTileN - 1) / Cfg::kTileN), static_cast<unsigned>(n_splits));
+  UML_CUDA(launch_kernel(kern, grid, dim3(256), Cfg::kSmemBytes, st, kCG, true, ta, tb, M, N, K, n_splits, out, ldo));
   return 0;
 }
 

@@ -161,7 +161,7 @@ class _PinnedRing:
 
     def __init__(self, n: int, steps_per_epoch: int):
         self.n = n
-        depth = min(80, max(2, -(-self.RUN_AHEAD // max(1, steps_per_epoch)) + 1))
+        depth = min(80, max(3, -(-self.RUN_AHEAD // max(1, steps_per_epoch)) + 2))
         # ONE pinned allocation, sliced: cudaHostAlloc costs milliseconds per call whatever the size
         arena = torch.empty(depth * max(n, 1), dtype=torch.int64, pin_memory=True)
         self.bufs = [arena[i * n:(i + 1) * n] for i in range(depth)]
@@ -169,22 +169,67 @@ class _PinnedRing:
         self.turn = -1
 
     def acquire(self) -> torch.Tensor:
+        """Next buffer of the ring (its ``_ring_slot`` attribute names the slot to release later)."""
         self.turn = (self.turn + 1) % len(self.bufs)
         ev = self.events[self.turn]
         if ev is not None:
             ev.synchronize()  # copies issued len(bufs) epochs ago; complete unless the host is very far ahead
-        return self.bufs[self.turn]
+        buf = self.bufs[self.turn]
+        buf._ring_slot = self.turn
+        return buf
 
-    def release_current(self):
-        """Call after the last asynchronous copy out of the current buffer has been enqueued."""
-        ev = self.events[self.turn]
+    def release(self, buf):
+        """Call after the last asynchronous copy out of ``buf`` has been enqueued."""
+        slot = buf._ring_slot
+        ev = self.events[slot]
         if ev is None:
-            ev = self.events[self.turn] = torch.cuda.Event()
+            ev = self.events[slot] = torch.cuda.Event()
         ev.record()
 
 
 def _draw_int64(generator=None) -> int:
     return int(torch.empty((), dtype=torch.int64).random_(generator=generator).item())
+
+
+class _SamplerWorker:
+    """One background thread that computes permutations ahead of time (the native sampler releases the GIL)."""
+
+    _inst = None
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = cls()
+        return cls._inst
+
+    def __init__(self):
+        import queue
+        import threading
+        self.q = queue.SimpleQueue()
+        threading.Thread(target=self._loop, daemon=True, name="uml-sampler").start()
+
+    def _loop(self):
+        while True:
+            seed, n, out, done = self.q.get()
+            try:
+                _native_randperm(seed, n, out=out)
+            finally:
+                done.set()
+
+    def submit(self, seed, n, out):
+        import threading
+        done = threading.Event()
+        self.q.put((seed, n, out, done))
+        return done
+
+
+def _peek_next_sampler_seed() -> int:
+    """The sampler seed the NEXT iterator of a shuffled loader will draw if nothing else consumes the global
+    generator first: replay `base seed, sampler seed` on a copy of the global generator's state."""
+    g = torch.Generator()
+    g.set_state(torch.get_rng_state())
+    _draw_int64(g)
+    return _draw_int64(g)
 
 
 class BankLoader:
@@ -215,6 +260,10 @@ class BankLoader:
         self.dataset = bank
         self._ring = None   # pinned permutation buffers (CUDA banks only), created at the first shuffled epoch
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
+        # speculative next epoch: (seed, buffer, done-event) computed by the sampler thread while this epoch runs
+        self._spec = None
+        self.speculate = True
+        self.spec_hits = self.spec_misses = 0
 
     def __len__(self):
         n = len(self.bank)
@@ -236,22 +285,42 @@ class _BankIter:
         if loader.shuffle and loader.num_workers > 0:
             self._draw()
 
+    def _next_buffer(self):
+        l = self.l
+        if l.bank.device.type == "cuda":
+            if l._ring is None:
+                l._ring = _PinnedRing(self.n, len(l))
+            return l._ring.acquire()
+        return torch.empty(self.n, dtype=torch.int64)
+
     def _draw(self):
         l = self.l
-        on_gpu = l.bank.device.type == "cuda"
-        if on_gpu and l._ring is None:
-            l._ring = _PinnedRing(self.n, len(l))
-        if l._ring is not None and l._live is not None:
-            l._ring.release_current()  # the previous epoch's copies are all enqueued by now
-        buf = l._ring.acquire() if l._ring is not None else None
+        if l._ring is not None and l._live is not None and l._live.perm_host is not None:
+            l._ring.release(l._live.perm_host)  # the previous epoch's copies are all enqueued by now
         if l.generator is None:
-            # fresh generator seeded from the global stream: the native sampler restates torch.randperm for this
-            # case bit-exactly and ~9x faster at ImageNet size (csrc/sampler.cu), straight into pinned memory
-            self.perm_host = _native_randperm(_draw_int64(None), self.n, out=buf)
-        elif buf is not None:
-            self.perm_host = torch.randperm(self.n, generator=l.generator, out=buf)
+            # Fresh generator seeded from the global stream: the native sampler restates torch.randperm for this
+            # case bit-exactly and ~9x faster at ImageNet size (csrc/sampler.cu), straight into pinned memory.
+            # The permutation was normally computed already, by the sampler thread, while the previous epoch
+            # ran: the seed this epoch would draw was predicted from a copy of the global generator.  The real
+            # draw below decides - a wrong guess (another consumer of the generator in between) just recomputes.
+            seed = _draw_int64(None)
+            spec, l._spec = l._spec, None
+            if spec is not None:
+                spec[2].wait()
+            if spec is not None and spec[0] == seed:
+                self.perm_host = spec[1]
+                l.spec_hits += 1
+            else:
+                l.spec_misses += spec is not None
+                buf = spec[1] if spec is not None else self._next_buffer()
+                self.perm_host = _native_randperm(seed, self.n, out=buf)
+            if l.speculate and self.n > 1:
+                nxt = _peek_next_sampler_seed()
+                buf = self._next_buffer()
+                l._spec = (nxt, buf, _SamplerWorker.get().submit(nxt, self.n, buf))
         else:
-            self.perm_host = torch.randperm(self.n, generator=l.generator)
+            buf = self._next_buffer()
+            self.perm_host = torch.randperm(self.n, generator=l.generator, out=buf)
         l._live = self
         if l.upload == "epoch":
             # asynchronous copy from pinned memory on the current stream: a pageable source would make the host wait

@@ -231,7 +231,7 @@ class StepEngine:
         return a, k, scale_params
 
     def _kernels_per_step(self, k, bf16):
-        n = ((1 if self.shadow_banks else k) + 5 + (0 if self._w16_valid else 1)) if bf16 else 4
+        n = ((1 if self.shadow_banks else k) + 4 + (0 if self._w16_valid else 1)) if bf16 else 4
         return n + (k if self.learnable else 0) + (1 if self.world > 1 else 0)
 
     def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):

@@ -98,6 +98,12 @@ def _dist():
     return 0, 1
 
 
+def _dbg(msg):
+    if os.environ.get("UML_BENCH_VERBOSE"):
+        torch.cuda.synchronize()
+        print(f"[train] {msg}", file=sys.stderr, flush=True)
+
+
 def validate(model, val_loader, device="cuda"):
     """(val_loss, val_acc) over the loader's bank: accuracy over all rows, loss = mean over the
     loader's batches of the batch-mean CE (the reference's weighting, finetune.py:310-312).  One logit +
@@ -228,6 +234,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
             if t_start is not None:
                 timing["rows"] = timing.get("rows", 0) + (img.n if img is not None else 0) + (txt.n if txt is not None else 0)
         engine.run(batches, alpha, lrs, slot0=i)
+        _dbg(f"chunk at {i} (+{n}) done")
         for j in range(n):
             if stats_to_host == "step":
                 engine.copy_slot_to_host(i + j)
@@ -240,7 +247,9 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
         if last_step % eval_freq == 0:
             flush()
             snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            _dbg("before validate")
             val_loss, val_acc = validate(model, val_loader, device=device)
+            _dbg("after validate")
             testlog = ""
             if test_loader is not None:
                 _, test_acc = validate(model, test_loader, device=device)

@@ -281,7 +281,9 @@ def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[
 
 
 def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadWorkspace], row_loss=None, row_pred=None,
-                     row_correct=None, row_dscale=None, n_rows: Optional[int] = None):
+                     row_correct=None, row_dscale=None, n_rows: Optional[int] = None, stats=None):
+    """``stats`` (optional, training mode only): [nseg, 4] fp32 record the fix-up launch fills with the per-run
+    statistics, instead of a separate reduce_tile_stats launch."""
     _need(X, torch.bfloat16, "X")
     _need(W_bf16, torch.bfloat16, "W")
     _need(labels_i32, torch.int32, "labels")
@@ -289,7 +291,8 @@ def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadW
     G, ldg, fac = (ws.G.data_ptr(), ws.ldg, ws.fac.data_ptr()) if ws is not None else (None, 0, None)
     check(_lib.load().uml_head_fwd_ce_bf16(X.data_ptr(), n_rows, X.shape[1], W_bf16.data_ptr(), W_bf16.shape[0],
                                            labels_i32.data_ptr(), C.byref(segs), G, ldg, _ptr(row_loss),
-                                           _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), fac, _stream()))
+                                           _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), fac,
+                                           _ptr(stats) if ws is not None else None, _stream()))
 
 
 def tc_dw_splits(n_rows: int, dim: int, n_classes: int) -> int:
