@@ -6,8 +6,9 @@
 Metric (BASELINE.json): UML train samples/sec (image + text rows consumed per second).
 Workload at N=1 (``config.workload``): cfg3 = ImageNet full-data shapes, "ViT-L/14" 768-d features,
 1000-class shared linear head + unpaired text bank, preset ``clip_linear`` arithmetic (logit scale
-exp(4.60517), AdamW) at the THROUGHPUT batch of 18944 (=148*128) rows per modality per GPU (SURVEY.md section 8d;
-the reference's own batch of 32 is a latency-bound regime reported separately by --workload cfg2).
+exp(4.60517), AdamW) at the THROUGHPUT batch of 34304 image + 3584 text rows per GPU and step (296 tiles of 128 rows
+= two waves over 148 SMs; the text batch is sized so that 8 GPUs still fit the 29940-row text bank; SURVEY.md
+section 8d; the reference's own batch of 32 is a latency-bound regime reported separately by --workload cfg2).
 Synthetic seeded banks, random-init/zero-shot-init head.  One "step" = one full UML iteration:
 gather(img) + gather(txt) -> shared head forward -> logit scale + softmax CE -> dW -> AdamW.
 
@@ -16,7 +17,8 @@ gather(img) + gather(txt) -> shared head forward -> logit scale + softmax CE -> 
            from pinned host memory every step and every step's loss record copied back to the host.
 ``roofline`` dominant kernel (head forward/CE/G, tcgen05) timed with CUDA events inside the run.
 ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference step on the host cores.
-Multi-GPU (torchrun): data-parallel, fixed per-GPU batch (weak scaling), one NCCL all-reduce of dW per step.
+Multi-GPU (torchrun): data-parallel, fixed per-GPU batch (weak scaling), banks row-sharded over the ranks with a
+per-rank sampler, one NCCL all-reduce of dW per step issued from inside the step launcher.
 """
 from __future__ import annotations
 
@@ -35,16 +37,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (n_img_bank, n_txt_bank, dim, classes, batch_per_modality_per_gpu, n_val, logit)
-    # throughput batch: 148 SMs x 128-row tiles = 18944 rows per modality -> 2 x 18944 rows per step are exactly
-    # two waves of forward tiles (16384 would leave 14% of the second wave idle)
-    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, n_val=4096,
+    # batch / batch_txt: rows per modality per GPU and step.  cfg3: 34304 image + 3584 text rows = 296 forward tiles of
+    # 128 rows = exactly two waves over 148 SMs; the text batch is sized so that 8 GPUs together (28672 rows) still
+    # fit the 29940-row CUPL text bank - per-GPU work stays fixed from 1 to 8 GPUs (weak scaling).
+    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=34304, batch_txt=3584, n_val=4096,
                  desc="ImageNet full-data CLIP ViT-L/14 768-d features + CUPL text, linear head, throughput batch"),
-    "cfg3_b16k": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=16384, n_val=4096,
-                      desc="cfg3 at 16384 rows per modality per GPU"),
-    "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, n_val=4000,
+    "cfg3_sym": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, batch_txt=18944, n_val=4096,
+                     desc="cfg3 with 18944 rows per modality per GPU (text epochs of two steps)"),
+    "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, batch_txt=32, n_val=4000,
                  desc="ImageNet 16-shot CLIP ViT-B/16 512-d features + CUPL text, linear head, reference batch 32"),
-    "cfg3_refB": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=32, n_val=4096,
+    "cfg3_refB": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=32, batch_txt=32, n_val=4096,
                       desc="cfg3 banks at the reference batch of 32"),
 }
 ALPHA, LR, WD, LOGIT = 0.5, 1e-3, 0.01, 4.60517
@@ -149,7 +151,7 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(1)
-    D, C, B = wl["dim"], wl["classes"], wl["batch"]
+    D, C, B, BT = wl["dim"], wl["classes"], wl["batch"], wl["batch_txt"]
     n_img = min(wl["n_img"], bank_rows)
     xi = torch.randn(n_img, D, generator=g)
     yi = torch.randint(0, C, (n_img,), generator=g)
@@ -157,7 +159,7 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
     yt = torch.arange(wl["n_txt"]) % C
     st = O.HeadState(head=O.zero_shot_weights(xt, yt, C), img_scale=math.exp(LOGIT), txt_scale=math.exp(LOGIT))
     opt = O.OracleOptimizer(st.param_dict(), "adamw", LR, WD)
-    il, tl = O.OracleLoader(n_img, B), O.OracleLoader(wl["n_txt"], B)
+    il, tl = O.OracleLoader(n_img, B), O.OracleLoader(wl["n_txt"], BT)
     torch.manual_seed(2)
     il.iter(); tl.iter()
 
@@ -182,15 +184,17 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
             break
     dt = time.perf_counter() - t0
     return dict(value=rows / dt, ms_per_step=1e3 * dt / done, steps=done, cores=cores,
-                sample=f"{done} steps of B={B}/modality on a {n_img}-row sample of the image bank, {cores} threads")
+                sample=f"{done} steps of {B} image + {BT} text rows on a {n_img}-row sample of the image bank, {cores} threads")
 
 
 # -----------------------------------------------------------------------------------------------
 # our arm
 # -----------------------------------------------------------------------------------------------
 
-def build_banks(wl, dev):
-    from uml_b200.engine.datasets.utils import FeatureBank
+def build_banks(wl, dev, rank=0, world=1):
+    """Seeded synthetic banks of the workload's shapes.  world > 1: this rank's row shard of the image and text
+    banks (per-rank sampler, uml_b200.engine.datasets.shard_bank); the validation bank stays whole."""
+    from uml_b200.engine.datasets.utils import FeatureBank, shard_bank
 
     g = torch.Generator(device=dev).manual_seed(1)
     D, C = wl["dim"], wl["classes"]
@@ -200,7 +204,21 @@ def build_banks(wl, dev):
     txt_y = (torch.arange(wl["n_txt"], device=dev) % C)
     val = torch.randn(wl["n_val"], D, device=dev, generator=g)
     val_y = torch.randint(0, C, (wl["n_val"],), device=dev, generator=g)
-    return FeatureBank(img, img_y, dev), FeatureBank(txt, txt_y, dev), FeatureBank(val, val_y, dev)
+    if world > 1:
+        ib, tb = shard_bank(img, img_y, rank, world, dev), shard_bank(txt, txt_y, rank, world, dev)
+        del img, txt
+        torch.cuda.empty_cache()
+        return ib, tb, FeatureBank(val, val_y, dev), FeatureBank(txt_full_for_init(wl, dev), (torch.arange(wl["n_txt"], device=dev) % C), dev)
+    tb = FeatureBank(txt, txt_y, dev)
+    return FeatureBank(img, img_y, dev), tb, FeatureBank(val, val_y, dev), tb
+
+
+def txt_full_for_init(wl, dev):
+    """The whole text bank again (same seed stream as build_banks) - the zero-shot initialisation uses every row."""
+    g = torch.Generator(device=dev).manual_seed(1)
+    torch.randn(wl["n_img"], wl["dim"], device=dev, generator=g)
+    torch.randint(0, wl["classes"], (wl["n_img"],), device=dev, generator=g)
+    return torch.randn(wl["n_txt"], wl["dim"], device=dev, generator=g)
 
 
 def make_model(wl, dev, txt_bank):
@@ -230,19 +248,20 @@ def run_ours(args, wl, rank, world, dev):
     from uml_b200.engine.trainer import StepEngine
 
     dist = torch.distributed if world > 1 else None
-    img_bank, txt_bank, val_bank = build_banks(wl, dev)
-    B = wl["batch"]
-    GB = B * world  # global batch per modality (weak scaling: per-GPU rows fixed)
+    img_bank, txt_bank, val_bank, init_bank = build_banks(wl, dev, rank, world)
+    B, BT = wl["batch"], wl["batch_txt"]  # rows per GPU and step (weak scaling: fixed as GPUs are added)
+    shard = (rank, world) if world > 1 else None  # world > 1: per-rank sampler over this rank's bank shard
     K, W = args.steps, args.warmup
 
     # ---------------- device-resident arm: CUDA events around K steps ----------------------------
-    model, opt, sch = make_model(wl, dev, txt_bank)
-    engine = StepEngine(model, opt, dev, B, B, log_slots=64, precision=args.precision, world_size=world)
-    il = BankLoader(img_bank, GB, shuffle=True, upload="epoch")
-    tl = BankLoader(txt_bank, GB, shuffle=True, upload="epoch")
+    model, opt, sch = make_model(wl, dev, init_bank)
+    engine = StepEngine(model, opt, dev, B, BT, log_slots=64, precision=args.precision, world_size=world)
+    il = BankLoader(img_bank, B, shuffle=True, upload="epoch", shard_of=shard)
+    tl = BankLoader(txt_bank, BT, shuffle=True, upload="epoch", shard_of=shard)
     torch.manual_seed(2)
     ii, ti = iter(il), iter(tl)
 
+    slow = [(0.0, -1), (0.0, -1)]  # slowest single fetch of the image / text loader and the step it happened at
     host_split = [0.0, 0.0]  # seconds in the loaders / in engine.run (host-side enqueue cost, reported on stderr)
     CHUNK = 10  # iterations enqueued per library call (uml_linear_run), as finetune.train does
 
@@ -252,12 +271,19 @@ def run_ours(args, wl, rank, world, dev):
         batches, lrs, rows_ = [], [], 0
         t0 = time.perf_counter()
         for _ in range(n):
+            ta = time.perf_counter()
             img, ii = ft.fetch_next(il, ii)
+            tb = time.perf_counter()
             txt, ti = ft.fetch_next(tl, ti)
+            tc = time.perf_counter()
+            if tb - ta > slow[0][0]:
+                slow[0] = (tb - ta, i + len(batches))
+            if tc - tb > slow[1][0]:
+                slow[1] = (tc - tb, i + len(batches))
             batches.append((img, txt))
             lrs.append(sch.get_last_lr()[0])
             sch.step()
-            rows_ += img.n + txt.n
+            rows_ += (img.global_n or img.n) + (txt.global_n or txt.n)
         t1 = time.perf_counter()
         engine.run(batches, ALPHA, lrs, slot0=i)
         host_split[0] += t1 - t0
@@ -267,7 +293,7 @@ def run_ours(args, wl, rank, world, dev):
     sampler = ClockSampler(dev.index or 0) if rank == 0 else None  # NVML set-up happens here, before the warm-up
     for i in range(W):
         step(i)
-    bf16_path = engine._use_bf16(2 * B)
+    bf16_path = engine._use_bf16(B + BT)
     dominant = "head_fwd_ce_bf16" if bf16_path else "head_bwd_dw_f32"
     engine.prepare_profile(K, only=[dominant])  # the roofline kernel is timed live inside the timed region
     torch.cuda.synchronize()
@@ -277,6 +303,7 @@ def run_ours(args, wl, rank, world, dev):
         sampler.start()
     n0 = _lib.LAUNCH_COUNT[0]
     host_split[0] = host_split[1] = 0.0
+    slow[0] = slow[1] = (0.0, -1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rows = 0
     prof = None
@@ -298,8 +325,9 @@ def run_ours(args, wl, rank, world, dev):
         pstats.Stats(prof, stream=sys.stderr).sort_stats("tottime").print_stats(14)
     host_ms = (time.perf_counter() - t_host0) * 1e3 / K  # enqueue cost per step (the loop never syncs)
     if rank == 0:
-        print(f"host per step: loaders {host_split[0] / K * 1e3:.4f} ms, engine.run {host_split[1] / K * 1e3:.4f} ms",
-              file=sys.stderr)
+        print(f"host per step: loaders {host_split[0] / K * 1e3:.4f} ms, engine.run {host_split[1] / K * 1e3:.4f} ms; slowest fetch: "
+              f"image {slow[0][0] * 1e3:.2f} ms at step {slow[0][1]}, text {slow[1][0] * 1e3:.2f} ms at step {slow[1][1]}; "
+              f"cpus usable {len(os.sched_getaffinity(0))}", file=sys.stderr)
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -329,13 +357,13 @@ def run_ours(args, wl, rank, world, dev):
         """ONE public train() call of warm + iters iterations; the timed region is iterations warm.. (wall clock,
         stream-synchronised on both sides): per step it holds the H2D copy of the step's index batches from pinned
         memory, the step, and the D2H copy of its loss record, read on the host before the clock stops."""
-        m2, o2, s2 = make_model(wl, dev, txt_bank)
+        m2, o2, s2 = make_model(wl, dev, init_bank)
         m2.precision = args.precision
-        il2 = BankLoader(img_bank, GB, shuffle=True, upload="step")
-        tl2 = BankLoader(txt_bank, GB, shuffle=True, upload="step")
+        il2 = BankLoader(img_bank, B, shuffle=True, upload="step", shard_of=shard)
+        tl2 = BankLoader(txt_bank, BT, shuffle=True, upload="step", shard_of=shard)
         vl2 = BankLoader(val_bank, 512, shuffle=False)
         torch.manual_seed(2)
-        tr = {"timing": {"warmup": warm}}
+        tr = {"timing": {"warmup": warm}, "indices": False}
         if dist:
             dist.barrier()
         _stage("e2e train() starts")
@@ -356,7 +384,7 @@ def run_ours(args, wl, rank, world, dev):
     e2e_value = e2e_rows / dt  # global rows (every rank walks the same global batches) over the slowest rank's time
     return dict(ms=ms, rows=rows, launches=launches, clocks=clocks, ktimes=ktimes, e2e_value=e2e_value,
                 host_ms=host_ms, breakdown=breakdown,
-                h2d=2 * GB * 8, d2h=2 * 4 * 4, loss_tail=loss_tail, GB=GB)
+                h2d=(B + BT) * 8, d2h=2 * 4 * 4, loss_tail=loss_tail)
 
 
 def main():
@@ -373,10 +401,12 @@ def main():
     wl = WORKLOADS[args.workload]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     peaks = measured_peaks()
-    D, C, B = wl["dim"], wl["classes"], wl["batch"]
+    D, C, B, BT = wl["dim"], wl["classes"], wl["batch"], wl["batch_txt"]
     config = {"workload": f"{args.workload}: {wl['desc']}", "dim": D, "classes": C, "img_bank_rows": wl["n_img"],
-              "txt_bank_rows": wl["n_txt"], "batch_per_modality_per_gpu": B, "global_batch": 2 * B * world,
-              "optimizer": "adamw", "alpha": ALPHA, "parallelism": f"dp{world}",
+              "txt_bank_rows": wl["n_txt"], "image_rows_per_gpu_step": B, "text_rows_per_gpu_step": BT,
+              "global_batch": (B + BT) * world, "optimizer": "adamw", "alpha": ALPHA, "parallelism": f"dp{world}",
+              "sampler": "single global permutation, bit-exact with the reference's DataLoader order" if world == 1 else
+                         "per-rank shard permutation (DistributedSampler-style, equal strided shards); NCCL all-reduce of dW per step",
               "l2_policy": "inputs larger than L2: every step gathers fresh rows from a 3.9 GB bank and rewrites a "
                            "67 MB gradient-logit matrix" if args.workload != "cfg2" else "working set fits L2 (few-shot)"}
 
@@ -409,7 +439,7 @@ def main():
         K = args.steps
         value = res["rows"] / (res["ms"] * 1e-3)
         used_bf16 = "head_fwd_ce_bf16" in res["ktimes"]
-        rows_per_gpu = 2 * B
+        rows_per_gpu = res["rows"] / (K * world)  # mean rows per GPU and step actually processed (epoch tails are short)
         if used_bf16:
             kname = "head_fwd_ce_bf16"
             kms = res["ktimes"][kname]

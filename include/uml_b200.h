@@ -72,6 +72,11 @@ int uml_gather_rows_labels_bf16(const float* bank, const int64_t* bank_labels, i
 int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const int64_t* idx0, int64_t n0,
                           const uint16_t* bank1, const int64_t* labels1, const int64_t* idx1, int64_t n1, int32_t dim,
                           uint16_t* out, int64_t ld_out, int32_t* out_labels /* nullable */, void* stream);
+/* The same copy with a small-footprint kernel (no shared memory, one warp per row) that can share the SMs with
+ * the GEMM kernels of the current step: uml_linear_run issues it on a side stream for the NEXT step's rows.   */
+int uml_gather2_rows_bf16_light(const uint16_t* bank0, const int64_t* labels0, const int64_t* idx0, int64_t n0,
+                                const uint16_t* bank1, const int64_t* labels1, const int64_t* idx1, int64_t n1, int32_t dim,
+                                uint16_t* out, int64_t ld_out, int32_t* out_labels /* nullable */, void* stream);
 int uml_gather_labels_i32(const int64_t* bank_labels, const int64_t* idx, int64_t n, int32_t* out,
                           void* stream);
 int uml_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* stream);
@@ -208,6 +213,9 @@ typedef struct {
   /* optional cudaEvent_t pairs recorded around {gather, forward, dW, update} on `stream` (bench.py) */
   void*         ev[8];
   int32_t       dp_allreduce;               /* != 0: all-reduce dW_out across the uml_dp_init ranks, then update W */
+  /* optional second operand buffers: with them uml_linear_run gathers step i+1's rows (into the buffer step i
+   * does not use) on a side stream while step i's GEMMs run                                                  */
+  uint16_t*     X16_alt;  int32_t* labels32_alt;
 } uml_linear_step_args;
 
 int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);
@@ -240,8 +248,19 @@ int uml_dp_shutdown(void);
 /* ---- sampler: the epoch permutation on the host, bit-exact with torch.randperm(n, generator=
  * torch.Generator().manual_seed(seed)) on the CPU - what RandomSampler draws once per epoch for the
  * DataLoaders of finetune.py:370-371 (MT19937 seeded with the low 32 bits of `seed`, Fisher-Yates
- * `z = rand() % (n - i)`), with the swap targets prefetched a window ahead.  Pure host code; `out`
- * (n int64, normally pinned memory) is then copied to the device asynchronously.  n < 2^32 / 20.      */
+ * `z = rand() % (n - i)`).  Pure host code; `out` (n int64, normally pinned memory) is copied to the device
+ * asynchronously by the caller.  n < 2^32 / 20.
+ * The prefix out[0..i] is final after iteration i, so the permutation can be produced incrementally:
+ * uml_randperm_begin seeds the generator and writes the identity, uml_randperm_advance(state, upto) runs the
+ * iterations needed to make out[0..upto) final (a host thread keeps that prefix ahead of the training loop).
+ * `state` is caller-owned scratch of UML_RANDPERM_STATE_BYTES bytes (8-byte aligned).                      */
+#define UML_RANDPERM_STATE_BYTES 3072
+int uml_randperm_begin(void* state /*host*/, uint64_t seed, int64_t n, int64_t* out /*host*/);
+int uml_randperm_advance(void* state /*host*/, int64_t upto);
+/* begin + advance in chunks, publishing the final-prefix length after each chunk: the body of a producer thread.
+ * uml_randperm_wait (any other thread) returns once out[0..upto) is final.                                  */
+int uml_randperm_run(void* state /*host*/, uint64_t seed, int64_t n, int64_t* out /*host*/, int64_t chunk);
+int uml_randperm_wait(const void* state /*host*/, int64_t upto);
 int uml_randperm_i64(uint64_t seed, int64_t n, int64_t* out /*host*/);
 
 #ifdef __cplusplus

@@ -189,39 +189,49 @@ def test_native_randperm_is_bit_exact_with_torch(n):
         assert got.dtype == torch.int64 and torch.equal(got, want), (n, seed)
 
 
-def test_speculative_epoch_permutations_hit_and_miss_without_changing_the_stream():
-    """The sampler thread precomputes the next epoch's permutation from a predicted seed; the index stream must be
-    the one torch's DataLoader produces whether the prediction holds (single loader) or not (another consumer of
-    the global generator draws in between)."""
-    def stream(n, bs, steps, speculate, disturb):
+def test_threaded_incremental_permutation_gives_the_dataloader_stream():
+    """Large banks: the epoch permutation is produced incrementally by a sampler thread while batches are consumed
+    (uml_randperm_begin / uml_randperm_advance); the index stream must still be torch's DataLoader stream."""
+    def stream(threaded):
         torch.manual_seed(77)
-        ld = BankLoader(_bank(n), bs, shuffle=True)
-        ld.speculate = speculate
+        ld = BankLoader(_bank(100_003), 9_001, shuffle=True)
+        ld.async_min_rows = 16 if threaded else 10 ** 9
         it, out = iter(ld), []
-        for s in range(steps):
+        for s in range(30):  # crosses two epoch boundaries (12 batches per epoch, the last one short)
             b, it = ft.fetch_next(ld, it)
             out.append(b.host_idx.clone())
-            if disturb and s % 3 == 2:
-                torch.rand(1)  # someone else draws from the global generator
-        return torch.cat(out), ld
+            assert torch.equal(b.idx.cpu(), b.host_idx)
+        return torch.cat(out)
 
-    for disturb in (False, True):
-        ref, _ = stream(37, 10, 41, False, disturb)
-        got, ld = stream(37, 10, 41, True, disturb)
-        assert torch.equal(ref, got)
-        if disturb:
-            assert ld.spec_misses > 0
-        else:
-            assert ld.spec_hits >= 9 and ld.spec_misses == 0
-    # and against torch itself
     torch.manual_seed(77)
-    dl = torch.utils.data.DataLoader(torch.arange(37), batch_size=10, shuffle=True)
+    dl = torch.utils.data.DataLoader(torch.arange(100_003), batch_size=9_001, shuffle=True)
     want, it = [], iter(dl)
-    for s in range(41):
+    for s in range(30):
         try:
             b = next(it)
         except StopIteration:
             it = iter(dl)
             b = next(it)
         want.append(b)
-    assert torch.equal(torch.cat(want), stream(37, 10, 41, True, False)[0])
+    want = torch.cat(want)
+    assert torch.equal(stream(False), want)
+    assert torch.equal(stream(True), want)
+
+
+def test_incremental_randperm_prefixes_are_final():
+    """After uml_randperm_advance(state, k) the first k entries already equal torch.randperm's."""
+    import ctypes as C
+    from uml_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator()
+    for n, seed in ((1, 3), (2, 3), (65, 9), (1000, 2 ** 40 + 5), (70_001, 123)):
+        g.manual_seed(seed)
+        want = torch.randperm(n, generator=g)
+        state = (C.c_ubyte * 3072)()
+        out = torch.empty(n, dtype=torch.int64)
+        _lib.check(lib.uml_randperm_begin(state, seed, n, out.data_ptr()))
+        for upto in (0, 1, 7, 63, 64, 65, n // 3, n // 2 + 1, n - 1, n):
+            upto = max(0, min(upto, n))
+            _lib.check(lib.uml_randperm_advance(state, upto))
+            assert torch.equal(out[:upto], want[:upto]), (n, seed, upto)
+        assert torch.equal(out, want)

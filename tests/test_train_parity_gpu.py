@@ -181,3 +181,44 @@ def test_bf16_adapter_path_tracks_fp32_training():
         assert (a - b).norm() / a.norm() < 1e-2, k
     for k in ("img_scale", "txt_scale"):
         assert abs(float(o32["model"][k]) - float(o16["model"][k])) < 5e-3
+
+
+def test_gather_prefetch_pipeline_is_bit_identical_to_the_sequential_launcher():
+    """uml_linear_run with the side-stream gather prefetch (double-buffered operands) must produce exactly the
+    weights and per-step stats of the sequential launcher: the prefetch only reorders independent work."""
+    from uml_b200.engine.trainer import StepEngine
+    D, C, B, steps = 768, 1000, 1536, 9
+    g = torch.Generator().manual_seed(4)
+    xi, yi = torch.randn(9000, D, generator=g), torch.randint(0, C, (9000,), generator=g)
+    xt, yt = torch.randn(4000, D, generator=g), torch.arange(4000) % C
+
+    def run(prefetch):
+        ib, tb = FeatureBank(xi, yi, DEV), FeatureBank(xt, yt, DEV)
+        torch.manual_seed(1)
+        model = UMLClip(f"synthetic:{D}", C, logit_scale_init=4.60517)
+        model.to(DEV)
+        model.zero_shot_init(tb)
+        model.to(DEV)
+        opt = build_optimizer(model.parameters(), "adamw", 1e-3, 0.01)
+        sch = build_lr_scheduler(opt, "cosine", 3, 100, warmup_type="linear", warmup_lr=1e-5)
+        eng = StepEngine(model, opt, DEV, B, B, log_slots=steps + 1, precision="bf16")
+        eng.prefetch = prefetch
+        il, tl = BankLoader(ib, B, shuffle=True), BankLoader(tb, B, shuffle=True)  # epochs of 6 / 3 steps: short batches
+        torch.manual_seed(9)
+        ii, ti = iter(il), iter(tl)
+        batches, lrs = [], []
+        for _ in range(steps):
+            a, ii = ft.fetch_next(il, ii)
+            b, ti = ft.fetch_next(tl, ti)
+            batches.append((a, b))
+            lrs.append(sch.get_last_lr()[0])
+            sch.step()
+        eng.run(batches[:4], 0.5, lrs[:4], slot0=0)   # two calls: the second starts while buffers are in flight
+        eng.run(batches[4:], 0.5, lrs[4:], slot0=4)
+        torch.cuda.synchronize()
+        return model.head.weight.detach().cpu().clone(), eng.read_log(list(range(steps)))
+
+    w_seq, log_seq = run(False)
+    w_pre, log_pre = run(True)
+    assert torch.equal(w_seq, w_pre)
+    assert log_seq == log_pre

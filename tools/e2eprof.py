@@ -20,15 +20,15 @@ def main():
     K = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     dev = torch.device("cuda", 0)
     wl = bench.WORKLOADS["cfg3"]
-    img_bank, txt_bank, val_bank = bench.build_banks(wl, dev)
+    img_bank, txt_bank, val_bank, _ = bench.build_banks(wl, dev)
     B = wl["batch"]
     for r in range(reps):
         m2, o2, s2 = bench.make_model(wl, dev, txt_bank)
         il2 = BankLoader(img_bank, B, shuffle=True, upload="step")
-        tl2 = BankLoader(txt_bank, B, shuffle=True, upload="step")
+        tl2 = BankLoader(txt_bank, wl["batch_txt"], shuffle=True, upload="step")
         vl2 = BankLoader(val_bank, 512, shuffle=False)
         torch.manual_seed(2)
-        tr = {"timing": {"warmup": 5}}
+        tr = {"timing": {"warmup": 5}, "indices": False}
         pr = cProfile.Profile() if r == reps - 1 else None
         with contextlib.redirect_stdout(io.StringIO()):
             if pr:

@@ -21,8 +21,8 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
     chunk = int(sys.argv[3]) if len(sys.argv) > 3 else 10
     dev = torch.device("cuda", 0)
-    wl = dict(bench.WORKLOADS["cfg3"], batch=B, n_img=int(os.environ.get("N_IMG", 200_000)))
-    img_bank, txt_bank, _ = bench.build_banks(wl, dev)
+    wl = dict(bench.WORKLOADS["cfg3"], batch=B, batch_txt=B, n_img=int(os.environ.get("N_IMG", 200_000)))
+    img_bank, txt_bank, _, _ = bench.build_banks(wl, dev)
     model, opt, sch = bench.make_model(wl, dev, txt_bank)
     engine = StepEngine(model, opt, dev, B, B, log_slots=64, precision="bf16")
     il = BankLoader(img_bank, B, shuffle=True, upload=os.environ.get("UPLOAD", "epoch"))

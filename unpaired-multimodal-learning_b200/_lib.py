@@ -44,7 +44,7 @@ class LinearStepArgs(C.Structure):
                 ("X16", c_vp), ("W16", c_vp), ("labels32", c_vp), ("partials", c_vp), ("tile_ws", c_vp),
                 ("max_splits", c_i32), ("w16_valid", c_i32), ("dW_out", c_vp), ("dW_scratch", c_vp),
                 ("scale_param", c_vp * 2), ("scale_m", c_vp * 2), ("scale_v", c_vp * 2), ("scale_step", c_i64 * 2),
-                ("ev", c_vp * 8), ("dp_allreduce", c_i32)]
+                ("ev", c_vp * 8), ("dp_allreduce", c_i32), ("X16_alt", c_vp), ("labels32_alt", c_vp)]
 
 
 class RunStep(C.Structure):
@@ -62,6 +62,7 @@ PROTOTYPES = {
     "uml_gather_rows_labels_bf16": [c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp],
     "uml_gather_labels_i32": [c_vp, c_vp, c_i64, c_vp, c_vp],
     "uml_gather2_rows_bf16": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
+    "uml_gather2_rows_bf16_light": [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp],
     "uml_cast_f32_to_bf16": [c_vp, c_vp, c_i64, c_vp],
     "uml_head_fwd_ce_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp],
     "uml_head_bwd_dw_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, C.POINTER(Update), c_vp],
@@ -93,6 +94,10 @@ PROTOTYPES = {
     "uml_dp_allreduce_f32": [c_vp, c_i64, c_vp],
     "uml_dp_shutdown": [],
     "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
+    "uml_randperm_begin": [c_vp, C.c_uint64, c_i64, c_vp],
+    "uml_randperm_advance": [c_vp, c_i64],
+    "uml_randperm_run": [c_vp, C.c_uint64, c_i64, c_vp, c_i64],
+    "uml_randperm_wait": [c_vp, c_i64],
 }
 
 _lib = None
@@ -100,7 +105,7 @@ _lib = None
 # kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {
     "uml_gather_rows_f32": 1, "uml_gather_rows_bf16": 1, "uml_gather_labels_i32": 1, "uml_cast_f32_to_bf16": 1,
-    "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1,
+    "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1, "uml_gather2_rows_bf16_light": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
     "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,

@@ -206,6 +206,40 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 
+// Same job as gather_copy2_kernel with a footprint small enough to share an SM with the GEMM kernels of the
+// CURRENT step (no shared memory, <= 40 registers): uml_linear_run launches it on a low-priority side stream
+// to fetch the NEXT step's rows while the tensor cores work.  One warp per row, 16-byte vectors, four rows in
+// flight per warp.
+__global__ void __launch_bounds__(256)
+    gather_direct2_kernel(CopySeg s0, CopySeg s1, int vec_per_row, uint4* __restrict__ out, int64_t out_pitch_vec,
+                          int32_t* __restrict__ out_labels) {
+  const int64_t n = s0.n + s1.n;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n; r += n_warps) {
+    const bool second = r >= s0.n;
+    const CopySeg& sg = second ? s1 : s0;
+    const int64_t src = __ldg(sg.idx + (second ? r - s0.n : r));
+    const uint4* row = reinterpret_cast<const uint4*>(sg.bank) + src * vec_per_row;
+    uint4* dst = out + r * out_pitch_vec;
+    if (lane == 0 && out_labels) out_labels[r] = static_cast<int32_t>(__ldg(sg.labels + src));
+    for (int v0 = 0; v0 < vec_per_row; v0 += 128) {
+      uint4 x[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j * 32 + lane;
+        if (v < vec_per_row) x[j] = __ldcs(row + v);  // streamed: a bank row is read once per epoch
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j * 32 + lane;
+        if (v < vec_per_row) dst[v] = x[j];
+      }
+    }
+  }
+}
+
 template <bool kBf16>
 static int launch_gather(const float* bank, int64_t bank_rows, int32_t dim, const int64_t* idx, int64_t n, void* out,
                          int64_t ld_out, cudaStream_t st, const int64_t* bank_labels = nullptr,
@@ -290,6 +324,26 @@ int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const i
   CopySeg b{reinterpret_cast<const unsigned char*>(bank1), idx1, labels1, n1};
   UML_CUDA(launch_kernel(gather_copy2_kernel, dim3(grid), dim3(32), smem, as_stream(stream), 1, true, a, b, row_bytes, rows,
                          reinterpret_cast<unsigned char*>(out), ld_out * 2, out_labels));
+  return 0;
+}
+
+int uml_gather2_rows_bf16_light(const uint16_t* bank0, const int64_t* labels0, const int64_t* idx0, int64_t n0,
+                                const uint16_t* bank1, const int64_t* labels1, const int64_t* idx1, int64_t n1, int32_t dim,
+                                uint16_t* out, int64_t ld_out, int32_t* out_labels, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(n0 >= 0 && n1 >= 0 && dim > 0 && out, "gather2_light: bad arguments");
+  UML_REQUIRE((n0 == 0 || (bank0 && idx0)) && (n1 == 0 || (bank1 && idx1)), "gather2_light: null bank or index pointer");
+  UML_REQUIRE(!out_labels || ((n0 == 0 || labels0) && (n1 == 0 || labels1)), "gather2_light: labels requested but not given");
+  if (n0 + n1 == 0) return 0;
+  UML_REQUIRE(dim % 8 == 0 && ld_out % 8 == 0, "gather2_light: rows must be 16B multiples");
+  UML_REQUIRE(((reinterpret_cast<uintptr_t>(bank0) | reinterpret_cast<uintptr_t>(bank1) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+              "gather2_light: pointers must be 16B aligned");
+  CopySeg a{reinterpret_cast<const unsigned char*>(bank0), idx0, labels0, n0};
+  CopySeg b{reinterpret_cast<const unsigned char*>(bank1), idx1, labels1, n1};
+  const int64_t blocks = std::min<int64_t>((n0 + n1 + 7) / 8, static_cast<int64_t>(sm_count()) * 4);
+  gather_direct2_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, b, dim / 8, reinterpret_cast<uint4*>(out),
+                                                                                      ld_out / 8, out_labels);
+  UML_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -4,10 +4,17 @@
 //
 // torch's algorithm (ATen randperm_cpu, n < 2^32/20): r = 0..n-1, then for i in [0, n-1):
 //   z = mt19937() % (n - i); swap(r[i], r[i + z])        with at::mt19937 seeded by the low 32 bits of `seed`.
-// The swaps hit a 10 MB array at random for the ImageNet bank (1.28 M rows) and are latency bound (~45 ns
-// each in torch: 57 ms per epoch, against 13 ms of GPU work per epoch at the throughput batch).  The random
-// sequence does not depend on the data, so the swap targets are generated a window ahead and prefetched; the
-// swaps themselves stay in program order, which keeps the result identical.
+//
+// Two properties make this cheap enough for a GPU that consumes > 150 M rows/s:
+//  * after iteration i the prefix r[0..i] is FINAL (later iterations only touch indices > i), so the permutation
+//    can be produced incrementally - the first batch of an epoch needs B iterations, not n.  uml_randperm_begin /
+//    uml_randperm_advance expose that; a host thread keeps the prefix ahead of the training loop;
+//  * the random draws do not depend on the data: the swap targets are drawn 64 iterations ahead of the swaps and
+//    prefetched, the swaps themselves stay in program order.
+// torch: 57 ms for the ImageNet bank (1.28 M rows, latency-bound random swaps over 10 MB); here ~6.5 ms.
+#include <sched.h>
+#include <time.h>
+
 #include <cstdint>
 #include <cstring>
 
@@ -15,66 +22,145 @@
 
 namespace {
 
-struct Mt19937 {  // MT19937, the parameters of std::mt19937 / at::mt19937
-  uint32_t s[624];
-  int next;
-  explicit Mt19937(uint32_t seed) {
-    s[0] = seed;
-    for (uint32_t j = 1; j < 624; ++j) s[j] = 1812433253u * (s[j - 1] ^ (s[j - 1] >> 30)) + j;
-    next = 624;
-  }
-  void twist() {
-    for (int k = 0; k < 624; ++k) {
-      const uint32_t y = (s[k] & 0x80000000u) | (s[(k + 1) % 624] & 0x7fffffffu);
-      s[k] = s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    next = 0;
-  }
-  inline uint32_t operator()() {
-    if (next >= 624) twist();
-    uint32_t y = s[next++];
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
-  }
-};
+constexpr int kAhead = 64;  // swap targets generated (and prefetched) this many iterations ahead of the swaps
 
-constexpr int kAhead = 64;  // swap targets generated (and prefetched) this many iterations early
+struct PermState {
+  uint32_t mt[624];
+  int32_t next;          // next unread word of mt[]
+  uint32_t ring[kAhead]; // z values of iterations [done, made)
+  int64_t n;
+  int64_t done;          // iterations performed = length of the final prefix (n - 1 iterations finish everything)
+  int64_t made;          // iterations whose z has been drawn (done <= made <= min(done + kAhead, n - 1))
+  int64_t* out;
+  int64_t published;     // length of the final prefix as seen by OTHER threads (release/acquire); -1 = failed
+};
+static_assert(sizeof(PermState) <= UML_RANDPERM_STATE_BYTES, "UML_RANDPERM_STATE_BYTES too small");
+
+inline void mt_seed(PermState& s, uint32_t seed) {
+  s.mt[0] = seed;
+  for (uint32_t j = 1; j < 624; ++j) s.mt[j] = 1812433253u * (s.mt[j - 1] ^ (s.mt[j - 1] >> 30)) + j;
+  s.next = 624;
+}
+
+inline void mt_twist(uint32_t* m) {
+  constexpr uint32_t kUpper = 0x80000000u, kLower = 0x7fffffffu, kMag = 0x9908b0dfu;
+  int k = 0;
+  for (; k < 624 - 397; ++k) {
+    const uint32_t y = (m[k] & kUpper) | (m[k + 1] & kLower);
+    m[k] = m[k + 397] ^ (y >> 1) ^ ((y & 1u) ? kMag : 0u);
+  }
+  for (; k < 623; ++k) {
+    const uint32_t y = (m[k] & kUpper) | (m[k + 1] & kLower);
+    m[k] = m[k + 397 - 624] ^ (y >> 1) ^ ((y & 1u) ? kMag : 0u);
+  }
+  const uint32_t y = (m[623] & kUpper) | (m[0] & kLower);
+  m[623] = m[396] ^ (y >> 1) ^ ((y & 1u) ? kMag : 0u);
+}
+
+inline uint32_t mt_next(PermState& s) {
+  if (s.next >= 624) {
+    mt_twist(s.mt);
+    s.next = 0;
+  }
+  uint32_t y = s.mt[s.next++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+
+// draw the z of iteration s.made (the draws happen strictly in iteration order, as in torch) and prefetch its target
+inline void draw_one(PermState& s) {
+  const uint32_t z = mt_next(s) % static_cast<uint32_t>(s.n - s.made);
+  s.ring[s.made % kAhead] = z;
+  __builtin_prefetch(s.out + s.made + z, 1, 1);
+  ++s.made;
+}
+
+// iterations [s.done, upto) ; upto <= n - 1.  One fused loop: the out-of-order core overlaps the generator, the
+// division and the (prefetched) swap of different iterations - measured faster than three blocked passes.
+void advance(PermState& s, int64_t upto) {
+  const int64_t m = s.n - 1;
+  int64_t* r = s.out;
+  while (s.made < m && s.made < s.done + kAhead) draw_one(s);
+  for (int64_t i = s.done; i < upto; ++i) {
+    const uint32_t z = s.ring[i % kAhead];
+    if (s.made < m) draw_one(s);  // refills the slot just read (made == i + kAhead)
+    const int64_t t = r[i];
+    r[i] = r[i + z];
+    r[i + z] = t;
+  }
+  s.done = upto;
+}
 
 }  // namespace
 
 extern "C" {
 
-int uml_randperm_i64(uint64_t seed, int64_t n, int64_t* out) {
-  UML_REQUIRE(out != nullptr || n == 0, "randperm: null output");
+int uml_randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out) {
+  UML_REQUIRE(state && (out != nullptr || n == 0), "randperm: null pointer");
   UML_REQUIRE(n >= 0 && n < static_cast<int64_t>(UINT32_MAX / 20), "randperm: n=%lld outside the 32-bit sampler range",
               static_cast<long long>(n));
+  PermState& s = *static_cast<PermState*>(state);
+  mt_seed(s, static_cast<uint32_t>(seed & 0xffffffffu));
+  s.n = n;
+  s.done = 0;
+  s.made = 0;
+  s.out = out;
   for (int64_t i = 0; i < n; ++i) out[i] = i;
-  if (n < 2) return 0;
-  Mt19937 gen(static_cast<uint32_t>(seed & 0xffffffffu));
-  const int64_t m = n - 1;  // number of swaps
-  uint32_t ring[kAhead];
-  int64_t made = 0;
-  for (; made < kAhead && made < m; ++made) {
-    const uint32_t z = gen() % static_cast<uint32_t>(n - made);
-    ring[made % kAhead] = z;
-    __builtin_prefetch(out + made + z, 1, 1);
-  }
-  for (int64_t i = 0; i < m; ++i) {
-    const uint32_t z = ring[i % kAhead];
-    if (made < m) {
-      const uint32_t zn = gen() % static_cast<uint32_t>(n - made);
-      ring[made % kAhead] = zn;
-      __builtin_prefetch(out + made + zn, 1, 1);
-      ++made;
-    }
-    const int64_t t = out[i];
-    out[i] = out[i + z];
-    out[i + z] = t;
-  }
   return 0;
+}
+
+int uml_randperm_advance(void* state, int64_t upto) {
+  UML_REQUIRE(state, "randperm: null state");
+  PermState& s = *static_cast<PermState*>(state);
+  // a final prefix of length `upto` needs min(upto, n - 1) iterations (the last element falls into place)
+  int64_t iters = upto < s.n - 1 ? upto : s.n - 1;
+  if (iters < 0) iters = 0;
+  if (iters > s.done) advance(s, iters);
+  return 0;
+}
+
+// The whole permutation, chunk by chunk, publishing the length of the final prefix after every chunk.  Meant to
+// be the body of a host thread (one C call, so a Python caller's interpreter lock is never needed in between).
+int uml_randperm_run(void* state, uint64_t seed, int64_t n, int64_t* out, int64_t chunk) {
+  UML_REQUIRE(state && chunk > 0, "randperm_run: bad arguments");
+  PermState& s = *static_cast<PermState*>(state);
+  __atomic_store_n(&s.published, static_cast<int64_t>(0), __ATOMIC_RELEASE);
+  int rc = uml_randperm_begin(state, seed, n, out);
+  int64_t upto = 0;
+  while (rc == 0 && upto < n) {
+    upto = upto + chunk < n ? upto + chunk : n;
+    rc = uml_randperm_advance(state, upto);
+    if (rc == 0) __atomic_store_n(&s.published, upto, __ATOMIC_RELEASE);
+  }
+  if (rc != 0) __atomic_store_n(&s.published, static_cast<int64_t>(-1), __ATOMIC_RELEASE);
+  return rc;
+}
+
+// Blocks (yielding the core) until uml_randperm_run on another thread has made out[0..upto) final.
+int uml_randperm_wait(const void* state, int64_t upto) {
+  UML_REQUIRE(state, "randperm_wait: null state");
+  const PermState& s = *static_cast<const PermState*>(state);
+  for (int spins = 0;; ++spins) {
+    const int64_t p = __atomic_load_n(&s.published, __ATOMIC_ACQUIRE);
+    UML_REQUIRE(p >= 0, "randperm_wait: the generating thread failed");
+    if (p >= upto) return 0;
+    if (spins < 64) {
+      sched_yield();
+    } else {  // leave the core to the producer (the process may be confined to very few CPUs)
+      timespec ts = {0, 20000};
+      nanosleep(&ts, nullptr);
+    }
+  }
+}
+
+int uml_randperm_i64(uint64_t seed, int64_t n, int64_t* out) {
+  alignas(16) unsigned char buf[UML_RANDPERM_STATE_BYTES];
+  int rc = uml_randperm_begin(buf, seed, n, out);
+  if (rc) return rc;
+  return uml_randperm_advance(buf, n);
 }
 
 }  // extern "C"

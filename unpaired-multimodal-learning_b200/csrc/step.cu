@@ -2,13 +2,92 @@
 // (reference loop body, vision_language/finetune.py:163-195) without returning to Python in between.
 // At the reference's batch sizes the step is launch-latency bound, at throughput batch sizes the host
 // must stay ahead of a ~150 us GPU step - either way per-kernel Python dispatch is what limits it.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 inline void rec(void* ev, void* stream) {
   if (ev) cudaEventRecord(static_cast<cudaEvent_t>(ev), uml::as_stream(stream));
 }
+
+// Side stream + events for the gather prefetch of uml_linear_run (one set per device, created on first use).
+struct Pipe {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr}, start = nullptr, mid = nullptr;
+  bool ok = false;
+};
+
+Pipe* get_pipe() {
+  static Pipe pipes[64];
+  static bool tried[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  Pipe& p = pipes[dev];
+  if (!tried[dev]) {
+    tried[dev] = true;
+    const char* e = getenv("UML_PREFETCH");
+    if (e && e[0] == '0') return nullptr;
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+    // lowest priority: the prefetch must never delay a kernel of the step it hides under
+    if (cudaStreamCreateWithPriority(&p.aux, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    bool good = true;
+    for (int i = 0; i < 2; ++i) {
+      good = good && cudaEventCreateWithFlags(&p.ready[i], cudaEventDisableTiming) == cudaSuccess;
+      good = good && cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    good = good && cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&p.mid, cudaEventDisableTiming) == cudaSuccess;
+    p.ok = good;
+  }
+  return p.ok ? &p : nullptr;
+}
+
+// Where in step i the gather of step i+1 is enqueued.  Measured on B200 (cfg3, 2 x 18944 rows): at the START of the
+// step (it then shares the machine with the forward and, mostly, the bandwidth-bound fix-up) 0.1925 ms/step;
+// AFTER forward + fix-up (sharing with the dW GEMM, which streams both operands from HBM) 0.237 ms/step - slower
+// than no prefetch at all (0.207).  Default: start.  UML_PREFETCH_AT=1 selects the second placement.
+bool prefetch_after_forward() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UML_PREFETCH_AT");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+// true when every non-empty run of the step can be gathered from bf16 shadow banks by one copy launch
+bool shadow_gatherable(const uml_linear_step_args* a) {
+  for (int i = 0; i < a->nseg; ++i) {
+    const uml_segment& s = a->seg[i];
+    if (s.n > 0 && !(s.rows16 && s.idx && !s.label_idx)) return false;
+  }
+  return true;
+}
+
+// both runs' rows + labels -> (X16, labels32) by one launch of the TMA copy kernel (or its small-footprint twin)
+int shadow_gather(const uml_linear_step_args* a, uint16_t* X16, int32_t* labels32, bool light, void* stream) {
+  const uml_segment* g[2] = {nullptr, nullptr};
+  int ng = 0;
+  for (int i = 0; i < a->nseg; ++i)
+    if (a->seg[i].n > 0) g[ng++] = &a->seg[i];
+  if (ng == 0) return 0;
+  auto fn = light ? uml_gather2_rows_bf16_light : uml_gather2_rows_bf16;
+  return fn(g[0]->rows16, g[0]->labels, g[0]->idx, g[0]->n, ng > 1 ? g[1]->rows16 : nullptr, ng > 1 ? g[1]->labels : nullptr,
+            ng > 1 ? g[1]->idx : nullptr, ng > 1 ? g[1]->n : 0, a->dim, X16, a->dim, labels32, stream);
+}
 }  // namespace
+
+// `mid` (optional) runs on the host right after the forward + fix-up launches were enqueued: the place where
+// uml_linear_run enqueues the next step's gather, so that it overlaps dW / update but not the bandwidth-bound fix-up
+struct StepHooks {
+  bool pregathered = false;
+  cudaEvent_t operand_free = nullptr;
+  int (*mid)(void*) = nullptr;
+  void* mid_arg = nullptr;
+};
+static int linear_step_impl(const uml_linear_step_args* a, void* stream, const StepHooks& hooks);
 
 // data parallel tail of a step: sum dW over the ranks, then the optimizer update on every rank
 static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void* stream) {
@@ -32,28 +111,105 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
   using namespace uml;
   UML_REQUIRE(base && steps && n_steps >= 0, "linear_run: bad arguments");
   uml_linear_step_args a = *base;
-  for (int i = 0; i < n_steps; ++i) {
-    const uml_run_step& s = steps[i];
-    for (int k = 0; k < a.nseg; ++k) {
-      a.seg[k].idx = s.idx[k];
-      a.seg[k].n = s.n[k];
-      a.seg[k].loss_weight = s.loss_weight[k];
-      a.scale_step[k] = s.scale_step[k];
+  auto patch = [&](uml_linear_step_args& t, const uml_run_step& s) {
+    for (int k = 0; k < t.nseg; ++k) {
+      t.seg[k].idx = s.idx[k];
+      t.seg[k].n = s.n[k];
+      t.seg[k].loss_weight = s.loss_weight[k];
+      t.scale_step[k] = s.scale_step[k];
     }
-    a.upd.lr = s.lr;
-    a.upd.step = s.opt_step;
-    a.stats = s.stats;
-    a.ev[2] = s.ev_fwd[0];
-    a.ev[3] = s.ev_fwd[1];
+    t.upd.lr = s.lr;
+    t.upd.step = s.opt_step;
+    t.stats = s.stats;
+    t.ev[2] = s.ev_fwd[0];
+    t.ev[3] = s.ev_fwd[1];
+  };
+
+  // Gather prefetch: step i+1's rows are copied into the operand buffer step i does not use, on a low-priority
+  // side stream, while step i's forward / fix-up / dW / update run.  (The copy depends only on the indices and
+  // the bank, never on the weights.)  Buffer b becomes free again once the dW kernel that read it has finished.
+  Pipe* pipe = nullptr;
+  if (a.precision == 1 && a.X16_alt && a.labels32_alt && n_steps > 1) {
+    bool all = true;
+    for (int i = 0; i < n_steps && all; ++i) {
+      uml_linear_step_args t = a;
+      patch(t, steps[i]);
+      all = shadow_gatherable(&t);
+    }
+    if (all) pipe = get_pipe();
+  }
+  uint16_t* xbuf[2] = {base->X16, base->X16_alt};
+  int32_t* lbuf[2] = {base->labels32, base->labels32_alt};
+  cudaStream_t main_st = as_stream(stream);
+  if (pipe) UML_CUDA(cudaEventRecord(pipe->start, main_st));  // everything enqueued so far may still read buffer 1
+
+  for (int i = 0; i < n_steps; ++i) {
+    patch(a, steps[i]);
     if (i > 0 && a.precision == 1) a.w16_valid = 1;  // the optimizer kernel of the previous step refreshed the shadow
-    const int rc = uml_linear_step(&a, stream);
+    if (!pipe) {
+      const int rc = uml_linear_step(&a, stream);
+      if (rc) return rc;
+      continue;
+    }
+    const int b = i & 1;
+    a.X16 = xbuf[b];
+    a.labels32 = lbuf[b];
+    if (i == 0) {
+      const int rc = shadow_gather(&a, xbuf[0], lbuf[0], false, stream);
+      if (rc) return rc;
+    } else {
+      UML_CUDA(cudaStreamWaitEvent(main_st, pipe->ready[b], 0));
+    }
+    struct Next {
+      Pipe* pipe;
+      uml_linear_step_args nx;
+      uint16_t* x;
+      int32_t* l;
+      cudaEvent_t wait_a, wait_b, ready;
+      cudaStream_t main_st;
+      bool have;
+    } next;
+    next.pipe = pipe;
+    next.have = i + 1 < n_steps;
+    if (next.have) {
+      next.nx = a;
+      patch(next.nx, steps[i + 1]);
+      next.x = xbuf[b ^ 1];
+      next.l = lbuf[b ^ 1];
+      next.wait_a = i == 0 ? pipe->start : pipe->freed[b ^ 1];  // the dW kernel that last read that buffer
+      next.wait_b = pipe->mid;
+      next.ready = pipe->ready[b ^ 1];
+      next.main_st = main_st;
+    }
+    StepHooks hooks;
+    hooks.pregathered = true;
+    hooks.operand_free = pipe->freed[b];
+    hooks.mid_arg = &next;
+    hooks.mid = [](void* p) -> int {
+      Next* n = static_cast<Next*>(p);
+      if (!n->have) return 0;
+      UML_CUDA(cudaEventRecord(n->pipe->mid, n->main_st));
+      UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_a, 0));
+      UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_b, 0));
+      const int rc = shadow_gather(&n->nx, n->x, n->l, true, n->pipe->aux);
+      if (rc) return rc;
+      UML_CUDA(cudaEventRecord(n->ready, n->pipe->aux));
+      return 0;
+    };
+    const int rc = linear_step_impl(&a, stream, hooks);
     if (rc) return rc;
   }
   return 0;
 }
 
-int uml_linear_step(const uml_linear_step_args* a, void* stream) {
+int uml_linear_step(const uml_linear_step_args* a, void* stream) { return linear_step_impl(a, stream, StepHooks()); }
+
+}  // extern "C"
+
+static int linear_step_impl(const uml_linear_step_args* a, void* stream, const StepHooks& hooks) {
   using namespace uml;
+  const bool pregathered = hooks.pregathered;
+  const cudaEvent_t operand_free = hooks.operand_free;
   UML_REQUIRE(a != nullptr, "linear_step: null args");
   UML_REQUIRE(a->nseg >= 1 && a->nseg <= UML_MAX_SEGMENTS, "linear_step: 1..2 segments");
   UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
@@ -84,28 +240,15 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
     ts.nseg = 0;
     int64_t off = 0;
     rec(a->ev[0], stream);
-    bool shadow_gather = true;  // every non-empty run has a bf16 shadow bank and gather indices
-    for (int i = 0; i < a->nseg; ++i) {
-      const uml_segment& s = a->seg[i];
-      if (s.n > 0 && !(s.rows16 && s.idx && !s.label_idx)) shadow_gather = false;
-    }
-    if (shadow_gather) {
-      // one launch of the TMA copy kernel for both runs (rows + labels)
-      const uml_segment* g[2] = {nullptr, nullptr};
-      int ng = 0;
-      for (int i = 0; i < a->nseg; ++i)
-        if (a->seg[i].n > 0) g[ng++] = &a->seg[i];
-      if (ng > 0) {
-        rc = uml_gather2_rows_bf16(g[0]->rows16, g[0]->labels, g[0]->idx, g[0]->n, ng > 1 ? g[1]->rows16 : nullptr,
-                                   ng > 1 ? g[1]->labels : nullptr, ng > 1 ? g[1]->idx : nullptr, ng > 1 ? g[1]->n : 0,
-                                   a->dim, a->X16, a->dim, a->labels32, stream);
-        if (rc) return rc;
-      }
+    const bool shadow = pregathered || shadow_gatherable(a);
+    if (shadow && !pregathered) {
+      rc = shadow_gather(a, a->X16, a->labels32, false, stream);
+      if (rc) return rc;
     }
     for (int i = 0; i < a->nseg; ++i) {
       const uml_segment& s = a->seg[i];
       if (s.n == 0) continue;
-      if (!shadow_gather) {
+      if (!shadow) {
         const float* rows = static_cast<const float*>(s.rows);
         UML_REQUIRE(s.ld == a->dim, "linear_step: bf16 path needs dense bank rows (ld == dim)");
         if (s.idx && !s.label_idx) {
@@ -130,6 +273,10 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
       off += s.n;
     }
     rec(a->ev[1], stream);
+    if (hooks.mid && !prefetch_after_forward()) {
+      rc = hooks.mid(hooks.mid_arg);
+      if (rc) return rc;
+    }
     if (total > 0) {
       rec(a->ev[2], stream);
       rc = uml_head_fwd_ce_bf16(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
@@ -137,6 +284,10 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
                                 a->stats, stream);  // the fix-up launch also reduces the per-run statistics
       if (rc) return rc;
       rec(a->ev[3], stream);
+    }
+    if (hooks.mid && prefetch_after_forward()) {
+      rc = hooks.mid(hooks.mid_arg);
+      if (rc) return rc;
     }
   }
 
@@ -181,6 +332,7 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
                             splits, stream);
   if (rc) return rc;
   rec(a->ev[5], stream);
+  if (operand_free) UML_CUDA(cudaEventRecord(operand_free, as_stream(stream)));  // X16 / labels32 may be overwritten
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
   if (!fused) {
     rc = uml_sum_partials(a->partials, splits, np, np, a->dW_out, stream);
@@ -201,5 +353,3 @@ int uml_linear_step(const uml_linear_step_args* a, void* stream) {
   rec(a->ev[7], stream);
   return rc;
 }
-
-}  // extern "C"

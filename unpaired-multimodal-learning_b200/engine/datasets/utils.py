@@ -127,6 +127,7 @@ class IndexBatch:
     n: int
     start: int = 0
     host_idx: Optional[torch.Tensor] = None  # the same indices on the host (tests / tracing)
+    global_n: Optional[int] = None           # set by per-rank (sharded) loaders: rows of the step over ALL ranks
 
 
 def local_slice(batch: "IndexBatch", rank: int, world: int) -> "IndexBatch":
@@ -137,6 +138,16 @@ def local_slice(batch: "IndexBatch", rank: int, world: int) -> "IndexBatch":
     idx = batch.idx[lo:hi] if batch.idx is not None else None
     host = batch.host_idx[lo:hi] if batch.host_idx is not None else None
     return IndexBatch(batch.bank, idx, hi - lo, batch.start + lo, host)
+
+
+def shard_bank(features: torch.Tensor, labels: torch.Tensor, rank: int, world: int, device="cuda") -> "FeatureBank":
+    """Rank ``rank``'s row shard of a bank for the per-rank sampler of data-parallel runs: rows rank, rank+world,
+    ... (strided, so class-sorted banks stay mixed), all shards cut to the same length N // world (the last
+    N % world rows are dropped, as DistributedSampler(drop_last=True) does).  Each rank then holds and shuffles only
+    its own rows: the epoch permutation - a sequential Fisher-Yates on the host - costs 1/world per rank instead
+    of capping every rank at the single global sampler's ~200 M rows/s."""
+    n = features.shape[0] // world
+    return FeatureBank(features[rank::world][:n], labels[rank::world][:n], device)
 
 
 def _native_randperm(seed: int, n: int, pin: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -191,45 +202,46 @@ def _draw_int64(generator=None) -> int:
     return int(torch.empty((), dtype=torch.int64).random_(generator=generator).item())
 
 
-class _SamplerWorker:
-    """One background thread that computes permutations ahead of time (the native sampler releases the GIL)."""
+class _EpochPerm:
+    """One epoch's permutation, produced incrementally by uml_randperm_begin / uml_randperm_advance.
 
-    _inst = None
+    Iteration i of torch's Fisher-Yates makes element i final, so a batch only needs the prefix that covers it.
+    Small permutations are finished on the spot; large ones (the 1.28 M-row ImageNet bank costs ~7 ms of
+    sequential host work) are advanced in chunks by a daemon thread while the training loop consumes the prefix -
+    ``wait(upto)`` blocks only if the loop catches up with the generator."""
 
-    @classmethod
-    def get(cls):
-        if cls._inst is None:
-            cls._inst = cls()
-        return cls._inst
+    CHUNK = 32768
 
-    def __init__(self):
-        import queue
+    def __init__(self, seed: int, n: int, out: torch.Tensor, threaded: bool):
+        import ctypes as C
         import threading
-        self.q = queue.SimpleQueue()
-        threading.Thread(target=self._loop, daemon=True, name="uml-sampler").start()
+        from ..._lib import check, load
+        self.n, self.out = n, out
+        self.ready = 0
+        self._lib, self._check = load(), check
+        if n >= (2 ** 32 - 1) // 20:  # torch switches to a 64-bit draw there; not a bank size this path sees
+            out.copy_(torch.randperm(n, generator=torch.Generator().manual_seed(seed)))
+            self.ready = n
+            return
+        self._state = (C.c_ubyte * 3072)()
+        if not threaded:
+            check(self._lib.uml_randperm_begin(self._state, seed & (2 ** 64 - 1), n, out.data_ptr()))
+            check(self._lib.uml_randperm_advance(self._state, n))
+            self.ready = n
+            return
+        # ONE C call is the whole thread body (progress is published through the state block), so the generator
+        # never waits for the interpreter lock between chunks while the training loop runs Python code
+        self._seed = seed & (2 ** 64 - 1)
+        self._threaded = True
+        threading.Thread(target=self._lib.uml_randperm_run, name="uml-sampler", daemon=True,
+                         args=(self._state, self._seed, n, out.data_ptr(), self.CHUNK)).start()
 
-    def _loop(self):
-        while True:
-            seed, n, out, done = self.q.get()
-            try:
-                _native_randperm(seed, n, out=out)
-            finally:
-                done.set()
-
-    def submit(self, seed, n, out):
-        import threading
-        done = threading.Event()
-        self.q.put((seed, n, out, done))
-        return done
-
-
-def _peek_next_sampler_seed() -> int:
-    """The sampler seed the NEXT iterator of a shuffled loader will draw if nothing else consumes the global
-    generator first: replay `base seed, sampler seed` on a copy of the global generator's state."""
-    g = torch.Generator()
-    g.set_state(torch.get_rng_state())
-    _draw_int64(g)
-    return _draw_int64(g)
+    def wait(self, upto: int):
+        """Returns once out[0:upto] is final."""
+        if self.ready >= upto:
+            return
+        self._check(self._lib.uml_randperm_wait(self._state, upto))
+        self.ready = upto
 
 
 class BankLoader:
@@ -251,19 +263,21 @@ class BankLoader:
 
     def __init__(self, bank: FeatureBank, batch_size: int, shuffle: bool = False, drop_last: bool = False,
                  num_workers: int = 0, generator: Optional[torch.Generator] = None, upload: str = "epoch",
-                 pin_memory: bool = True):
+                 pin_memory: bool = True, shard_of: Optional[tuple] = None):
+        """``shard_of=(rank, world)``: the bank is this rank's shard (``shard_bank``) of a data-parallel run and
+        ``batch_size`` the PER-RANK batch; batches are tagged with the global row count and every rank's sampler
+        seed is decorrelated by its rank.  The index stream is then no longer the single-process reference's."""
         if upload not in ("epoch", "step"):
             raise ValueError("upload must be 'epoch' or 'step'")
         self.bank, self.batch_size, self.shuffle = bank, int(batch_size), bool(shuffle)
         self.drop_last, self.num_workers, self.generator = bool(drop_last), int(num_workers), generator
         self.upload = upload
         self.dataset = bank
+        self.shard_of = shard_of
+        self._seed_mix = 0 if shard_of is None else ((shard_of[0] + 1) * 0x9E3779B97F4A7C15) & (2 ** 63 - 1)
         self._ring = None   # pinned permutation buffers (CUDA banks only), created at the first shuffled epoch
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
-        # speculative next epoch: (seed, buffer, done-event) computed by the sampler thread while this epoch runs
-        self._spec = None
-        self.speculate = True
-        self.spec_hits = self.spec_misses = 0
+        self.async_min_rows = 65536  # permutations at least this long are produced by a sampler thread
 
     def __len__(self):
         n = len(self.bank)
@@ -280,6 +294,8 @@ class _BankIter:
         self.pos = 0
         self.perm_host = None
         self.perm_dev = None
+        self.perm = None
+        self.uploaded = 0
         self.tail_drawn = False
         _draw_int64(loader.generator)  # base seed
         if loader.shuffle and loader.num_workers > 0:
@@ -297,35 +313,27 @@ class _BankIter:
         l = self.l
         if l._ring is not None and l._live is not None and l._live.perm_host is not None:
             l._ring.release(l._live.perm_host)  # the previous epoch's copies are all enqueued by now
+        buf = self._next_buffer()
+        self.perm = None
         if l.generator is None:
             # Fresh generator seeded from the global stream: the native sampler restates torch.randperm for this
-            # case bit-exactly and ~9x faster at ImageNet size (csrc/sampler.cu), straight into pinned memory.
-            # The permutation was normally computed already, by the sampler thread, while the previous epoch
-            # ran: the seed this epoch would draw was predicted from a copy of the global generator.  The real
-            # draw below decides - a wrong guess (another consumer of the generator in between) just recomputes.
-            seed = _draw_int64(None)
-            spec, l._spec = l._spec, None
-            if spec is not None:
-                spec[2].wait()
-            if spec is not None and spec[0] == seed:
-                self.perm_host = spec[1]
-                l.spec_hits += 1
-            else:
-                l.spec_misses += spec is not None
-                buf = spec[1] if spec is not None else self._next_buffer()
-                self.perm_host = _native_randperm(seed, self.n, out=buf)
-            if l.speculate and self.n > 1:
-                nxt = _peek_next_sampler_seed()
-                buf = self._next_buffer()
-                l._spec = (nxt, buf, _SamplerWorker.get().submit(nxt, self.n, buf))
+            # case bit-exactly (csrc/sampler.cu), straight into pinned memory, incrementally for large banks.
+            seed = _draw_int64(None) ^ l._seed_mix
+            self.perm = _EpochPerm(seed, self.n, buf, threaded=self.n >= l.async_min_rows)
+            self.perm_host = buf
         else:
-            buf = self._next_buffer()
             self.perm_host = torch.randperm(self.n, generator=l.generator, out=buf)
         l._live = self
         if l.upload == "epoch":
-            # asynchronous copy from pinned memory on the current stream: a pageable source would make the host wait
-            # for every kernel already enqueued and lose its lead over the GPU once per epoch
-            self.perm_dev = self.perm_host.to(l.bank.device, non_blocking=True)
+            if self.perm is not None and self.perm.ready < self.n:
+                # still being generated: the device copy is filled batch by batch as the prefix becomes final
+                self.perm_dev = torch.empty(self.n, dtype=torch.int64, device=l.bank.device)
+                self.uploaded = 0
+            else:
+                # asynchronous copy from pinned memory on the current stream: a pageable source would make the host
+                # wait for every kernel already enqueued and lose its lead over the GPU once per epoch
+                self.perm_dev = self.perm_host.to(l.bank.device, non_blocking=True)
+                self.uploaded = self.n
 
     def __iter__(self):
         return self
@@ -343,11 +351,17 @@ class _BankIter:
         take = min(l.batch_size, left)
         start = self.pos
         self.pos += take
+        gn = take * l.shard_of[1] if l.shard_of is not None else None  # equal shards: every rank has `take` rows
         if not l.shuffle:
-            return IndexBatch(l.bank, None, take, start)
+            return IndexBatch(l.bank, None, take, start, None, gn)
+        if self.perm is not None:
+            self.perm.wait(start + take)
         host = self.perm_host[start:start + take]
         if l.upload == "epoch":
+            if self.uploaded < start + take:
+                self.perm_dev[self.uploaded:start + take].copy_(self.perm_host[self.uploaded:start + take], non_blocking=True)
+                self.uploaded = start + take
             dev = self.perm_dev[start:start + take]
         else:
             dev = host.to(l.bank.device, non_blocking=True)
-        return IndexBatch(l.bank, dev, take, start, host)
+        return IndexBatch(l.bank, dev, take, start, host, gn)

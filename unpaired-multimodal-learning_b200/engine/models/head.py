@@ -52,10 +52,13 @@ def get_zero_shot_weights(text_dataset, num_classes, in_features, device="cuda")
     labels = getattr(text_dataset, "label_tensor", None)
     if feats is None:  # a FeatureBank
         feats, labels = text_dataset.features, text_dataset.labels
-    feats = feats.to(device=device, dtype=torch.float32)
-    labels = labels.to(device=device, dtype=torch.int64)
+    # One-off initialisation, done on the host: the CPU index_add_ accumulates rows in order, exactly like the
+    # reference's Python loop, and - unlike the atomic CUDA version - gives the same bits on every rank of a
+    # data-parallel run (replicas that start 1 ulp apart never re-converge).
+    feats = feats.detach().to(device="cpu", dtype=torch.float32)
+    labels = labels.detach().to(device="cpu", dtype=torch.int64)
     with torch.no_grad():
-        sums = torch.zeros(num_classes, in_features, device=device).index_add_(0, labels, feats)
+        sums = torch.zeros(num_classes, in_features).index_add_(0, labels, feats)
         counts = torch.bincount(labels, minlength=num_classes).clamp_min(1).unsqueeze(1)
         w = sums / counts
         w = w / w.norm(dim=1, keepdim=True).clamp_min(1e-12)

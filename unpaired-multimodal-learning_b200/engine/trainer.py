@@ -38,6 +38,21 @@ def dp_loss_weights(n_img_local, n_txt_local, alpha, n_img_global=None, n_txt_gl
     return wi, wt
 
 
+def _local(batch, rank, world):
+    """This rank's rows of a step's batch: a slice of a GLOBAL batch, or the batch itself when the loader already
+    is per-rank (sharded sampler, ``global_n`` set)."""
+    if batch is None or world == 1 or batch.global_n is not None:
+        return batch
+    return _local_slice(batch, rank, world)
+
+
+def _global_rows(batch, world):
+    """Rows of the global batch this step's mean is taken over (None in single-process runs)."""
+    if batch is None or world == 1:
+        return None
+    return batch.global_n if batch.global_n is not None else batch.n
+
+
 _DP_READY = False
 
 
@@ -79,6 +94,9 @@ class StepEngine:
             raise RuntimeError("StepEngine: the model must live on a CUDA device (no CPU path)")
         if self.world > 1:
             ensure_dp_comm()
+            # replicas must start from identical bits (they apply identical updates and are never re-synchronised)
+            for prm in model.parameters():
+                torch.distributed.broadcast(prm.data, src=0)
         self.learnable = bool(getattr(model, "learnable_temp", False))
         self.ws32: Optional[ops.HeadWorkspace] = None
         self.ws16: Optional[ops.HeadWorkspace] = None
@@ -92,6 +110,8 @@ class StepEngine:
         self.host_log = None
         self._event_pool = []
         self.profile_only = None
+        self.prefetch = True      # uml_linear_run gathers step i+1's rows on a side stream during step i
+        self.X16_alt = self.labels32_alt = None
         self.shadow_banks = True  # keep a bf16 copy of each bank in HBM (+50% bank memory) for the tensor-core path
         self._args = None
         self.single_call = True  # False: dispatch every kernel from Python (debugging)
@@ -220,6 +240,13 @@ class StepEngine:
             a.X16, a.W16, a.labels32 = self.X16.data_ptr(), self.W16.data_ptr(), self.labels32.data_ptr()
             a.partials, a.max_splits, a.w16_valid = self.partials.data_ptr(), self.max_splits, int(self._w16_valid)
             a.tile_ws = ws.fac.data_ptr()
+            if self.shadow_banks and self.prefetch:
+                if self.X16_alt is None:  # second operand buffer: the next step's rows are gathered while this one runs
+                    self.X16_alt = torch.empty_like(self.X16)
+                    self.labels32_alt = torch.empty_like(self.labels32)
+                a.X16_alt, a.labels32_alt = self.X16_alt.data_ptr(), self.labels32_alt.data_ptr()
+            else:
+                a.X16_alt = a.labels32_alt = None
         need_dw = self.world > 1 or (bf16 and self.opt.name == "sgd")
         if need_dw and self.dW is None:
             self.dW = torch.empty_like(W)
@@ -276,20 +303,17 @@ class StepEngine:
         n_all = len(batches)
         while j < n_all:
             img_g, txt_g = batches[j]
-            img = _local_slice(img_g, rank, self.world) if img_g is not None else None
-            txt = _local_slice(txt_g, rank, self.world) if txt_g is not None else None
+            img, txt = _local(img_g, rank, self.world), _local(txt_g, rank, self.world)
             n_i, n_t = (img.n if img else 0), (txt.n if txt else 0)
             bf16 = self._use_bf16(n_i + n_t)
             if self.adapter or not self.single_call or n_i == 0 and img is not None or n_t == 0 and txt is not None:
                 wgroup["lr"] = lrs[j]
                 for g in self.opt.param_groups:
                     g["lr"] = lrs[j]
-                self.step(img, txt, alpha, slot0 + j, img_g.n if (img_g is not None and self.world > 1) else None,
-                          txt_g.n if (txt_g is not None and self.world > 1) else None)
+                self.step(img, txt, alpha, slot0 + j, _global_rows(img_g, self.world), _global_rows(txt_g, self.world))
                 j += 1
                 continue
-            wi, wt = dp_loss_weights(n_i, n_t, alpha, img_g.n if (img_g is not None and self.world > 1) else None,
-                                     txt_g.n if (txt_g is not None and self.world > 1) else None)
+            wi, wt = dp_loss_weights(n_i, n_t, alpha, _global_rows(img_g, self.world), _global_rows(txt_g, self.world))
             a, k, scale_params = self._fill_base(img, txt, n_i, n_t, wi, wt, bf16)
             a.upd = self.opt.update_struct(self.W)      # hyper-parameters; lr / step are patched per step below
             wst = self.opt.slot(self.W)
@@ -301,14 +325,12 @@ class StepEngine:
                 ig, tg = batches[m]
                 if (ig is None) != (img_g is None) or (tg is None) != (txt_g is None):
                     break
-                il = _local_slice(ig, rank, self.world) if ig is not None else None
-                tl = _local_slice(tg, rank, self.world) if tg is not None else None
+                il, tl = _local(ig, rank, self.world), _local(tg, rank, self.world)
                 ni, nt = (il.n if il else 0), (tl.n if tl else 0)
                 if self._use_bf16(ni + nt) != bf16 or (il is not None and (ni == 0 or il.idx is None)) or \
                         (tl is not None and (nt == 0 or tl.idx is None)):
                     break
-                w_i, w_t = dp_loss_weights(ni, nt, alpha, ig.n if (ig is not None and self.world > 1) else None,
-                                           tg.n if (tg is not None and self.world > 1) else None)
+                w_i, w_t = dp_loss_weights(ni, nt, alpha, _global_rows(ig, self.world), _global_rows(tg, self.world))
                 rs = RunStep()
                 kk = 0
                 for b_, cnt, w_ in ((il, ni, w_i), (tl, nt, w_t)):
@@ -336,8 +358,7 @@ class StepEngine:
                 m += 1
             if not steps:  # the first step itself does not qualify (dense batch): fall back to the per-step path
                 wgroup["lr"] = lrs[j]
-                self.step(img, txt, alpha, slot0 + j, img_g.n if (img_g is not None and self.world > 1) else None,
-                          txt_g.n if (txt_g is not None and self.world > 1) else None)
+                self.step(img, txt, alpha, slot0 + j, _global_rows(img_g, self.world), _global_rows(txt_g, self.world))
                 j += 1
                 continue
             arr = (RunStep * len(steps))(*steps)

@@ -166,7 +166,11 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     bs_i = image_loader.batch_size if image_loader is not None else 0
     bs_t = text_loader.batch_size if text_loader is not None else 0
     precision = getattr(args, "precision", None) or getattr(model, "precision", "auto")
-    engine = StepEngine(model, optimizer, device, -(-bs_i // world), -(-bs_t // world),
+
+    def per_rank(loader, bs):  # a sharded (per-rank) loader's batch size already is the local one
+        return bs if (loader is not None and getattr(loader, "shard_of", None)) else -(-bs // world)
+
+    engine = StepEngine(model, optimizer, device, per_rank(image_loader, bs_i), per_rank(text_loader, bs_t),
                         log_slots=min(max(int(eval_freq), 1), int(max_iters)) + 1, precision=precision,
                         dist_group=None, world_size=world)
     if trace is not None:
@@ -223,7 +227,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
                 img, image_iter = fetch_next(image_loader, image_iter)
             if text_iter is not None:
                 txt, text_iter = fetch_next(text_loader, text_iter)
-            if trace is not None:
+            if trace is not None and trace.get("indices", True):
                 if img is not None:
                     trace.setdefault("img_idx", []).append(img.host_idx.clone())
                 if txt is not None:
@@ -232,7 +236,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
             lrs.append(scheduler.get_last_lr()[0])
             scheduler.step()
             if t_start is not None:
-                timing["rows"] = timing.get("rows", 0) + (img.n if img is not None else 0) + (txt.n if txt is not None else 0)
+                timing["rows"] = timing.get("rows", 0) + sum((b.global_n or b.n) for b in (img, txt) if b is not None)
         engine.run(batches, alpha, lrs, slot0=i)
         _dbg(f"chunk at {i} (+{n}) done")
         for j in range(n):
