@@ -445,7 +445,13 @@ def main():
             kms = res["ktimes"][kname]
             flops = 2.0 * rows_per_gpu * D * C  # algorithmic: the forward contraction only (4*D*C/sample is fwd+dW)
             roof = {"bound": "tensor", "kernel": kname, "achieved": flops / (kms * 1e-3) / 1e12,
-                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "traffic": None,
+                    "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch at this shape, from the
+                    # committed `ncu --set full` capture profiles/r01_step_v6.md (57-61 MB read + 28-34 MB written;
+                    # algorithmic: 58 MB of bf16 rows + 1.5 MB of weights read, 78 MB of G written, part of which is
+                    # still in L2 when the kernel ends)
+                    "traffic": 9.0e7 if (D, C) == (768, 1000) and abs(rows_per_gpu - 37888) < 4000 else None,
+                    "traffic_unit": "bytes per launch",
                     "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)"}
         else:
             kname = "head_bwd_dw_f32"

@@ -88,6 +88,10 @@ struct StepHooks {
   void* mid_arg = nullptr;
 };
 static int linear_step_impl(const uml_linear_step_args* a, void* stream, const StepHooks& hooks);
+int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                            const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
+                            int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
+                            void* ev_after_fwd, void* stream);  // tc_fwd.cu
 
 // data parallel tail of a step: sum dW over the ranks, then the optimizer update on every rank
 static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void* stream) {
@@ -279,11 +283,12 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     }
     if (total > 0) {
       rec(a->ev[2], stream);
-      rc = uml_head_fwd_ce_bf16(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
-                                static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                a->stats, stream);  // the fix-up launch also reduces the per-run statistics
+      // ev[2]..ev[3] bracket the tensor-core kernel alone; the fix-up launch (which also reduces the per-run
+      // statistics) follows it
+      rc = uml_head_fwd_ce_bf16_ev(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
+                                   static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
+                                   a->stats, a->ev[3], stream);
       if (rc) return rc;
-      rec(a->ev[3], stream);
     }
     if (hooks.mid && prefetch_after_forward()) {
       rc = hooks.mid(hooks.mid_arg);

@@ -592,6 +592,13 @@ __global__ void __launch_bounds__(1024)
 
 }  // namespace uml
 
+// Launches the forward kernel and (training mode) the fix-up; `ev_after_fwd` (optional cudaEvent_t) is recorded
+// between the two so that a caller can time the tensor-core kernel alone (bench.py's roofline line).
+int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                            const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
+                            int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
+                            void* ev_after_fwd, void* stream);
+
 extern "C" {
 
 #ifdef UML_FWD_TIMING
@@ -608,6 +615,16 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg,
                          float* row_loss, int32_t* row_pred, int32_t* row_correct, float* row_dscale,
                          float* tile_ws, uml_seg_stats* stats, void* stream) {
+  return uml_head_fwd_ce_bf16_ev(X, n_rows, dim, W, n_classes, labels, segs, G, ldg, row_loss, row_pred, row_correct,
+                                 row_dscale, tile_ws, stats, nullptr, stream);
+}
+
+}  // extern "C"
+
+int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                            const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
+                            int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
+                            void* ev_after_fwd, void* stream) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && n_rows >= 0 && dim > 0 && n_classes > 0, "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
@@ -661,6 +678,7 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   UML_CUDA(launch_kernel(kern, grid, dim3(kFwdThreads), kFwdSmemBytes, as_stream(stream), cg, true, tx, tw, tg, n_rows,
                          static_cast<int>(dim), static_cast<int>(n_classes), labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg,
                          row_loss, row_pred, row_correct, row_dscale, tile_ws, fac));
+  if (ev_after_fwd) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd), as_stream(stream)));
   if (G) {
     const int row_blocks = static_cast<int>((n_rows + 7) / 8);
     const int stat_blocks = stats ? segs->nseg : 0;
@@ -670,6 +688,8 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
   }
   return 0;
 }
+
+extern "C" {
 
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream) {
   using namespace uml;
