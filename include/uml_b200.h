@@ -259,7 +259,10 @@ int uml_randperm_begin(void* state /*host*/, uint64_t seed, int64_t n, int64_t* 
 int uml_randperm_advance(void* state /*host*/, int64_t upto);
 /* begin + advance in chunks, publishing the final-prefix length after each chunk: the body of a producer thread.
  * uml_randperm_wait (any other thread) returns once out[0..upto) is final.                                  */
-int uml_randperm_run(void* state /*host*/, uint64_t seed, int64_t n, int64_t* out /*host*/, int64_t chunk);
+int uml_randperm_run(void* state /*host*/, uint64_t seed, int64_t n, int64_t* out /*host*/, int64_t chunk,
+                     int32_t prefilled /* out already holds 0..n-1 */,
+                     int64_t* next_out /* optional: filled with 0..n-1 afterwards, for the next epoch */);
+int uml_randperm_next_filled(const void* state /*host*/);   /* 1 once next_out holds the identity (NOT a status) */
 int uml_randperm_wait(const void* state /*host*/, int64_t upto);
 int uml_randperm_i64(uint64_t seed, int64_t n, int64_t* out /*host*/);
 

@@ -96,7 +96,8 @@ PROTOTYPES = {
     "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
     "uml_randperm_begin": [c_vp, C.c_uint64, c_i64, c_vp],
     "uml_randperm_advance": [c_vp, c_i64],
-    "uml_randperm_run": [c_vp, C.c_uint64, c_i64, c_vp, c_i64],
+    "uml_randperm_run": [c_vp, C.c_uint64, c_i64, c_vp, c_i64, c_i32, c_vp],
+    "uml_randperm_next_filled": [c_vp],
     "uml_randperm_wait": [c_vp, c_i64],
 }
 

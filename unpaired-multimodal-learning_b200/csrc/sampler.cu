@@ -33,6 +33,7 @@ struct PermState {
   int64_t made;          // iterations whose z has been drawn (done <= made <= min(done + kAhead, n - 1))
   int64_t* out;
   int64_t published;     // length of the final prefix as seen by OTHER threads (release/acquire); -1 = failed
+  int64_t next_filled;   // 1 once the NEXT epoch's buffer holds the identity (uml_randperm_run's last act)
 };
 static_assert(sizeof(PermState) <= UML_RANDPERM_STATE_BYTES, "UML_RANDPERM_STATE_BYTES too small");
 
@@ -98,7 +99,13 @@ void advance(PermState& s, int64_t upto) {
 
 extern "C" {
 
+static int randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out, bool prefilled);
+
 int uml_randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out) {
+  return randperm_begin(state, seed, n, out, false);
+}
+
+static int randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out, bool prefilled) {
   UML_REQUIRE(state && (out != nullptr || n == 0), "randperm: null pointer");
   UML_REQUIRE(n >= 0 && n < static_cast<int64_t>(UINT32_MAX / 20), "randperm: n=%lld outside the 32-bit sampler range",
               static_cast<long long>(n));
@@ -108,7 +115,8 @@ int uml_randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out) {
   s.done = 0;
   s.made = 0;
   s.out = out;
-  for (int64_t i = 0; i < n; ++i) out[i] = i;
+  if (!prefilled)
+    for (int64_t i = 0; i < n; ++i) out[i] = i;
   return 0;
 }
 
@@ -124,19 +132,36 @@ int uml_randperm_advance(void* state, int64_t upto) {
 
 // The whole permutation, chunk by chunk, publishing the length of the final prefix after every chunk.  Meant to
 // be the body of a host thread (one C call, so a Python caller's interpreter lock is never needed in between).
-int uml_randperm_run(void* state, uint64_t seed, int64_t n, int64_t* out, int64_t chunk) {
+// `prefilled`: `out` already holds the identity.  `next_out` (optional): once this permutation is complete the
+// thread writes the identity into the NEXT epoch's buffer, so that epoch starts with the first swap instead of
+// a 10 MB fill (the seed of the next epoch is not known yet, the identity is).
+int uml_randperm_run(void* state, uint64_t seed, int64_t n, int64_t* out, int64_t chunk, int32_t prefilled,
+                     int64_t* next_out) {
   UML_REQUIRE(state && chunk > 0, "randperm_run: bad arguments");
   PermState& s = *static_cast<PermState*>(state);
   __atomic_store_n(&s.published, static_cast<int64_t>(0), __ATOMIC_RELEASE);
-  int rc = uml_randperm_begin(state, seed, n, out);
+  __atomic_store_n(&s.next_filled, static_cast<int64_t>(0), __ATOMIC_RELEASE);
+  int rc = randperm_begin(state, seed, n, out, prefilled != 0);
   int64_t upto = 0;
   while (rc == 0 && upto < n) {
     upto = upto + chunk < n ? upto + chunk : n;
     rc = uml_randperm_advance(state, upto);
     if (rc == 0) __atomic_store_n(&s.published, upto, __ATOMIC_RELEASE);
   }
-  if (rc != 0) __atomic_store_n(&s.published, static_cast<int64_t>(-1), __ATOMIC_RELEASE);
-  return rc;
+  if (rc != 0) {
+    __atomic_store_n(&s.published, static_cast<int64_t>(-1), __ATOMIC_RELEASE);
+    return rc;
+  }
+  if (next_out) {
+    for (int64_t i = 0; i < n; ++i) next_out[i] = i;
+    __atomic_store_n(&s.next_filled, static_cast<int64_t>(1), __ATOMIC_RELEASE);
+  }
+  return 0;
+}
+
+// 1 when the thread running uml_randperm_run on `state` has finished writing the identity into next_out
+int uml_randperm_next_filled(const void* state) {
+  return static_cast<int>(__atomic_load_n(&static_cast<const PermState*>(state)->next_filled, __ATOMIC_ACQUIRE));
 }
 
 // Blocks (yielding the core) until uml_randperm_run on another thread has made out[0..upto) final.

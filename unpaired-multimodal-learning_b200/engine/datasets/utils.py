@@ -212,12 +212,14 @@ class _EpochPerm:
 
     CHUNK = 32768
 
-    def __init__(self, seed: int, n: int, out: torch.Tensor, threaded: bool):
+    def __init__(self, seed: int, n: int, out: torch.Tensor, threaded: bool, prefilled: bool = False,
+                 next_out: Optional[torch.Tensor] = None):
         import ctypes as C
         import threading
         from ..._lib import check, load
         self.n, self.out = n, out
         self.ready = 0
+        self.next_out = None
         self._lib, self._check = load(), check
         if n >= (2 ** 32 - 1) // 20:  # torch switches to a 64-bit draw there; not a bank size this path sees
             out.copy_(torch.randperm(n, generator=torch.Generator().manual_seed(seed)))
@@ -233,8 +235,13 @@ class _EpochPerm:
         # never waits for the interpreter lock between chunks while the training loop runs Python code
         self._seed = seed & (2 ** 64 - 1)
         self._threaded = True
+        self.next_out = next_out  # the thread leaves the identity there for the next epoch (its seed is not known yet)
         threading.Thread(target=self._lib.uml_randperm_run, name="uml-sampler", daemon=True,
-                         args=(self._state, self._seed, n, out.data_ptr(), self.CHUNK)).start()
+                         args=(self._state, self._seed, n, out.data_ptr(), self.CHUNK, int(prefilled),
+                               next_out.data_ptr() if next_out is not None else None)).start()
+
+    def next_filled(self) -> bool:
+        return self.next_out is not None and bool(self._lib.uml_randperm_next_filled(self._state))
 
     def wait(self, upto: int):
         """Returns once out[0:upto] is final."""
@@ -275,6 +282,7 @@ class BankLoader:
         self.dataset = bank
         self.shard_of = shard_of
         self._seed_mix = 0 if shard_of is None else ((shard_of[0] + 1) * 0x9E3779B97F4A7C15) & (2 ** 63 - 1)
+        self._dev_ring, self._dev_turn = None, 0  # device copies of the permutation (large banks), alternating
         self._ring = None   # pinned permutation buffers (CUDA banks only), created at the first shuffled epoch
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
         self.async_min_rows = 65536  # permutations at least this long are produced by a sampler thread
@@ -313,21 +321,32 @@ class _BankIter:
         l = self.l
         if l._ring is not None and l._live is not None and l._live.perm_host is not None:
             l._ring.release(l._live.perm_host)  # the previous epoch's copies are all enqueued by now
-        buf = self._next_buffer()
         self.perm = None
         if l.generator is None:
             # Fresh generator seeded from the global stream: the native sampler restates torch.randperm for this
             # case bit-exactly (csrc/sampler.cu), straight into pinned memory, incrementally for large banks.
             seed = _draw_int64(None) ^ l._seed_mix
-            self.perm = _EpochPerm(seed, self.n, buf, threaded=self.n >= l.async_min_rows)
+            threaded = self.n >= l.async_min_rows
+            prev = l._live.perm if l._live is not None else None
+            if threaded and prev is not None and prev.next_filled():
+                buf, prefilled = prev.next_out, True  # the previous epoch's thread left the identity in this buffer
+            else:
+                buf, prefilled = self._next_buffer(), False
+            nxt = self._next_buffer() if threaded else None
+            self.perm = _EpochPerm(seed, self.n, buf, threaded, prefilled, nxt)
             self.perm_host = buf
         else:
-            self.perm_host = torch.randperm(self.n, generator=l.generator, out=buf)
+            self.perm_host = torch.randperm(self.n, generator=l.generator, out=self._next_buffer())
         l._live = self
         if l.upload == "epoch":
             if self.perm is not None and self.perm.ready < self.n:
-                # still being generated: the device copy is filled batch by batch as the prefix becomes final
-                self.perm_dev = torch.empty(self.n, dtype=torch.int64, device=l.bank.device)
+                # still being generated: the device copy is filled batch by batch as the prefix becomes final.
+                # Two device buffers per loader, alternating: a fresh 10 MB allocation at an epoch boundary can
+                # mean a cudaMalloc (milliseconds, synchronising); stream order makes the reuse safe.
+                if l._dev_ring is None:
+                    l._dev_ring = [torch.empty(self.n, dtype=torch.int64, device=l.bank.device) for _ in range(2)]
+                l._dev_turn ^= 1
+                self.perm_dev = l._dev_ring[l._dev_turn]
                 self.uploaded = 0
             else:
                 # asynchronous copy from pinned memory on the current stream: a pageable source would make the host
