@@ -387,17 +387,72 @@ def run_ours(args, wl, rank, world, dev):
                 h2d=(B + BT) * 8, d2h=2 * 4 * 4, loss_tail=loss_tail)
 
 
+def run_gaussian(args):
+    """--workload cfg1: the Gaussian_experiment step (train.yaml: dim_obs 50, dim_common 128, dim_latent 10, batch 512 per
+    modality, Adam 1e-3, mode xy) - a latency-bound two-launch step.  value/e2e: the public train_model_steps call
+    (sampler on the host, index batches uploaded per epoch, losses read back once); cpu_baseline: the oracle port."""
+    import types
+    from oracle import uml_oracle as O
+    from uml_b200 import _lib, gaussian as G
+
+    dev = torch.device("cuda", 0)
+    kw = dict(seed=42, num_samples=10000, dim_c=10, dim_x=5, dim_y=5, dim_obs=50, noise_std=0.09, attenuate_x=True,
+              attenuation=0.05, shared_latent_distribution_type="gaussian")
+    d = G.generate_data(kw)
+    dx, dy = d["x"][:5000], d["y"][:5000]
+    K, W, B = args.steps, args.warmup, 512
+    torch.manual_seed(0)
+    model = G.SharedAutoencoder(50, 128, 10, device=dev)
+    g = torch.Generator()
+    g.manual_seed(42)
+    loader = G.unpaired_loader(G.UnpairedDataset(dx, dy, dev), B, generator=g)
+    opt = G.Adam(model, lr=1e-3)
+    a = types.SimpleNamespace(mode="xy", alpha_x=1.0, alpha_y=1.0)
+    G.train_model_steps(model, loader, opt, W, args=a)
+    torch.cuda.synchronize()
+    n0 = _lib.LAUNCH_COUNT[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    hist = G.train_model_steps(model, loader, opt, K, args=a)  # ends with the D2H read of the K loss records
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    p = {k: v.cpu() for k, v in model.state_dict().items()}
+    t1 = time.perf_counter()
+    O.gaussian_train(p, dx, dy, num_steps=200, batch_size=B, lr=1e-3, mode="xy")
+    cpu = 200 * 2 * B / (time.perf_counter() - t1)
+    line = {"metric": "UML train samples/sec (img+text)", "value": K * 2 * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg1: Gaussian_experiment linear UML (train.yaml), x+y rows", "dim_obs": 50, "dim_common": 128,
+                       "dim_latent": 10, "batch_per_modality": B, "mode": "xy", "l2_policy": "working set (29 k parameters, 2 MB of data) lives in L2"},
+            "e2e": {"value": K * 2 * B / wall, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
+                    "note": "index permutation uploaded once per epoch (9 steps)"},
+            "gpu_launches": _lib.LAUNCH_COUNT[0] - n0, "final_losses": {"loss_x": hist["loss_x"][-1], "loss_y": hist["loss_y"][-1]},
+            "roofline": {"bound": "latency", "kernel": "gauss_fwd_bwd_kernel + gauss_update_kernel", "achieved": None, "peak": None,
+                         "unit": "us/step", "frac": None, "traffic": None},
+            "cpu_baseline": {"value": cpu, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "200 steps of the oracle port (fp32 torch ops on the host)"}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1"])
     ap.add_argument("--precision", type=str, default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "cfg1":
+        if args.impl == "reference" or not torch.cuda.is_available():
+            raise SystemExit("bench.py --workload cfg1 runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
+        return run_gaussian(args)
     wl = WORKLOADS[args.workload]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     peaks = measured_peaks()

@@ -245,6 +245,24 @@ int uml_dp_init(const void* id_128_bytes /*host*/, int32_t rank, int32_t world);
 int uml_dp_allreduce_f32(float* buf, int64_t n, void* stream);
 int uml_dp_shutdown(void);
 
+/* ---- a-14  linear analogue: Gaussian_experiment's SharedAutoencoder step (model.py:5-49, main.py:47-59) ------
+ * params: ONE flat fp32 buffer in the reference's construction order, weight then bias per layer:
+ *   in_head_x, in_head_y, shared_encoder.0, shared_encoder.2, shared_decoder.0, shared_decoder.2, out_head_x,
+ *   out_head_y   (uml_gauss_param_count floats).  data_x / data_y: [n, dim_obs] fp32; idx: the sampler's [batch]
+ * int64 indices (rows are idx % n_m, UnpairedDataset.__getitem__).  mode_xy != 0: loss = alpha_x MSE(x) +
+ * alpha_y MSE(y); else loss = MSE(x) and the y heads are left untouched.  Adam with torch's defaults semantics.
+ * loss_out[2] = {loss_x, loss_y} of this step (device).  These two return COUNTS, not a status:             */
+int uml_gauss_param_count(int32_t dim_obs, int32_t dim_common, int32_t dim_latent);
+int uml_gauss_workspace_floats(int32_t dim_obs, int32_t dim_common, int32_t dim_latent, int64_t batch);
+int uml_gauss_step(float* params, float* adam_m, float* adam_v, int32_t dim_obs, int32_t dim_common, int32_t dim_latent,
+                   const float* data_x, int64_t n_x, const float* data_y, int64_t n_y, const int64_t* idx, int64_t batch,
+                   int32_t mode_xy, float alpha_x, float alpha_y, double lr, double beta1, double beta2, double eps,
+                   int64_t step, float* workspace, float* loss_out, void* stream);
+/* validation forward (main.py:68-72): loss_out[2] = MSE of both modalities over n_rows dense rows          */
+int uml_gauss_eval(const float* params, int32_t dim_obs, int32_t dim_common, int32_t dim_latent, const float* data_x,
+                   const float* data_y, int64_t n_rows, float* workspace /* >= 2*ceil(n_rows/16) floats */,
+                   float* loss_out, void* stream);
+
 /* ---- sampler: the epoch permutation on the host, bit-exact with torch.randperm(n, generator=
  * torch.Generator().manual_seed(seed)) on the CPU - what RandomSampler draws once per epoch for the
  * DataLoaders of finetune.py:370-371 (MT19937 seeded with the low 32 bits of `seed`, Fisher-Yates

@@ -235,3 +235,16 @@ def test_incremental_randperm_prefixes_are_final():
             _lib.check(lib.uml_randperm_advance(state, upto))
             assert torch.equal(out[:upto], want[:upto]), (n, seed, upto)
         assert torch.equal(out, want)
+
+
+def test_gaussian_generate_data_is_bit_exact_with_the_reference():
+    """uml_b200.gaussian.generate_data (data.py:29-61) against tensors recorded from the reference."""
+    import ast
+    from uml_b200 import gaussian as G
+    cfg = ast.literal_eval(str(M["gauss/cfg"]))
+    base = dict(seed=cfg["seed"], num_samples=cfg["num_samples"], dim_c=cfg["dim_c"], dim_x=cfg["dim_x"], dim_y=cfg["dim_y"],
+                dim_obs=cfg["dim_obs"], noise_std=cfg["noise_std"], attenuate_x=True, attenuation=cfg["attenuation"])
+    d1 = G.generate_data(dict(base, shared_latent_distribution_type="gaussian"))
+    assert np.array_equal(d1["x"].numpy(), M["gauss/x"]) and np.array_equal(d1["y"].numpy(), M["gauss/y"])
+    d2 = G.generate_data(dict(base, seed=44, shared_latent_distribution_type="laplace"))
+    assert np.array_equal(d2["y"].numpy(), M["gauss/y_laplace"])

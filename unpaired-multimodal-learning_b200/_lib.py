@@ -93,6 +93,11 @@ PROTOTYPES = {
     "uml_dp_init": [c_vp, c_i32, c_i32],
     "uml_dp_allreduce_f32": [c_vp, c_i64, c_vp],
     "uml_dp_shutdown": [],
+    "uml_gauss_param_count": [c_i32, c_i32, c_i32],
+    "uml_gauss_workspace_floats": [c_i32, c_i32, c_i32, c_i64],
+    "uml_gauss_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_f32, c_f32,
+                       c_f64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp, c_vp],
+    "uml_gauss_eval": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
     "uml_randperm_begin": [c_vp, C.c_uint64, c_i64, c_vp],
     "uml_randperm_advance": [c_vp, c_i64],
@@ -106,7 +111,7 @@ _lib = None
 # kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {
     "uml_gather_rows_f32": 1, "uml_gather_rows_bf16": 1, "uml_gather_labels_i32": 1, "uml_cast_f32_to_bf16": 1,
-    "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1, "uml_gather2_rows_bf16_light": 1,
+    "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1, "uml_gather2_rows_bf16_light": 1, "uml_gauss_step": 2, "uml_gauss_eval": 2,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
     "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1,
     "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,
