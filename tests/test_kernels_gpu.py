@@ -394,3 +394,29 @@ def test_tc_gemm_layouts(case):
     torch.cuda.synchronize()
     assert torch.isfinite(got).all()
     assert (got - ref).abs().max().item() <= tol, (got - ref).abs().max().item()
+
+
+def test_grad_diagnostics_match_autograd():
+    """a-13: the engine's opt-in gradient probes against torch autograd on the CPU (finetune.py:190-206)."""
+    from uml_b200.engine.datasets.utils import FeatureBank, IndexBatch
+    from uml_b200.engine.models.head import UMLClip
+    from uml_b200.engine.optimizer.optim import build_optimizer
+    from uml_b200.engine.trainer import StepEngine
+    xi, yi, xt, yt, w, g = _mk(5, 300, 200, 64, 64, 37)
+    model = UMLClip("synthetic:64", 37, logit_scale_init=2.0)
+    model.head.weight.data.copy_(w)
+    model.to(DEV)
+    eng = StepEngine(model, build_optimizer(model.parameters(), "adamw", 1e-3, 0.0), DEV, 64, 64)
+    ii, ti = torch.randint(0, 300, (50,), generator=g), torch.randint(0, 200, (41,), generator=g)
+    ib, tb = FeatureBank(xi, yi, DEV), FeatureBank(xt, yt, DEV)
+    got = eng.grad_diagnostics(IndexBatch(ib, ii.to(DEV), 50, 0, ii), IndexBatch(tb, ti.to(DEV), 41, 0, ti))
+    W = w.clone().requires_grad_(True)
+    s = math.exp(2.0)
+    gi, = torch.autograd.grad(torch.nn.functional.cross_entropy(xi[ii] @ W.t() * s, yi[ii]), W)
+    gt, = torch.autograd.grad(torch.nn.functional.cross_entropy(xt[ti] @ W.t() * s, yt[ti]), W)
+    gi, gt = gi.flatten(), gt.flatten()
+    assert abs(got["train/img_grad_norm"] - float(gi.norm())) < 1e-4 * float(gi.norm())
+    assert abs(got["train/txt_grad_norm"] - float(gt.norm())) < 1e-4 * float(gt.norm())
+    assert abs(got["train/grad_direction_sim"] - float(torch.dot(gi, gt) / (gi.norm() * gt.norm()))) < 1e-4
+    assert abs(got["train/grad_agreement_rate"] - float((torch.sign(gi) == torch.sign(gt)).float().mean())) < 2e-3
+    assert torch.equal(model.head.weight.detach().cpu(), w)  # a probe: nothing was updated

@@ -562,6 +562,43 @@ class StepEngine:
                                     weight_decay=g["weight_decay"], betas=g["betas"], eps=g["eps"],
                                     decoupled=(self.opt.name == "adamw"), shadow=shadow)
 
+    def local_batches(self, pair):
+        """This rank's (image, text) rows of a step's pair of batches."""
+        rank = torch.distributed.get_rank() if self.world > 1 else 0
+        return _local(pair[0], rank, self.world), _local(pair[1], rank, self.world)
+
+    # ------------------------------------------------------------------------------------ diagnostics (a-13)
+    def grad_diagnostics(self, img: Optional[IndexBatch], txt: Optional[IndexBatch]):
+        """The reference's per-step gradient probes (finetune.py:190-191, 200-206) for one pair of batches at the
+        CURRENT weights: grad_img = d image_loss / d head.weight, grad_txt = d text_loss / d head.weight (each a
+        plain mean CE, no alpha), their cosine, norms and sign-agreement rate.  Opt-in and off the hot path: two
+        exact fp32 forward/dW passes, one per modality, then one reduction kernel; nothing is updated.  Returns
+        the reference's logger keys; one host read of 4 floats."""
+        if self.adapter:
+            raise NotImplementedError("gradient diagnostics are wired for the linear head")
+        W = self.W.data
+        rows = max(img.n if img is not None else 0, txt.n if txt is not None else 0, 1)
+        if getattr(self, "_diag", None) is None or self._diag[0].max_rows < rows:
+            self._diag = (ops.HeadWorkspace(rows, self.C, self.device), torch.zeros_like(W), torch.zeros_like(W),
+                          torch.empty(4 * 1024, device=self.device), torch.empty(4, device=self.device))
+        ws, g_img, g_txt, scratch, out4 = self._diag
+        s_i, s_t, sd_i, sd_t = self._scales()
+        for b, s, sd, g in ((img, s_i, sd_i, g_img), (txt, s_t, sd_t, g_txt)):
+            if b is None or b.n == 0:
+                g.zero_()
+                continue
+            feats, labels, idx = self._view(b)
+            run = [ops.Run(feats, labels, idx, b.n, s, 1.0, scale_dev=sd)]
+            ops.head_fwd_ce_f32(run, W, ws)
+            ops.head_bwd_dw_f32(run, W, ws, dW=g)
+        both = img is not None and txt is not None and img.n > 0 and txt.n > 0
+        ops.grad_diag(g_img, g_txt, scratch, out4)
+        dot, aa, bb, agree = out4.tolist()
+        ni, nt = aa ** 0.5, bb ** 0.5
+        return {"train/grad_direction_sim": dot / (ni * nt) if both and ni > 0 and nt > 0 else 0.0,
+                "train/img_grad_norm": ni, "train/txt_grad_norm": nt,
+                "train/grad_agreement_rate": agree / W.numel() if both else 0.0}
+
     # ------------------------------------------------------------------------------------ readback
     def copy_slot_to_host(self, slot):
         """Asynchronous D2H of one step's stats record into a pinned host ring (no host sync)."""

@@ -200,6 +200,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     # Steps are enqueued in chunks that end at the next evaluation point, so that the host issues ONE library
     # call per chunk instead of a Python round trip per kernel; the loaders are advanced in the reference's order
     # (image batch, then text batch, per step) so the sampler stream is unchanged.
+    grad_diag = bool(getattr(args, "grad_diagnostics", False) or (trace is not None and trace.get("grad_diagnostics")))
     per_step = trace is not None and bool(trace.get("record_weights"))
     # small chunks: the host prepares chunk c+1 (sampler draws, index uploads) while the GPU runs chunk c
     max_chunk = 1 if per_step else 8
@@ -250,6 +251,14 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
 
         if last_step % eval_freq == 0:
             flush()
+            if grad_diag:
+                # the reference's per-step gradient probes (finetune.py:190-206), here at evaluation cadence on the
+                # chunk's last batches and at the weights after that step
+                diag = engine.grad_diagnostics(*engine.local_batches(batches[-1]))
+                if trace is not None:
+                    trace.setdefault("grad_diag", []).append((last_step, diag))
+                if logger is not None:
+                    logger.log(dict(diag, iter=last_step))
             snapshot = {k: v.detach().clone() for k, v in model.state_dict().items()}
             _dbg("before validate")
             val_loss, val_acc = validate(model, val_loader, device=device)
