@@ -344,11 +344,11 @@ def run_ours(args, wl, rank, world, dev):
     ktimes = engine.kernel_times_ms()
     loss_tail = engine.read_log([W + K - 1])[0]
     # per-kernel breakdown of the step from a few extra (untimed) steps with every kernel bracketed
-    engine.prepare_profile(8)
-    for i in range(8):
-        step(W + K + i)
+    engine.prepare_profile(16)
+    step(W + K, 16)
     torch.cuda.synchronize()
     breakdown = engine.kernel_times_ms()
+    breakdown.update(engine.step_timeline_ms())
     del engine
     _stage("breakdown done")
 

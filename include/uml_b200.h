@@ -163,6 +163,17 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
 #define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 255) / 256) * 64 + (n_rows) * 16)
 /* per-run {mean loss, dscale, hits, rows} from the forward kernel's per-tile partials (fixed order)     */
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream);
+/* The same forward without its fix-up pass: G receives the unnormalised bf16 exp(l - m_running) and tile_ws the
+ * per-row normalisation factors; only valid as the producer of uml_head_bwd_dw_fix_bf16, which applies
+ * `G = G~ * factor - onehot * coef` to every operand stage in shared memory (the "softmax-minus-onehot term fused
+ * into the dW prologue") and reduces the per-run statistics into `stats` with an otherwise idle warp.        */
+int uml_head_fwd_ce_deferred_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                                  const int32_t* labels, const uml_tc_segments* segs /*host*/, uint16_t* G, int64_t ldg,
+                                  float* tile_ws, void* stream);
+int uml_head_bwd_dw_fix_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
+                             int32_t n_classes, float* partials, int32_t n_splits,
+                             const uml_tc_segments* segs /*host; NULL: G is already final (plain dW)*/,
+                             const int32_t* labels, const float* tile_ws, uml_seg_stats* stats /*nullable*/, void* stream);
 /* dW_partial[s] = (G^T X) over the s-th K split; partials: [n_splits, n_classes, dim] fp32.       */
 int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
                          int32_t n_classes, float* partials, int32_t n_splits, void* stream);
@@ -231,7 +242,7 @@ typedef struct {
   int64_t        opt_step;                       /* 1-based optimizer step of the head                        */
   int64_t        scale_step[UML_MAX_SEGMENTS];
   uml_seg_stats* stats;                          /* where this step's per-run results go                      */
-  void*          ev_fwd[2];                      /* optional cudaEvent_t pair around the forward kernel       */
+  void*          ev[8];                          /* optional cudaEvent_t pairs, as uml_linear_step_args.ev    */
 } uml_run_step;
 int uml_linear_run(const uml_linear_step_args* base /*host*/, const uml_run_step* steps /*host*/, int32_t n_steps,
                    void* stream);

@@ -47,11 +47,27 @@ Pipe* get_pipe() {
 // Where in step i the gather of step i+1 is enqueued.  Measured on B200 (cfg3, 2 x 18944 rows): at the START of the
 // step (it then shares the machine with the forward and, mostly, the bandwidth-bound fix-up) 0.1925 ms/step;
 // AFTER forward + fix-up (sharing with the dW GEMM, which streams both operands from HBM) 0.237 ms/step - slower
-// than no prefetch at all (0.207).  Default: start.  UML_PREFETCH_AT=1 selects the second placement.
-bool prefetch_after_forward() {
+// than no prefetch at all (0.207); right AFTER THE FORWARD KERNEL (sharing with fix-up, dW, update) 0.189 ms/step
+// with the forward kernel running undisturbed (67.5 us instead of 84 us).  UML_PREFETCH_AT = 0 | 1 | 2 selects
+// start / after fix-up / after the forward kernel (default 2).
+int prefetch_placement() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UML_PREFETCH_AT");
+    cached = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+  }
+  return cached;
+}
+
+// UML_FUSE_FIX=1: the deferred softmax normalisation is applied in the dW prologue (tc_gemm kFix: each G stage is
+// rescaled in shared memory between the TMA arrival and the MMA) instead of by a fix-up pass over G after the
+// forward kernel.  Bit-identical results, but measured SLOWER on B200 (cfg3): 0.231 vs 0.189 ms/step - the dW
+// GEMM with two MN-major operands already moves ~100 KB through shared memory per 950-cycle stage, the transform's
+// extra 32 KB per stage makes it shared-memory bound.  Default: the fix-up kernel.
+bool fuse_fix() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UML_FUSE_FIX");
     cached = (e && e[0] == '1') ? 1 : 0;
   }
   return cached == 1;
@@ -86,12 +102,13 @@ struct StepHooks {
   cudaEvent_t operand_free = nullptr;
   int (*mid)(void*) = nullptr;
   void* mid_arg = nullptr;
+  cudaEvent_t after_fwd_kernel = nullptr;  // placement 2: recorded between the forward kernel and its fix-up
 };
 static int linear_step_impl(const uml_linear_step_args* a, void* stream, const StepHooks& hooks);
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream);  // tc_fwd.cu
+                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2 = nullptr);  // tc_fwd.cu
 
 // data parallel tail of a step: sum dW over the ranks, then the optimizer update on every rank
 static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void* stream) {
@@ -125,8 +142,7 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     t.upd.lr = s.lr;
     t.upd.step = s.opt_step;
     t.stats = s.stats;
-    t.ev[2] = s.ev_fwd[0];
-    t.ev[3] = s.ev_fwd[1];
+    for (int k = 0; k < 8; ++k) t.ev[k] = s.ev[k];
   };
 
   // Gather prefetch: step i+1's rows are copied into the operand buffer step i does not use, on a low-priority
@@ -171,10 +187,11 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
       int32_t* l;
       cudaEvent_t wait_a, wait_b, ready;
       cudaStream_t main_st;
-      bool have;
+      bool have, record_mid;
     } next;
     next.pipe = pipe;
     next.have = i + 1 < n_steps;
+    next.record_mid = prefetch_placement() != 2;
     if (next.have) {
       next.nx = a;
       patch(next.nx, steps[i + 1]);
@@ -189,10 +206,11 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     hooks.pregathered = true;
     hooks.operand_free = pipe->freed[b];
     hooks.mid_arg = &next;
+    hooks.after_fwd_kernel = (prefetch_placement() == 2 && next.have) ? pipe->mid : nullptr;
     hooks.mid = [](void* p) -> int {
       Next* n = static_cast<Next*>(p);
       if (!n->have) return 0;
-      UML_CUDA(cudaEventRecord(n->pipe->mid, n->main_st));
+      if (n->record_mid) UML_CUDA(cudaEventRecord(n->pipe->mid, n->main_st));
       UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_a, 0));
       UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_b, 0));
       const int rc = shadow_gather(&n->nx, n->x, n->l, true, n->pipe->aux);
@@ -277,7 +295,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
       off += s.n;
     }
     rec(a->ev[1], stream);
-    if (hooks.mid && !prefetch_after_forward()) {
+    if (hooks.mid && prefetch_placement() == 0) {
       rc = hooks.mid(hooks.mid_arg);
       if (rc) return rc;
     }
@@ -287,10 +305,10 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
       // statistics) follows it
       rc = uml_head_fwd_ce_bf16_ev(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
                                    static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                   a->stats, a->ev[3], stream);
+                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, hooks.after_fwd_kernel);
       if (rc) return rc;
     }
-    if (hooks.mid && prefetch_after_forward()) {
+    if (hooks.mid && prefetch_placement() != 0) {
       rc = hooks.mid(hooks.mid_arg);
       if (rc) return rc;
     }
@@ -333,8 +351,25 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   int splits = uml_tc_dw_splits(total, a->dim, a->n_classes);
   if (splits > a->max_splits) splits = a->max_splits;
   rec(a->ev[4], stream);
-  rc = uml_head_bwd_dw_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes, a->partials,
-                            splits, stream);
+  if (fuse_fix()) {
+    // the forward skipped its fix-up pass: the dW prologue normalises every G stage in shared memory
+    uml_tc_segments ts2;
+    memset(&ts2, 0, sizeof(ts2));
+    for (int i = 0; i < a->nseg; ++i) {
+      const uml_segment& sg = a->seg[i];
+      if (sg.n == 0) continue;
+      ts2.seg_rows[ts2.nseg] = sg.n;
+      ts2.scale[ts2.nseg] = sg.scale;
+      ts2.loss_weight[ts2.nseg] = sg.loss_weight;
+      ts2.scale_dev[ts2.nseg] = sg.scale_dev;
+      ts2.nseg++;
+    }
+    rc = uml_head_bwd_dw_fix_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
+                                  a->partials, splits, &ts2, a->labels32, a->tile_ws, a->stats, stream);
+  } else {
+    rc = uml_head_bwd_dw_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes, a->partials,
+                              splits, stream);
+  }
   if (rc) return rc;
   rec(a->ev[5], stream);
   if (operand_free) UML_CUDA(cudaEventRecord(operand_free, as_stream(stream)));  // X16 / labels32 may be overwritten

@@ -597,7 +597,8 @@ __global__ void __launch_bounds__(1024)
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream);
+                            void* ev_after_fwd, void* stream, int defer_fixup = 0, void* ev_after_fwd2 = nullptr);
+int64_t uml_fwd_tiles(int64_t n_rows);
 
 extern "C" {
 
@@ -624,7 +625,7 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream) {
+                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && n_rows >= 0 && dim > 0 && n_classes > 0, "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
@@ -679,7 +680,8 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
                          static_cast<int>(dim), static_cast<int>(n_classes), labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg,
                          row_loss, row_pred, row_correct, row_dscale, tile_ws, fac));
   if (ev_after_fwd) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd), as_stream(stream)));
-  if (G) {
+  if (ev_after_fwd2) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd2), as_stream(stream)));
+  if (G && !defer_fixup) {
     const int row_blocks = static_cast<int>((n_rows + 7) / 8);
     const int stat_blocks = stats ? segs->nseg : 0;
     UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks)), dim3(256), 0, as_stream(stream), 1,
@@ -689,7 +691,23 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
   return 0;
 }
 
+// 128-row tiles the forward kernel writes per-tile partials for (its work units are pairs of tiles in CTA-pair mode)
+int64_t uml_fwd_tiles(int64_t n_rows) {
+  const int cg = uml::fwd_cta_group(n_rows);
+  return ((n_rows + uml::kFwdBlockM * cg - 1) / (uml::kFwdBlockM * cg)) * cg;
+}
+
 extern "C" {
+
+// Forward WITHOUT the fix-up pass: G receives the unnormalised exp(l - m_running) and tile_ws the per-row factors;
+// uml_head_bwd_dw_fix_bf16 finishes the normalisation in its prologue (and reduces the statistics).
+int uml_head_fwd_ce_deferred_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                                  const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg,
+                                  float* tile_ws, void* stream) {
+  UML_REQUIRE(G && tile_ws, "head_fwd_ce_deferred_bf16: G and tile_ws are required");
+  return uml_head_fwd_ce_bf16_ev(X, n_rows, dim, W, n_classes, labels, segs, G, ldg, nullptr, nullptr, nullptr, nullptr,
+                                 tile_ws, nullptr, nullptr, stream, 1);
+}
 
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream) {
   using namespace uml;

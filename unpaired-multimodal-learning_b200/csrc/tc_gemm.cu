@@ -20,6 +20,8 @@
 
 #include "common.cuh"
 
+int64_t uml_fwd_tiles(int64_t n_rows);  // tc_fwd.cu: 128-row tiles the forward kernel writes partials for
+
 namespace uml {
 
 constexpr int kGBlockK = 64;
@@ -39,10 +41,27 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
-template <bool kAMn, bool kBMn, bool kOutBf16, int kCG>
+// dW prologue (kFix): the A operand is the forward kernel's UNNORMALISED bf16 exp(l - m_running); the deferred
+// softmax normalisation and the one-hot term are applied to each A stage in shared memory, between the TMA
+// arrival and the MMA, by the four warps that are idle until the epilogue:
+//   G[b, c] = A[b, c] * fac[b][c / 64] - [c == y_b] * gcoef_b          (what g_fixup_kernel did in a pass over HBM/L2)
+struct FixArgs {
+  const float* fac;         // [rows, 16] per-row, per-64-class factors written by the forward kernel
+  const int32_t* labels;    // [rows]
+  int64_t n0;               // rows >= n0 belong to the second run
+  float gcoef[2];           // loss_weight / n * scale per run ...
+  float dcoef[2];           // ... or loss_weight / n, multiplied by *scale_dev[run] when that is set
+  const float* scale_dev[2];
+  const float* tile_part;   // forward kernel's per-tile partial statistics (reduced here by one idle warp)
+  int64_t n_tiles;
+  int nseg;
+  uml_seg_stats* stats;
+};
+
+template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
 __global__ void __launch_bounds__(256, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int64_t M,
-                   int64_t N, int64_t K, int n_splits, void* __restrict__ out_v, int64_t ldo) {
+                   int64_t N, int64_t K, int n_splits, void* __restrict__ out_v, int64_t ldo, FixArgs fix) {
   using Cfg = GemmCfg<kCG>;
   constexpr int kGStages = Cfg::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -50,7 +69,8 @@ __global__ void __launch_bounds__(256, 1)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + kGStages;
   uint64_t* tfull_bar = empty_bar + kGStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  uint64_t* ready_bar = tfull_bar + 1;  // kFix: stage transformed in BOTH CTAs of the pair (lives on the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready_bar + kGStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (kCG == 2) ? cluster_ctarank() : 0u;
@@ -68,8 +88,11 @@ __global__ void __launch_bounds__(256, 1)
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kGStages; ++s) {
-      mbar_init(&full_bar[s], kCG);  // one arrival per producer of the pair (tx bytes counted on the leader)
+      // plain: one arrival per producer of the pair, tx bytes counted on the leader.  kFix: every CTA tracks its
+      // OWN loads (its transform warps must know when its stage landed) and the MMA waits on ready_bar instead
+      mbar_init(&full_bar[s], kFix ? 1 : kCG);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&ready_bar[s], 4 * kCG);
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -96,7 +119,7 @@ __global__ void __launch_bounds__(256, 1)
         unsigned char* a = smem + s * Cfg::kStageBytes;
         unsigned char* b = a + Cfg::kABytes;
         const int32_t k0 = kb * kGBlockK;
-        if (kCG == 1) {
+        if (kCG == 1 || kFix) {
           mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
           if (kAMn) {
             tma_load_2d(a, &tmap_a, &full_bar[s], static_cast<int32_t>(m_cta), k0);
@@ -139,7 +162,7 @@ __global__ void __launch_bounds__(256, 1)
       uint32_t it = 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
         const uint32_t s = it % kGStages, ph = (it / kGStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(kFix ? &ready_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
         const uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -162,7 +185,94 @@ __global__ void __launch_bounds__(256, 1)
       else umma_commit(tfull_bar);
     }
     __syncwarp();
+  } else if (kFix && warp == 3) {
+    // ------------------------------------------------ per-run statistics (one idle warp of one CTA) ---------
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && fix.stats) {
+      for (int sgi = 0; sgi < fix.nseg; ++sgi) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t i = lane; i < fix.n_tiles * 4; i += 32) {
+          const float* p = fix.tile_part + (i * 2 + sgi) * 4;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[k] += p[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+          fix.stats[sgi].loss_mean = acc[3] > 0.f ? acc[0] / acc[3] : 0.f;
+          fix.stats[sgi].dscale = acc[1];
+          fix.stats[sgi].correct = static_cast<int32_t>(acc[2] + 0.5f);
+          fix.stats[sgi].n = static_cast<int32_t>(acc[3] + 0.5f);
+        }
+      }
+    }
   } else if (warp >= 4) {
+    if (kFix) {
+      // ---------------------------------------------- A-stage transform (see FixArgs) -----------------------
+      // thread -> (k row r of the stage, 64-class box b); a row is 128 B = 8 chunks of 16 B, chunk c of row r sits
+      // at physical chunk c ^ (r & 7) (SWIZZLE_128B): a quarter warp touches all 32 banks exactly once
+      const int t = threadIdx.x - 128, r = t & 63, b = t >> 6;
+      const int grp = static_cast<int>(m_cta / 64) + b;
+      const uint32_t lead_ready = kCG == 2 ? mapa_cta(smem_u32(&ready_bar[0]), 0) : 0u;
+      // per-row metadata (factor, one-hot coefficient, label position) is fetched ONE k-block ahead: an L2 round
+      // trip per stage on the transform's critical path made the whole GEMM twice as slow
+      auto load_meta = [&](int kb, float& f, float& gc, int& lc) {
+        const int64_t row = static_cast<int64_t>(kb) * kGBlockK + r;
+        f = 0.f; gc = 0.f; lc = -1;
+        if (kb < kb_hi && row < K) {
+          f = __ldg(fix.fac + row * 16 + grp);
+          const bool sg = row >= fix.n0;
+          const float* sd = sg ? fix.scale_dev[1] : fix.scale_dev[0];
+          gc = sd ? (sg ? fix.dcoef[1] : fix.dcoef[0]) * __ldg(sd) : (sg ? fix.gcoef[1] : fix.gcoef[0]);
+          lc = __ldg(fix.labels + row) - grp * 64;
+        }
+      };
+      float f_nx, gc_nx;
+      int lc_nx;
+      load_meta(kb_lo, f_nx, gc_nx, lc_nx);
+      uint32_t it = 0;
+      for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
+        const uint32_t s = it % kGStages, ph = (it / kGStages) & 1;
+        const bool live = static_cast<int64_t>(kb) * kGBlockK + r < K;
+        const float f = f_nx, gc = gc_nx;
+        const int lc = lc_nx;
+        load_meta(kb + 1, f_nx, gc_nx, lc_nx);
+        mbar_wait(&full_bar[s], ph);
+        if (live) {
+          unsigned char* rowp = smem + s * Cfg::kStageBytes + b * kGBoxBytes + r * 128;
+          uint4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const uint4*>(rowp + ((c ^ (r & 7)) << 4));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 p = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[i]));
+              p.x *= f;
+              p.y *= f;
+              __nv_bfloat162 h = __floats2bfloat162_rn(p.x, p.y);
+              w[i] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(rowp + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (lc >= 0 && lc < 64) {
+            // the one-hot term: G = G~ * f - coef, recomputed from the ORIGINAL element so that the rounding is the
+            // fix-up kernel's (multiply, subtract, one rounding)
+            const int c = lc >> 3, e = lc & 7;
+            const uint32_t word = (&v[c].x)[e >> 1];
+            const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&word));
+            const float val = ((e & 1) ? p.y : p.x) * f - gc;
+            reinterpret_cast<__nv_bfloat16*>(rowp + ((c ^ (r & 7)) << 4))[e] = __float2bfloat16_rn(val);
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          if (kCG == 2 && !leader) mbar_arrive_remote(lead_ready + s * 8);
+          else mbar_arrive(&ready_bar[s]);
+        }
+      }
+    }
     // ------------------------------------------------ epilogue (every CTA: its own 128 rows) ------
     const int q = warp - 4;
     const int64_t m = m_cta + q * 32 + lane;
@@ -246,11 +356,11 @@ static int gemm_splits(int64_t M, int64_t N, int64_t K, int cg) {
   return static_cast<int>(s);
 }
 
-template <bool kAMn, bool kBMn, bool kOutBf16, int kCG>
+template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
 static int launch_tc_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, int n_splits,
-                          void* out, int64_t ldo, cudaStream_t st) {
+                          void* out, int64_t ldo, cudaStream_t st, const FixArgs& fix = FixArgs()) {
   using Cfg = GemmCfg<kCG>;
-  auto kern = tc_gemm_kernel<kAMn, kBMn, kOutBf16, kCG>;
+  auto kern = tc_gemm_kernel<kAMn, kBMn, kOutBf16, kCG, kFix>;
   static bool attr_set = false;
   if (!attr_set) {
     UML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -258,12 +368,13 @@ static int launch_tc_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int64_t 
   }
   const dim3 grid(static_cast<unsigned>((M + Cfg::kTileM - 1) / Cfg::kTileM) * kCG,
                   static_cast<unsigned>((N + Cfg::kTileN - 1) / Cfg::kTileN), static_cast<unsigned>(n_splits));
-  UML_CUDA(launch_kernel(kern, grid, dim3(256), Cfg::kSmemBytes, st, kCG, true, ta, tb, M, N, K, n_splits, out, ldo));
+  UML_CUDA(launch_kernel(kern, grid, dim3(256), Cfg::kSmemBytes, st, kCG, true, ta, tb, M, N, K, n_splits, out, ldo, fix));
   return 0;
 }
 
 static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B, int64_t ldb, bool b_mn, int64_t M,
-                   int64_t N, int64_t K, void* out, int64_t ldo, bool out_bf16, int n_splits, cudaStream_t st) {
+                   int64_t N, int64_t K, void* out, int64_t ldo, bool out_bf16, int n_splits, cudaStream_t st,
+                   const FixArgs* fix = nullptr) {
   UML_REQUIRE(A && B && out && M > 0 && N > 0 && K > 0 && n_splits >= 1, "tc_gemm: bad arguments");
   UML_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "tc_gemm: leading dimensions must be multiples of 8 (16-byte bf16 rows)");
   UML_REQUIRE(!out_bf16 || n_splits == 1, "tc_gemm: split-K needs the fp32 partial output");
@@ -282,6 +393,11 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb * 2, 64, kGBlockK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   } else {
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, kGBlockK, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  if (fix) {
+    UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: the A-stage transform is instantiated for the dW layout only");
+    return cg == 2 ? launch_tc_gemm<true, true, false, 2, true>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
+                   : launch_tc_gemm<true, true, false, 1, true>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);
   }
 #define UML_GEMM_CASE(AM, BM, OB)                                                                              \
   if (a_mn == AM && b_mn == BM && out_bf16 == OB)                                                              \
@@ -317,6 +433,13 @@ int uml_tc_dw_splits(int64_t n_rows, int32_t dim, int32_t n_classes) {
 
 int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
                          int32_t n_classes, float* partials, int32_t n_splits, void* stream) {
+  return uml_head_bwd_dw_fix_bf16(G, ldg, X, n_rows, dim, n_classes, partials, n_splits, nullptr, nullptr, nullptr, nullptr,
+                                  stream);
+}
+
+int uml_head_bwd_dw_fix_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim,
+                             int32_t n_classes, float* partials, int32_t n_splits, const uml_tc_segments* segs,
+                             const int32_t* labels, const float* tile_ws, uml_seg_stats* stats, void* stream) {
   using namespace uml;
   UML_REQUIRE(G && X && partials && n_rows > 0 && dim > 0 && n_classes > 0 && n_splits >= 1,
               "head_bwd_dw_bf16: bad arguments");
@@ -324,7 +447,28 @@ int uml_head_bwd_dw_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int6
               "head_bwd_dw_bf16: dim must be a multiple of 8 and ldg a multiple of 64 >= n_classes");
   UML_REQUIRE((reinterpret_cast<uintptr_t>(partials) & 15u) == 0, "head_bwd_dw_bf16: partials must be 16B aligned");
   // dW[c,d] = sum_b G[b,c] X[b,d]: A = G stored [K=b, M=c], B = X stored [K=b, N=d]
-  return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream));
+  if (!segs)
+    return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream));
+  // G holds the forward kernel's unnormalised probabilities (defer_fixup): finish them in the prologue
+  UML_REQUIRE(labels && tile_ws && segs->nseg >= 1 && segs->nseg <= UML_MAX_SEGMENTS, "head_bwd_dw_fix_bf16: bad arguments");
+  const int64_t tiles = uml_fwd_tiles(n_rows);
+  FixArgs fx;
+  memset(&fx, 0, sizeof(fx));
+  fx.tile_part = tile_ws;
+  fx.fac = tile_ws + tiles * 32;
+  fx.labels = labels;
+  fx.n_tiles = tiles;
+  fx.nseg = segs->nseg;
+  fx.stats = stats;
+  fx.n0 = segs->nseg > 1 ? segs->seg_rows[0] : INT64_MAX;
+  for (int i = 0; i < 2; ++i) {
+    const int j = i < segs->nseg ? i : 0;
+    const double n = static_cast<double>(segs->seg_rows[j] > 0 ? segs->seg_rows[j] : 1);
+    fx.dcoef[i] = static_cast<float>(static_cast<double>(segs->loss_weight[j]) / n);
+    fx.gcoef[i] = fx.dcoef[i] * segs->scale[j];
+    fx.scale_dev[i] = segs->scale_dev[j];
+  }
+  return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
 }
 
 }  // extern "C"

@@ -23,6 +23,9 @@ import torch
 from .. import ops
 from .datasets.utils import IndexBatch, local_slice as _local_slice
 
+import os as _os
+
+_FUSE_FIX = _os.environ.get("UML_FUSE_FIX", "0") == "1"  # mirrors csrc/step.cu: fix-up fused into the dW prologue
 BF16_MIN_ROWS = 1024  # below this the step is launch-bound and the exact fp32 path is used
 
 
@@ -151,6 +154,21 @@ class StepEngine:
                 out[k] = sum(ts) / len(ts)
         return out
 
+    def step_timeline_ms(self):
+        """From a profiled run with every kernel bracketed: mean time between the END of one bracketed kernel and the
+        START of the next one on the stream (fix-up kernel + launch gaps fall in 'fwd_end->dw_start')."""
+        p = self.profile or {}
+        f, d, u = p.get("head_fwd_ce_bf16", []), p.get("head_bwd_dw_bf16", []), p.get("adamw_step_partials", [])
+        n = min(len(f), len(d), len(u))
+        if n < 2:
+            return {}
+        mean = lambda xs: sum(xs) / len(xs)
+        out = {"fwd_end->dw_start": mean([f[i][1].elapsed_time(d[i][0]) for i in range(n)]),
+               "dw_end->update_start": mean([d[i][1].elapsed_time(u[i][0]) for i in range(n)]),
+               "update_end->next_fwd_start": mean([u[i][1].elapsed_time(f[i + 1][0]) for i in range(n - 1)]),
+               "fwd_start->next_fwd_start": mean([f[i][0].elapsed_time(f[i + 1][0]) for i in range(n - 1)])}
+        return out
+
     def _scales(self):
         si, st = self.model.scales()
         if self.learnable:  # device scalars, read by the kernels; never synchronise to fetch them
@@ -258,7 +276,7 @@ class StepEngine:
         return a, k, scale_params
 
     def _kernels_per_step(self, k, bf16):
-        n = ((1 if self.shadow_banks else k) + 4 + (0 if self._w16_valid else 1)) if bf16 else 4
+        n = ((1 if self.shadow_banks else k) + (3 if _FUSE_FIX else 4) + (0 if self._w16_valid else 1)) if bf16 else 4
         return n + (k if self.learnable else 0) + (1 if self.world > 1 else 0)
 
     def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):
@@ -349,10 +367,13 @@ class StepEngine:
                 self.slot_modalities[slot] = (ig is not None, tg is not None)
                 rs.stats = self.stats_log[slot].data_ptr()
                 if self.profile is not None:
-                    nm = "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32"
-                    if not self.profile_only or nm in self.profile_only:
+                    names = ("gather_bf16", "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32",
+                             "head_bwd_dw_bf16" if bf16 else "head_bwd_dw_f32", "adamw_step_partials")
+                    for jn, nm in enumerate(names):
+                        if (not bf16 and jn in (0, 3)) or (self.profile_only and nm not in self.profile_only):
+                            continue
                         e0, e1 = self._event_pool.pop() if self._event_pool else self._new_event_pair()
-                        rs.ev_fwd[0], rs.ev_fwd[1] = e0.cuda_event, e1.cuda_event
+                        rs.ev[2 * jn], rs.ev[2 * jn + 1] = e0.cuda_event, e1.cuda_event
                         self.profile.setdefault(nm, []).append((e0, e1))
                 steps.append(rs)
                 m += 1
