@@ -263,7 +263,7 @@ def run_ours(args, wl, rank, world, dev):
 
     slow = [(0.0, -1), (0.0, -1)]  # slowest single fetch of the image / text loader and the step it happened at
     host_split = [0.0, 0.0]  # seconds in the loaders / in engine.run (host-side enqueue cost, reported on stderr)
-    CHUNK = 10  # iterations enqueued per library call (uml_linear_run), as finetune.train does
+    CHUNK = 16  # iterations enqueued per library call (uml_linear_run), as finetune.train does
 
     def step(i, n=1):
         """Enqueue iterations i .. i+n-1; returns the number of (global) rows they consume."""
@@ -313,9 +313,12 @@ def run_ours(args, wl, rank, world, dev):
         prof.enable()
     t_host0 = time.perf_counter()
     e0.record()
-    i = 0
+    i, ramp = 0, 2
     while i < K:
-        n = min(CHUNK, K - i)
+        # chunk sizes ramp up 2, 4, 8, ...: the queue is empty when the clock starts, and while the host prepares a
+        # chunk's batches the GPU only has the previous chunk to work on
+        n = min(CHUNK, ramp, K - i)
+        ramp *= 2
         rows += step(W + i, n)
         i += n
     e1.record()

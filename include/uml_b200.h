@@ -255,6 +255,22 @@ int uml_dp_unique_id(void* out_128_bytes /*host*/);
 int uml_dp_init(const void* id_128_bytes /*host*/, int32_t rank, int32_t world);
 int uml_dp_allreduce_f32(float* buf, int64_t n, void* stream);
 int uml_dp_shutdown(void);
+/* Two-shot all-reduce over NVLink peer memory for the head gradient (one node): every rank allocates an exchange
+ * block (uml_dp_p2p_alloc -> 64-byte CUDA IPC handle), the handles are all-gathered by the caller and opened with
+ * uml_dp_p2p_open; from then on a data-parallel step sums dW with ONE kernel per rank (peer loads of 1/world of
+ * the data, peer stores of the reduced slice, two flag round trips) instead of ncclAllReduce.  Deterministic and
+ * bit-identical on all ranks.  uml_dp_allreduce_p2p sums the ranks' input halves of the blocks into every rank's
+ * output half; uml_dp_p2p_failed() != 0 after a peer stopped answering (2 s watchdog, no hang).             */
+int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes /*host*/);
+int uml_dp_p2p_open(const void* handles /*host: world x 64 bytes, rank order*/, int32_t rank, int32_t world);
+int uml_dp_allreduce_p2p(int64_t n, void* stream);
+/* the whole data-parallel tail of a step in ONE kernel per rank: split-K sum of the local dW partials -> exchange
+ * over peer memory -> Adam/AdamW on every rank (+ bf16 shadow).  partials == NULL: the local sum already sits in
+ * the exchange block's input half.                                                                           */
+int uml_dp_fused_adam_update(const float* partials, int32_t n_splits, int64_t split_stride, int64_t n, float* p, float* m,
+                             float* v, double lr, double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                             int32_t decoupled, uint16_t* p_bf16, void* stream);
+int uml_dp_p2p_failed(void);
 
 /* ---- a-14  linear analogue: Gaussian_experiment's SharedAutoencoder step (model.py:5-49, main.py:47-59) ------
  * params: ONE flat fp32 buffer in the reference's construction order, weight then bias per layer:

@@ -110,17 +110,42 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
                             void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2 = nullptr);  // tc_fwd.cu
 
+float* uml_dp_p2p_input(int64_t n);   // dp.cu: this rank's exchange buffers of the peer-memory all-reduce (or NULL)
+float* uml_dp_p2p_output(int64_t n);
+
+// where the local gradient sum of a data-parallel step goes: straight into the peer-visible exchange buffer when
+// the NVLink all-reduce is set up, else into dW_out (NCCL reduces that in place)
+static float* dp_local_sum_target(const uml_linear_step_args* a, int64_t np) {
+  float* x = uml_dp_p2p_input(np);
+  return x ? x : a->dW_out;
+}
+
 // data parallel tail of a step: sum dW over the ranks, then the optimizer update on every rank
 static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void* stream) {
-  int rc = uml_dp_allreduce_f32(a->dW_out, np, stream);
+  int rc;
+  const float* grad = a->dW_out;
+  if (uml_dp_p2p_input(np)) {
+    if (a->upd.kind != 3) {  // exchange + Adam fused (the local sum already is in the exchange buffer)
+      rec(a->ev[6], stream);
+      rc = uml_dp_fused_adam_update(nullptr, 0, 0, np, a->W, a->upd.m, a->upd.v, a->upd.lr, a->upd.beta1, a->upd.beta2,
+                                    a->upd.eps, a->upd.weight_decay, a->upd.step, a->upd.kind == 1,
+                                    a->precision == 1 ? a->W16 : nullptr, stream);
+      rec(a->ev[7], stream);
+      return rc;
+    }
+    rc = uml_dp_allreduce_p2p(np, stream);
+    grad = uml_dp_p2p_output(np);
+  } else {
+    rc = uml_dp_allreduce_f32(a->dW_out, np, stream);
+  }
   if (rc) return rc;
   uint16_t* shadow = a->precision == 1 ? a->W16 : nullptr;
   rec(a->ev[6], stream);
   if (a->upd.kind == 3)
-    rc = uml_sgd_step(a->W, a->dW_out, nullptr, 0.f, a->upd.m, np, a->upd.lr, a->upd.momentum, a->upd.weight_decay,
+    rc = uml_sgd_step(a->W, grad, nullptr, 0.f, a->upd.m, np, a->upd.lr, a->upd.momentum, a->upd.weight_decay,
                       a->upd.step, shadow, stream);
   else
-    rc = uml_adamw_step(a->W, a->dW_out, nullptr, 0.f, a->upd.m, a->upd.v, np, a->upd.lr, a->upd.beta1, a->upd.beta2,
+    rc = uml_adamw_step(a->W, grad, nullptr, 0.f, a->upd.m, a->upd.v, np, a->upd.lr, a->upd.beta1, a->upd.beta2,
                         a->upd.eps, a->upd.weight_decay, a->upd.step, a->upd.kind == 1, shadow, stream);
   rec(a->ev[7], stream);
   return rc;
@@ -335,7 +360,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   const int64_t np_all = static_cast<int64_t>(a->n_classes) * a->dim;
   if (total == 0 && !dp) return 0;
   if (total == 0) {  // a rank without rows still takes part in the all-reduce, contributing zeros
-    UML_CUDA(cudaMemsetAsync(a->dW_out, 0, np_all * sizeof(float), as_stream(stream)));
+    UML_CUDA(cudaMemsetAsync(dp_local_sum_target(a, np_all), 0, np_all * sizeof(float), as_stream(stream)));
     return dp_reduce_and_update(a, np_all, stream);
   }
   if (a->precision == 0) {
@@ -343,7 +368,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     memset(&none, 0, sizeof(none));
     rec(a->ev[4], stream);
     rc = uml_head_bwd_dw_f32(a->seg, a->nseg, a->dim, static_cast<const float*>(a->G), a->ldg, a->n_classes, a->W,
-                             a->dW_out, fused ? &a->upd : &none, stream);
+                             dp ? dp_local_sum_target(a, np_all) : a->dW_out, fused ? &a->upd : &none, stream);
     rec(a->ev[5], stream);
     if (rc || !dp) return rc;
     return dp_reduce_and_update(a, np_all, stream);
@@ -375,7 +400,16 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   if (operand_free) UML_CUDA(cudaEventRecord(operand_free, as_stream(stream)));  // X16 / labels32 may be overwritten
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
   if (!fused) {
-    rc = uml_sum_partials(a->partials, splits, np, np, a->dW_out, stream);
+    if (dp && a->upd.kind != 3 && uml_dp_p2p_input(np)) {
+      // data parallel over NVLink peer memory: split-K sum + exchange + Adam in ONE kernel per rank
+      rec(a->ev[6], stream);
+      rc = uml_dp_fused_adam_update(a->partials, splits, np, np, a->W, a->upd.m, a->upd.v, a->upd.lr, a->upd.beta1,
+                                    a->upd.beta2, a->upd.eps, a->upd.weight_decay, a->upd.step, a->upd.kind == 1, a->W16,
+                                    stream);
+      rec(a->ev[7], stream);
+      return rc;
+    }
+    rc = uml_sum_partials(a->partials, splits, np, np, dp ? dp_local_sum_target(a, np) : a->dW_out, stream);
     if (rc || !dp) return rc;
     return dp_reduce_and_update(a, np, stream);
   }

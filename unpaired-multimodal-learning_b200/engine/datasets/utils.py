@@ -286,6 +286,7 @@ class BankLoader:
         self._ring = None   # pinned permutation buffers (CUDA banks only), created at the first shuffled epoch
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
         self.async_min_rows = 65536  # permutations at least this long are produced by a sampler thread
+        self._prepared = None        # shard mode: the next epoch's permutation, already being generated
 
     def __len__(self):
         n = len(self.bank)
@@ -325,16 +326,27 @@ class _BankIter:
         if l.generator is None:
             # Fresh generator seeded from the global stream: the native sampler restates torch.randperm for this
             # case bit-exactly (csrc/sampler.cu), straight into pinned memory, incrementally for large banks.
-            seed = _draw_int64(None) ^ l._seed_mix
             threaded = self.n >= l.async_min_rows
-            prev = l._live.perm if l._live is not None else None
-            if threaded and prev is not None and prev.next_filled():
-                buf, prefilled = prev.next_out, True  # the previous epoch's thread left the identity in this buffer
+            if l.shard_of is not None:
+                # Per-rank sampler: its seeding protocol is ours (the index stream is not the single-process
+                # reference's anyway), so the seed of epoch e+1 is drawn when epoch e STARTS and that permutation is
+                # generated in the background during epoch e - an epoch boundary then costs nothing, which matters
+                # when a shard's epoch is only a handful of steps long (8 GPUs: 4.7 steps).
+                self.perm, l._prepared = l._prepared, None
+                if self.perm is None:
+                    self.perm = _EpochPerm(_draw_int64(None) ^ l._seed_mix, self.n, self._next_buffer(), threaded)
+                l._prepared = _EpochPerm(_draw_int64(None) ^ l._seed_mix, self.n, self._next_buffer(), threaded)
+                self.perm_host = self.perm.out
             else:
-                buf, prefilled = self._next_buffer(), False
-            nxt = self._next_buffer() if threaded else None
-            self.perm = _EpochPerm(seed, self.n, buf, threaded, prefilled, nxt)
-            self.perm_host = buf
+                seed = _draw_int64(None)
+                prev = l._live.perm if l._live is not None else None
+                if threaded and prev is not None and prev.next_filled():
+                    buf, prefilled = prev.next_out, True  # the previous epoch's thread left the identity in this buffer
+                else:
+                    buf, prefilled = self._next_buffer(), False
+                nxt = self._next_buffer() if threaded else None
+                self.perm = _EpochPerm(seed, self.n, buf, threaded, prefilled, nxt)
+                self.perm_host = buf
         else:
             self.perm_host = torch.randperm(self.n, generator=l.generator, out=self._next_buffer())
         l._live = self

@@ -80,6 +80,34 @@ def ensure_dp_comm():
     _DP_READY = True
 
 
+_P2P_FLOATS = 0
+
+
+def ensure_dp_p2p(max_floats: int):
+    """Exchange blocks of the NVLink peer-memory all-reduce (csrc/dp.cu), sized for gradients of ``max_floats``:
+    allocate, all-gather the CUDA IPC handles through torch.distributed, open the peers.  UML_DP_P2P=0 keeps NCCL."""
+    global _P2P_FLOATS
+    import ctypes as C
+    import os
+    from .._lib import check, load
+    dist = torch.distributed
+    if os.environ.get("UML_DP_P2P", "1") == "0" or dist.get_backend() != "nccl" or max_floats <= _P2P_FLOATS:
+        return
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world > 16:
+        return
+    h = (C.c_ubyte * 64)()
+    check(load().uml_dp_p2p_alloc(int(max_floats), h))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.tensor(list(h), dtype=torch.uint8, device=dev)
+    allh = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+    check(load().uml_dp_p2p_open(C.c_char_p(raw), rank, world))
+    dist.barrier()
+    _P2P_FLOATS = int(max_floats)
+
+
 class StepEngine:
     def __init__(self, model, optimizer, device, max_img_rows: int, max_txt_rows: int, log_slots: int = 128,
                  precision: str = "auto", dist_group=None, world_size: int = 1):
@@ -97,6 +125,7 @@ class StepEngine:
             raise RuntimeError("StepEngine: the model must live on a CUDA device (no CPU path)")
         if self.world > 1:
             ensure_dp_comm()
+            ensure_dp_p2p(self.W.numel())
             # replicas must start from identical bits (they apply identical updates and are never re-synchronised)
             for prm in model.parameters():
                 torch.distributed.broadcast(prm.data, src=0)
@@ -277,7 +306,8 @@ class StepEngine:
 
     def _kernels_per_step(self, k, bf16):
         n = ((1 if self.shadow_banks else k) + (3 if _FUSE_FIX else 4) + (0 if self._w16_valid else 1)) if bf16 else 4
-        return n + (k if self.learnable else 0) + (1 if self.world > 1 else 0)
+        # data parallel: the fused peer-memory tail replaces the update launch; over NCCL: + split sum + all-reduce
+        return n + (k if self.learnable else 0) + (0 if self.world == 1 or _P2P_FLOATS else 2)
 
     def _step_single_call(self, img, txt, n_i, n_t, wi, wt, slot, bf16):
         """The whole iteration enqueued by uml_linear_step (csrc/step.cu): Python only fills a struct."""
