@@ -74,3 +74,31 @@ def test_two_rank_gradient_equals_single_process():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_per_rank_sharded_loaders_cover_their_shards_every_epoch():
+    """shard_bank + BankLoader(shard_of=...): equal strided shards, every epoch of a rank is a permutation of its
+    shard (with and without the sampler thread), ranks are decorrelated, batches carry the global row count."""
+    from uml_b200 import finetune as ft
+    from uml_b200.engine.datasets.utils import BankLoader, shard_bank
+    feats, labels = torch.arange(1003 * 2, dtype=torch.float32).view(1003, 2), torch.arange(1003)
+    for threshold in (16, 10 ** 9):
+        banks = [shard_bank(feats, labels, r, 4, "cpu") for r in range(4)]
+        assert all(len(b) == 250 for b in banks)
+        assert torch.equal(banks[1].labels, labels[1::4][:250])
+        torch.manual_seed(5)
+        loaders = [BankLoader(b, 64, shuffle=True, shard_of=(r, 4)) for r, b in enumerate(banks)]
+        for ld in loaders:
+            ld.async_min_rows = threshold
+        its, seen = [iter(ld) for ld in loaders], [[] for _ in loaders]
+        for _ in range(12):
+            for r, ld in enumerate(loaders):
+                b, its[r] = ft.fetch_next(ld, its[r])
+                assert b.global_n == b.n * 4
+                seen[r].append(b.host_idx.clone())
+        for r in range(4):
+            idx = torch.cat(seen[r])
+            for e in range(3):
+                assert sorted(idx[e * 250:(e + 1) * 250].tolist()) == list(range(250))
+            assert not torch.equal(idx[:250], idx[250:500])
+        assert not torch.equal(torch.cat(seen[0]), torch.cat(seen[1]))

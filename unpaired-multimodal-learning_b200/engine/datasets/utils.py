@@ -202,6 +202,34 @@ def _draw_int64(generator=None) -> int:
     return int(torch.empty((), dtype=torch.int64).random_(generator=generator).item())
 
 
+class _SamplerThread:
+    """One long-lived daemon thread that runs permutation jobs (each job is a single C call that releases the GIL).
+    Spawning a Python thread per epoch costs 0.1-0.2 ms of main-thread time - too much when an epoch is five
+    steps long (8-GPU shards)."""
+
+    _inst = None
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = cls()
+        return cls._inst
+
+    def __init__(self):
+        import queue
+        import threading
+        self.q = queue.SimpleQueue()
+        threading.Thread(target=self._loop, daemon=True, name="uml-sampler").start()
+
+    def _loop(self):
+        while True:
+            fn, args = self.q.get()
+            fn(*args)
+
+    def submit(self, fn, *args):
+        self.q.put((fn, args))
+
+
 class _EpochPerm:
     """One epoch's permutation, produced incrementally by uml_randperm_begin / uml_randperm_advance.
 
@@ -213,7 +241,7 @@ class _EpochPerm:
     CHUNK = 32768
 
     def __init__(self, seed: int, n: int, out: torch.Tensor, threaded: bool, prefilled: bool = False,
-                 next_out: Optional[torch.Tensor] = None):
+                 next_out: Optional[torch.Tensor] = None, queued: bool = False):
         import ctypes as C
         import threading
         from ..._lib import check, load
@@ -236,9 +264,12 @@ class _EpochPerm:
         self._seed = seed & (2 ** 64 - 1)
         self._threaded = True
         self.next_out = next_out  # the thread leaves the identity there for the next epoch (its seed is not known yet)
-        threading.Thread(target=self._lib.uml_randperm_run, name="uml-sampler", daemon=True,
-                         args=(self._state, self._seed, n, out.data_ptr(), self.CHUNK, int(prefilled),
-                               next_out.data_ptr() if next_out is not None else None)).start()
+        args = (self._state, self._seed, n, out.data_ptr(), self.CHUNK, int(prefilled),
+                next_out.data_ptr() if next_out is not None else None)
+        if queued:   # shard mode: jobs are prepared an epoch ahead, FIFO order on one persistent thread is fine
+            _SamplerThread.get().submit(self._lib.uml_randperm_run, *args)
+        else:        # the training loop waits for this one right away: its own thread, never queued behind another
+            threading.Thread(target=self._lib.uml_randperm_run, name="uml-sampler", daemon=True, args=args).start()
 
     def next_filled(self) -> bool:
         return self.next_out is not None and bool(self._lib.uml_randperm_next_filled(self._state))
@@ -287,10 +318,19 @@ class BankLoader:
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
         self.async_min_rows = 65536  # permutations at least this long are produced by a sampler thread
         self._prepared = None        # shard mode: the next epoch's permutation, already being generated
+        self._shard_base, self._shard_epoch = 0, 0
 
     def __len__(self):
         n = len(self.bank)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def _shard_seed(self) -> int:
+        """Seed of the next epoch of a per-rank loader: splitmix64 of (base, epoch counter)."""
+        self._shard_epoch += 1
+        z = (self._shard_base + 0x9E3779B97F4A7C15 * self._shard_epoch) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+        return (z ^ (z >> 31)) & (2 ** 63 - 1)
 
     def __iter__(self):
         return _BankIter(self)
@@ -306,7 +346,8 @@ class _BankIter:
         self.perm = None
         self.uploaded = 0
         self.tail_drawn = False
-        _draw_int64(loader.generator)  # base seed
+        if loader.shard_of is None:
+            _draw_int64(loader.generator)  # base seed (the reference DataLoader's protocol)
         if loader.shuffle and loader.num_workers > 0:
             self._draw()
 
@@ -334,8 +375,9 @@ class _BankIter:
                 # when a shard's epoch is only a handful of steps long (8 GPUs: 4.7 steps).
                 self.perm, l._prepared = l._prepared, None
                 if self.perm is None:
-                    self.perm = _EpochPerm(_draw_int64(None) ^ l._seed_mix, self.n, self._next_buffer(), threaded)
-                l._prepared = _EpochPerm(_draw_int64(None) ^ l._seed_mix, self.n, self._next_buffer(), threaded)
+                    l._shard_base = _draw_int64(None) ^ l._seed_mix  # ONE draw from the global generator per loader
+                    self.perm = _EpochPerm(l._shard_seed(), self.n, self._next_buffer(), threaded)
+                l._prepared = _EpochPerm(l._shard_seed(), self.n, self._next_buffer(), threaded, queued=True)
                 self.perm_host = self.perm.out
             else:
                 seed = _draw_int64(None)
