@@ -377,16 +377,22 @@ def run_ours(args, wl, rank, world, dev):
 
     import contextlib
     import io
+    # The timed region of one call is only ~10 ms long, so a single host hiccup (page faults of a fresh pinned ring,
+    # a scheduler preemption) can halve it: the call is repeated and the MEDIAN reported, all values kept.
+    e2e_all = []
     with contextlib.redirect_stdout(io.StringIO()):
-        dt, e2e_rows = e2e_run(max(W, 3), K)
-    if dist:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
+        for _ in range(3):
+            dt_i, e2e_rows = e2e_run(max(W, 3), K)
+            if dist:
+                t = torch.tensor([dt_i], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_i = float(t.item())
+            e2e_all.append(dt_i)
+    dt = sorted(e2e_all)[1]
     _stage("e2e done")
     e2e_value = e2e_rows / dt  # global rows (every rank walks the same global batches) over the slowest rank's time
     return dict(ms=ms, rows=rows, launches=launches, clocks=clocks, ktimes=ktimes, e2e_value=e2e_value,
-                host_ms=host_ms, breakdown=breakdown,
+                host_ms=host_ms, breakdown=breakdown, e2e_all=[e2e_rows / x for x in e2e_all],
                 h2d=(B + BT) * 8, d2h=2 * 4 * 4, loss_tail=loss_tail)
 
 
@@ -526,7 +532,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if used_bf16 else "f32", "data": "synthetic",
                 "config": config, "clocks": res["clocks"],
                 "e2e": {"value": res["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": res["h2d"],
-                        "d2h_bytes_per_step": res["d2h"]},
+                        "d2h_bytes_per_step": res["d2h"], "stat": "median of 3 train() calls",
+                        "all": [round(x) for x in res["e2e_all"]]},
                 "gpu_launches": res["launches"], "host_enqueue_ms_per_step": res["host_ms"], "roofline": roof,
                 "step_tensor_frac": {"achieved_tflops_per_gpu": step_flops / (res["ms"] / K * 1e-3) / 1e12,
                                      "of_sustained_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_sustained"],
