@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gather.cuh"
 
 namespace uml {
 
@@ -105,13 +106,6 @@ __global__ void gather_labels_kernel(const int64_t* __restrict__ labels, const i
 // is the one whose stores were committed at `it - 1`, so one store group may stay in flight.
 constexpr int kCopyStagesFull = 4;   // stand-alone launch: 4 x 48 KB
 constexpr int kCopyStagesLight = 3;  // side-stream launch next to a GEMM CTA: 3 x <= 9 KB
-
-struct CopySeg {
-  const unsigned char* bank;   // row-major, row_bytes per row
-  const int64_t* idx;          // gather indices (required)
-  const int64_t* labels;       // bank labels (int64) or nullptr
-  int64_t n;
-};
 
 template <int kCopyStages>
 __global__ void __launch_bounds__(32)
@@ -216,31 +210,9 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
     gather_direct2_kernel(CopySeg s0, CopySeg s1, int vec_per_row, uint4* __restrict__ out, int64_t out_pitch_vec,
                           int32_t* __restrict__ out_labels) {
-  const int64_t n = s0.n + s1.n;
-  const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t r = warp; r < n; r += n_warps) {
-    const bool second = r >= s0.n;
-    const CopySeg& sg = second ? s1 : s0;
-    const int64_t src = __ldg(sg.idx + (second ? r - s0.n : r));
-    const uint4* row = reinterpret_cast<const uint4*>(sg.bank) + src * vec_per_row;
-    uint4* dst = out + r * out_pitch_vec;
-    if (lane == 0 && out_labels) out_labels[r] = static_cast<int32_t>(__ldg(sg.labels + src));
-    for (int v0 = 0; v0 < vec_per_row; v0 += 128) {
-      uint4 x[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int v = v0 + j * 32 + lane;
-        if (v < vec_per_row) x[j] = __ldcs(row + v);  // streamed: a bank row is read once per epoch
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int v = v0 + j * 32 + lane;
-        if (v < vec_per_row) dst[v] = x[j];
-      }
-    }
-  }
+  gather_rows_by_warp(s0, s1, vec_per_row, out, out_pitch_vec, out_labels, warp, n_warps);
 }
 
 template <bool kBf16>

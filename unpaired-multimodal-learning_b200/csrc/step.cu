@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gather.cuh"
 
 namespace {
 inline void rec(void* ev, void* stream) {
@@ -49,12 +50,14 @@ Pipe* get_pipe() {
 // AFTER forward + fix-up (sharing with the dW GEMM, which streams both operands from HBM) 0.237 ms/step - slower
 // than no prefetch at all (0.207); right AFTER THE FORWARD KERNEL (sharing with fix-up, dW, update) 0.189 ms/step
 // with the forward kernel running undisturbed (67.5 us instead of 84 us).  UML_PREFETCH_AT = 0 | 1 | 2 selects
-// start / after fix-up / after the forward kernel (default 2).
+// start / after fix-up / after the forward kernel (default 2).  Placement 3 needs no side stream: the copy of step
+// i+1's rows rides in step i's fix-up launch as extra, interleaved CTAs - measured 0.1936 ms/step against 0.1862 for
+// placement 2 (two bandwidth-bound jobs in one launch just add up: 49.7 us for the launch instead of 24.5 us).
 int prefetch_placement() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UML_PREFETCH_AT");
-    cached = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    cached = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
   }
   return cached;
 }
@@ -106,12 +109,14 @@ struct StepHooks {
   int (*mid)(void*) = nullptr;
   void* mid_arg = nullptr;
   cudaEvent_t after_fwd_kernel = nullptr;  // placement 2: recorded between the forward kernel and its fix-up
+  const uml::GatherJob* merged = nullptr;  // placement 3: the fix-up launch also copies the NEXT step's rows
 };
 static int linear_step_impl(const uml_linear_step_args* a, void* stream, const StepHooks& hooks);
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2 = nullptr);  // tc_fwd.cu
+                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2 = nullptr,
+                            const uml::GatherJob* job = nullptr);  // tc_fwd.cu
 
 float* uml_dp_p2p_input(int64_t n);   // dp.cu: this rank's exchange buffers of the peer-memory all-reduce (or NULL)
 float* uml_dp_p2p_output(int64_t n);
@@ -205,7 +210,7 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     if (i == 0) {
       const int rc = shadow_gather(&a, xbuf[0], lbuf[0], false, stream);
       if (rc) return rc;
-    } else {
+    } else if (prefetch_placement() != 3 || fuse_fix()) {
       UML_CUDA(cudaStreamWaitEvent(main_st, pipe->ready[b], 0));
     }
     struct Next {
@@ -233,6 +238,28 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     StepHooks hooks;
     hooks.pregathered = true;
     hooks.operand_free = pipe->freed[b];
+    GatherJob gjob;
+    memset(&gjob, 0, sizeof(gjob));
+    const bool merged = prefetch_placement() == 3 && !fuse_fix();
+    if (merged) {
+      if (next.have) {
+        const uml_segment* g[2] = {nullptr, nullptr};
+        int ng = 0;
+        for (int k = 0; k < next.nx.nseg; ++k)
+          if (next.nx.seg[k].n > 0) g[ng++] = &next.nx.seg[k];
+        if (ng > 0) {
+          gjob.s0 = CopySeg{reinterpret_cast<const unsigned char*>(g[0]->rows16), g[0]->idx, g[0]->labels, g[0]->n};
+          if (ng > 1) gjob.s1 = CopySeg{reinterpret_cast<const unsigned char*>(g[1]->rows16), g[1]->idx, g[1]->labels, g[1]->n};
+          gjob.vec_per_row = a.dim / 8;
+          gjob.out = reinterpret_cast<uint4*>(next.x);
+          gjob.out_pitch_vec = a.dim / 8;
+          gjob.out_labels = next.l;
+          gjob.blocks = 4 * sm_count();
+          hooks.merged = &gjob;
+        }
+      }
+      next.have = false;  // nothing for the side stream to do
+    }
     hooks.mid_arg = &next;
     hooks.after_fwd_kernel = (prefetch_placement() == 2 && next.have) ? pipe->mid : nullptr;
     hooks.mid = [](void* p) -> int {
@@ -333,7 +360,15 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
       // statistics) follows it
       rc = uml_head_fwd_ce_bf16_ev(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
                                    static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, hooks.after_fwd_kernel);
+                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, hooks.after_fwd_kernel,
+                                   fuse_fix() ? nullptr : hooks.merged);
+      if (rc) return rc;
+    } else if (hooks.merged) {
+      // no rows on this rank this step, hence no fix-up launch to ride in: copy the next step's rows directly
+      const GatherJob& j = *hooks.merged;
+      rc = uml_gather2_rows_bf16_light(reinterpret_cast<const uint16_t*>(j.s0.bank), j.s0.labels, j.s0.idx, j.s0.n,
+                                       reinterpret_cast<const uint16_t*>(j.s1.bank), j.s1.labels, j.s1.idx, j.s1.n, a->dim,
+                                       reinterpret_cast<uint16_t*>(j.out), a->dim, j.out_labels, stream);
       if (rc) return rc;
     }
     if (hooks.mid && prefetch_placement() != 0) {

@@ -28,6 +28,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "gather.cuh"
 
 namespace uml {
 
@@ -524,14 +525,28 @@ __device__ void tile_stats_block(const float* __restrict__ tile_part, int64_t n_
 __global__ void __launch_bounds__(256)
     g_fixup_kernel(__nv_bfloat16* __restrict__ G, int64_t ldg, int64_t n_rows, const int32_t* __restrict__ labels,
                    const float* __restrict__ fac, FwdSegs segs, const float* __restrict__ tile_part, int64_t n_tiles,
-                   int row_blocks, uml_seg_stats* __restrict__ stats) {
+                   int row_blocks, int stat_blocks, uml_seg_stats* __restrict__ stats, GatherJob job) {
   pdl_trigger();
   pdl_wait();
-  if (static_cast<int>(blockIdx.x) >= row_blocks) {
-    tile_stats_block(tile_part, n_tiles, static_cast<int>(blockIdx.x) - row_blocks, stats);
+  // CTA roles: [0, stat_blocks) reduce the statistics; the rest are fix-up CTAs with, every (R+1)-th, a CTA that
+  // copies rows of the NEXT step's operand (job.blocks of them, interleaved so both kinds run from the start)
+  if (static_cast<int>(blockIdx.x) < stat_blocks) {
+    tile_stats_block(tile_part, n_tiles, static_cast<int>(blockIdx.x), stats);
     return;
   }
-  const int64_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  int j = static_cast<int>(blockIdx.x) - stat_blocks;
+  if (job.blocks > 0) {
+    const int R = row_blocks / job.blocks > 0 ? row_blocks / job.blocks : 1;
+    const int k = j / (R + 1), r = j - k * (R + 1);
+    if (r == R && k < job.blocks) {
+      gather_rows_by_warp(job.s0, job.s1, job.vec_per_row, job.out, job.out_pitch_vec, job.out_labels,
+                          static_cast<int64_t>(k) * 8 + (threadIdx.x >> 5), static_cast<int64_t>(job.blocks) * 8);
+      return;
+    }
+    j -= k < job.blocks ? k : job.blocks;
+  }
+  if (j >= row_blocks) return;
+  const int64_t row = static_cast<int64_t>(j) * 8 + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
   const int label = labels[row];
@@ -597,7 +612,8 @@ __global__ void __launch_bounds__(1024)
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream, int defer_fixup = 0, void* ev_after_fwd2 = nullptr);
+                            void* ev_after_fwd, void* stream, int defer_fixup = 0, void* ev_after_fwd2 = nullptr,
+                            const uml::GatherJob* job = nullptr);
 int64_t uml_fwd_tiles(int64_t n_rows);
 
 extern "C" {
@@ -625,7 +641,7 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2) {
+                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2, const uml::GatherJob* job) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && n_rows >= 0 && dim > 0 && n_classes > 0, "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
@@ -684,9 +700,14 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
   if (G && !defer_fixup) {
     const int row_blocks = static_cast<int>((n_rows + 7) / 8);
     const int stat_blocks = stats ? segs->nseg : 0;
-    UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks)), dim3(256), 0, as_stream(stream), 1,
-                           true, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels, static_cast<const float*>(fac), fs,
-                           static_cast<const float*>(tile_ws), units * cg, row_blocks, stats));
+    GatherJob gj;
+    memset(&gj, 0, sizeof(gj));
+    if (job) gj = *job;
+    if (gj.blocks > row_blocks) gj.blocks = row_blocks;
+    UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks + gj.blocks)), dim3(256), 0,
+                           as_stream(stream), 1, true, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels,
+                           static_cast<const float*>(fac), fs, static_cast<const float*>(tile_ws), units * cg, row_blocks,
+                           stat_blocks, stats, gj));
   }
   return 0;
 }
