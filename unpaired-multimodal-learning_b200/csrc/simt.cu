@@ -94,9 +94,10 @@ __device__ __forceinline__ void apply_update(const DeviceUpdate& u, float* p, in
 //   A_K: A(m,k) = rowA(m)[k]   else A(m,k) = rowA(k)[m]
 //   B_K: B(k,n) = rowB(n)[k]   else B(k,n) = rowB(k)[n]
 // -------------------------------------------------------------------------------------------------
-constexpr int kBK = 16;
-
-template <int BM, int BN, bool A_K, bool B_K>
+// kBK: depth of a staged k-tile.  The small-tile instantiation (reference batch sizes: a 64 x 1000 x 512 forward
+// is 64 CTAs of 32 x 32) is bound by the latency of one dependent global-load -> shared -> sync round per k-tile,
+// not by FMAs, so it stages 64 deep (8 rounds instead of 32 for D = 512).
+template <int BM, int BN, bool A_K, bool B_K, int kBK = 16>
 __global__ void __launch_bounds__(256)
     sgemm_kernel(RowSrc A, RowSrc B, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha,
                  float* __restrict__ P, DeviceUpdate upd) {
@@ -183,7 +184,7 @@ static int launch_sgemm(const RowSrc& A, const RowSrc& B, float* C, int64_t ldc,
     sgemm_kernel<64, 64, A_K, B_K><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd);
   } else {
     dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((M + 31) / 32));
-    sgemm_kernel<32, 32, A_K, B_K><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd);
+    sgemm_kernel<32, 32, A_K, B_K, 64><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd);
   }
   UML_CUDA(cudaGetLastError());
   return 0;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(256)
     eval_kernel(const float* __restrict__ X, int64_t ldx, const int64_t* __restrict__ labels, int64_t n_rows, int D,
                 const float* __restrict__ W, int C, float scale, float* __restrict__ row_loss,
                 int32_t* __restrict__ row_pred) {
-  constexpr int BM = 32, BN = 64, TM = 2, TN = 4;
+  constexpr int BM = 32, BN = 64, TM = 2, TN = 4, kBK = 16;
   __shared__ float Xs[kBK][BM + 4];
   __shared__ float Ws[kBK][BN + 4];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
