@@ -87,7 +87,9 @@ int uml_cast_f32_to_bf16(const float* src, uint16_t* dst, int64_t n, void* strea
 int uml_head_fwd_ce_f32(const uml_segment* segs /*host*/, int32_t nseg, int32_t dim,
                         const float* W, int32_t n_classes, float* G, int64_t ldg,
                         float* row_loss, int32_t* row_correct, float* row_dscale,
-                        uml_seg_stats* stats, void* stream);
+                        uml_seg_stats* stats, int64_t g_capacity_rows /* rows G has room for; >= 2x the step's rows lets small
+                           batches split the contraction over planes of G (0 = exactly the step's rows) */,
+                        void* stream);
 
 /* ---- K4  dW = G^T X (autograd of the above; finetune.py:190-193), optionally fused with the
  *          optimizer update so the gradient never round-trips HBM -------------------------------- */
@@ -227,6 +229,7 @@ typedef struct {
   /* optional second operand buffers: with them uml_linear_run gathers step i+1's rows (into the buffer step i
    * does not use) on a side stream while step i's GEMMs run                                                  */
   uint16_t*     X16_alt;  int32_t* labels32_alt;
+  int64_t       g_capacity_rows;            /* rows the G workspace has room for (fp32 path: split-K planes); 0 = rows */
 } uml_linear_step_args;
 
 int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);

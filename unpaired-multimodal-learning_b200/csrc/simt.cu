@@ -100,8 +100,15 @@ __device__ __forceinline__ void apply_update(const DeviceUpdate& u, float* p, in
 template <int BM, int BN, bool A_K, bool B_K, int kBK = 16>
 __global__ void __launch_bounds__(256)
     sgemm_kernel(RowSrc A, RowSrc B, float* __restrict__ C, int64_t ldc, int64_t M, int64_t N, int64_t K, float alpha,
-                 float* __restrict__ P, DeviceUpdate upd) {
+                 float* __restrict__ P, DeviceUpdate upd, int64_t plane) {
   constexpr int TM = BM / 16, TN = BN / 16;
+  // split-K over gridDim.z: split z sums k in [k_lo, k_hi) into its own output plane (C + z * plane); the consumer
+  // adds the planes in a fixed order.  Used by the small-batch forward, where 64 CTAs would leave half the SMs idle.
+  const int64_t k_tiles = (K + kBK - 1) / kBK;
+  const int64_t k_lo = (k_tiles * blockIdx.z / gridDim.z) * kBK;
+  const int64_t k_hi_raw = (k_tiles * (blockIdx.z + 1) / gridDim.z) * kBK;
+  const int64_t k_hi = k_hi_raw < K ? k_hi_raw : K;
+  if (C) C += blockIdx.z * plane;
   __shared__ float As[kBK][BM + 4];
   __shared__ float Bs[kBK][BN + 4];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -112,20 +119,20 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  for (int64_t k0 = 0; k0 < K; k0 += kBK) {
+  for (int64_t k0 = k_lo; k0 < k_hi; k0 += kBK) {
     // ---- stage A tile: BM x kBK ----
     if (A_K) {
       for (int e = t; e < BM * kBK; e += 256) {
         const int m = e / kBK, k = e % kBK;
         float x = 0.f;
-        if (m0 + m < M && k0 + k < K) x = A.row(m0 + m)[k0 + k];
+        if (m0 + m < M && k0 + k < k_hi) x = A.row(m0 + m)[k0 + k];
         As[k][m] = x;
       }
     } else {
       for (int e = t; e < BM * kBK; e += 256) {
         const int k = e / BM, m = e % BM;
         float x = 0.f;
-        if (m0 + m < M && k0 + k < K) x = A.row(k0 + k)[m0 + m];
+        if (m0 + m < M && k0 + k < k_hi) x = A.row(k0 + k)[m0 + m];
         As[k][m] = x;
       }
     }
@@ -133,14 +140,14 @@ __global__ void __launch_bounds__(256)
       for (int e = t; e < BN * kBK; e += 256) {
         const int n = e / kBK, k = e % kBK;
         float x = 0.f;
-        if (n0 + n < N && k0 + k < K) x = B.row(n0 + n)[k0 + k];
+        if (n0 + n < N && k0 + k < k_hi) x = B.row(n0 + n)[k0 + k];
         Bs[k][n] = x;
       }
     } else {
       for (int e = t; e < BN * kBK; e += 256) {
         const int k = e / BN, n = e % BN;
         float x = 0.f;
-        if (n0 + n < N && k0 + k < K) x = B.row(k0 + k)[n0 + n];
+        if (n0 + n < N && k0 + k < k_hi) x = B.row(k0 + k)[n0 + n];
         Bs[k][n] = x;
       }
     }
@@ -176,15 +183,17 @@ __global__ void __launch_bounds__(256)
 
 template <bool A_K, bool B_K>
 static int launch_sgemm(const RowSrc& A, const RowSrc& B, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                        float alpha, float* P, const DeviceUpdate& upd, cudaStream_t st) {
+                        float alpha, float* P, const DeviceUpdate& upd, cudaStream_t st, int splits = 1,
+                        int64_t plane = 0) {
   if (M <= 0 || N <= 0) return 0;
+  UML_REQUIRE(splits >= 1 && (splits == 1 || (upd.kind == 0 && C && plane >= M * ldc)), "sgemm: bad split-K arguments");
   const int64_t ctas64 = ((M + 63) / 64) * ((N + 63) / 64);
   if (ctas64 >= 2 * sm_count()) {
-    dim3 grid(static_cast<unsigned>((N + 63) / 64), static_cast<unsigned>((M + 63) / 64));
-    sgemm_kernel<64, 64, A_K, B_K><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd);
+    dim3 grid(static_cast<unsigned>((N + 63) / 64), static_cast<unsigned>((M + 63) / 64), static_cast<unsigned>(splits));
+    sgemm_kernel<64, 64, A_K, B_K><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd, plane);
   } else {
-    dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((M + 31) / 32));
-    sgemm_kernel<32, 32, A_K, B_K, 64><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd);
+    dim3 grid(static_cast<unsigned>((N + 31) / 32), static_cast<unsigned>((M + 31) / 32), static_cast<unsigned>(splits));
+    sgemm_kernel<32, 32, A_K, B_K, 64><<<grid, 256, 0, st>>>(A, B, C, ldc, M, N, K, alpha, P, upd, plane);
   }
   UML_CUDA(cudaGetLastError());
   return 0;
@@ -222,10 +231,18 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
 
 __global__ void __launch_bounds__(256)
     softmax_ce_grad_kernel(float* __restrict__ L, int64_t ldl, int C, SegInfo seg, float* __restrict__ row_loss,
-                           int32_t* __restrict__ row_correct, float* __restrict__ row_dscale) {
+                           int32_t* __restrict__ row_correct, float* __restrict__ row_dscale, int planes, int64_t plane) {
   __shared__ float sh[8];
   __shared__ int sh_arg;
   const int64_t r = blockIdx.x;
+  if (planes > 1) {  // split-K forward: raw logits = sum of the planes, in plane order
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float x = L[r * ldl + c];
+      for (int z = 1; z < planes; ++z) x += L[z * plane + r * ldl + c];
+      L[r * ldl + c] = x;
+    }
+    __syncthreads();
+  }
   const bool s = r >= seg.n0;
   const int64_t l = s ? r - seg.n0 : r;
   const int64_t n_seg = s ? seg.n1 : seg.n0;
@@ -484,7 +501,7 @@ extern "C" {
 
 int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, const float* W, int32_t n_classes,
                         float* G, int64_t ldg, float* row_loss, int32_t* row_correct, float* row_dscale,
-                        uml_seg_stats* stats, void* stream) {
+                        uml_seg_stats* stats, int64_t g_capacity_rows, void* stream) {
   using namespace uml;
   if (check_segs(segs, nseg)) return 1;
   UML_REQUIRE(W && G && row_loss && row_correct && row_dscale && stats && dim > 0 && n_classes > 0 && ldg >= n_classes,
@@ -494,8 +511,17 @@ int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, cons
   if (total > 0) {
     DeviceUpdate none;
     memset(&none, 0, sizeof(none));
+    // small batches: split the contraction over up to 8 planes of G (when the caller's G has room for them) so that
+    // the logit GEMM fills the machine; the softmax kernel adds the planes back in a fixed order
+    const int64_t ctas = ((total + 31) / 32) * ((n_classes + 31) / 32);
+    int splits = 1;
+    if (ctas < 2 * sm_count() && g_capacity_rows >= 2 * total) {
+      const int64_t want = (2 * sm_count() + ctas - 1) / ctas, room = g_capacity_rows / total, deep = (dim + 63) / 64;
+      splits = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, room), std::min<int64_t>(deep, 8))));
+    }
+    const int64_t plane = total * ldg;
     if (launch_sgemm<true, true>(seg_src(segs, nseg), dense_src(W, dim), G, ldg, total, n_classes, dim, 1.f, nullptr,
-                                 none, st))
+                                 none, st, splits, plane))
       return 1;
     SegInfo si;
     si.n0 = n0;
@@ -509,7 +535,7 @@ int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, cons
       si.weight[i] = s.loss_weight;
     }
     softmax_ce_grad_kernel<<<static_cast<unsigned>(total), 256, 0, st>>>(G, ldg, n_classes, si, row_loss, row_correct,
-                                                                        row_dscale);
+                                                                        row_dscale, splits, plane);
     UML_CUDA(cudaGetLastError());
   }
   seg_stats_kernel<<<nseg, 1024, 0, st>>>(row_loss, row_correct, row_dscale, n0, n1, stats);

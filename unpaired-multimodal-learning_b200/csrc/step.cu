@@ -301,7 +301,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     UML_REQUIRE(a->row_dscale, "linear_step: fp32 path needs row_dscale");
     rec(a->ev[2], stream);
     rc = uml_head_fwd_ce_f32(a->seg, a->nseg, a->dim, a->W, a->n_classes, static_cast<float*>(a->G), a->ldg,
-                             a->row_loss, a->row_correct, a->row_dscale, a->stats, stream);
+                             a->row_loss, a->row_correct, a->row_dscale, a->stats, a->g_capacity_rows, stream);
     if (rc) return rc;
     rec(a->ev[3], stream);
   } else {

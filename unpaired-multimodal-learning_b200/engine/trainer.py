@@ -281,7 +281,7 @@ class StepEngine:
         a.nseg, a.precision = k, int(bf16)
         W = self.W.data
         a.W = W.data_ptr()
-        a.G, a.ldg = ws.G.data_ptr(), ws.ldg
+        a.G, a.ldg, a.g_capacity_rows = ws.G.data_ptr(), ws.ldg, ws.G.shape[0]
         a.row_loss, a.row_correct, a.row_dscale = ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr()
         if bf16:
             a.X16, a.W16, a.labels32 = self.X16.data_ptr(), self.W16.data_ptr(), self.labels32.data_ptr()

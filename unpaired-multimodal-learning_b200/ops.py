@@ -153,7 +153,10 @@ class HeadWorkspace:
     def __init__(self, max_rows: int, n_classes: int, device, bf16: bool = False):
         self.max_rows, self.n_classes = int(max_rows), int(n_classes)
         self.ldg = ((n_classes + 63) // 64) * 64
-        self.G = torch.empty((max_rows, self.ldg), device=device, dtype=torch.bfloat16 if bf16 else torch.float32)
+        # fp32 workspaces of small steps get room for 8 split-K planes of raw logits (a few MB): the latency-bound
+        # reference-batch forward then spreads its contraction over the whole machine
+        g_rows = max_rows if (bf16 or max_rows > 2048) else 8 * max_rows
+        self.G = torch.empty((g_rows, self.ldg), device=device, dtype=torch.bfloat16 if bf16 else torch.float32)
         self.row_loss = torch.empty(max_rows, device=device, dtype=torch.float32)
         self.row_correct = torch.empty(max_rows, device=device, dtype=torch.int32)
         self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
@@ -180,7 +183,7 @@ def head_fwd_ce_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, sta
     stats = ws.stats if stats is None else stats
     check(_lib.load().uml_head_fwd_ce_f32(arr, n, W.shape[1], W.data_ptr(), W.shape[0], ws.G.data_ptr(), ws.ldg,
                                           ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr(),
-                                          stats.data_ptr(), _stream()))
+                                          stats.data_ptr(), ws.G.shape[0], _stream()))
 
 
 def head_bwd_dw_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, dW: Optional[torch.Tensor] = None,
