@@ -5,25 +5,25 @@
 //   logits[b,c] = scale_b * sum_d X[b,d] W[c,d]         bf16 x bf16 -> fp32 in TMEM
 //   G[b,c]      = w_b * scale_b / n_b * (softmax(logits)[b,c] - [c == y_b])     written as bf16
 //
-// One persistent CTA per SM, 384 threads, warp-specialised:
-//   warp 11    TMA producer : X tile 128x64 + W chunk 256x64 per stage, 4 stages, SWIZZLE_128B
-//   warp 10    MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, accumulators in
-//                             TMEM; two 256-column accumulator buffers so the MMA of class chunk j+1
-//                             overlaps the epilogue of chunk j
+// One persistent CTA per SM (CTA pairs: cta_group::2), 384 threads, warp-specialised:
+//   warp 11    TMA producer : X tile 128x64 + this CTA's half of the W chunk (128x64) per stage, 5 stages,
+//                             SWIZZLE_128B; completion is counted on the pair leader's barrier
+//   warp 10    MMA issuer   : (leader CTA) tcgen05.mma cta_group::2 kind::f16, M=256 (pair) N=256 K=16,
+//                             accumulators in TMEM; two 256-column accumulator buffers so the MMA of class chunk
+//                             j+1 overlaps the epilogue of chunk j
 //   warp 8     TMEM allocator
-//   warps 4-7  epilogue     : one thread per row (TMEM lane).  Per chunk: tcgen05.ld, scale, running
-//                             row max / sum (online softmax), argmax, label logit; the unnormalised
-//                             probabilities exp(l - m_running) are staged in shared memory in the
-//                             128B-swizzled layout and leave as coalesced TMA stores.
-//   warps 8-11 normaliser   : a 1000-class fp32 row needs 1000 TMEM columns and an SM has 512, so the
-//                             row cannot wait in TMEM for its final max/sum.  Instead, when a tile's
-//                             last chunk is done the epilogue hands the per-row, per-chunk factors
-//                             exp(m_chunk - m_final) / sum * coef to these warps through shared memory;
-//                             they re-read the tile's 256 KB (written microseconds ago, L2 resident),
-//                             apply the factor and the one-hot term and write the final G - one warp
-//                             per row, 32 independent 16-byte loads in flight per lane - while the
-//                             other warps are already working on the next tile.
-// Logits never exist in HBM in fp32, nothing is recomputed, and HBM sees G once.
+//   warps 0-7  epilogue     : two groups of four warps that own alternate class chunks; one thread per row
+//                             (TMEM lane).  Per chunk ONE sweep, 64 columns at a time: tcgen05.ld, scale, running
+//                             row max / sum (online softmax), label logit, index-free hit flag; the unnormalised
+//                             probabilities exp(l - m_running) are staged in shared memory in the 128B-swizzled
+//                             layout and leave as coalesced TMA stores.  At the end of a tile the group that
+//                             finishes last merges both groups' row statistics (through shared memory).
+// A 1000-class fp32 row needs 1000 TMEM columns and an SM has 512, so a row cannot wait in TMEM for its final
+// max / sum: the normalisation is DEFERRED - per row and 64-column group the factor exp(m_group - m_final) / sum *
+// coef goes to a small side array and g_fixup_kernel (below) applies it, together with the one-hot term, in one
+// coalesced pass over G while it is still in L2.  (Alternatives measured: normaliser warps inside this kernel - slower;
+// the same transform applied to the dW kernel's operand stages - bit-identical but shared-memory bound, see tc_gemm.cu.)
+// Logits never exist in HBM in fp32 and nothing is recomputed.
 #include <cstdlib>
 #include <type_traits>
 

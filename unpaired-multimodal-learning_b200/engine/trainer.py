@@ -8,11 +8,13 @@ log that the caller reads at evaluation cadence.
 
 Two arithmetic paths (chosen per step from the row count unless forced):
   fp32  SIMT kernels, exact like the reference; rows are gathered inside the GEMMs by index and the
-        optimizer update runs in the dW epilogue: 3 launches for the linear head.
-  bf16  tcgen05 kernels: TMA gather+cast -> fused forward/CE/G -> split-K dW -> optimizer update that
-        also sums the split-K partials and refreshes the bf16 weight shadow.
-Data-parallel runs (``dist_group``): every rank takes its slice of the global batch, gradients are
-summed with one NCCL all-reduce per step and every rank applies the same update.
+        optimizer update runs in the dW epilogue: 4 launches for the linear head.
+  bf16  tcgen05 kernels: row gather from the bf16 shadow banks (prefetched one step ahead on a side stream)
+        -> fused forward/CE/G -> fix-up -> split-K dW -> optimizer update that also sums the split-K
+        partials and refreshes the bf16 weight shadow: 5 launches, enqueued by one C call per chunk of steps.
+Data-parallel runs: every rank takes its slice of the global batch (or owns a bank shard with its own sampler);
+the step ends with one kernel per rank that sums the local partials, exchanges the gradient over NVLink peer
+memory and applies the identical update everywhere (ncclAllReduce from inside the launcher as the fallback).
 """
 from __future__ import annotations
 
