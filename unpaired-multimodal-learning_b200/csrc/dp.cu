@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(kArThreads)
       }
       x[i] = g;
     }
-    __threadfence_system();
+    // device-scope fence per block; the block that signals the peers issues the system-scope fence (fences are
+    // cumulative: what it observed through the counter is ordered before its flag stores)
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(&counters[0], 1u) == gridDim.x - 1;
     __syncthreads();
