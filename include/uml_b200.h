@@ -288,6 +288,11 @@ int uml_gauss_step(float* params, float* adam_m, float* adam_v, int32_t dim_obs,
                    const float* data_x, int64_t n_x, const float* data_y, int64_t n_y, const int64_t* idx, int64_t batch,
                    int32_t mode_xy, float alpha_x, float alpha_y, double lr, double beta1, double beta2, double eps,
                    int64_t step, float* workspace, float* loss_out, void* stream);
+/* n_steps consecutive steps in one call: idx_list is a HOST array of device index batches, loss_log[2*i..] gets step i */
+int uml_gauss_run(float* params, float* adam_m, float* adam_v, int32_t dim_obs, int32_t dim_common, int32_t dim_latent,
+                  const float* data_x, int64_t n_x, const float* data_y, int64_t n_y, const int64_t* const* idx_list /*host*/,
+                  int32_t n_steps, int64_t batch, int32_t mode_xy, float alpha_x, float alpha_y, double lr, double beta1,
+                  double beta2, double eps, int64_t first_step, float* workspace, float* loss_log, void* stream);
 /* validation forward (main.py:68-72): loss_out[2] = MSE of both modalities over n_rows dense rows          */
 int uml_gauss_eval(const float* params, int32_t dim_obs, int32_t dim_common, int32_t dim_latent, const float* data_x,
                    const float* data_y, int64_t n_rows, float* workspace /* >= 2*ceil(n_rows/16) floats */,

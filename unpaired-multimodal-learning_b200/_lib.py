@@ -106,6 +106,8 @@ PROTOTYPES = {
     "uml_gauss_workspace_floats": [c_i32, c_i32, c_i32, c_i64],
     "uml_gauss_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_f32, c_f32,
                        c_f64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp, c_vp],
+    "uml_gauss_run": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i64, c_i32, c_f32, c_f32,
+                      c_f64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp, c_vp],
     "uml_gauss_eval": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
     "uml_randperm_begin": [c_vp, C.c_uint64, c_i64, c_vp],

@@ -45,55 +45,87 @@ static GaussLayout make_layout(int obs, int com, int lat) {
 }
 
 // ---- shared-memory helpers (all called by the whole CTA) -----------------------------------------------
+// Activations live TRANSPOSED in shared memory, [feature][row] with a row stride of kLdA = R + 4 floats: the 16 rows
+// of a feature are four float4, and consecutive features sit 80 B apart so that a quarter warp's 16-byte accesses
+// fall into distinct bank groups.  Every helper gives a thread 8 (or 16) independent accumulators - the first
+// version had one dependent FMA chain per thread and ran at ~5 MAC/cycle/SM (72 us per step).
+constexpr int kLdA = kGaussRows + 4;
+
 // W [out, in] global row-major -> shared with leading dimension in + 1
 __device__ void stage_weight(const float* __restrict__ g, float* s, int out, int in) {
   for (int i = threadIdx.x; i < out * in; i += blockDim.x) s[(i / in) * (in + 1) + (i % in)] = g[i];
 }
-// y[r][j] = b[j] + sum_k x[r][k] W[j][k]
-__device__ void dense_fwd(const float* x, int ldx, const float* W, const float* b, int in, int out, float* y, int ldy, int R) {
-  for (int o = threadIdx.x; o < R * out; o += blockDim.x) {
-    const int r = o / out, j = o - r * out;
+__device__ __forceinline__ void fma8(float (&a)[8], float w, const float4& x0, const float4& x1) {
+  a[0] = fmaf(w, x0.x, a[0]); a[1] = fmaf(w, x0.y, a[1]); a[2] = fmaf(w, x0.z, a[2]); a[3] = fmaf(w, x0.w, a[3]);
+  a[4] = fmaf(w, x1.x, a[4]); a[5] = fmaf(w, x1.y, a[5]); a[6] = fmaf(w, x1.z, a[6]); a[7] = fmaf(w, x1.w, a[7]);
+}
+// y[j][r] = b[j] + sum_k W[j][k] x[k][r]      thread -> (output feature j, half of the 16 rows)
+template <bool kRelu>
+__device__ void dense_fwd(const float* x, const float* W, const float* b, int in, int out, float* y, float* y_relu) {
+  for (int o = threadIdx.x; o < 2 * out; o += blockDim.x) {
+    const int j = o >> 1, h = (o & 1) * 8;
     const float* w = W + j * (in + 1);
-    const float* xr = x + r * ldx;
-    float a0 = b[j], a1 = 0.f;
-    int k = 0;
-    for (; k + 1 < in; k += 2) {
-      a0 = fmaf(xr[k], w[k], a0);
-      a1 = fmaf(xr[k + 1], w[k + 1], a1);
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = b[j];
+#pragma unroll 4
+    for (int k = 0; k < in; ++k) {
+      const float4* xr = reinterpret_cast<const float4*>(x + k * kLdA + h);
+      fma8(a, w[k], xr[0], xr[1]);
     }
-    if (k < in) a0 = fmaf(xr[k], w[k], a0);
-    y[r * ldy + j] = a0 + a1;
+    float4* yo = reinterpret_cast<float4*>(y + j * kLdA + h);
+    yo[0] = make_float4(a[0], a[1], a[2], a[3]);
+    yo[1] = make_float4(a[4], a[5], a[6], a[7]);
+    if (kRelu) {
+      float4* ro = reinterpret_cast<float4*>(y_relu + j * kLdA + h);
+      ro[0] = make_float4(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f), fmaxf(a[2], 0.f), fmaxf(a[3], 0.f));
+      ro[1] = make_float4(fmaxf(a[4], 0.f), fmaxf(a[5], 0.f), fmaxf(a[6], 0.f), fmaxf(a[7], 0.f));
+    }
   }
 }
-// dx[r][k] = sum_j dy[r][j] W[j][k]   (optionally masked by pre[r][k] > 0: the ReLU in front of this layer's input)
-__device__ void dense_bwd_data(const float* dy, int ldy, const float* W, int in, int out, float* dx, int ldx, int R,
-                               const float* pre, int ldp) {
-  for (int o = threadIdx.x; o < R * in; o += blockDim.x) {
-    const int r = o / in, k = o - r * in;
-    const float* d = dy + r * ldy;
-    float a = 0.f;
-    for (int j = 0; j < out; ++j) a = fmaf(d[j], W[j * (in + 1) + k], a);
-    if (pre && !(pre[r * ldp + k] > 0.f)) a = 0.f;
-    dx[r * ldx + k] = a;
+// dx[k][r] = sum_j W[j][k] dy[j][r]   (optionally masked by pre[k][r] > 0: the ReLU in front of this layer's input)
+__device__ void dense_bwd_data(const float* dy, const float* W, int in, int out, float* dx, const float* pre) {
+  for (int o = threadIdx.x; o < 2 * in; o += blockDim.x) {
+    const int k = o >> 1, h = (o & 1) * 8;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j = 0; j < out; ++j) {
+      const float4* dr = reinterpret_cast<const float4*>(dy + j * kLdA + h);
+      fma8(a, W[j * (in + 1) + k], dr[0], dr[1]);
+    }
+    if (pre) {
+      const float* pr = pre + k * kLdA + h;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (!(pr[i] > 0.f)) a[i] = 0.f;
+    }
+    float4* xo = reinterpret_cast<float4*>(dx + k * kLdA + h);
+    xo[0] = make_float4(a[0], a[1], a[2], a[3]);
+    xo[1] = make_float4(a[4], a[5], a[6], a[7]);
   }
 }
-// gW[j][k] = sum_r dy[r][j] x[r][k],  gb[j] = sum_r dy[r][j]   -> this CTA's slot of the partial buffer
-__device__ void dense_bwd_weight(const float* dy, int ldy, const float* x, int ldx, int in, int out, int R,
-                                 float* __restrict__ gW, float* __restrict__ gb) {
+// gW[j][k] = sum_r dy[j][r] x[k][r],  gb[j] = sum_r dy[j][r]   -> this CTA's slot of the partial buffer
+__device__ void dense_bwd_weight(const float* dy, const float* x, int in, int out, float* __restrict__ gW,
+                                 float* __restrict__ gb) {
   for (int o = threadIdx.x; o < out * in; o += blockDim.x) {
     const int j = o / in, k = o - j * in;
-    float a = 0.f;
-    for (int r = 0; r < R; ++r) a = fmaf(dy[r * ldy + j], x[r * ldx + k], a);
-    gW[o] = a;
+    const float4* d = reinterpret_cast<const float4*>(dy + j * kLdA);
+    const float4* xv = reinterpret_cast<const float4*>(x + k * kLdA);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < kGaussRows / 4; ++q) {
+      const float4 dd = d[q], xx = xv[q];
+      a0 = fmaf(dd.x, xx.x, a0); a1 = fmaf(dd.y, xx.y, a1); a2 = fmaf(dd.z, xx.z, a2); a3 = fmaf(dd.w, xx.w, a3);
+    }
+    gW[o] = (a0 + a1) + (a2 + a3);
   }
   for (int j = threadIdx.x; j < out; j += blockDim.x) {
+    const float4* d = reinterpret_cast<const float4*>(dy + j * kLdA);
     float a = 0.f;
-    for (int r = 0; r < R; ++r) a += dy[r * ldy + j];
+#pragma unroll
+    for (int q = 0; q < kGaussRows / 4; ++q) a += (d[q].x + d[q].y) + (d[q].z + d[q].w);
     gb[j] = a;
   }
-}
-__device__ void relu_copy(const float* h, float* r, int n) {
-  for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] = fmaxf(h[i], 0.f);
 }
 
 struct GaussData {
@@ -107,29 +139,30 @@ struct GaussData {
 __global__ void __launch_bounds__(kGaussThreads)
     gauss_fwd_bwd_kernel(const float* __restrict__ P, GaussLayout L, GaussData D, float* __restrict__ partial,
                          float* __restrict__ loss_part) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int m = blockIdx.y, tile = blockIdx.x, n_tiles = gridDim.x;
   const int obs = L.obs, com = L.com, lat = L.lat;
   constexpr int R = kGaussRows;
   // ---- carve shared memory
   float* p = sm;
-  auto carve = [&](int n) { float* r = p; p += n; return r; };
+  auto carve = [&](int n) { float* r = p; p += (n + 3) & ~3; return r; };  // 16-byte aligned pieces (float4 access)
   float* Win = carve(com * (obs + 1));  float* bin = carve(com);
   float* We0 = carve(lat * (com + 1));  float* be0 = carve(lat);
   float* We2 = carve(lat * (lat + 1));  float* be2 = carve(lat);
   float* Wd0 = carve(lat * (lat + 1));  float* bd0 = carve(lat);
   float* Wd2 = carve(com * (lat + 1));  float* bd2 = carve(com);
   float* Wout = carve(obs * (com + 1)); float* bout = carve(obs);
-  float* v = carve(R * obs);    // input rows
-  float* a0 = carve(R * com);   // in_head output
-  float* h1 = carve(R * lat);   float* r1 = carve(R * lat);
-  float* z = carve(R * lat);    // latent
-  float* h2 = carve(R * lat);   float* r2 = carve(R * lat);
-  float* a3 = carve(R * com);   // decoder output
-  float* dr = carve(R * obs);   // recon, then d recon
-  float* dA = carve(R * com);   // gradient scratch (wide)
-  float* dB = carve(R * lat);   // gradient scratch (narrow)
-  float* dC = carve(R * lat);
+  // activations, transposed: [feature][kLdA]
+  float* v = carve(obs * kLdA);    // input rows
+  float* a0 = carve(com * kLdA);   // in_head output
+  float* h1 = carve(lat * kLdA);   float* r1 = carve(lat * kLdA);
+  float* z = carve(lat * kLdA);    // latent
+  float* h2 = carve(lat * kLdA);   float* r2 = carve(lat * kLdA);
+  float* a3 = carve(com * kLdA);   // decoder output
+  float* dr = carve(obs * kLdA);   // recon, then d recon
+  float* dA = carve(com * kLdA);   // gradient scratch (wide)
+  float* dB = carve(lat * kLdA);   // gradient scratch (narrow)
+  float* dC = carve(lat * kLdA);
   __shared__ float red[kGaussThreads / 32];
 
   stage_weight(P + L.in_w[m], Win, com, obs);
@@ -143,34 +176,33 @@ __global__ void __launch_bounds__(kGaussThreads)
   for (int i = threadIdx.x; i < obs; i += blockDim.x) bout[i] = P[L.out_b[m] + i];
   const int64_t row0 = static_cast<int64_t>(tile) * R;
   for (int i = threadIdx.x; i < R * obs; i += blockDim.x) {
-    const int r = i / obs, c = i - r * obs;
+    const int r = i / obs, c = i - r * obs;  // coalesced over the features of a row
     float x = 0.f;
     if (row0 + r < D.B) {
       const int64_t src = (D.idx ? D.idx[row0 + r] : row0 + r) % D.n[m];  // UnpairedDataset.__getitem__: idx % len
       x = D.data[m][src * obs + c];
     }
-    v[i] = x;
+    v[c * kLdA + r] = x;
   }
   __syncthreads();
 
   // ---- forward
-  dense_fwd(v, obs, Win, bin, obs, com, a0, com, R);      __syncthreads();
-  dense_fwd(a0, com, We0, be0, com, lat, h1, lat, R);     __syncthreads();
-  relu_copy(h1, r1, R * lat);                             __syncthreads();
-  dense_fwd(r1, lat, We2, be2, lat, lat, z, lat, R);      __syncthreads();
-  dense_fwd(z, lat, Wd0, bd0, lat, lat, h2, lat, R);      __syncthreads();
-  relu_copy(h2, r2, R * lat);                             __syncthreads();
-  dense_fwd(r2, lat, Wd2, bd2, lat, com, a3, com, R);     __syncthreads();
-  dense_fwd(a3, com, Wout, bout, com, obs, dr, obs, R);   __syncthreads();
+  dense_fwd<false>(v, Win, bin, obs, com, a0, nullptr);     __syncthreads();
+  dense_fwd<true>(a0, We0, be0, com, lat, h1, r1);          __syncthreads();
+  dense_fwd<false>(r1, We2, be2, lat, lat, z, nullptr);     __syncthreads();
+  dense_fwd<true>(z, Wd0, bd0, lat, lat, h2, r2);           __syncthreads();
+  dense_fwd<false>(r2, Wd2, bd2, lat, com, a3, nullptr);    __syncthreads();
+  dense_fwd<false>(a3, Wout, bout, com, obs, dr, nullptr);  __syncthreads();
 
   // ---- loss (sum of squares of this tile) and d recon
   float ss = 0.f;
   const float ds = D.dscale[m];
   for (int i = threadIdx.x; i < R * obs; i += blockDim.x) {
-    const bool valid = row0 + i / obs < D.B;
-    const float diff = valid ? dr[i] - v[i] : 0.f;
+    const int c = i / R, r = i - c * R;
+    const bool valid = row0 + r < D.B;
+    const float diff = valid ? dr[c * kLdA + r] - v[c * kLdA + r] : 0.f;
     ss = fmaf(diff, diff, ss);
-    dr[i] = diff * ds;
+    dr[c * kLdA + r] = diff * ds;
   }
   ss = warp_sum(ss);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
@@ -184,17 +216,17 @@ __global__ void __launch_bounds__(kGaussThreads)
 
   // ---- backward: every layer writes its gradient slot, then propagates
   float* g = partial + (static_cast<int64_t>(m) * n_tiles + tile) * L.total;
-  dense_bwd_weight(dr, obs, a3, com, com, obs, R, g + L.out_w[m], g + L.out_b[m]);
-  dense_bwd_data(dr, obs, Wout, com, obs, dA, com, R, nullptr, 0);            __syncthreads();   // d a3
-  dense_bwd_weight(dA, com, r2, lat, lat, com, R, g + L.d2_w, g + L.d2_b);
-  dense_bwd_data(dA, com, Wd2, lat, com, dB, lat, R, h2, lat);                __syncthreads();   // d h2
-  dense_bwd_weight(dB, lat, z, lat, lat, lat, R, g + L.d0_w, g + L.d0_b);
-  dense_bwd_data(dB, lat, Wd0, lat, lat, dC, lat, R, nullptr, 0);             __syncthreads();   // d latent
-  dense_bwd_weight(dC, lat, r1, lat, lat, lat, R, g + L.e2_w, g + L.e2_b);
-  dense_bwd_data(dC, lat, We2, lat, lat, dB, lat, R, h1, lat);                __syncthreads();   // d h1
-  dense_bwd_weight(dB, lat, a0, com, com, lat, R, g + L.e0_w, g + L.e0_b);
-  dense_bwd_data(dB, lat, We0, com, lat, dA, com, R, nullptr, 0);             __syncthreads();   // d a0
-  dense_bwd_weight(dA, com, v, obs, obs, com, R, g + L.in_w[m], g + L.in_b[m]);
+  dense_bwd_weight(dr, a3, com, obs, g + L.out_w[m], g + L.out_b[m]);
+  dense_bwd_data(dr, Wout, com, obs, dA, nullptr);             __syncthreads();   // d a3
+  dense_bwd_weight(dA, r2, lat, com, g + L.d2_w, g + L.d2_b);
+  dense_bwd_data(dA, Wd2, lat, com, dB, h2);                   __syncthreads();   // d h2
+  dense_bwd_weight(dB, z, lat, lat, g + L.d0_w, g + L.d0_b);
+  dense_bwd_data(dB, Wd0, lat, lat, dC, nullptr);              __syncthreads();   // d latent
+  dense_bwd_weight(dC, r1, lat, lat, g + L.e2_w, g + L.e2_b);
+  dense_bwd_data(dC, We2, lat, lat, dB, h1);                   __syncthreads();   // d h1
+  dense_bwd_weight(dB, a0, com, lat, g + L.e0_w, g + L.e0_b);
+  dense_bwd_data(dB, We0, com, lat, dA, nullptr);              __syncthreads();   // d a0
+  dense_bwd_weight(dA, v, obs, com, g + L.in_w[m], g + L.in_b[m]);
 }
 
 struct GaussAdam {
@@ -236,7 +268,7 @@ static size_t gauss_smem_bytes(const GaussLayout& L) {
   size_t f = static_cast<size_t>(com) * (obs + 1) + com + static_cast<size_t>(lat) * (com + 1) + lat +
              2 * (static_cast<size_t>(lat) * (lat + 1) + lat) + static_cast<size_t>(com) * (lat + 1) + com +
              static_cast<size_t>(obs) * (com + 1) + obs;
-  f += static_cast<size_t>(R) * (2 * obs + 3 * com + 7 * lat);
+  f += static_cast<size_t>(R + 4) * (2 * obs + 3 * com + 7 * lat) + 4 * 32;  // + alignment slack of the carve
   return f * sizeof(float);
 }
 
@@ -303,6 +335,22 @@ int uml_gauss_step(float* params, float* adam_m, float* adam_v, int32_t dim_obs,
       params, adam_m, adam_v, L, partial, tiles, D.dscale[0] != 0.f, D.dscale[1] != 0.f, A, loss_part,
       static_cast<float>(1.0 / cnt), loss_out);
   UML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// n_steps consecutive steps enqueued by one call (the step is latency bound and a Python round trip per step costs more
+// than its two kernels): idx_list[i] is step i's device index batch, loss_log + 2 i receives its {loss_x, loss_y}.
+int uml_gauss_run(float* params, float* adam_m, float* adam_v, int32_t dim_obs, int32_t dim_common, int32_t dim_latent,
+                  const float* data_x, int64_t n_x, const float* data_y, int64_t n_y, const int64_t* const* idx_list,
+                  int32_t n_steps, int64_t batch, int32_t mode_xy, float alpha_x, float alpha_y, double lr, double beta1,
+                  double beta2, double eps, int64_t first_step, float* workspace, float* loss_log, void* stream) {
+  UML_REQUIRE(idx_list && n_steps >= 0 && loss_log, "gauss_run: bad arguments");
+  for (int i = 0; i < n_steps; ++i) {
+    const int rc = uml_gauss_step(params, adam_m, adam_v, dim_obs, dim_common, dim_latent, data_x, n_x, data_y, n_y,
+                                  idx_list[i], batch, mode_xy, alpha_x, alpha_y, lr, beta1, beta2, eps, first_step + i,
+                                  workspace, loss_log + 2 * i, stream);
+    if (rc) return rc;
+  }
   return 0;
 }
 

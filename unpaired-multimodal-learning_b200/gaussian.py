@@ -165,24 +165,35 @@ def train_model_steps(model: SharedAutoencoder, data_loader: BankLoader, optimiz
     ws = torch.empty(int(lib.uml_gauss_workspace_floats(model.dim_obs, model.dim_common, model.dim_latent, B)), device=model.device)
     log = torch.zeros((num_steps, 2), device=model.device)
     stream = torch.cuda.current_stream().cuda_stream
+    import ctypes as C
     it = iter(data_loader)
     out = {"loss_x": [], "loss_y": [], "loss": [], "val": []}
-    for step in range(num_steps):
-        try:
-            batch = next(it)
-        except StopIteration:
-            it = iter(data_loader)
-            batch = next(it)
-        if trace is not None:
-            trace.setdefault("idx", []).append(batch.host_idx.clone())
-        optimizer.step_count += 1
-        check(lib.uml_gauss_step(model.flat.data_ptr(), optimizer.m.data_ptr(), optimizer.v.data_ptr(), model.dim_obs,
-                                 model.dim_common, model.dim_latent, ds.data_x.data_ptr(), ds.len_x, ds.data_y.data_ptr(),
-                                 ds.len_y, batch.idx.data_ptr(), batch.n, int(mode == "xy"), alpha_x, alpha_y, optimizer.lr,
-                                 optimizer.betas[0], optimizer.betas[1], optimizer.eps, optimizer.step_count, ws.data_ptr(),
-                                 log[step].data_ptr(), stream))
-        if eval_every and val_data_x is not None and (step + 1) % eval_every == 0:
-            out["val"].append((step,) + validate(model, val_data_x, val_data_y))
+    chunk_max = 32  # steps enqueued per library call (a Python round trip per step costs more than the step's kernels)
+    step = 0
+    while step < num_steps:
+        n = min(chunk_max, num_steps - step)
+        if eval_every and val_data_x is not None:
+            n = min(n, eval_every - step % eval_every)  # a chunk ends at the next validation point
+        batches = []
+        for _ in range(n):
+            try:
+                batch = next(it)
+            except StopIteration:
+                it = iter(data_loader)
+                batch = next(it)
+            if trace is not None:
+                trace.setdefault("idx", []).append(batch.host_idx.clone())
+            batches.append(batch)
+        ptrs = (C.c_void_p * n)(*[b.idx.data_ptr() for b in batches])
+        check(lib.uml_gauss_run(model.flat.data_ptr(), optimizer.m.data_ptr(), optimizer.v.data_ptr(), model.dim_obs,
+                                model.dim_common, model.dim_latent, ds.data_x.data_ptr(), ds.len_x, ds.data_y.data_ptr(),
+                                ds.len_y, ptrs, n, B, int(mode == "xy"), alpha_x, alpha_y, optimizer.lr, optimizer.betas[0],
+                                optimizer.betas[1], optimizer.eps, optimizer.step_count + 1, ws.data_ptr(),
+                                log[step].data_ptr(), stream))
+        optimizer.step_count += n
+        step += n
+        if eval_every and val_data_x is not None and step % eval_every == 0:
+            out["val"].append((step - 1,) + validate(model, val_data_x, val_data_y))
     host = log.cpu()
     out["loss_x"], out["loss_y"] = host[:, 0].tolist(), host[:, 1].tolist()
     out["loss"] = [(alpha_x * a + alpha_y * b) if mode == "xy" else a for a, b in zip(out["loss_x"], out["loss_y"])]
