@@ -308,8 +308,11 @@ def run_ours(args, wl, rank, world, dev):
         return rows_
 
     sampler = ClockSampler(dev.index or 0) if rank == 0 else None  # NVML set-up happens here, before the warm-up
-    for i in range(W):
-        step(i)
+    i = 0
+    while i < W:  # warm-up in chunks of two: the chunked launcher (side stream, events, second operand buffer) is set up
+        n = min(2, W - i)
+        step(i, n)
+        i += n
     bf16_path = engine._use_bf16(B + BT)
     dominant = "head_fwd_ce_bf16" if bf16_path else "head_bwd_dw_f32"
     engine.prepare_profile(K, only=[dominant])  # the roofline kernel is timed live inside the timed region

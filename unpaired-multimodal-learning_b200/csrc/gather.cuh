@@ -22,6 +22,15 @@ struct GatherJob {
   int blocks;                  // CTAs of the launch that work on this job (0 = none)
 };
 
+// Fix-up -> dW hand-over at split granularity: the fix-up launch counts its finished 8-row CTAs per K split of the dW
+// GEMM (split boundaries are multiples of 64 rows), the dW kernel - running concurrently on another stream - lets
+// each split start as soon as ITS rows of G are final instead of waiting for the whole fix-up pass.
+struct FixupSignal {
+  unsigned* done;     // [n_splits] counters, zeroed before the forward kernel
+  int n_splits;
+  int64_t num_kb;     // ceil(rows / 64)
+};
+
 #ifdef __CUDACC__
 // rows warp_id, warp_id + n_warps, ... of the concatenated runs: one warp per row, 16-byte vectors, four in flight
 __device__ __forceinline__ void gather_rows_by_warp(const CopySeg& s0, const CopySeg& s1, int vec_per_row, uint4* __restrict__ out,

@@ -12,9 +12,14 @@ inline void rec(void* ev, void* stream) {
   if (ev) cudaEventRecord(static_cast<cudaEvent_t>(ev), uml::as_stream(stream));
 }
 
+bool overlap_fixup();
+
 // Side stream + events for the gather prefetch of uml_linear_run (one set per device, created on first use).
 struct Pipe {
   cudaStream_t aux = nullptr;
+  cudaStream_t aux2 = nullptr;          // the dW GEMM when it overlaps the fix-up launch
+  cudaEvent_t dw_done = nullptr, fwd_done = nullptr;
+  unsigned* split_done = nullptr;       // [8] fix-up CTAs finished per dW split, then one int: watchdog flag
   cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr}, start = nullptr, mid = nullptr;
   bool ok = false;
 };
@@ -40,6 +45,11 @@ Pipe* get_pipe() {
     }
     good = good && cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
     good = good && cudaEventCreateWithFlags(&p.mid, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&p.dw_done, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaEventCreateWithFlags(&p.fwd_done, cudaEventDisableTiming) == cudaSuccess;
+    good = good && cudaStreamCreateWithPriority(&p.aux2, cudaStreamNonBlocking, hi) == cudaSuccess;
+    if (overlap_fixup())  // (a device allocation synchronises: only when the experiment is switched on)
+      good = good && cudaMalloc(&p.split_done, 64) == cudaSuccess && cudaMemset(p.split_done, 0, 64) == cudaSuccess;
     p.ok = good;
   }
   return p.ok ? &p : nullptr;
@@ -71,6 +81,19 @@ bool fuse_fix() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UML_FUSE_FIX");
+    cached = (e && e[0] == '1') ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+// UML_OVERLAP_FIXUP=1: the dW GEMM is launched on a second stream as soon as the forward kernel ends and each of its K
+// splits starts when the fix-up CTAs of ITS rows are done (per-split counters), instead of the whole GEMM waiting for
+// the whole fix-up pass.  Bit-identical, but measured SLOWER on B200 (cfg3): 0.205 vs 0.185 ms/step - the resident,
+// waiting GEMM CTAs plus the prefetching gather leave the fix-up CTAs almost no registers to run in.  Default: off.
+bool overlap_fixup() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UML_OVERLAP_FIXUP");
     cached = (e && e[0] == '1') ? 1 : 0;
   }
   return cached == 1;
@@ -116,7 +139,9 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
                             void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2 = nullptr,
-                            const uml::GatherJob* job = nullptr);  // tc_fwd.cu
+                            const uml::GatherJob* job = nullptr, const uml::FixupSignal* sig = nullptr);  // tc_fwd.cu
+int uml_head_bwd_dw_gated_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                               float* partials, int32_t n_splits, const unsigned* done, int* failed, void* stream);  // tc_gemm.cu
 
 float* uml_dp_p2p_input(int64_t n);   // dp.cu: this rank's exchange buffers of the peer-memory all-reduce (or NULL)
 float* uml_dp_p2p_output(int64_t n);
@@ -287,6 +312,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   using namespace uml;
   const bool pregathered = hooks.pregathered;
   const cudaEvent_t operand_free = hooks.operand_free;
+  Pipe* opipe = nullptr;  // set when this step's dW runs on the second stream, overlapping the fix-up launch
   UML_REQUIRE(a != nullptr, "linear_step: null args");
   UML_REQUIRE(a->nseg >= 1 && a->nseg <= UML_MAX_SEGMENTS, "linear_step: 1..2 segments");
   UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
@@ -355,14 +381,40 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
       if (rc) return rc;
     }
     if (total > 0) {
+      // fix-up / dW overlap: counters zeroed before the forward kernel, dW launched on aux2 right after it
+      int splits_o = uml_tc_dw_splits(total, a->dim, a->n_classes);
+      if (splits_o > a->max_splits) splits_o = a->max_splits;
+      opipe = (overlap_fixup() && !fuse_fix() && splits_o >= 1 && splits_o <= 8) ? get_pipe() : nullptr;
+      FixupSignal sig;
+      memset(&sig, 0, sizeof(sig));
+      cudaEvent_t after_fwd = hooks.after_fwd_kernel;
+      if (opipe) {
+        UML_CUDA(cudaMemsetAsync(opipe->split_done, 0, 64, as_stream(stream)));
+        sig.done = opipe->split_done;
+        sig.n_splits = splits_o;
+        sig.num_kb = (total + 63) / 64;
+        if (!after_fwd) after_fwd = opipe->fwd_done;
+      }
       rec(a->ev[2], stream);
       // ev[2]..ev[3] bracket the tensor-core kernel alone; the fix-up launch (which also reduces the per-run
       // statistics) follows it
       rc = uml_head_fwd_ce_bf16_ev(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
                                    static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, hooks.after_fwd_kernel,
-                                   fuse_fix() ? nullptr : hooks.merged);
+                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, after_fwd,
+                                   fuse_fix() ? nullptr : hooks.merged, opipe ? &sig : nullptr);
       if (rc) return rc;
+      if (opipe) {
+        // the GEMM goes to the second stream behind "forward kernel done"; the fix-up launch just enqueued on the main
+        // stream runs concurrently and releases the GEMM's splits one by one
+        cudaStream_t s2 = opipe->aux2;
+        UML_CUDA(cudaStreamWaitEvent(s2, after_fwd, 0));
+        rec(a->ev[4], s2);
+        rc = uml_head_bwd_dw_gated_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
+                                        a->partials, splits_o, opipe->split_done, reinterpret_cast<int*>(opipe->split_done + 8), s2);
+        if (rc) return rc;
+        rec(a->ev[5], s2);
+        UML_CUDA(cudaEventRecord(opipe->dw_done, s2));
+      }
     } else if (hooks.merged) {
       // no rows on this rank this step, hence no fix-up launch to ride in: copy the next step's rows directly
       const GatherJob& j = *hooks.merged;
@@ -413,6 +465,10 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   }
   int splits = uml_tc_dw_splits(total, a->dim, a->n_classes);
   if (splits > a->max_splits) splits = a->max_splits;
+  if (opipe) {
+    UML_CUDA(cudaStreamWaitEvent(as_stream(stream), opipe->dw_done, 0));  // the GEMM was launched with the forward
+    rc = 0;
+  } else {
   rec(a->ev[4], stream);
   if (fuse_fix()) {
     // the forward skipped its fix-up pass: the dW prologue normalises every G stage in shared memory
@@ -435,6 +491,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   }
   if (rc) return rc;
   rec(a->ev[5], stream);
+  }
   if (operand_free) UML_CUDA(cudaEventRecord(operand_free, as_stream(stream)));  // X16 / labels32 may be overwritten
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
   if (!fused) {

@@ -525,7 +525,7 @@ __device__ void tile_stats_block(const float* __restrict__ tile_part, int64_t n_
 __global__ void __launch_bounds__(256)
     g_fixup_kernel(__nv_bfloat16* __restrict__ G, int64_t ldg, int64_t n_rows, const int32_t* __restrict__ labels,
                    const float* __restrict__ fac, FwdSegs segs, const float* __restrict__ tile_part, int64_t n_tiles,
-                   int row_blocks, int stat_blocks, uml_seg_stats* __restrict__ stats, GatherJob job) {
+                   int row_blocks, int stat_blocks, uml_seg_stats* __restrict__ stats, GatherJob job, FixupSignal sig) {
   pdl_trigger();
   pdl_wait();
   // CTA roles: [0, stat_blocks) reduce the statistics; the rest are fix-up CTAs with, every (R+1)-th, a CTA that
@@ -547,8 +547,8 @@ __global__ void __launch_bounds__(256)
   }
   if (j >= row_blocks) return;
   const int64_t row = static_cast<int64_t>(j) * 8 + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
+  if (row < n_rows) {
   const int label = labels[row];
   const bool sg = row >= segs.n0;
   const float* sdev = sg ? segs.scale_dev[1] : segs.scale_dev[0];
@@ -584,6 +584,17 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint4*>(g + c) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
+  }  // row < n_rows
+  if (sig.done) {  // this CTA's 8 rows are final: count it for the dW split they belong to
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t kb = (static_cast<int64_t>(j) * 8) / 64;
+      int sp = sig.n_splits - 1;
+      while (sp > 0 && (sig.num_kb * sp) / sig.n_splits > kb) --sp;
+      atomicAdd(sig.done + sp, 1u);
+    }
+  }
 }
 
 static int fwd_cta_group(int64_t n_rows) {
@@ -613,7 +624,7 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
                             void* ev_after_fwd, void* stream, int defer_fixup = 0, void* ev_after_fwd2 = nullptr,
-                            const uml::GatherJob* job = nullptr);
+                            const uml::GatherJob* job = nullptr, const uml::FixupSignal* sig = nullptr);
 int64_t uml_fwd_tiles(int64_t n_rows);
 
 extern "C" {
@@ -641,7 +652,8 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
 int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
                             const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
                             int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
-                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2, const uml::GatherJob* job) {
+                            void* ev_after_fwd, void* stream, int defer_fixup, void* ev_after_fwd2, const uml::GatherJob* job,
+                            const uml::FixupSignal* sig) {
   using namespace uml;
   UML_REQUIRE(X && W && labels && segs && n_rows >= 0 && dim > 0 && n_classes > 0, "head_fwd_ce_bf16: bad arguments");
   UML_REQUIRE(dim % 8 == 0, "head_fwd_ce_bf16: dim (%d) must be a multiple of 8 (16-byte bf16 rows for TMA)", dim);
@@ -704,10 +716,13 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
     memset(&gj, 0, sizeof(gj));
     if (job) gj = *job;
     if (gj.blocks > row_blocks) gj.blocks = row_blocks;
+    FixupSignal fsig;
+    memset(&fsig, 0, sizeof(fsig));
+    if (sig) fsig = *sig;
     UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks + gj.blocks)), dim3(256), 0,
                            as_stream(stream), 1, true, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels,
                            static_cast<const float*>(fac), fs, static_cast<const float*>(tile_ws), units * cg, row_blocks,
-                           stat_blocks, stats, gj));
+                           stat_blocks, stats, gj, fsig));
   }
   return 0;
 }

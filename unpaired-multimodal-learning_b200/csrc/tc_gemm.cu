@@ -56,6 +56,10 @@ struct FixArgs {
   int64_t n_tiles;
   int nseg;
   uml_seg_stats* stats;
+  // any instantiation: let split z start only when wait_done[z] >= wait_expected[z] (fix-up CTAs of its rows finished)
+  const unsigned* wait_done;
+  unsigned wait_expected[8];
+  int* wait_failed;
 };
 
 template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
@@ -112,6 +116,22 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (every CTA) -------------------
     if (lane == 0) {
+      if (fix.wait_done) {
+        // the A operand of this split is still being finalised by the concurrently running fix-up launch
+        const unsigned need = fix.wait_expected[split];
+        const long long t0 = clock64();
+        for (;;) {
+          unsigned v;
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(fix.wait_done + split) : "memory");
+          if (v >= need) break;
+          if (clock64() - t0 > 400000000ll) {  // ~0.2 s: never hang the GPU; the caller checks the flag
+            *fix.wait_failed = 1;
+            break;
+          }
+          __nanosleep(100);
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of G -> this thread's TMA reads
+      }
       uint32_t it = 0;
       for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
         const uint32_t s = it % kGStages, ph = (it / kGStages) & 1;
@@ -394,6 +414,11 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
   } else {
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, kGBlockK, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
+  if (fix && !fix->fac) {  // wait-only: plain dW kernel whose splits are gated by the fix-up counters
+    UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: split gating is wired for the dW layout only");
+    return cg == 2 ? launch_tc_gemm<true, true, false, 2, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
+                   : launch_tc_gemm<true, true, false, 1, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);
+  }
   if (fix) {
     UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: the A-stage transform is instantiated for the dW layout only");
     return cg == 2 ? launch_tc_gemm<true, true, false, 2, true>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
@@ -413,6 +438,24 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
 }
 
 }  // namespace uml
+
+// dW whose K splits wait for the fix-up launch's per-split counters (see FixupSignal); library-internal
+int uml_head_bwd_dw_gated_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                               float* partials, int32_t n_splits, const unsigned* done, int* failed, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(G && X && partials && done && failed && n_rows > 0 && n_splits >= 1 && n_splits <= 8, "dw_gated: bad arguments");
+  FixArgs fx;
+  memset(&fx, 0, sizeof(fx));
+  fx.wait_done = done;
+  fx.wait_failed = failed;
+  const int64_t num_kb = (n_rows + kGBlockK - 1) / kGBlockK;
+  for (int sp = 0; sp < n_splits; ++sp) {
+    const int64_t r_lo = (num_kb * sp / n_splits) * kGBlockK, r_hi_raw = (num_kb * (sp + 1) / n_splits) * kGBlockK;
+    const int64_t r_hi = r_hi_raw < n_rows ? r_hi_raw : n_rows;
+    fx.wait_expected[sp] = r_hi > r_lo ? static_cast<unsigned>((r_hi - r_lo + 7) / 8) : 0u;
+  }
+  return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
+}
 
 extern "C" {
 

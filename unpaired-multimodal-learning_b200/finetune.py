@@ -204,7 +204,10 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     per_step = trace is not None and bool(trace.get("record_weights"))
     # small chunks: the host prepares chunk c+1 (sampler draws, index uploads) while the GPU runs chunk c
     max_chunk = 1 if per_step else 16
-    ramp = 1  # chunk sizes ramp up 1, 2, 4, ... after every point where the queue is empty (start, evaluations)
+    # Chunk sizes ramp up 1, 1, 2, 2, 4, 4, ... after every point where the queue is empty (start, evaluations): each
+    # size is used twice so that preparing a chunk (sampler + uploads, ~0.1 ms per step) never takes longer than the
+    # GPU needs for the chunk already queued (plain doubling does: the GPU then idles during the whole ramp).
+    ramp = 2  # the chunk size is ramp // 2
     # trace["timing"] = {"warmup": W}: wall-clock seconds of iterations W.. (stream-synchronised on both sides,
     # including the read-back of their stats) land in trace["timing"]["seconds"] - bench.py's end-to-end arm
     timing = trace.get("timing") if trace is not None else None
@@ -214,8 +217,8 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     while i < max_iters and not stop:
         next_eval = i if i % eval_freq == 0 else (i // eval_freq + 1) * eval_freq
         n = min(next_eval, max_iters - 1) - i + 1
-        n = max(1, min(n, max_chunk, ramp))
-        ramp = min(2 * ramp, max_chunk)
+        n = max(1, min(n, max_chunk, 1 << ((ramp // 2) - 1)))
+        ramp = min(ramp + 1, 2 * (max_chunk.bit_length()))
         if timing is not None:
             if i < timing["warmup"]:
                 n = min(n, timing["warmup"] - i)
@@ -223,7 +226,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
                 flush()
                 torch.cuda.current_stream().synchronize()
                 t_start = time.perf_counter()
-                ramp = 2
+                ramp = 3
                 n = min(n, 1)
         batches, lrs = [], []
         for _ in range(n):
@@ -254,7 +257,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
         last_step = i - 1
 
         if last_step % eval_freq == 0:
-            ramp = 1
+            ramp = 2
             flush()
             if grad_diag:
                 # the reference's per-step gradient probes (finetune.py:190-206), here at evaluation cadence on the
