@@ -307,7 +307,7 @@ int uml_gauss_eval(const float* params, int32_t dim_obs, int32_t dim_common, int
  * uml_randperm_begin seeds the generator and writes the identity, uml_randperm_advance(state, upto) runs the
  * iterations needed to make out[0..upto) final (a host thread keeps that prefix ahead of the training loop).
  * `state` is caller-owned scratch of UML_RANDPERM_STATE_BYTES bytes (8-byte aligned).                      */
-#define UML_RANDPERM_STATE_BYTES 3072
+#define UML_RANDPERM_STATE_BYTES 3072   /* `out` doubles as scratch: its upper half holds the 32-bit working array */
 int uml_randperm_begin(void* state /*host*/, uint64_t seed, int64_t n, int64_t* out /*host*/);
 int uml_randperm_advance(void* state /*host*/, int64_t upto);
 /* begin + advance in chunks, publishing the final-prefix length after each chunk: the body of a producer thread.

@@ -57,7 +57,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", *objs, "-o", LIB_PATH, "-ldl"]
+    cmd = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", *objs, "-o", LIB_PATH, "-ldl", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

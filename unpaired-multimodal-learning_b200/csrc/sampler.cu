@@ -15,7 +15,12 @@
 #include <sched.h>
 #include <time.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,6 +37,9 @@ struct PermState {
   int64_t done;          // iterations performed = length of the final prefix (n - 1 iterations finish everything)
   int64_t made;          // iterations whose z has been drawn (done <= made <= min(done + kAhead, n - 1))
   int64_t* out;
+  uint32_t* work;        // the permutation being built, 32-bit, in the UPPER half of out's memory (half the cache
+                         // footprint of the random swaps: 5 MB instead of 10 MB for the ImageNet bank)
+  int64_t converted;     // out[0..converted) holds the final int64 prefix
   int64_t published;     // length of the final prefix as seen by OTHER threads (release/acquire); -1 = failed
   int64_t next_filled;   // 1 once the NEXT epoch's buffer holds the identity (uml_randperm_run's last act)
 };
@@ -75,7 +83,7 @@ inline uint32_t mt_next(PermState& s) {
 inline void draw_one(PermState& s) {
   const uint32_t z = mt_next(s) % static_cast<uint32_t>(s.n - s.made);
   s.ring[s.made % kAhead] = z;
-  __builtin_prefetch(s.out + s.made + z, 1, 1);
+  __builtin_prefetch(s.work + s.made + z, 1, 1);
   ++s.made;
 }
 
@@ -83,16 +91,23 @@ inline void draw_one(PermState& s) {
 // division and the (prefetched) swap of different iterations - measured faster than three blocked passes.
 void advance(PermState& s, int64_t upto) {
   const int64_t m = s.n - 1;
-  int64_t* r = s.out;
+  uint32_t* r = s.work;
   while (s.made < m && s.made < s.done + kAhead) draw_one(s);
   for (int64_t i = s.done; i < upto; ++i) {
     const uint32_t z = s.ring[i % kAhead];
     if (s.made < m) draw_one(s);  // refills the slot just read (made == i + kAhead)
-    const int64_t t = r[i];
+    const uint32_t t = r[i];
     r[i] = r[i + z];
     r[i + z] = t;
   }
   s.done = upto;
+}
+
+// out[converted..upto) <- the final 32-bit entries.  The work array occupies bytes [4n, 8n) of out: writing out[j]
+// (bytes 8j..8j+7) can only overwrite work entries 2j-n and 2j-n+1, both <= j, i.e. already converted.
+void convert(PermState& s, int64_t upto) {
+  for (int64_t j = s.converted; j < upto; ++j) s.out[j] = static_cast<int64_t>(s.work[j]);
+  if (upto > s.converted) s.converted = upto;
 }
 
 }  // namespace
@@ -115,8 +130,10 @@ static int randperm_begin(void* state, uint64_t seed, int64_t n, int64_t* out, b
   s.done = 0;
   s.made = 0;
   s.out = out;
+  s.work = reinterpret_cast<uint32_t*>(out) + n;  // upper half of the n x 8 bytes
+  s.converted = 0;
   if (!prefilled)
-    for (int64_t i = 0; i < n; ++i) out[i] = i;
+    for (int64_t i = 0; i < n; ++i) s.work[i] = static_cast<uint32_t>(i);
   return 0;
 }
 
@@ -127,6 +144,9 @@ int uml_randperm_advance(void* state, int64_t upto) {
   int64_t iters = upto < s.n - 1 ? upto : s.n - 1;
   if (iters < 0) iters = 0;
   if (iters > s.done) advance(s, iters);
+  // iteration i makes element i final; after n - 1 iterations the last element is in place too
+  const int64_t final_len = s.done >= s.n - 1 ? s.n : s.done;
+  convert(s, upto < final_len ? upto : final_len);
   return 0;
 }
 
@@ -142,18 +162,77 @@ int uml_randperm_run(void* state, uint64_t seed, int64_t n, int64_t* out, int64_
   __atomic_store_n(&s.published, static_cast<int64_t>(0), __ATOMIC_RELEASE);
   __atomic_store_n(&s.next_filled, static_cast<int64_t>(0), __ATOMIC_RELEASE);
   int rc = randperm_begin(state, seed, n, out, prefilled != 0);
-  int64_t upto = 0;
-  while (rc == 0 && upto < n) {
-    upto = upto + chunk < n ? upto + chunk : n;
-    rc = uml_randperm_advance(state, upto);
-    if (rc == 0) __atomic_store_n(&s.published, upto, __ATOMIC_RELEASE);
-  }
   if (rc != 0) {
     __atomic_store_n(&s.published, static_cast<int64_t>(-1), __ATOMIC_RELEASE);
     return rc;
   }
+  const int64_t m = n > 0 ? n - 1 : 0;  // swaps to perform
+  static int pipelined = -1;
+  if (pipelined < 0) {
+    const char* e = getenv("UML_SAMPLER_PIPELINE");
+    pipelined = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!pipelined) {  // single thread: draw-ahead ring + swaps fused in one loop
+    int64_t upto = 0;
+    while (upto < n) {
+      upto = upto + chunk < n ? upto + chunk : n;
+      rc = uml_randperm_advance(state, upto);
+      if (rc != 0) {
+        __atomic_store_n(&s.published, static_cast<int64_t>(-1), __ATOMIC_RELEASE);
+        return rc;
+      }
+      __atomic_store_n(&s.published, upto, __ATOMIC_RELEASE);
+    }
+    if (next_out) {
+      uint32_t* w = reinterpret_cast<uint32_t*>(next_out) + n;
+      for (int64_t i = 0; i < n; ++i) w[i] = static_cast<uint32_t>(i);
+      __atomic_store_n(&s.next_filled, static_cast<int64_t>(1), __ATOMIC_RELEASE);
+    }
+    return 0;
+  }
+  // Two-stage pipeline: a helper thread draws the swap targets (MT19937 + modulo, ~3 ns each), this thread performs
+  // the swaps (~3 ns each, cache-miss bound) and publishes the final prefix - the two halves of the work overlap.
+  constexpr int kBlk = 4096, kRing = 16;
+  std::vector<uint32_t> ring(static_cast<size_t>(kBlk) * kRing);
+  std::atomic<int64_t> produced{0}, consumed{0};  // in blocks
+  const int64_t n_blocks = (m + kBlk - 1) / kBlk;
+  std::thread producer([&] {
+    for (int64_t b = 0; b < n_blocks; ++b) {
+      while (b - consumed.load(std::memory_order_acquire) >= kRing) sched_yield();
+      uint32_t* z = ring.data() + (b % kRing) * kBlk;
+      const int64_t i0 = b * kBlk, cnt = m - i0 < kBlk ? m - i0 : kBlk;
+      for (int64_t k = 0; k < cnt; ++k) z[k] = mt_next(s) % static_cast<uint32_t>(n - (i0 + k));
+      produced.store(b + 1, std::memory_order_release);
+    }
+  });
+  uint32_t* r = s.work;
+  int64_t next_pub = chunk < n ? chunk : n;
+  for (int64_t b = 0; b < n_blocks; ++b) {
+    while (produced.load(std::memory_order_acquire) <= b) sched_yield();
+    const uint32_t* z = ring.data() + (b % kRing) * kBlk;
+    const int64_t i0 = b * kBlk, cnt = m - i0 < kBlk ? m - i0 : kBlk;
+    for (int64_t k = 0; k < cnt; ++k) {
+      if (k + kAhead < cnt) __builtin_prefetch(r + i0 + k + kAhead + z[k + kAhead], 1, 1);
+      const int64_t i = i0 + k;
+      const uint32_t t = r[i];
+      r[i] = r[i + z[k]];
+      r[i + z[k]] = t;
+    }
+    consumed.store(b + 1, std::memory_order_release);
+    s.done = i0 + cnt;
+    while (next_pub <= s.done && next_pub < n) {  // publish whole chunks of the final prefix
+      convert(s, next_pub);
+      __atomic_store_n(&s.published, next_pub, __ATOMIC_RELEASE);
+      next_pub = next_pub + chunk < n ? next_pub + chunk : n;
+    }
+  }
+  producer.join();
+  s.made = m;
+  convert(s, n);
+  __atomic_store_n(&s.published, n, __ATOMIC_RELEASE);
   if (next_out) {
-    for (int64_t i = 0; i < n; ++i) next_out[i] = i;
+    uint32_t* w = reinterpret_cast<uint32_t*>(next_out) + n;  // the work half of the next epoch's buffer
+    for (int64_t i = 0; i < n; ++i) w[i] = static_cast<uint32_t>(i);
     __atomic_store_n(&s.next_filled, static_cast<int64_t>(1), __ATOMIC_RELEASE);
   }
   return 0;

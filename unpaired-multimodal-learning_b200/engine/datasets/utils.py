@@ -411,6 +411,37 @@ class _BankIter:
     def __iter__(self):
         return self
 
+    def batches_left(self) -> int:
+        """Batches this epoch can still yield without re-iterating (0 when exhausted)."""
+        l = self.l
+        left = self.n - self.pos
+        if left <= 0:
+            return 0
+        return left // l.batch_size if l.drop_last else -(-left // l.batch_size)
+
+    def take_chunk(self, k: int):
+        """The next k batches of THIS epoch (k <= batches_left()) with one wait on the sampler and - for
+        ``upload="step"`` - ONE host->device copy of the contiguous index range instead of one per batch."""
+        l = self.l
+        if not l.shuffle or l.upload != "step":
+            return [next(self) for _ in range(k)]
+        if self.perm_host is None:
+            self._draw()
+        start = self.pos
+        total = min(k * l.batch_size, self.n - start)
+        if self.perm is not None:
+            self.perm.wait(start + total)
+        host = self.perm_host[start:start + total]
+        dev = host.to(l.bank.device, non_blocking=True)
+        out, off = [], 0
+        while off < total:
+            take = min(l.batch_size, total - off)
+            gn = take * l.shard_of[1] if l.shard_of is not None else None
+            out.append(IndexBatch(l.bank, dev[off:off + take], take, start + off, host[off:off + take], gn))
+            off += take
+        self.pos = start + total
+        return out
+
     def __next__(self) -> IndexBatch:
         l = self.l
         if l.shuffle and self.perm_host is None:

@@ -660,6 +660,17 @@ class StepEngine:
         slot %= self.log_slots
         self.host_log[slot].copy_(self.stats_log[slot], non_blocking=True)
 
+    def copy_slots_to_host(self, slot0, n):
+        """copy_slot_to_host for n consecutive steps with one asynchronous copy per contiguous run of ring slots."""
+        if self.host_log is None:
+            self.host_log = torch.zeros((self.log_slots, 2, 4), dtype=torch.float32).pin_memory()
+        s = slot0 % self.log_slots
+        while n > 0:
+            k = min(n, self.log_slots - s)
+            self.host_log[s:s + k].copy_(self.stats_log[s:s + k], non_blocking=True)
+            n -= k
+            s = 0
+
     def read_log(self, slots, from_host_ring=False):
         """Per-step stats for the given slots: one synchronising D2H of the device log, or - when every
         step already pushed its record with ``copy_slot_to_host`` - a stream sync and a host read."""

@@ -229,27 +229,40 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
                 ramp = 3
                 n = min(n, 1)
         batches, lrs = [], []
-        for _ in range(n):
-            img = txt = None
-            if image_iter is not None:
-                img, image_iter = fetch_next(image_loader, image_iter)
-            if text_iter is not None:
-                txt, text_iter = fetch_next(text_loader, text_iter)
-            if trace is not None and trace.get("indices", True):
-                if img is not None:
-                    trace.setdefault("img_idx", []).append(img.host_idx.clone())
-                if txt is not None:
-                    trace.setdefault("txt_idx", []).append(txt.host_idx.clone())
-            batches.append((img, txt))
-            lrs.append(scheduler.get_last_lr()[0])
-            scheduler.step()
-            if t_start is not None:
-                timing["rows"] = timing.get("rows", 0) + sum((b.global_n or b.n) for b in (img, txt) if b is not None)
+        while len(batches) < n:
+            # whole runs of batches inside the current epochs are taken at once (one sampler wait and, for per-step
+            # uploads, one host->device copy per loader); a step where a loader starts a new epoch goes through
+            # fetch_next so that the loaders draw from the global generator in the reference's order
+            k = n - len(batches)
+            for it_ in (image_iter, text_iter):
+                if it_ is not None:
+                    k = min(k, it_.batches_left() if hasattr(it_, "batches_left") else 0)
+            if k >= 1:
+                imgs = image_iter.take_chunk(k) if image_iter is not None else [None] * k
+                txts = text_iter.take_chunk(k) if text_iter is not None else [None] * k
+            else:
+                img = txt = None
+                if image_iter is not None:
+                    img, image_iter = fetch_next(image_loader, image_iter)
+                if text_iter is not None:
+                    txt, text_iter = fetch_next(text_loader, text_iter)
+                imgs, txts = [img], [txt]
+            for img, txt in zip(imgs, txts):
+                if trace is not None and trace.get("indices", True):
+                    if img is not None:
+                        trace.setdefault("img_idx", []).append(img.host_idx.clone())
+                    if txt is not None:
+                        trace.setdefault("txt_idx", []).append(txt.host_idx.clone())
+                batches.append((img, txt))
+                lrs.append(scheduler.get_last_lr()[0])
+                scheduler.step()
+                if t_start is not None:
+                    timing["rows"] = timing.get("rows", 0) + sum((b.global_n or b.n) for b in (img, txt) if b is not None)
         engine.run(batches, alpha, lrs, slot0=i)
         _dbg(f"chunk at {i} (+{n}) done")
+        if stats_to_host == "step":
+            engine.copy_slots_to_host(i, n)
         for j in range(n):
-            if stats_to_host == "step":
-                engine.copy_slot_to_host(i + j)
             pending.append((i + j, lrs[j]))
         if per_step:
             trace.setdefault("weights", []).append({k: v.detach().cpu().clone() for k, v in model.state_dict().items()})
