@@ -248,3 +248,28 @@ def test_gaussian_generate_data_is_bit_exact_with_the_reference():
     assert np.array_equal(d1["x"].numpy(), M["gauss/x"]) and np.array_equal(d1["y"].numpy(), M["gauss/y"])
     d2 = G.generate_data(dict(base, seed=44, shared_latent_distribution_type="laplace"))
     assert np.array_equal(d2["y"].numpy(), M["gauss/y_laplace"])
+
+
+@pytest.mark.parametrize("upload", ["step", "epoch"])
+def test_take_chunk_yields_the_per_step_stream(upload):
+    """train() takes whole runs of batches inside an epoch at once (_BankIter.take_chunk: one sampler wait, one index
+    upload); the batches must be exactly the ones next() would have produced, short last batch included."""
+    def stream(chunked):
+        torch.manual_seed(31)
+        ld = BankLoader(_bank(1003), 64, shuffle=True, upload=upload)
+        it, out = iter(ld), []
+        while len(out) < 40:
+            k = min(5, it.batches_left()) if chunked else 0
+            if k >= 1:
+                got = it.take_chunk(k)
+            else:
+                b, it = ft.fetch_next(ld, it)
+                got = [b]
+            for b in got:
+                assert torch.equal(b.idx.cpu(), b.host_idx) and b.n == b.host_idx.numel()
+                out.append(b.host_idx.clone())
+        return out[:40]
+
+    a, b = stream(False), stream(True)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert sorted(torch.cat(a[:16]).tolist()) == list(range(1003))  # an epoch = 15 full batches + one of 43 rows

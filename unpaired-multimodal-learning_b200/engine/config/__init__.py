@@ -50,5 +50,9 @@ _add("--alpha", type=float, default=0.0, help="weight of the text loss during cr
 _add("--flip_projection", type=bool, default=False)
 _add("--common_dim", type=int, default=0, help="common dimension")
 # additions of this implementation
+_add("--dp-sampler", type=str, default="global", choices=["global", "sharded"],
+     help="data-parallel runs (torchrun): 'global' = every rank draws the reference's global permutation and takes its "
+          "slice of each batch (bit-exact order); 'sharded' = every rank owns a strided row shard of the banks and "
+          "shuffles it itself (the sampler cost drops by the number of ranks)")
 _add("--precision", type=str, default="auto", choices=["auto", "fp32", "bf16"],
      help="fp32 = exact SIMT kernels, bf16 = tcgen05 tensor-core kernels, auto = by batch size")

@@ -371,8 +371,18 @@ def setup(datasets, hparams, args):
     scheduler = build_lr_scheduler(optimizer, hparams["lr_scheduler"], hparams["warmup_iter"], hparams["max_iter"],
                                    warmup_type=hparams["warmup_type"], warmup_lr=hparams["warmup_min_lr"])
     bs, nw = hparams["batch_size"], args.num_workers
-    image_loader = BankLoader(datasets["img_tr_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
-    text_loader = BankLoader(datasets["text_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
+    rank, world = _dist()
+    if world > 1 and getattr(args, "dp_sampler", "global") == "sharded":
+        # per-rank sampler: every rank keeps and shuffles only its strided row shard; bs stays the GLOBAL batch size
+        from .engine.datasets.utils import shard_bank
+        ib, tb = datasets["img_tr_bank"], datasets["text_bank"]
+        image_loader = BankLoader(shard_bank(ib.features, ib.labels, rank, world, device), -(-bs // world), shuffle=True,
+                                  num_workers=nw, shard_of=(rank, world))
+        text_loader = BankLoader(shard_bank(tb.features, tb.labels, rank, world, device), -(-bs // world), shuffle=True,
+                                 num_workers=nw, shard_of=(rank, world))
+    else:
+        image_loader = BankLoader(datasets["img_tr_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
+        text_loader = BankLoader(datasets["text_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
     if args.modality == "image":
         text_loader = None
         print("=> Running Unimodal: Image Only Model")
