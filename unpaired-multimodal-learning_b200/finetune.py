@@ -447,6 +447,10 @@ def main(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     args.device = f"cuda:{local_rank}"
     torch.cuda.set_device(local_rank)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():
+        # launched with torchrun: one rank per GPU, data parallel over the rows of every batch
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=torch.device(args.device))
     args.use_clip = args.vision_model == "" and args.language_model == ""
     encoder_name = args.clip_encoder if args.use_clip else f"{args.vision_model}-{args.language_model}"
     args.savepath = savedir(args.result_dir, args.dataset, encoder_name, args.train_shot, args.seed, args.text_type,
