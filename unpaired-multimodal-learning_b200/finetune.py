@@ -401,7 +401,7 @@ def setup(datasets, hparams, args):
     logger.log({"test/test_loss": test_loss, "test/test_acc": test_acc})
     test_dict = {"test_acc": test_acc, "val_acc": result["val_acc"], "model": result["model"], "iter": result["iter"]}
     print(f"=> Test Acc: {test_acc:.4f}")
-    if not FLAG or getattr(args, "overwrite", False):
+    if (not FLAG or getattr(args, "overwrite", False)) and _dist()[0] == 0:  # replicas are identical: rank 0 writes
         print(f"=> Saving Test Results for hparams to {test_path}")
         torch.save(test_dict, test_path)
     return test_dict
@@ -427,7 +427,7 @@ def sweep(datasets, hyperparams, args):
         print(f"=> Best Val Acc (so far): {best_val:.4f} | Test Acc (corresponding): {best_test:.4f}")
         print(f"=> Best Hyperparameters (so far): {best_hp}")
         print("--------------------------------------------------------\n")
-    if not FLAG or getattr(args, "overwrite", False):
+    if (not FLAG or getattr(args, "overwrite", False)) and _dist()[0] == 0:
         print(f"=> Saving results across all hparams to {args.savepath}")
         torch.save(results, os.path.join(args.savepath, "results.pth"))
     k = int(torch.argmax(torch.tensor(results["val_acc"])))
