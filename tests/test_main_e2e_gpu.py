@@ -1,0 +1,49 @@
+"""finetune.main end to end on bank FILES in the reference's layout (features.py:32-44, 152-248): the CLI namespace the
+reference builds, a sweep over a (tiny) preset, result files where collect_results.py expects them, checkpoint keys the
+reference's UMLClip can load with strict=False."""
+import os
+
+import pytest
+import torch
+
+from oracle.synth import synth_banks
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import uml_b200  # noqa: F401
+    from uml_b200 import features as F, finetune as ft
+    from uml_b200.engine.config import parser
+    from uml_b200.engine.optimizer.default import HYPER_DICT
+
+
+def test_main_runs_a_sweep_from_bank_files(tmp_path):
+    C, D = 20, 64
+    xi, yi, xt, yt, xv, yv = synth_banks(3, C, D, D, 16 * C, 6, 4 * C)
+    g = torch.Generator().manual_seed(5)
+    proto = torch.cat([xi[yi == c].mean(0, keepdim=True) for c in range(C)])
+    yte = torch.randint(0, C, (500,), generator=g)
+    xte = proto[yte] + 0.8 * torch.randn(500, D, generator=g)
+    fdir, rdir = str(tmp_path / "features"), str(tmp_path / "experiments")
+    lab2cname = {c: f"class_{c}" for c in range(C)}
+    F.write_text_bank(F.text_outdir(fdir, "ViT-B/16", "synthset", "cupl"), xt, yt, lab2cname=lab2cname)
+    F.write_image_bank(F.img_outdir(fdir, "ViT-B/16", "synthset", "crop", 16, 1, "train"), train=(xi, yi), val=(xv, yv),
+                       lab2cname=lab2cname)
+    F.write_image_bank(F.img_outdir(fdir, "ViT-B/16", "synthset", "crop", 16, 1, "test"), test=(xte, yte), lab2cname=lab2cname)
+    HYPER_DICT["unit_test"] = dict(HYPER_DICT["clip_linear"], lr=[1e-3, 1e-4], weight_decay=[0.0], max_iter=[300], patience=[3])
+    args = parser.parse_args(["--dataset", "synthset", "--train-shot", "16", "--seed", "1", "--clip-encoder", "ViT-B/16",
+                              "--modality", "crossmodal", "--text_type", "cupl", "--hyperparams", "unit_test", "--alpha", "0.5",
+                              "--feature_dir", fdir, "--result_dir", rdir, "--num-workers", "0", "--eval_test"])
+    results, best_val, best_test = ft.main(args)
+    assert len(results["test_acc"]) == 2 and best_test > 0.5 and best_val > 0.5      # chance is 0.05
+    base = os.path.join(rdir, "synthset-shot_16-seed_1", "ViT-B-16")
+    assert os.path.isdir(base)
+    found = [os.path.join(r, f) for r, _, fs in os.walk(base) for f in fs]
+    assert sum(f.endswith("test_result.pth") for f in found) == 2
+    assert any(f.endswith("results.pth") for f in found) and any(f.endswith("log.txt") for f in found)
+    ck = torch.load([f for f in found if f.endswith("test_result.pth")][0], map_location="cpu")
+    assert set(ck) >= {"test_acc", "val_acc", "model", "iter"} and list(ck["model"]) == ["head.weight"]
+    assert ck["model"]["head.weight"].shape == (C, D)
+    # a second call finds the saved results and does not retrain (reference behaviour: finetune.py:331-335)
+    results2, _, best_test2 = ft.main(args)
+    assert results2["test_acc"] == results["test_acc"] and best_test2 == best_test

@@ -217,7 +217,9 @@ int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are expected to be 64 bytes");
   UML_REQUIRE(max_floats > 0 && handle_out_64_bytes, "dp_p2p_alloc: bad arguments");
   max_floats = (max_floats + 3) / 4 * 4;
-  if (p2p.local) {
+  if (p2p.local) {  // re-sizing: unmap the peers' blocks, free ours
+    for (int p = 0; p < p2p.world; ++p)
+      if (p2p.ready && p != p2p.rank && p2p.peer[p]) cudaIpcCloseMemHandle(p2p.peer[p]);
     cudaFree(p2p.local);
     p2p = P2P();
   }
