@@ -11,20 +11,24 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import uml_b200  # noqa: F401,E402
 from uml_b200 import finetune as ft  # noqa: E402
 from uml_b200.engine.datasets.utils import BankLoader, FeatureBank  # noqa: E402
-from uml_b200.engine.models.head import UMLClip  # noqa: E402
+from uml_b200.engine.models.head import UML, UMLClip  # noqa: E402
 from uml_b200.engine.optimizer.optim import build_optimizer  # noqa: E402
 from uml_b200.engine.optimizer.scheduler import build_lr_scheduler  # noqa: E402
 from uml_b200.engine.trainer import StepEngine  # noqa: E402
 
 
-def run(world, rank, dev, prec, B, D, C, steps, banks):
+def run(world, rank, dev, prec, B, D, C, steps, banks, adapter_dv=0):
     (xi, yi), (xt, yt) = banks
     ib, tb = FeatureBank(xi, yi, dev), FeatureBank(xt, yt, dev)
     torch.manual_seed(1)
-    model = UMLClip(f"synthetic:{D}", C, logit_scale_init=4.60517)
-    model.to(dev)
-    model.zero_shot_init(tb)
-    model.to(dev)
+    if adapter_dv:   # UML with the linear adapter img_proj (Dv -> D) and learnable temperatures (preset "linear")
+        model = UML(f"synthetic:{adapter_dv}", D, C, learnable_temp=True)
+        model.to(dev)
+    else:
+        model = UMLClip(f"synthetic:{D}", C, logit_scale_init=4.60517)
+        model.to(dev)
+        model.zero_shot_init(tb)
+        model.to(dev)
     opt = build_optimizer(model.parameters(), "adamw", 1e-3, 0.01)
     sch = build_lr_scheduler(opt, "cosine", 5, 100, warmup_type="linear", warmup_lr=1e-5)
     eng = StepEngine(model, opt, dev, -(-B // world), -(-B // world), log_slots=steps + 1, precision=prec, world_size=world)
@@ -49,7 +53,11 @@ def run(world, rank, dev, prec, B, D, C, steps, banks):
         dist.all_gather(ds, eng.dW)
         if rank == 0:
             print(f"    [{prec}] last all-reduced dW identical on all ranks: {all(torch.equal(ds[0], d) for d in ds)}")
-    return model.head.weight.detach().clone(), eng.read_log(list(range(steps)))
+    w = model.head.weight.detach().clone()
+    if adapter_dv:
+        w = torch.cat([w.flatten(), model.img_proj.weight.detach().flatten(), model.img_scale.detach().view(1),
+                       model.txt_scale.detach().view(1)])
+    return w, eng.read_log(list(range(steps)))
 
 
 def main():
@@ -59,12 +67,13 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    for prec, B, D, C, steps, tol in (("fp32", 30, 512, 100, 12, 2e-5), ("bf16", 2051, 768, 1000, 12, 2e-3)):
+    for prec, B, D, C, steps, tol, dv in (("fp32", 30, 512, 100, 12, 2e-5, 0), ("bf16", 2051, 768, 1000, 12, 2e-3, 0),
+                                          ("bf16", 2051, 512, 100, 8, 5e-3, 256)):
         g = torch.Generator().manual_seed(3)
-        banks = ((torch.randn(5000, D, generator=g), torch.randint(0, C, (5000,), generator=g)),
-                 (torch.randn(3001, D, generator=g), torch.arange(3001) % C))
-        w_dp, log_dp = run(world, rank, dev, prec, B, D, C, steps, banks)
-        w_1, log_1 = run(1, 0, dev, prec, B, D, C, steps, banks)
+        banks = ((torch.randn(5000, dv or D, generator=g) * (0.05 if dv else 1.0), torch.randint(0, C, (5000,), generator=g)),
+                 (torch.randn(3001, D, generator=g) * (0.05 if dv else 1.0), torch.arange(3001) % C))
+        w_dp, log_dp = run(world, rank, dev, prec, B, D, C, steps, banks, dv)
+        w_1, log_1 = run(1, 0, dev, prec, B, D, C, steps, banks, dv)
         err = float((w_dp - w_1).norm() / w_1.norm())
         # every rank must hold the same weights
         ws = [torch.empty_like(w_dp) for _ in range(world)]
@@ -75,7 +84,7 @@ def main():
             print(f"    rank0 vs rank1: max |dW| {float(d.max()):.3e}, differing elements {int((d > 0).sum())} of {d.numel()}, "
                   f"rows touched {int((d > 0).any(dim=1).sum())}")
         if rank == 0:
-            print(f"[{prec}] B={B} world={world}: |W_dp - W_single| / |W| = {err:.3e} (tol {tol}); ranks identical: {same}; "
+            print(f"[{prec}{' adapter' if dv else ''}] B={B} world={world}: |W_dp - W_single| / |W| = {err:.3e} (tol {tol}); ranks identical: {same}; "
                   f"local loss step0 {log_dp[0]} vs global {log_1[0]}")
         ok = ok and err < tol and same
     flag = torch.tensor([1 if ok else 0], device=dev)
