@@ -45,6 +45,10 @@ WORKLOADS = {
                  desc="ImageNet full-data CLIP ViT-L/14 768-d features + CUPL text, linear head, throughput batch"),
     "cfg3_sym": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, batch_txt=18944, n_val=4096,
                      desc="cfg3 with 18944 rows per modality per GPU (text epochs of two steps)"),
+    # DINOv2 ViT-g (1536-d) image bank + OpenLLaMA-3B (3200-d) text bank, linear adapter img_proj 1536 -> 3200 + shared
+    # head, learnable temperatures (preset "linear"), throughput batch; a 200 k-row sample of the image bank
+    "cfg4": dict(n_img=200_000, n_txt=29_940, dim=3200, dv=1536, classes=1000, batch=8192, batch_txt=8192, n_val=4096,
+                 desc="DINOv2 ViT-g 1536-d image + OpenLLaMA-3B 3200-d text features, adapter + shared head, throughput batch"),
     "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, batch_txt=32, n_val=4000,
                  desc="ImageNet 16-shot CLIP ViT-B/16 512-d features + CUPL text, linear head, reference batch 32"),
     "cfg3_refB": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=32, batch_txt=32, n_val=4096,
@@ -199,11 +203,11 @@ def build_banks(wl, dev, rank=0, world=1):
 
     g = torch.Generator(device=dev).manual_seed(1)
     D, C = wl["dim"], wl["classes"]
-    img = torch.randn(wl["n_img"], D, device=dev, generator=g)
+    img = torch.randn(wl["n_img"], wl.get("dv", D), device=dev, generator=g)
     img_y = torch.randint(0, C, (wl["n_img"],), device=dev, generator=g)
     txt = torch.randn(wl["n_txt"], D, device=dev, generator=g)
     txt_y = (torch.arange(wl["n_txt"], device=dev) % C)
-    val = torch.randn(wl["n_val"], D, device=dev, generator=g)
+    val = torch.randn(wl["n_val"], wl.get("dv", D), device=dev, generator=g)
     val_y = torch.randint(0, C, (wl["n_val"],), device=dev, generator=g)
     if world > 1:
         ib, tb = shard_bank(img, img_y, rank, world, dev), shard_bank(txt, txt_y, rank, world, dev)
@@ -217,7 +221,7 @@ def build_banks(wl, dev, rank=0, world=1):
 def txt_full_for_init(wl, dev):
     """The whole text bank again (same seed stream as build_banks) - the zero-shot initialisation uses every row."""
     g = torch.Generator(device=dev).manual_seed(1)
-    torch.randn(wl["n_img"], wl["dim"], device=dev, generator=g)
+    torch.randn(wl["n_img"], wl.get("dv", wl["dim"]), device=dev, generator=g)
     torch.randint(0, wl["classes"], (wl["n_img"],), device=dev, generator=g)
     return torch.randn(wl["n_txt"], wl["dim"], device=dev, generator=g)
 
@@ -228,10 +232,15 @@ def make_model(wl, dev, txt_bank):
     from uml_b200.engine.optimizer.scheduler import build_lr_scheduler
 
     torch.manual_seed(1)
-    model = UMLClip(f"synthetic:{wl['dim']}", wl["classes"], logit_scale_init=LOGIT)
-    model.to(dev)
-    model.zero_shot_init(txt_bank)
-    model.to(dev)
+    if wl.get("dv"):  # adapter variant (reference UML with img_proj, head.py:63-84), preset "linear": learnable temperatures
+        from uml_b200.engine.models.head import UML
+        model = UML(f"synthetic:{wl['dv']}", wl["dim"], wl["classes"], learnable_temp=True)
+        model.to(dev)
+    else:
+        model = UMLClip(f"synthetic:{wl['dim']}", wl["classes"], logit_scale_init=LOGIT)
+        model.to(dev)
+        model.zero_shot_init(txt_bank)
+        model.to(dev)
     opt = build_optimizer(model.parameters(), "adamw", LR, WD)
     sch = build_lr_scheduler(opt, "cosine", 50, 12800, warmup_type="linear", warmup_lr=1e-5)
     return model, opt, sch
@@ -551,6 +560,9 @@ def main():
         roof["kernel_ms"] = {k: round(v, 5) for k, v in res["ktimes"].items()}
         roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in res["breakdown"].items()}
         step_flops = 4.0 * D * C * rows_per_gpu
+        if wl.get("dv"):  # image row 4 Dv D + 6 D C (proj fwd + dW_proj + head fwd + dW + dZ), text row 4 D C
+            fi, ftx = 4.0 * wl["dv"] * D + 6.0 * D * C, 4.0 * D * C
+            step_flops = rows_per_gpu * (fi * B + ftx * BT) / (B + BT)
         line = {"metric": "UML train samples/sec (img+text)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": K, "warmup": args.warmup, "ms_per_step": res["ms"] / K, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if used_bf16 else "f32", "data": "synthetic",
@@ -562,9 +574,12 @@ def main():
                 "step_tensor_frac": {"achieved_tflops_per_gpu": step_flops / (res["ms"] / K * 1e-3) / 1e12,
                                      "of_sustained_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_sustained"],
                                      "of_burst_peak": step_flops / (res["ms"] / K * 1e-3) / 1e12 / peaks["tf_burst"],
-                                     "algorithmic_flops_per_sample": 4.0 * D * C},
+                                     "algorithmic_flops_per_sample": step_flops / rows_per_gpu},
                 "final_losses": res["loss_tail"]}
-        if world == 1:
+        if world == 1 and wl.get("dv"):
+            line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port",
+                                    "sample": "not run: the CPU port in bench.py covers the linear-head step only"}
+        elif world == 1:
             try:
                 r = cpu_reference_run(wl, 10 ** 6, 1, budget_s=args.cpu_seconds)
                 line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",

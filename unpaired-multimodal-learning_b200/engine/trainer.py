@@ -575,9 +575,9 @@ class StepEngine:
                 ops.gather_rows_labels(feats, labels, idx, self.X16[n_i:n], self.labels32[n_i:n])
             rows_l.append(n_t); scales.append(s_t); weights.append(wt); sdevs.append(sd_t)
         segs = ops.tc_segments(rows_l, scales, weights, sdevs if self.learnable else None)
-        ops.head_fwd_ce_bf16(self.X16, self.W16, self.labels32, segs, ws, None, n_rows=n)
         stats = self.stats_log[slot]
-        ops.reduce_tile_stats(ws.fac, n, len(rows_l), stats)
+        self._timed("head_fwd_ce_bf16", ops.head_fwd_ce_bf16, self.X16, self.W16, self.labels32, segs, ws, None, n_rows=n,
+                    stats=stats)  # the fix-up launch also reduces the per-run statistics
         if self.learnable:
             k = 0
             if n_i:
