@@ -502,6 +502,9 @@ def main():
     config = {"workload": f"{args.workload}: {wl['desc']}", "dim": D, "classes": C, "img_bank_rows": wl["n_img"],
               "txt_bank_rows": wl["n_txt"], "image_rows_per_gpu_step": B, "text_rows_per_gpu_step": BT,
               "global_batch": (B + BT) * world, "optimizer": "adamw", "alpha": ALPHA, "parallelism": f"dp{world}",
+              "inputs": "value: banks and the timed steps' index batches resident in HBM when the clock starts (rows are "
+                        "gathered from the banks inside the timed region); e2e: sampler + per-step index uploads + loss "
+                        "read-back inside the timed region",
               "sampler": "single global permutation, bit-exact with the reference's DataLoader order" if world == 1 else
                          "per-rank shard permutation (DistributedSampler-style, equal strided shards); NCCL all-reduce of dW per step",
               "l2_policy": "inputs larger than L2: every step gathers fresh rows from a 3.9 GB bank and rewrites a "
