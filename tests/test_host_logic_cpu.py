@@ -273,3 +273,39 @@ def test_take_chunk_yields_the_per_step_stream(upload):
     a, b = stream(False), stream(True)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     assert sorted(torch.cat(a[:16]).tolist()) == list(range(1003))  # an epoch = 15 full batches + one of 43 rows
+
+
+def test_bank_v2_round_trip_is_lossless(tmp_path):
+    """features.write_bank_v2 / load_bank_v2 / convert_bank: bit-identical features and labels, the bf16 shadow equals
+    the on-device cast, class_order/class_starts reproduce the per-class row lists TextTensorDataset builds."""
+    g = torch.Generator().manual_seed(8)
+    feats, labels = torch.randn(1237, 40, generator=g), torch.randint(0, 17, (1237,), generator=g)
+    eot = torch.randint(0, 77, (1237,), generator=g)
+    v1 = str(tmp_path / "text.pth")
+    F.write_text_bank(v1, feats, labels, eot, prompts={"a": ["x"]}, lab2cname={0: "zero"})
+    (v2,) = F.convert_bank(v1)
+    hdr = F.read_bank_v2_header(v2)
+    assert hdr["rows"] == 1237 and hdr["dim"] == 40 and hdr["classes"] == int(labels.max()) + 1
+    assert all(s["offset"] % 4096 == 0 for s in hdr["sections"].values())
+    t, _, meta = F.load_bank_v2(v2, device="cpu")
+    assert torch.equal(t["features"], feats) and torch.equal(t["labels"], labels) and torch.equal(t["eot_indices"], eot)
+    assert torch.equal(t["features_bf16"], feats.to(torch.bfloat16))
+    assert meta["prompts"] == {"a": ["x"]} and meta["lab2cname"] == {0: "zero"}
+    for c in torch.unique(labels).tolist():
+        rows = t["class_order"][t["class_starts"][c]:t["class_starts"][c + 1]]
+        assert torch.equal(rows, torch.nonzero(labels == c, as_tuple=True)[0])
+    # image train file: two splits
+    v1i = str(tmp_path / "img.pth")
+    F.write_image_bank(v1i, train=(feats[:800], labels[:800]), val=(feats[800:], labels[800:]), lab2cname={0: "zero"})
+    files = F.convert_bank(v1i, str(tmp_path / "img.bank2"), with_bf16=False)
+    assert [os.path.basename(f) for f in files] == ["img.bank2.train", "img.bank2.val"]
+    tv, hv, _ = F.load_bank_v2(files[1], device="cpu")
+    assert torch.equal(tv["features"], feats[800:]) and "features_bf16" not in tv and hv["rows"] == 437
+    # load_feature_bank prefers the v2 file next to the v1 one and falls back to the v1 dict
+    F.convert_bank(v1i)
+    b2, m2 = F.load_feature_bank(v1i, device="cpu", split="train")
+    assert torch.equal(b2.features, feats[:800]) and torch.equal(b2.labels, labels[:800]) and m2["lab2cname"] == {0: "zero"}
+    assert torch.equal(b2.bf16(), feats[:800].to(torch.bfloat16))  # the shadow came from the file, no device cast needed
+    os.remove(os.path.splitext(v1i)[0] + ".bank2.train")
+    b1, _ = F.load_feature_bank(v1i, device="cpu", split="train")
+    assert torch.equal(b1.features, b2.features) and torch.equal(b1.labels, b2.labels)

@@ -47,3 +47,12 @@ def test_main_runs_a_sweep_from_bank_files(tmp_path):
     # a second call finds the saved results and does not retrain (reference behaviour: finetune.py:331-335)
     results2, _, best_test2 = ft.main(args)
     assert results2["test_acc"] == results["test_acc"] and best_test2 == best_test
+    # the same run from v2 bank files (features.convert_bank: mapped, streamed to HBM, bf16 shadow included) is identical
+    F.convert_bank(F.img_outdir(fdir, "ViT-B/16", "synthset", "crop", 16, 1, "train"))
+    F.convert_bank(F.img_outdir(fdir, "ViT-B/16", "synthset", "crop", 16, 1, "test"))
+    args3 = parser.parse_args(["--dataset", "synthset", "--train-shot", "16", "--seed", "1", "--clip-encoder", "ViT-B/16",
+                               "--modality", "crossmodal", "--text_type", "cupl", "--hyperparams", "unit_test", "--alpha", "0.5",
+                               "--feature_dir", fdir, "--result_dir", str(tmp_path / "experiments_v2"), "--num-workers", "0",
+                               "--eval_test"])
+    results3, _, best_test3 = ft.main(args3)
+    assert results3["test_acc"] == results["test_acc"] and results3["val_acc"] == results["val_acc"]

@@ -33,7 +33,7 @@ from .engine.optimizer.optim import build_optimizer
 from .engine.optimizer.scheduler import build_lr_scheduler
 from .engine.tools.utils import Tee, makedirs, set_random_seed
 from .engine.trainer import StepEngine
-from .features import img_outdir, load_image_bank, load_text_bank, text_outdir
+from .features import img_outdir, load_feature_bank, load_image_bank, load_text_bank, text_outdir
 
 EVAL_FREQ = 100  # evaluate on the val bank every 100 iterations (early stopping)
 FLAG = 0         # 1: run although the experiment directory already holds a result
@@ -476,19 +476,20 @@ def main(args):
         te_path = img_outdir(args.feature_dir, image_encoder, args.dataset, args.image_augmentation, args.train_shot,
                              args.seed, "test")
         print(f"=> Loading image features from: {tr_path} and {te_path}")
-        tr, te = load_image_bank(tr_path), load_image_bank(te_path)
-        lab2cname = tr.get("lab2cname") or te.get("lab2cname") or tf.get("lab2cname")
-        args.img_indim = int(tr["train"]["features"].shape[1])
+        dev = args.device
+        # v2 bank files next to the .pth ones (features.convert_bank) are mapped and streamed to HBM; else the v1 dicts
+        tr_bank, tr_meta = load_feature_bank(tr_path, dev, "train")
+        val_bank, _ = load_feature_bank(tr_path, dev, "val")
+        te_bank, te_meta = load_feature_bank(te_path, dev)
+        lab2cname = tr_meta.get("lab2cname") or te_meta.get("lab2cname") or tf.get("lab2cname")
+        args.img_indim = int(tr_bank.dim)
         args.text_indim = int(tf["features"].shape[1])
         if args.use_clip and args.img_indim != args.text_indim:
             raise ValueError("CLIP image and text features must share a width")
-        args.nclasses = len(lab2cname) if lab2cname else int(max(tr["train"]["labels"].max(), te["labels"].max())) + 1
-        dev = args.device
+        args.nclasses = len(lab2cname) if lab2cname else int(max(tr_bank.labels.max(), te_bank.labels.max())) + 1
         datasets = {
             "text_ds": text_ds, "text_bank": FeatureBank.from_text_dataset(text_ds, dev),
-            "img_tr_bank": FeatureBank(tr["train"]["features"], tr["train"]["labels"], dev),
-            "img_val_bank": FeatureBank(tr["val"]["features"], tr["val"]["labels"], dev),
-            "img_te_bank": FeatureBank(te["features"], te["labels"], dev),
+            "img_tr_bank": tr_bank, "img_val_bank": val_bank, "img_te_bank": te_bank,
         }
         results, best_val, best_test = sweep(datasets, HYPER_DICT[args.hyperparams], args)
         del datasets
