@@ -147,10 +147,12 @@ class ClockSampler:
 # reference arm / cpu baseline: the oracle port of the reference step on the host cores
 # -----------------------------------------------------------------------------------------------
 
-def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
+def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None, device="cpu"):
     """Times the reference's step algorithm (oracle port: per-sample fetch + collate, F.linear,
     F.cross_entropy, two autograd.grad sweeps + backward, AdamW - finetune.py:163-195) on all host
-    threads.  The image bank is a seeded sample of ``bank_rows`` rows of the workload's shape."""
+    threads.  The image bank is a seeded sample of ``bank_rows`` rows of the workload's shape.
+    ``device="cuda"``: the same port as eager PyTorch on one GPU - the banks stay on the host like the reference's
+    datasets, each batch is collated there and copied over, the step's torch ops run on the device."""
     from oracle import uml_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
@@ -162,8 +164,10 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
     yi = torch.randint(0, C, (n_img,), generator=g)
     xt = torch.randn(wl["n_txt"], D, generator=g)
     yt = torch.arange(wl["n_txt"]) % C
-    st = O.HeadState(head=O.zero_shot_weights(xt, yt, C), img_scale=math.exp(LOGIT), txt_scale=math.exp(LOGIT))
+    st = O.HeadState(head=O.zero_shot_weights(xt, yt, C).to(device), img_scale=math.exp(LOGIT), txt_scale=math.exp(LOGIT))
     opt = O.OracleOptimizer(st.param_dict(), "adamw", LR, WD)
+    on_gpu = torch.device(device).type == "cuda"
+    gpu_ms = [0.0]
     il, tl = O.OracleLoader(n_img, B), O.OracleLoader(wl["n_txt"], BT)
     torch.manual_seed(2)
     il.iter(); tl.iter()
@@ -173,8 +177,16 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
         # default_collate over a map-style dataset: one row at a time, then stack
         xb = torch.stack([xi[int(j)] for j in ii]); yb = torch.stack([yi[int(j)] for j in ii])
         tb = torch.stack([xt[int(j)] for j in it]); ub = torch.stack([yt[int(j)] for j in it])
+        if on_gpu:
+            xb, yb, tb, ub = (t.to(device, non_blocking=True) for t in (xb, yb, tb, ub))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _, grads = O.uml_step_grads_autograd(st, xb, yb, tb, ub, ALPHA)
         opt.step(grads, O.lr_at(i, LR, "cosine", 50, 12800))
+        if on_gpu:
+            e1.record()
+            torch.cuda.synchronize()  # the reference reads the losses every step (finetune.py:197-206)
+            gpu_ms[0] += e0.elapsed_time(e1)
         return ii.numel() + it.numel()
 
     for i in range(warmup):
@@ -188,8 +200,12 @@ def cpu_reference_run(wl, steps, warmup, bank_rows=65536, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return dict(value=rows / dt, ms_per_step=1e3 * dt / done, steps=done, cores=cores,
-                sample=f"{done} steps of {B} image + {BT} text rows on a {n_img}-row sample of the image bank, {cores} threads")
+    out = dict(value=rows / dt, ms_per_step=1e3 * dt / done, steps=done, cores=cores,
+               sample=f"{done} steps of {B} image + {BT} text rows on a {n_img}-row sample of the image bank, {cores} threads")
+    if on_gpu:  # the torch ops alone (batch already on the device), without the host-side collate
+        out["device_ms_per_step"] = gpu_ms[0] / done
+        out["device_only_value"] = rows / (gpu_ms[0] * 1e-3)
+    return out
 
 
 # -----------------------------------------------------------------------------------------------
@@ -480,13 +496,161 @@ def run_gaussian(args):
     print(json.dumps(line))
 
 
+def run_sweep(args):
+    """--workload cfg2_sweep: the reference's real few-shot workload - the hyper-parameter sweep of preset `clip_linear`
+    (lr x weight decay, engine/optimizer/default.py:17-31) times its alpha sweep over the SAME cfg2 banks - with
+    --heads combinations trained in lock step (finetune.train_group / uml_sweep_run: four launches per step of all
+    heads).  value: device-resident (every head's epoch permutation in HBM before the clock starts); e2e: ONE public
+    train_group() call; `sequential`: the same banks through the single-head engine (finetune.train), which is what
+    the sweep costs one combination at a time."""
+    import contextlib
+    import io
+    import uml_b200  # noqa: F401
+    from uml_b200 import _lib, finetune as ft
+    from uml_b200.engine.datasets.utils import BankLoader
+    from uml_b200.engine.models.head import UMLClip, get_zero_shot_weights
+    from uml_b200.engine.optimizer.optim import build_optimizer
+    from uml_b200.engine.optimizer.scheduler import build_lr_scheduler
+    from uml_b200.engine.sweep import HeadGroup
+
+    wl = WORKLOADS["cfg2"]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+    img_bank, txt_bank, val_bank, _ = build_banks(wl, dev)
+    D, C, B, BT = wl["dim"], wl["classes"], wl["batch"], wl["batch_txt"]
+    H, K, W = args.heads, args.steps, args.warmup
+    grid = [(lr, wd, al) for al in (0.2, 0.5, 0.7, 1.0, 1.5) for lr in (1e-3, 1e-4) for wd in (0.0, 0.01, 0.001)]
+    grid = [grid[k % len(grid)] for k in range(H)]
+    W0 = get_zero_shot_weights(txt_bank, C, D)
+
+    def make_heads(n, upload="epoch"):
+        ms, os_, ss, il, tl, vl = [], [], [], [], [], []
+        with contextlib.redirect_stdout(io.StringIO()):
+            for k in range(n):
+                lr, wd, _ = grid[k]
+                m = UMLClip(f"synthetic:{D}", C, logit_scale_init=LOGIT)
+                m.precision = "fp32"
+                m.load_state_dict({"head.weight": W0.clone()})
+                m.to(dev)
+                o = build_optimizer(m.parameters(), "adamw", lr, wd)
+                rng = torch.Generator().manual_seed(100 + k)
+                ms.append(m); os_.append(o)
+                ss.append(build_lr_scheduler(o, "cosine", 50, 12800, warmup_type="linear", warmup_lr=1e-5))
+                il.append(BankLoader(img_bank, B, shuffle=True, upload=upload, rng=rng))
+                tl.append(BankLoader(txt_bank, BT, shuffle=True, upload=upload, rng=rng))
+                vl.append(BankLoader(val_bank, 32, shuffle=False, rng=rng))
+        return ms, os_, ss, il, tl, vl
+
+    alphas = [g[2] for g in grid]
+    # ---------------- device-resident arm ------------------------------------------------------------------------
+    ms_, os_, ss, il, tl, vl = make_heads(H)
+    group = HeadGroup(ms_, os_, img_bank, txt_bank, B, BT, dev, log_slots=W + K + 1)
+    iti, itt = [iter(l) for l in il], [iter(l) for l in tl]
+    assert W + K <= min(len(il[0]), len(tl[0])), "keep warm-up + steps inside one epoch of the few-shot banks"
+
+    def chunk(n, i0):
+        pi = [it.take_run(n) for it in iti]
+        pt = [it.take_run(n) for it in itt]
+        lrs = [[s.lr_at(i0 + j, s.base_lrs[0]) for s in ss] for j in range(n)]
+        return ([p[0] for p in pi], [p[0] for p in pt], pi[0][1], pt[0][1], [(B, BT)] * n, lrs)
+
+    a = chunk(W, 0)
+    group.run(*a, alphas, [True] * H, slot0=0)
+    a = chunk(K, W)  # the timed steps' permutations are in HBM (uploaded when the epoch was drawn)
+    group.time_last_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    n0 = _lib.LAUNCH_COUNT[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    i = 0
+    while i < K:  # one library call per 16 steps, like train_group's chunks
+        n = min(16, K - i)
+        group.run(a[0], a[1], a[2] + i * B, a[3] + i * BT, a[4][i:i + n], a[5][i:i + n], alphas, [True] * H, slot0=W + i)
+        i += n
+    e1.record()
+    host_ms = (time.perf_counter() - t0) * 1e3 / K
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    sampler.close()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.LAUNCH_COUNT[0] - n0
+    ktimes = group.kernel_times_ms()
+    tail = group.read_log([W + K - 1], True, True)
+    rows = H * K * (B + BT)
+    del group
+
+    # ---------------- end-to-end arm: one public train_group() call ----------------------------------------------
+    def e2e_group():
+        ms2, os2, ss2, il2, tl2, vl2 = make_heads(H)
+        trs = [None] * H  # per-step records are only materialised for heads that ask for them
+        trs[0] = {"indices": False, "timing": {"warmup": max(W, 3)}}
+        with contextlib.redirect_stdout(io.StringIO()):
+            ft.train_group(ms2, il2, tl2, vl2, None, os2, ss2, device=dev, max_iters=max(W, 3) + K, alphas=alphas,
+                           eval_freq=10 ** 9, patience=5, traces=trs)
+        assert trs[0]["timing"]["iters"] == K
+        return trs[0]["timing"]["seconds"]
+
+    e2e_all = [e2e_group() for _ in range(3)]
+    e2e_dt = sorted(e2e_all)[1]
+
+    # ---------------- the same sweep one combination at a time (single-head engine) ------------------------------
+    def sequential():
+        ms2, os2, ss2, il2, tl2, vl2 = make_heads(1, upload="epoch")
+        tr = {"timing": {"warmup": max(W, 3)}, "indices": False}
+        with contextlib.redirect_stdout(io.StringIO()):
+            ft.train(ms2[0], il2[0], tl2[0], vl2[0], None, os2[0], ss2[0], device=dev, max_iters=max(W, 3) + K,
+                     alpha=alphas[0], eval_freq=10 ** 9, patience=5, trace=tr)
+        return tr["timing"]["seconds"] / K
+    seq = sorted(sequential() for _ in range(3))[1]
+
+    kms = ktimes.get("sweep_dw_update", float("nan"))
+    # algorithmic bytes of the dW + optimizer launch: W, m, v read and written once per head (24 B/parameter; the
+    # gradient itself never reaches HBM) plus the step's G and feature rows read once
+    bytes_ = H * (24.0 * C * D + 4.0 * (B + BT) * (C + D))
+    roof = {"bound": "hbm", "kernel": "sweep_dw_update_kernel", "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
+            "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
+            "algorithmic_bytes_per_launch": bytes_, "kernel_ms": {k: round(v, 5) for k, v in ktimes.items()}}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {"metric": "UML train samples/sec (img+text)", "value": rows / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg2_sweep: {wl['desc']}; {H} hyper-parameter combinations (lr x wd x alpha) in lock step",
+                       "heads": H, "dim": D, "classes": C, "img_bank_rows": wl["n_img"], "txt_bank_rows": wl["n_txt"],
+                       "image_rows_per_head_step": B, "text_rows_per_head_step": BT, "optimizer": "adamw",
+                       "l2_policy": f"per step {H} x 6.1 MB of weights and optimizer state stream through HBM "
+                                    f"({H * 6.1:.0f} MB{', larger than L2' if H * 6.1 > 126 else ', fits L2'})"},
+            "clocks": clocks,
+            "e2e": {"value": rows / e2e_dt, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": H * 2 * 16,
+                    "note": "one train_group() call; permutations uploaded once per epoch; stats read back at the end",
+                    "stat": "median of 3 calls", "all": [round(rows / x) for x in e2e_all]},
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms, "roofline": roof,
+            "sequential": {"ms_per_head_step": seq * 1e3, "samples_per_s": (B + BT) / seq,
+                           "speedup_of_lock_step": (rows / e2e_dt) / ((B + BT) / seq),
+                           "note": "finetune.train() of one combination on the same banks (single-head fp32 engine), end to end"},
+            "final_losses": {"image_loss": tail["image_loss"][0][0], "text_loss": tail["text_loss"][0][0]}}
+    try:
+        r = cpu_reference_run(wl, 10 ** 6, 1, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    except Exception as e:
+        line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1"])
+    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1", "cfg2_sweep"])
+    ap.add_argument("--heads", type=int, default=30, help="cfg2_sweep: hyper-parameter combinations trained in lock step (<= 32)")
+    ap.add_argument("--ref-device", type=str, default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: 'cuda' times the same port as eager PyTorch on one GPU (collate on the host, "
+                         "H2D, fp32 torch ops on the device) - the like-for-like GPU baseline of SURVEY 8d")
     ap.add_argument("--precision", type=str, default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     args = ap.parse_args()
@@ -495,6 +659,10 @@ def main():
         if args.impl == "reference" or not torch.cuda.is_available():
             raise SystemExit("bench.py --workload cfg1 runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
         return run_gaussian(args)
+    if args.workload == "cfg2_sweep":
+        if args.impl == "reference" or not torch.cuda.is_available():
+            raise SystemExit("bench.py --workload cfg2_sweep runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
+        return run_sweep(args)
     wl = WORKLOADS[args.workload]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     peaks = measured_peaks()
@@ -513,7 +681,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_run(wl, args.steps, args.warmup, budget_s=150.0)
+        r = cpu_reference_run(wl, args.steps, args.warmup, budget_s=150.0, device=args.ref_device)
         line = {"impl": "reference", "metric": "UML train samples/sec (img+text)", "value": r["value"], "unit": "samples/s",
                 "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -522,6 +690,11 @@ def main():
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        if args.ref_device == "cuda":  # informational like-for-like arm; the driver's arm is the CPU one
+            line.update(ref_device="cuda", eager_gpu={"device_ms_per_step": r["device_ms_per_step"],
+                                                      "device_only_samples_per_s": r["device_only_value"],
+                                                      "note": "torch eager fp32 ops of the port on one GPU; value/e2e include the "
+                                                              "host-side per-sample collate and the H2D copy of every batch"})
         print(json.dumps(line))
         return
 

@@ -298,6 +298,45 @@ int uml_gauss_eval(const float* params, int32_t dim_obs, int32_t dim_common, int
                    const float* data_y, int64_t n_rows, float* workspace /* >= 2*ceil(n_rows/16) floats */,
                    float* loss_out, void* stream);
 
+/* ---- sweep-level batching: the lr x weight-decay (x alpha) combinations that
+ * finetune.py:406-448 (`sweep`) and engine/optimizer/default.py:17-31 (`HYPER_DICT`) train one after the other over the
+ * SAME banks advance here in lock step - K heads with their own weights, optimizer state, sampler stream, lr, weight
+ * decay and alpha; one step of all K heads is four launches.  Exact fp32 arithmetic per head (the *_f32 family), linear
+ * head without adapter and with fixed logit scales (UMLClip, head.py:131-137).  All heads share bank sizes and batch
+ * sizes, so head k's batch for modality s is perm[s][k][pos[s] .. pos[s]+n) with a common position.            */
+#define UML_SWEEP_MAX_HEADS 32
+typedef struct {
+  int32_t        n_heads, dim, n_classes;
+  int32_t        kind;            /* uml_update.kind: 1 AdamW, 2 Adam (L2), 3 SGD momentum (L2)                */
+  const float*   bank[2];         /* fp32 rows of the image / text bank (NULL for an absent modality)           */
+  int64_t        bank_ld[2];
+  const int64_t* labels[2];       /* bank labels                                                                 */
+  const int64_t* perm[2][UML_SWEEP_MAX_HEADS]; /* host array of DEVICE pointers: head k's epoch permutation        */
+  int64_t        perm_len[2];     /* entries in every permutation (= bank rows)                                  */
+  int64_t        pos[2];          /* where the first step's batches start inside the permutations                */
+  float          scale[2];        /* logit scales of the image / text run                                        */
+  float*         W;               /* [n_heads][head_stride] weights, each head a [n_classes][dim] matrix         */
+  float*         m;               /* exp_avg | momentum buffers, same layout                                     */
+  float*         v;               /* exp_avg_sq (unused for SGD)                                                 */
+  int64_t        head_stride;
+  float*         G;               /* scratch [n_heads][max_rows][ldg]                                            */
+  int64_t        ldg, max_rows;
+  float*         row_loss;        /* scratch [n_heads][max_rows]                                                 */
+  int32_t*       row_correct;     /* scratch [n_heads][max_rows]                                                 */
+  uml_seg_stats* stats;           /* out [n_steps][n_heads][2]: {image run, text run} of every step              */
+  float          beta1, beta2, eps, momentum;
+  int64_t        step;            /* 1-based optimizer step of the first step (all heads count alike)            */
+  float          weight_decay[UML_SWEEP_MAX_HEADS];
+  float          alpha[UML_SWEEP_MAX_HEADS];       /* text-loss weight per head (finetune.py:188)               */
+  uint8_t        active[UML_SWEEP_MAX_HEADS];      /* 0: the head stopped early, nothing of it is touched       */
+  void*          ev[8];           /* optional cudaEvent_t pairs recorded around the four launches of the LAST step:
+                                     logits, softmax/CE, dW + update, stats (NULL = not timed)                    */
+} uml_sweep_args;
+/* n_steps consecutive steps: step i consumes rows[2i] image rows and rows[2i+1] text rows per head (host array;
+ * the last batch of an epoch is short) with learning rates lr[i*n_heads + k] (host array).                      */
+int uml_sweep_run(const uml_sweep_args* args /*host*/, int32_t n_steps, const int64_t* rows /*host*/,
+                  const float* lr /*host*/, void* stream);
+
 /* ---- sampler: the epoch permutation on the host, bit-exact with torch.randperm(n, generator=
  * torch.Generator().manual_seed(seed)) on the CPU - what RandomSampler draws once per epoch for the
  * DataLoaders of finetune.py:370-371 (MT19937 seeded with the low 32 bits of `seed`, Fisher-Yates

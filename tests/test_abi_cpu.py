@@ -44,3 +44,47 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in re.sub(r'""".*?"""', "", text, flags=re.S).replace("# oracle", ""), f
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """sizeof and every field offset of the ctypes mirrors equal what a C compiler makes of include/uml_b200.h."""
+    import ctypes
+    import shutil
+    import subprocess
+    pairs = {"uml_segment": _lib.Segment, "uml_seg_stats": _lib.SegStats, "uml_update": _lib.Update,
+             "uml_tc_segments": _lib.TcSegments, "uml_linear_step_args": _lib.LinearStepArgs,
+             "uml_run_step": _lib.RunStep, "uml_sweep_args": _lib.SweepArgs}
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "uml_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
+def test_sweep_run_validates_arguments_before_touching_the_device():
+    import ctypes as C
+    lib = _lib.load()
+    a = _lib.SweepArgs()
+    rows, lr = (C.c_int64 * 2)(4, 4), (C.c_float * 1)(1e-3)
+    a.n_heads = 0
+    assert lib.uml_sweep_run(C.byref(a), 1, rows, lr, None) != 0
+    assert b"heads" in lib.uml_last_error()
+    a.n_heads, a.dim, a.n_classes, a.ldg, a.kind = 1, 8, 4, 4, 7
+    assert lib.uml_sweep_run(C.byref(a), 1, rows, lr, None) != 0
+    assert b"optimizer kind" in lib.uml_last_error()
+    a.kind = 1
+    assert lib.uml_sweep_run(C.byref(a), 1, rows, lr, None) != 0  # null buffers
+    assert b"null buffer" in lib.uml_last_error()

@@ -309,3 +309,66 @@ def test_bank_v2_round_trip_is_lossless(tmp_path):
     os.remove(os.path.splitext(v1i)[0] + ".bank2.train")
     b1, _ = F.load_feature_bank(v1i, device="cpu", split="train")
     assert torch.equal(b1.features, b2.features) and torch.equal(b1.labels, b2.labels)
+
+
+# ------------------------------------------------------------------------------------------------
+# sweep batching: a private generator standing in for the global one, and run-wise advancing
+# ------------------------------------------------------------------------------------------------
+
+def _drive(img, txt, val, steps, eval_every):
+    """The order in which train() touches its loaders: iter(image), iter(text); per step image batch then text batch
+    (re-iterating on exhaustion); an iter(val) per evaluation."""
+    seq = []
+    ii, ti = iter(img), iter(txt)
+    for s in range(steps):
+        for name in ("i", "t"):
+            ld, it = (img, ii) if name == "i" else (txt, ti)
+            try:
+                b = next(it)
+            except StopIteration:
+                it = iter(ld)
+                b = next(it)
+            if name == "i":
+                ii = it
+            else:
+                ti = it
+            seq.append(b.host_idx.clone())
+        if s % eval_every == 0:
+            iter(val)
+    return seq
+
+
+@pytest.mark.parametrize("nw", [0, 2])
+def test_private_rng_reproduces_the_global_stream(nw):
+    mk = lambda rng: (BankLoader(_bank(53), 8, shuffle=True, num_workers=nw, rng=rng),
+                      BankLoader(_bank(31), 8, shuffle=True, num_workers=nw, rng=rng),
+                      BankLoader(_bank(20), 8, shuffle=False, num_workers=nw, rng=rng))
+    torch.manual_seed(4242)
+    want = _drive(*mk(None), steps=30, eval_every=7)
+    torch.manual_seed(1)  # the global stream must not matter any more
+    got = _drive(*mk(torch.Generator().manual_seed(4242)), steps=30, eval_every=7)
+    assert len(want) == len(got) == 60
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+
+
+def test_take_run_matches_batchwise_iteration():
+    """take_run(k) advances exactly like k next() calls (same draws, same spans), including across epoch ends."""
+    g1, g2 = torch.Generator().manual_seed(9), torch.Generator().manual_seed(9)
+    a, b = BankLoader(_bank(53), 8, shuffle=True, rng=g1), BankLoader(_bank(53), 8, shuffle=True, rng=g2)
+    ia, ib = iter(a), iter(b)
+    for want_k in (1, 3, 10, 2, 7, 7, 1):
+        if ia.batches_left() == 0:
+            ia = iter(a)
+        k = min(want_k, ia.batches_left())
+        perm, start, total = ia.take_run(k)
+        got = perm[start:start + total]
+        ref = []
+        for _ in range(k):
+            try:
+                x = next(ib)
+            except StopIteration:
+                ib = iter(b)
+                x = next(ib)
+            ref.append(x.host_idx)
+        assert torch.equal(got, torch.cat(ref))

@@ -53,6 +53,21 @@ class RunStep(C.Structure):
                 ("scale_step", c_i64 * 2), ("stats", c_vp), ("ev", c_vp * 8)]
 
 
+SWEEP_MAX_HEADS = 32
+
+
+class SweepArgs(C.Structure):
+    """uml_sweep_args"""
+    _fields_ = [("n_heads", c_i32), ("dim", c_i32), ("n_classes", c_i32), ("kind", c_i32),
+                ("bank", c_vp * 2), ("bank_ld", c_i64 * 2), ("labels", c_vp * 2),
+                ("perm", (c_vp * SWEEP_MAX_HEADS) * 2), ("perm_len", c_i64 * 2), ("pos", c_i64 * 2),
+                ("scale", c_f32 * 2), ("W", c_vp), ("m", c_vp), ("v", c_vp), ("head_stride", c_i64),
+                ("G", c_vp), ("ldg", c_i64), ("max_rows", c_i64), ("row_loss", c_vp), ("row_correct", c_vp),
+                ("stats", c_vp), ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32), ("momentum", c_f32),
+                ("step", c_i64), ("weight_decay", c_f32 * SWEEP_MAX_HEADS), ("alpha", c_f32 * SWEEP_MAX_HEADS),
+                ("active", C.c_uint8 * SWEEP_MAX_HEADS), ("ev", c_vp * 8)]
+
+
 # name -> argtypes; every function returns int except uml_last_error
 PROTOTYPES = {
     "uml_abi_version": [],
@@ -109,6 +124,7 @@ PROTOTYPES = {
     "uml_gauss_run": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i32, c_i64, c_i32, c_f32, c_f32,
                       c_f64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp, c_vp],
     "uml_gauss_eval": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
+    "uml_sweep_run": [C.POINTER(SweepArgs), c_i32, c_vp, c_vp, c_vp],
     "uml_randperm_i64": [C.c_uint64, c_i64, c_vp],
     "uml_randperm_begin": [c_vp, C.c_uint64, c_i64, c_vp],
     "uml_randperm_advance": [c_vp, c_i64],

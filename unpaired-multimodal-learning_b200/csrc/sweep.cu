@@ -1,0 +1,435 @@
+// Sweep-level batching of the exact fp32 step (reference: the hyper-parameter loop of
+// vision_language/finetune.py:406-448 over engine/optimizer/default.py's grids).
+//
+// The reference trains the lr x weight-decay (x alpha) combinations of a sweep one after the other over the SAME
+// feature banks, each a 32-row step that cannot fill one SM.  Here K heads (own weights, optimizer state, sampler
+// stream, lr, weight decay and alpha) advance in lock step: every launch carries a head index in gridDim.z / .y, so
+// one step of all K heads is four launches and the dW + optimizer kernel streams K x 24 B/parameter from HBM with the
+// whole machine.  Per head the arithmetic is the single-head fp32 path's (simt.cu): sequential-k FFMA logits, the same
+// softmax / CE / argmax row kernel, dW summed over rows in order, torch.optim's update rules in the epilogue.
+//
+// Layout in HBM: W, m, v are [K][C*D] slabs (head_stride apart); G is [K][rows][ldg] scratch; every head reads its
+// own epoch permutation (device int64) at the common position `pos` - the heads share bank and batch sizes, so their
+// epochs turn over on the same steps.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace uml {
+namespace sweep {
+
+constexpr int kMaxHeads = UML_SWEEP_MAX_HEADS;
+
+struct SweepDev {
+  const float* bank[2];
+  const int64_t* labels[2];
+  int64_t ld[2];
+  int64_t n0, n1;   // rows of the image run / text run in this step
+  int64_t pos[2];   // position of the step's batch inside each head's permutation
+  const int64_t* perm[2][kMaxHeads];
+  float* W;
+  float* m;
+  float* v;
+  int64_t head_stride;
+  float* G;
+  int64_t ldg, g_stride;
+  float* row_loss;
+  int32_t* row_correct;
+  int64_t row_stride;
+  uml_seg_stats* stats;  // [K][2] for this step
+  int dim, n_classes;
+  float scale[2];
+  float alpha[kMaxHeads];
+  uint32_t active_mask;
+  // optimizer (kind: 1 AdamW, 2 Adam with L2, 3 SGD momentum with L2); per-head scalars derived on the host in double
+  int kind, first_step;
+  float beta1, beta2, eps, momentum, bc2_sqrt_inv;
+  float lr[kMaxHeads], step_size[kMaxHeads], decay[kMaxHeads], wd[kMaxHeads];
+};
+
+__device__ __forceinline__ bool head_active(const SweepDev& p, int head) { return (p.active_mask >> head) & 1u; }
+
+// bank row and bank label of logical row r (image run first, then the text run) of head `head`
+__device__ __forceinline__ int64_t bank_row(const SweepDev& p, int head, int64_t r, bool& is_txt) {
+  is_txt = r >= p.n0;
+  const int64_t l = is_txt ? r - p.n0 : r;
+  const int64_t* pm = is_txt ? p.perm[1][head] : p.perm[0][head];
+  return pm[(is_txt ? p.pos[1] : p.pos[0]) + l];
+}
+__device__ __forceinline__ const float* row_ptr(const SweepDev& p, int head, int64_t r) {
+  bool s;
+  const int64_t src = bank_row(p, head, r, s);
+  return (s ? p.bank[1] : p.bank[0]) + src * (s ? p.ld[1] : p.ld[0]);
+}
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int w = 1; w < (blockDim.x >> 5); ++w) r = fmaxf(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) r += sh[w];
+  __syncthreads();
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. raw logits  G_k = [X_img ; X_txt]_k W_k^T     grid (ceil(C/32), ceil(rows/32), K)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sweep_logits_kernel(const __grid_constant__ SweepDev p) {
+  constexpr int BM = 32, BN = 32, kBK = 64, TM = 2, TN = 2;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  __shared__ float As[kBK][BM + 1];
+  __shared__ float Bs[kBK][BN + 1];
+  __shared__ const float* rowp[BM];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t R = p.n0 + p.n1;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * BM;
+  const int c0 = blockIdx.x * BN;
+  const int D = p.dim, C = p.n_classes;
+  if (t < BM) rowp[t] = (m0 + t < R) ? row_ptr(p, head, m0 + t) : nullptr;
+  __syncthreads();
+  const float* __restrict__ W = p.W + head * p.head_stride;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += kBK) {
+#pragma unroll
+    for (int e = t; e < BM * kBK; e += 256) {
+      const int m = e / kBK, k = e % kBK;
+      const float* rp = rowp[m];
+      As[k][m] = (rp != nullptr && k0 + k < D) ? rp[k0 + k] : 0.f;
+    }
+#pragma unroll
+    for (int e = t; e < BN * kBK; e += 256) {
+      const int n = e / kBK, k = e % kBK;
+      Bs[k][n] = (c0 + n < C && k0 + k < D) ? W[static_cast<int64_t>(c0 + n) * D + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* __restrict__ G = p.G + head * p.g_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t r = m0 + ty * TM + i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = c0 + tx * TN + j;
+      if (c < C) G[r * p.ldg + c] = acc[i][j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2. per-row softmax / CE / argmax; the raw logits row becomes G = w s / n (softmax - onehot)   grid (rows, K)
+//    (F.cross_entropy x2 and the weighted sum, finetune.py:186-188; same arithmetic as simt.cu's row kernel)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sweep_softmax_kernel(const __grid_constant__ SweepDev p) {
+  const int head = blockIdx.y;
+  if (!head_active(p, head)) return;
+  __shared__ float sh[8];
+  __shared__ int sh_arg;
+  const int64_t r = blockIdx.x;
+  const int C = p.n_classes;
+  bool s;
+  const int64_t src = bank_row(p, head, r, s);
+  const int label = static_cast<int>((s ? p.labels[1] : p.labels[0])[src]);
+  const int64_t n_seg = s ? p.n1 : p.n0;
+  const float scale = s ? p.scale[1] : p.scale[0];
+  const float weight = s ? p.alpha[head] : 1.f;
+  float* row = p.G + head * p.g_stride + r * p.ldg;
+  const float label_raw = row[label];  // read before the row is overwritten with G
+
+  float mx = -INFINITY;
+  int arg = INT_MAX;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float x = row[c] * scale;
+    if (x > mx) { mx = x; arg = c; }
+  }
+  if (threadIdx.x == 0) sh_arg = INT_MAX;
+  const float bmax = block_max(mx, sh);  // its barriers publish sh_arg
+  if (mx == bmax) atomicMin(&sh_arg, arg);  // first maximal index, like torch.argmax
+  float se = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(row[c] * scale - bmax);
+  const float sum = block_sum(se, sh);
+  const float inv = 1.f / sum;
+  const float gcoef = weight * scale / static_cast<float>(n_seg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float pr = expf(row[c] * scale - bmax) * inv;
+    if (c == label) pr -= 1.f;
+    row[c] = pr * gcoef;
+  }
+  __syncthreads();  // sh_arg complete (every atomicMin precedes this barrier)
+  if (threadIdx.x == 0) {
+    p.row_loss[head * p.row_stride + r] = logf(sum) - (label_raw * scale - bmax);
+    p.row_correct[head * p.row_stride + r] = (sh_arg == label) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. dW_k = G_k^T [X_img ; X_txt]_k with the optimizer update in the epilogue   grid (ceil(D/64), ceil(C/64), K)
+//    (autograd of the head + torch.optim.AdamW / Adam / SGD, finetune.py:190-195, optim.py:42-70)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void update_one(const SweepDev& p, float lr, float step_size, float decay, float wd, float& w,
+                                           float& m, float& v, float g) {
+  if (p.kind == 3) {  // SGD momentum, L2 decay folded into the gradient
+    g = fmaf(wd, w, g);
+    const float b = p.first_step ? g : fmaf(p.momentum, m, g);
+    m = b;
+    w = w - lr * b;
+    return;
+  }
+  if (p.kind == 1) w *= decay;             // AdamW: decoupled decay
+  else if (wd != 0.f) g = fmaf(wd, w, g);  // Adam: L2
+  m = m + (g - m) * (1.f - p.beta1);
+  v = v * p.beta2 + (1.f - p.beta2) * g * g;
+  const float denom = sqrtf(v) * p.bc2_sqrt_inv + p.eps;
+  w = w - step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_constant__ SweepDev p) {
+  constexpr int BM = 64, BN = 64, kBK = 32, TM = 4, TN = 4;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  __shared__ __align__(16) float As[kBK][BM + 4];  // G tile   [row][class]
+  __shared__ __align__(16) float Bs[kBK][BN + 4];  // X tile   [row][dim]
+  __shared__ const float* rowp[kBK];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t R = p.n0 + p.n1;
+  const int c0 = blockIdx.y * BM, d0 = blockIdx.x * BN;
+  const int D = p.dim, C = p.n_classes;
+  const float* __restrict__ G = p.G + head * p.g_stride;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int64_t r0 = 0; r0 < R; r0 += kBK) {
+    if (t < kBK) rowp[t] = (r0 + t < R) ? row_ptr(p, head, r0 + t) : nullptr;
+    __syncthreads();
+#pragma unroll
+    for (int e = t; e < BM * kBK; e += 256) {
+      const int k = e / BM, m = e % BM;
+      As[k][m] = (r0 + k < R && c0 + m < C) ? G[(r0 + k) * p.ldg + c0 + m] : 0.f;
+    }
+#pragma unroll
+    for (int e = t; e < BN * kBK; e += 256) {
+      const int k = e / BN, n = e % BN;
+      const float* rp = rowp[k];
+      Bs[k][n] = (rp != nullptr && d0 + n < D) ? rp[d0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * TM]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * TN]);
+      const float a[TM] = {a4.x, a4.y, a4.z, a4.w}, b[TN] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
+  float* __restrict__ W = p.W + head * p.head_stride;
+  float* __restrict__ Mo = p.m + head * p.head_stride;
+  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
+  const int d = d0 + tx * TN;
+  const bool vec = (D % 4 == 0) && (d + TN <= D);  // slabs are 16-byte aligned (checked by the launcher)
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int c = c0 + ty * TM + i;
+    if (c >= C) continue;
+    const int64_t off = static_cast<int64_t>(c) * D + d;
+    if (vec) {
+      float4 w4 = *reinterpret_cast<const float4*>(W + off);
+      float4 m4 = *reinterpret_cast<const float4*>(Mo + off);
+      float4 v4 = Vo ? *reinterpret_cast<const float4*>(Vo + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      update_one(p, lr, step_size, decay, wd, w4.x, m4.x, v4.x, acc[i][0]);
+      update_one(p, lr, step_size, decay, wd, w4.y, m4.y, v4.y, acc[i][1]);
+      update_one(p, lr, step_size, decay, wd, w4.z, m4.z, v4.z, acc[i][2]);
+      update_one(p, lr, step_size, decay, wd, w4.w, m4.w, v4.w, acc[i][3]);
+      *reinterpret_cast<float4*>(W + off) = w4;
+      *reinterpret_cast<float4*>(Mo + off) = m4;
+      if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4;
+    } else {
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        if (d + j >= D) continue;
+        float w = W[off + j], mm = Mo[off + j], vv = Vo ? Vo[off + j] : 0.f;
+        update_one(p, lr, step_size, decay, wd, w, mm, vv, acc[i][j]);
+        W[off + j] = w;
+        Mo[off + j] = mm;
+        if (Vo) Vo[off + j] = vv;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 4. per-head, per-run {mean loss, hits, rows} in a fixed summation order   grid (2, K)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sweep_stats_kernel(const __grid_constant__ SweepDev p) {
+  const int head = blockIdx.y, s = blockIdx.x;
+  if (!head_active(p, head)) return;
+  __shared__ float sh[8];
+  const int64_t beg = s ? p.n0 : 0, n = s ? p.n1 : p.n0;
+  const float* rl = p.row_loss + head * p.row_stride + beg;
+  const int32_t* rc = p.row_correct + head * p.row_stride + beg;
+  float ls = 0.f;
+  int hits = 0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    ls += rl[i];
+    hits += rc[i];
+  }
+  const float lsum = block_sum(ls, sh);
+  const float hsum = block_sum(static_cast<float>(hits), sh);
+  if (threadIdx.x == 0) {
+    uml_seg_stats& o = p.stats[head * 2 + s];
+    o.loss_mean = n > 0 ? lsum / static_cast<float>(n) : 0.f;
+    o.dscale = 0.f;
+    o.correct = static_cast<int32_t>(hsum + 0.5f);
+    o.n = static_cast<int32_t>(n);
+  }
+}
+
+}  // namespace sweep
+}  // namespace uml
+
+extern "C" {
+
+int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows, const float* lr, void* stream) {
+  using namespace uml;
+  using namespace uml::sweep;
+  UML_REQUIRE(a && rows && lr && n_steps >= 0, "sweep_run: null argument");
+  const int K = a->n_heads;
+  UML_REQUIRE(K >= 1 && K <= kMaxHeads, "sweep_run: 1..%d heads", kMaxHeads);
+  UML_REQUIRE(a->dim > 0 && a->n_classes > 0 && a->ldg >= a->n_classes, "sweep_run: bad shape");
+  UML_REQUIRE(a->kind >= 1 && a->kind <= 3, "sweep_run: optimizer kind must be 1 (AdamW), 2 (Adam) or 3 (SGD)");
+  UML_REQUIRE(a->W && a->m && (a->kind == 3 || a->v) && a->G && a->row_loss && a->row_correct && a->stats,
+              "sweep_run: null buffer");
+  UML_REQUIRE(a->head_stride >= static_cast<int64_t>(a->n_classes) * a->dim, "sweep_run: head_stride too small");
+  if (a->dim % 4 == 0) {  // the vector epilogue's alignment contract
+    UML_REQUIRE(a->head_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(a->W) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(a->m) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->v) & 15) == 0,
+                "sweep_run: W, m, v slabs must be 16-byte aligned");
+  }
+  cudaStream_t st = as_stream(stream);
+  SweepDev p;
+  memset(&p, 0, sizeof(p));
+  uint32_t mask = 0;
+  for (int k = 0; k < K; ++k) {
+    if (!a->active[k]) continue;
+    mask |= 1u << k;
+    for (int s = 0; s < 2; ++s) p.perm[s][k] = a->perm[s][k];
+    p.alpha[k] = a->alpha[k];
+    p.wd[k] = a->weight_decay[k];
+  }
+  if (mask == 0 || n_steps == 0) return 0;
+  for (int s = 0; s < 2; ++s) {
+    p.bank[s] = a->bank[s];
+    p.labels[s] = a->labels[s];
+    p.ld[s] = a->bank_ld[s];
+    p.scale[s] = a->scale[s];
+  }
+  p.W = a->W;
+  p.m = a->m;
+  p.v = a->v;
+  p.head_stride = a->head_stride;
+  p.G = a->G;
+  p.ldg = a->ldg;
+  p.row_loss = a->row_loss;
+  p.row_correct = a->row_correct;
+  p.dim = a->dim;
+  p.n_classes = a->n_classes;
+  p.active_mask = mask;
+  p.kind = a->kind;
+  p.beta1 = a->beta1;
+  p.beta2 = a->beta2;
+  p.eps = a->eps;
+  p.momentum = a->momentum;
+  int64_t pos[2] = {a->pos[0], a->pos[1]};
+  for (int i = 0; i < n_steps; ++i) {
+    const int64_t n0 = rows[2 * i], n1 = rows[2 * i + 1], R = n0 + n1;
+    UML_REQUIRE(n0 >= 0 && n1 >= 0 && R > 0 && R <= a->max_rows, "sweep_run: step %d has %lld rows (capacity %lld)", i,
+                static_cast<long long>(R), static_cast<long long>(a->max_rows));
+    for (int s = 0; s < 2; ++s) {
+      const int64_t n = s ? n1 : n0;
+      if (n == 0) continue;
+      UML_REQUIRE(a->bank[s] && a->labels[s] && pos[s] >= 0 && pos[s] + n <= a->perm_len[s],
+                  "sweep_run: step %d runs past the end of permutation %d", i, s);
+      for (int k = 0; k < K; ++k)
+        UML_REQUIRE(!((mask >> k) & 1u) || a->perm[s][k], "sweep_run: head %d has no permutation %d", k, s);
+    }
+    p.n0 = n0;
+    p.n1 = n1;
+    p.pos[0] = pos[0];
+    p.pos[1] = pos[1];
+    p.g_stride = a->max_rows * a->ldg;
+    p.row_stride = a->max_rows;
+    p.stats = a->stats + static_cast<int64_t>(i) * K * 2;
+    const double t = static_cast<double>(a->step + i);
+    const double bc1 = 1.0 - pow(static_cast<double>(a->beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(a->beta2), t);
+    p.bc2_sqrt_inv = static_cast<float>(1.0 / sqrt(bc2));
+    p.first_step = (a->step + i) <= 1;
+    for (int k = 0; k < K; ++k) {
+      const float l = lr[static_cast<int64_t>(i) * K + k];
+      p.lr[k] = l;
+      p.step_size[k] = static_cast<float>(static_cast<double>(l) / bc1);
+      p.decay[k] = static_cast<float>(1.0 - static_cast<double>(l) * static_cast<double>(a->weight_decay[k]));
+    }
+    const unsigned rt = static_cast<unsigned>((R + 31) / 32), ct = static_cast<unsigned>((a->n_classes + 31) / 32);
+    const bool timed = i == n_steps - 1;
+    auto mark = [&](int e) -> int {
+      if (timed && a->ev[e]) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev[e]), st));
+      return 0;
+    };
+    if (mark(0)) return 1;
+    sweep_logits_kernel<<<dim3(ct, rt, K), 256, 0, st>>>(p);
+    UML_CUDA(cudaGetLastError());
+    if (mark(1) || mark(2)) return 1;
+    sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
+    UML_CUDA(cudaGetLastError());
+    if (mark(3) || mark(4)) return 1;
+    sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
+    UML_CUDA(cudaGetLastError());
+    if (mark(5) || mark(6)) return 1;
+    sweep_stats_kernel<<<dim3(2, K), 256, 0, st>>>(p);
+    UML_CUDA(cudaGetLastError());
+    if (mark(7)) return 1;
+    pos[0] += n0;
+    pos[1] += n1;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -56,3 +56,6 @@ _add("--dp-sampler", type=str, default="global", choices=["global", "sharded"],
           "shuffles it itself (the sampler cost drops by the number of ranks)")
 _add("--precision", type=str, default="auto", choices=["auto", "fp32", "bf16"],
      help="fp32 = exact SIMT kernels, bf16 = tcgen05 tensor-core kernels, auto = by batch size")
+_add("--sweep-batched", action="store_true", default=False,
+     help="train the hyper-parameter combinations of the sweep in lock step on one GPU (one step of all heads = four "
+          "launches) instead of one after the other; every combination gets its own seeded sampler stream")

@@ -301,8 +301,11 @@ class BankLoader:
 
     def __init__(self, bank: FeatureBank, batch_size: int, shuffle: bool = False, drop_last: bool = False,
                  num_workers: int = 0, generator: Optional[torch.Generator] = None, upload: str = "epoch",
-                 pin_memory: bool = True, shard_of: Optional[tuple] = None):
-        """``shard_of=(rank, world)``: the bank is this rank's shard (``shard_bank``) of a data-parallel run and
+                 pin_memory: bool = True, shard_of: Optional[tuple] = None, rng: Optional[torch.Generator] = None):
+        """``rng``: a generator that stands in for the GLOBAL default CPU generator in the protocol above (base seeds and
+        sampler seeds are drawn from it) - lets several independent runs live in one process, each with the index
+        stream it would have had alone after ``torch.manual_seed`` (sweep-level batching, ``engine/sweep.py``).
+        ``shard_of=(rank, world)``: the bank is this rank's shard (``shard_bank``) of a data-parallel run and
         ``batch_size`` the PER-RANK batch; batches are tagged with the global row count and every rank's sampler
         seed is decorrelated by its rank.  The index stream is then no longer the single-process reference's."""
         if upload not in ("epoch", "step"):
@@ -312,6 +315,7 @@ class BankLoader:
         self.upload = upload
         self.dataset = bank
         self.shard_of = shard_of
+        self.rng = rng
         self._seed_mix = 0 if shard_of is None else ((shard_of[0] + 1) * 0x9E3779B97F4A7C15) & (2 ** 63 - 1)
         self._dev_ring, self._dev_turn = None, 0  # device copies of the permutation (large banks), alternating
         self._ring = None   # pinned permutation buffers (CUDA banks only), created at the first shuffled epoch
@@ -347,7 +351,8 @@ class _BankIter:
         self.uploaded = 0
         self.tail_drawn = False
         if loader.shard_of is None:
-            _draw_int64(loader.generator)  # base seed (the reference DataLoader's protocol)
+            # base seed (the reference DataLoader's protocol)
+            _draw_int64(loader.generator if loader.generator is not None else loader.rng)
         if loader.shuffle and loader.num_workers > 0:
             self._draw()
 
@@ -380,7 +385,7 @@ class _BankIter:
                 l._prepared = _EpochPerm(l._shard_seed(), self.n, self._next_buffer(), threaded, queued=True)
                 self.perm_host = self.perm.out
             else:
-                seed = _draw_int64(None)
+                seed = _draw_int64(l.rng)
                 prev = l._live.perm if l._live is not None else None
                 if threaded and prev is not None and prev.next_filled():
                     buf, prefilled = prev.next_out, True  # the previous epoch's thread left the identity in this buffer
@@ -418,6 +423,27 @@ class _BankIter:
         if left <= 0:
             return 0
         return left // l.batch_size if l.drop_last else -(-left // l.batch_size)
+
+    def take_run(self, k: int):
+        """Advance over the next k batches of THIS epoch (k <= batches_left()) without materialising them: returns
+        ``(perm_dev, start, total)`` - the device copy of the epoch's permutation, final and uploaded through
+        ``start + total``.  For callers that hand the kernels a permutation pointer plus a position (sweep batching)."""
+        l = self.l
+        if not l.shuffle or l.upload != "epoch":
+            raise ValueError("take_run needs a shuffled loader with upload='epoch'")
+        if self.perm_host is None:
+            self._draw()
+        start = self.pos
+        total = min(k * l.batch_size, self.n - start)
+        if l.drop_last:
+            total -= total % l.batch_size
+        if self.perm is not None:
+            self.perm.wait(start + total)
+        if self.uploaded < start + total:
+            self.perm_dev[self.uploaded:start + total].copy_(self.perm_host[self.uploaded:start + total], non_blocking=True)
+            self.uploaded = start + total
+        self.pos = start + total
+        return self.perm_dev, start, total
 
     def take_chunk(self, k: int):
         """The next k batches of THIS epoch (k <= batches_left()) with one wait on the sampler and - for

@@ -104,10 +104,9 @@ def _dbg(msg):
         print(f"[train] {msg}", file=sys.stderr, flush=True)
 
 
-def validate(model, val_loader, device="cuda"):
-    """(val_loss, val_acc) over the loader's bank: accuracy over all rows, loss = mean over the
-    loader's batches of the batch-mean CE (the reference's weighting, finetune.py:310-312).  One logit +
-    argmax kernel streams the bank; logits never reach the host."""
+def validate_enqueue(model, val_loader):
+    """Launches the evaluation of ``validate`` and returns ``(loss, hits, n_rows)`` - two one-element DEVICE tensors
+    and the row count - without synchronising; callers that evaluate many heads read them back together."""
     iter(val_loader)  # a DataLoader iterator draws a base seed from the global RNG; keep the stream aligned
     bank, bs = val_loader.bank, val_loader.batch_size
     n = len(bank)
@@ -136,6 +135,14 @@ def validate(model, val_loader, device="cuda"):
     out_loss = torch.empty(1, device=dev)
     out_hits = torch.empty(1, device=dev, dtype=torch.int32)
     ops.eval_reduce(row_loss, row_pred, hit_labels, bs, out_loss, out_hits)
+    return out_loss, out_hits, n
+
+
+def validate(model, val_loader, device="cuda"):
+    """(val_loss, val_acc) over the loader's bank: accuracy over all rows, loss = mean over the
+    loader's batches of the batch-mean CE (the reference's weighting, finetune.py:310-312).  One logit +
+    argmax kernel streams the bank; logits never reach the host."""
+    out_loss, out_hits, n = validate_enqueue(model, val_loader)
     return float(out_loss.item()), int(out_hits.item()) / n
 
 
@@ -319,6 +326,193 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     return out
 
 
+def train_group(models, image_loaders, text_loaders, val_loaders, test_loaders, optimizers, schedulers, device="cuda",
+                max_iters=1000, alphas=1.0, eval_freq=EVAL_FREQ, patience=5, loggers=None, traces=None, tags=None):
+    """K runs of ``train`` advanced in lock step over shared banks (sweep-level batching): one step of all
+    K heads is four launches (``engine/sweep.py``, ``csrc/sweep.cu``) instead of K latency-bound steps.
+
+    Every argument that ``train`` takes once is a list with one entry per head (``max_iters``, ``alphas`` and
+    ``patience`` may be scalars); returns the list of ``train``'s result dicts.  Head k follows exactly the loop of
+    ``train`` - evaluation at ``i % eval_freq == 0``, strict-improvement early stopping, best state restored - with
+    its own sampler stream: its loaders draw their seeds from their own ``rng`` generator in the order a stand-alone
+    run draws them from the global generator, so head k reproduces ``torch.manual_seed(s); train(...)`` when its
+    generator was seeded with ``s``.  (The reference's sequential sweep lets one global stream run through all
+    combinations; the order inside each run is the same, the seeds differ.)"""
+    from .engine.sweep import HeadGroup, group_blockers
+
+    K = len(models)
+    as_list = lambda x: list(x) if isinstance(x, (list, tuple)) else [x] * K
+    max_iters, alphas, patience = as_list(max_iters), [float(a) for a in as_list(alphas)], as_list(patience)
+    image_loaders = as_list(image_loaders) if image_loaders is not None else [None] * K
+    text_loaders = as_list(text_loaders) if text_loaders is not None else [None] * K
+    test_loaders = as_list(test_loaders) if test_loaders is not None else [None] * K
+    loggers = as_list(loggers) if loggers is not None else [None] * K
+    traces = as_list(traces) if traces is not None else [None] * K
+    tags = as_list(tags) if tags is not None else [f"head {k}" for k in range(K)]
+    why = group_blockers(models, optimizers, image_loaders, text_loaders)
+    if _dist()[1] > 1:
+        why.append("data-parallel runs are not batched")
+    if why:
+        raise ValueError("train_group: " + "; ".join(why))
+    has_img, has_txt = image_loaders[0] is not None, text_loaders[0] is not None
+    assert has_img or has_txt, "At least one of the loaders should be provided"
+    il0, tl0 = image_loaders[0], text_loaders[0]
+    for m in models:
+        m.train()
+    log_slots = min(max(int(eval_freq), 1), int(max(max_iters))) + 1
+    group = HeadGroup(models, optimizers, il0.bank if has_img else None, tl0.bank if has_txt else None,
+                      il0.batch_size if has_img else 0, tl0.batch_size if has_txt else 0, device, log_slots=log_slots)
+    outs = [{"iter": None, "val_acc": None, "model": None, "val_classwise": None, "val_loss": None, "model_records": []}
+            for _ in range(K)]
+    for tr in traces:
+        if tr is not None:
+            tr["engine"] = group
+    # the reference's order per run: iter(image_loader), iter(text_loader) (finetune.py:157-158)
+    img_it, txt_it = [None] * K, [None] * K
+    for k in range(K):
+        if has_img:
+            img_it[k] = iter(image_loaders[k])
+        if has_txt:
+            txt_it[k] = iter(text_loaders[k])
+    running = [max_iters[k] > 0 for k in range(K)]
+    no_improve = [0] * K
+    pending = []  # (step, lrs of the step) whose stats have not been read back yet
+    last = None
+
+    def flush():
+        nonlocal last
+        if not pending:
+            return
+        cols = group.read_log([s for s, _, _ in pending], has_img, has_txt)
+        for j, (_, lrs, act) in enumerate(pending):
+            for k in range(K):
+                if not act[k] or (traces[k] is None and loggers[k] is None):
+                    continue
+                rec = {"image_loss": cols["image_loss"][j][k], "text_loss": cols["text_loss"][j][k],
+                       "img_acc": cols["img_acc"][j][k], "text_acc": cols["text_acc"][j][k]}
+                if traces[k] is not None:
+                    traces[k].setdefault("stats", []).append(dict(rec, lr=lrs[k]))
+                if loggers[k] is not None:
+                    loggers[k].log({"train/image_loss": rec["image_loss"], "train/text_loss": rec["text_loss"],
+                                    "train/image_acc": rec["img_acc"], "train/text_acc": rec["text_acc"], "train/lr": lrs[k]})
+        last = {name: col[-1] for name, col in cols.items()}
+        pending.clear()
+
+    def take(loaders, its, k, n):
+        """Head k's next n batches of one modality: re-iterates the loader first when its epoch is over (drawing the
+        base seed and, at the first batch, the sampler seed - the order fetch_next produces)."""
+        if its[k].batches_left() == 0:
+            its[k] = iter(loaders[k])
+        return its[k].take_run(n)
+
+    def left(loaders, its):
+        b = its[0].batches_left()
+        return b if b > 0 else len(loaders[0])
+
+    max_chunk = 64
+    # traces[0]["timing"] = {"warmup": W}: wall-clock seconds of iterations W.. (stream-synchronised on both sides,
+    # including the read-back of their stats) land in traces[0]["timing"]["seconds"] - bench.py's end-to-end arm
+    timing = traces[0].get("timing") if traces[0] is not None else None
+    t_start = None
+    i = 0
+    while any(running):
+        next_eval = i if i % eval_freq == 0 else (i // eval_freq + 1) * eval_freq
+        last_iter = min(max_iters[k] for k in range(K) if running[k]) - 1
+        n = min(next_eval, last_iter) - i + 1
+        n = max(1, min(n, max_chunk, log_slots - i % log_slots))
+        if timing is not None:
+            if i < timing["warmup"]:
+                n = min(n, timing["warmup"] - i)
+            elif t_start is None:
+                flush()
+                torch.cuda.current_stream().synchronize()
+                t_start = time.perf_counter()
+        if has_img:
+            n = min(n, left(image_loaders, img_it))
+        if has_txt:
+            n = min(n, left(text_loaders, txt_it))
+        perms_i, perms_t, span_i, span_t = [None] * K, [None] * K, None, None
+        for k in range(K):  # image then text per head: the order the reference's step draws in
+            if has_img:
+                perms_i[k], st, tot = take(image_loaders, img_it, k, n)
+                assert span_i in (None, (st, tot)), "heads left lock step"
+                span_i = (st, tot)
+            if has_txt:
+                perms_t[k], st, tot = take(text_loaders, txt_it, k, n)
+                assert span_t in (None, (st, tot)), "heads left lock step"
+                span_t = (st, tot)
+        bs_i, bs_t = (il0.batch_size if has_img else 0), (tl0.batch_size if has_txt else 0)
+        rows = [(min(bs_i, span_i[1] - j * bs_i) if has_img else 0, min(bs_t, span_t[1] - j * bs_t) if has_txt else 0)
+                for j in range(n)]
+        assert all(r[0] >= 0 and r[1] >= 0 and r[0] + r[1] > 0 for r in rows), rows
+        lrs = []
+        for j in range(n):
+            lrs.append([sch.get_last_lr()[0] for sch in schedulers])
+            for sch in schedulers:
+                sch.step()
+        for k in range(K):
+            tr = traces[k]
+            if tr is not None and tr.get("indices", True) and running[k]:
+                for name, its, span, bs in (("img_idx", img_it, span_i, bs_i), ("txt_idx", txt_it, span_t, bs_t)):
+                    if span is not None:
+                        host = its[k].perm_host[span[0]:span[0] + span[1]]
+                        tr.setdefault(name, []).extend(c.clone() for c in host.split(bs))
+        act = list(running)
+        group.run(perms_i if has_img else None, perms_t if has_txt else None, span_i[0] if has_img else 0,
+                  span_t[0] if has_txt else 0, rows, lrs, alphas, act, slot0=i)
+        for j in range(n):
+            pending.append((i + j, lrs[j], act))
+        i += n
+        last_step = i - 1
+
+        if last_step % eval_freq == 0:
+            flush()
+            heads = [k for k in range(K) if running[k]]
+            # every head's evaluation is enqueued before anything is read back: one synchronisation per round
+            results = [validate_enqueue(models[k], val_loaders[k]) for k in heads]
+            tests = [validate_enqueue(models[k], test_loaders[k]) if test_loaders[k] is not None else None for k in heads]
+            snaps = group.W.clone()
+            losses = torch.cat([r[0] for r in results]).cpu().tolist()
+            hits = torch.cat([r[1] for r in results]).cpu().tolist()
+            for h, k in enumerate(heads):
+                val_loss, val_acc = float(losses[h]), int(hits[h]) / results[h][2]
+                testlog = ""
+                if tests[h] is not None:
+                    testlog = f" | Test Acc: {int(tests[h][1].item()) / tests[h][2]:.4f}"
+                if outs[k]["val_acc"] is None or val_acc > outs[k]["val_acc"]:
+                    w = snaps[k, :group.C * group.D].view(group.C, group.D).cpu()
+                    outs[k].update(iter=last_step, val_acc=val_acc, val_loss=val_loss, model={"head.weight": w})
+                    no_improve[k] = 0
+                else:
+                    no_improve[k] += 1
+                if traces[k] is not None:
+                    traces[k].setdefault("evals", []).append((last_step, val_loss, val_acc))
+                if loggers[k] is not None:
+                    loggers[k].log({"val/val_loss": val_loss, "val/val_acc": val_acc, "iter": last_step})
+                print(f"[{tags[k]}] Iter {last_step} | Img Loss: {last['image_loss'][k]:.4f} | "
+                      f"Text Loss: {last['text_loss'][k]:.4f} | Img Acc: {last['img_acc'][k]:.4f} | "
+                      f"Text Acc: {last['text_acc'][k]:.4f} | Val Loss: {val_loss:.4f} | Val Acc {val_acc:.4f}{testlog} | "
+                      f"Count {no_improve[k]}/{patience[k]}")
+                if no_improve[k] >= patience[k]:
+                    print(f"=> [{tags[k]}] Early stopping at Iter {last_step}")
+                    running[k] = False
+        for k in range(K):
+            if running[k] and i >= max_iters[k]:
+                running[k] = False
+    flush()
+    if timing is not None and t_start is not None:
+        torch.cuda.current_stream().synchronize()
+        timing["seconds"], timing["iters"] = time.perf_counter() - t_start, i - timing["warmup"]
+    for k in range(K):
+        extra = {n_: v for n_, v in models[k].state_dict().items() if n_ not in outs[k]["model"]}
+        models[k].load_state_dict({**extra, **outs[k]["model"]})
+        val_loss, val_acc = validate(models[k], val_loaders[k], device=device)
+        if loggers[k] is not None:
+            loggers[k].log({"val/best_val_loss": val_loss, "val/best_val_acc": val_acc, "iter": outs[k]["iter"]})
+        print(f"=> [{tags[k]}] Best Val Loss {val_loss:.4f}, Val Acc {val_acc:.4f} at Iter {outs[k]['iter']}")
+    return outs
+
+
 # ------------------------------------------------------------------------------------------------
 # orchestration
 # ------------------------------------------------------------------------------------------------
@@ -339,7 +533,11 @@ def setup_wandb_logger(hparams, args):
                       reinit="finish_previous")
 
 
-def setup(datasets, hparams, args):
+def _prepare(datasets, hparams, args, rng=None):
+    """What ``setup`` does before the loop (finetune.py:323-384 of the reference): checkpoint directory, model,
+    zero-shot initialisation, optimizer, scheduler, loaders.  Returns ``{"done": stored result}`` when the run's
+    ``test_result.pth`` already exists.  ``rng``: generator the run's loaders draw their seeds from instead of the
+    global one (batched sweeps)."""
     logger = setup_wandb_logger(hparams, args)
     device = args.device
     ckpt_dir = os.path.join(args.savepath, hparam_str(hparams["optim"], hparams["lr"], hparams["weight_decay"],
@@ -349,7 +547,7 @@ def setup(datasets, hparams, args):
     test_path = os.path.join(ckpt_dir, "test_result.pth")
     if os.path.exists(test_path) and not FLAG:
         print(f"=> Skipping {ckpt_dir} as it already exists!")
-        return torch.load(test_path, map_location=device)
+        return {"done": torch.load(test_path, map_location=device)}
     print(f"=> Setting up {ckpt_dir}")
     freeze = args.hyperparams == "linear"
     if args.use_clip:
@@ -381,30 +579,95 @@ def setup(datasets, hparams, args):
         text_loader = BankLoader(shard_bank(tb.features, tb.labels, rank, world, device), -(-bs // world), shuffle=True,
                                  num_workers=nw, shard_of=(rank, world))
     else:
-        image_loader = BankLoader(datasets["img_tr_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
-        text_loader = BankLoader(datasets["text_bank"], bs, shuffle=True, drop_last=False, num_workers=nw)
+        image_loader = BankLoader(datasets["img_tr_bank"], bs, shuffle=True, drop_last=False, num_workers=nw, rng=rng)
+        text_loader = BankLoader(datasets["text_bank"], bs, shuffle=True, drop_last=False, num_workers=nw, rng=rng)
     if args.modality == "image":
         text_loader = None
         print("=> Running Unimodal: Image Only Model")
     elif args.modality == "text":
         image_loader = None
         print("=> Running Unimodal: Text Only Model")
-    val_loader = BankLoader(datasets["img_val_bank"], bs, shuffle=False, num_workers=nw)
-    test_loader = BankLoader(datasets["img_te_bank"], bs, shuffle=False, num_workers=nw)
+    val_loader = BankLoader(datasets["img_val_bank"], bs, shuffle=False, num_workers=nw, rng=rng)
+    test_loader = BankLoader(datasets["img_te_bank"], bs, shuffle=False, num_workers=nw, rng=rng)
+    return dict(model=model, optimizer=optimizer, scheduler=scheduler, image_loader=image_loader, text_loader=text_loader,
+                val_loader=val_loader, test_loader=test_loader, logger=logger, ckpt_dir=ckpt_dir, test_path=test_path,
+                hparams=hparams)
 
-    result = train(model, image_loader, text_loader, val_loader, test_loader if args.eval_test else None, optimizer,
-                   scheduler, device=device, max_iters=hparams["max_iter"], alpha=args.alpha, eval_freq=EVAL_FREQ,
-                   patience=hparams["patience"], capture_features_during_training=False, features_pth=ckpt_dir,
-                   args=args, logger=logger)
-    test_loss, test_acc = validate(model, test_loader, device=device)
-    del model
-    logger.log({"test/test_loss": test_loss, "test/test_acc": test_acc})
+
+def _finish(ctx, result, args):
+    """The tail of ``setup`` (finetune.py:386-403): test accuracy of the restored best state, ``test_result.pth``."""
+    test_loss, test_acc = validate(ctx["model"], ctx["test_loader"], device=args.device)
+    ctx["model"] = None
+    ctx["logger"].log({"test/test_loss": test_loss, "test/test_acc": test_acc})
     test_dict = {"test_acc": test_acc, "val_acc": result["val_acc"], "model": result["model"], "iter": result["iter"]}
     print(f"=> Test Acc: {test_acc:.4f}")
     if (not FLAG or getattr(args, "overwrite", False)) and _dist()[0] == 0:  # replicas are identical: rank 0 writes
-        print(f"=> Saving Test Results for hparams to {test_path}")
-        torch.save(test_dict, test_path)
+        print(f"=> Saving Test Results for hparams to {ctx['test_path']}")
+        torch.save(test_dict, ctx["test_path"])
     return test_dict
+
+
+def setup(datasets, hparams, args):
+    ctx = _prepare(datasets, hparams, args)
+    if "done" in ctx:
+        return ctx["done"]
+    result = train(ctx["model"], ctx["image_loader"], ctx["text_loader"], ctx["val_loader"],
+                   ctx["test_loader"] if args.eval_test else None, ctx["optimizer"], ctx["scheduler"], device=args.device,
+                   max_iters=hparams["max_iter"], alpha=args.alpha, eval_freq=EVAL_FREQ, patience=hparams["patience"],
+                   capture_features_during_training=False, features_pth=ctx["ckpt_dir"], args=args, logger=ctx["logger"])
+    return _finish(ctx, result, args)
+
+
+def setup_group(datasets, combos, args):
+    """``setup`` for several hyper-parameter combinations at once: the runs that can share a HeadGroup (same shapes,
+    optimizer kind, batch size; no adapter, fixed temperatures) train in lock step (``train_group``), the rest one
+    after the other.  Run k's loaders draw from their own generator seeded ``args.seed * 1000003 + k`` (``k``: position
+    in ``combos``) - or from the global stream when ``args.seed < 0`` - so a combination's result does not depend
+    on which others run with it."""
+    from .engine.sweep import MAX_HEADS, group_blockers
+
+    results = [None] * len(combos)
+    ctxs = {}
+    for n, hp in enumerate(combos):
+        print(f"=> Preparing {n + 1}/{len(combos)}: {hp}")
+        seed = args.seed * 1000003 + n if args.seed >= 0 else int(torch.empty((), dtype=torch.int64).random_().item())
+        ctx = _prepare(datasets, hp, args, rng=torch.Generator().manual_seed(seed))
+        if "done" in ctx:
+            results[n] = ctx["done"]
+        else:
+            ctxs[n] = ctx
+    todo = sorted(ctxs)
+    while todo:
+        # greedy grouping: everything compatible with the first open run joins it
+        first, members = todo[0], [todo[0]]
+        for n in todo[1:]:
+            if len(members) >= MAX_HEADS:
+                break
+            cand = members + [n]
+            if not group_blockers([ctxs[c]["model"] for c in cand], [ctxs[c]["optimizer"] for c in cand],
+                                  [ctxs[c]["image_loader"] for c in cand], [ctxs[c]["text_loader"] for c in cand]):
+                members = cand
+        solo = group_blockers([ctxs[first]["model"]], [ctxs[first]["optimizer"]], [ctxs[first]["image_loader"]],
+                              [ctxs[first]["text_loader"]]) or _dist()[1] > 1
+        todo = [n for n in todo if n not in members]
+        col = lambda key: [ctxs[c][key] for c in members]
+        if solo:  # not batchable at all (adapter, learnable temperature, data parallel): the plain loop, same loaders
+            c = ctxs[first]
+            outs = [train(c["model"], c["image_loader"], c["text_loader"], c["val_loader"],
+                          c["test_loader"] if args.eval_test else None, c["optimizer"], c["scheduler"],
+                          device=args.device, max_iters=c["hparams"]["max_iter"], alpha=args.alpha,
+                          eval_freq=EVAL_FREQ, patience=c["hparams"]["patience"], args=args, logger=c["logger"])]
+        else:
+            print(f"=> Training {len(members)} combinations in lock step: {members}")
+            outs = train_group(col("model"), col("image_loader"), col("text_loader"), col("val_loader"),
+                               col("test_loader") if args.eval_test else None, col("optimizer"), col("scheduler"),
+                               device=args.device, max_iters=[ctxs[c]["hparams"]["max_iter"] for c in members],
+                               alphas=args.alpha, eval_freq=EVAL_FREQ,
+                               patience=[ctxs[c]["hparams"]["patience"] for c in members], loggers=col("logger"),
+                               tags=[f"run {c + 1}" for c in members])
+        for c, out in zip(members, outs):
+            results[c] = _finish(ctxs.pop(c), out, args)
+    return results
 
 
 def sweep(datasets, hyperparams, args):
@@ -414,10 +677,12 @@ def sweep(datasets, hyperparams, args):
     results = {"test_acc": [], "val_acc": [], "hparams": [], "model_records": []}
     best_val = best_test = 0
     best_hp = None
-    for n, combo in enumerate(combos):
-        hp = dict(zip(keys, combo))
+    hps = [dict(zip(keys, combo)) for combo in combos]
+    # --sweep-batched: the combinations train in lock step on one GPU (setup_group) instead of one after the other
+    pre = setup_group(datasets, hps, args) if getattr(args, "sweep_batched", False) else None
+    for n, hp in enumerate(hps):
         print(f"=> Running {n + 1}/{len(combos)}: {hp}")
-        res = setup(datasets, hp, args)
+        res = pre[n] if pre is not None else setup(datasets, hp, args)
         results["test_acc"].append(res["test_acc"])
         results["val_acc"].append(res["val_acc"])
         results["hparams"].append(hp)
