@@ -85,8 +85,10 @@ def test_sweep_run_against_oracle(C, D, optim):
             assert abs(got["text_loss"][i][k] - stats["text_loss"]) <= 1e-4 * max(1.0, abs(stats["text_loss"]))
             assert abs(got["img_acc"][i][k] - stats["img_acc"]) < 1e-6
             assert abs(got["text_acc"][i][k] - stats["text_acc"]) < 1e-6
-        err = (w - st.head).abs().max() / st.head.abs().max()
-        assert err < 1e-4, (k, float(err))
+        # Adam divides by |g| + eps: the few elements whose gradient (plus L2 term) nearly cancels amplify fp32
+        # summation-order noise, so the maximum gets the stated 1e-3 and the mean a much tighter bound
+        diff = (w - st.head).abs() / st.head.abs().max()
+        assert float(diff.max()) < 1e-3 and float(diff.mean()) < 1e-6, (k, float(diff.max()), float(diff.mean()))
         assert opts[k].slot(models[k].head.weight)["step"] == len(rows)
 
 

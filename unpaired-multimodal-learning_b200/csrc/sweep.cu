@@ -41,6 +41,7 @@ struct SweepDev {
   float scale[2];
   float alpha[kMaxHeads];
   uint32_t active_mask;
+  int vec_rows;  // dim % 4 == 0 and every bank row / weight row starts on a 16-byte boundary
   // optimizer (kind: 1 AdamW, 2 Adam with L2, 3 SGD momentum with L2); per-head scalars derived on the host in double
   int kind, first_step;
   float beta1, beta2, eps, momentum, bc2_sqrt_inv;
@@ -82,14 +83,18 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1. raw logits  G_k = [X_img ; X_txt]_k W_k^T     grid (ceil(C/32), ceil(rows/32), K)
+// 1. raw logits  G_k = [X_img ; X_txt]_k W_k^T     grid (ceil(C/64), ceil(rows/64), K)
+//    64 x 64 tile, 4 x 4 per thread.  Both operands are k-contiguous in HBM (bank rows, weight rows) and stay that way
+//    in shared memory, so staging is a straight 16-byte copy; a thread owns rows ty + 16 i and classes tx + 16 j, which
+//    makes the float4 reads along k conflict-free (quarter-warp lanes are 68 floats apart) and the stores coalesced.
+//    Per element the sum still runs over k in ascending order with one FFMA per term.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sweep_logits_kernel(const __grid_constant__ SweepDev p) {
-  constexpr int BM = 32, BN = 32, kBK = 64, TM = 2, TN = 2;
+  constexpr int BM = 64, BN = 64, kBK = 64, LD = kBK + 4, TM = 4, TN = 4;
   const int head = blockIdx.z;
   if (!head_active(p, head)) return;
-  __shared__ float As[kBK][BM + 1];
-  __shared__ float Bs[kBK][BN + 1];
+  __shared__ __align__(16) float As[BM][LD];
+  __shared__ __align__(16) float Bs[BN][LD];
   __shared__ const float* rowp[BM];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
   const int64_t R = p.n0 + p.n1;
@@ -106,40 +111,65 @@ __global__ void __launch_bounds__(256) sweep_logits_kernel(const __grid_constant
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   for (int k0 = 0; k0 < D; k0 += kBK) {
+    if (p.vec_rows) {  // dim % 4 == 0 and 16-byte aligned rows: k < D implies k + 3 < D
 #pragma unroll
-    for (int e = t; e < BM * kBK; e += 256) {
-      const int m = e / kBK, k = e % kBK;
-      const float* rp = rowp[m];
-      As[k][m] = (rp != nullptr && k0 + k < D) ? rp[k0 + k] : 0.f;
-    }
+      for (int f = t; f < BM * (kBK / 4); f += 256) {
+        const int m = f / (kBK / 4), k = k0 + 4 * (f % (kBK / 4));
+        const float* rp = rowp[m];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rp != nullptr && k < D) x = *reinterpret_cast<const float4*>(rp + k);
+        *reinterpret_cast<float4*>(&As[m][k - k0]) = x;
+      }
 #pragma unroll
-    for (int e = t; e < BN * kBK; e += 256) {
-      const int n = e / kBK, k = e % kBK;
-      Bs[k][n] = (c0 + n < C && k0 + k < D) ? W[static_cast<int64_t>(c0 + n) * D + k0 + k] : 0.f;
+      for (int f = t; f < BN * (kBK / 4); f += 256) {
+        const int n = f / (kBK / 4), k = k0 + 4 * (f % (kBK / 4));
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + n < C && k < D) x = *reinterpret_cast<const float4*>(W + static_cast<int64_t>(c0 + n) * D + k);
+        *reinterpret_cast<float4*>(&Bs[n][k - k0]) = x;
+      }
+    } else {
+#pragma unroll 4
+      for (int e = t; e < BM * kBK; e += 256) {
+        const int m = e / kBK, k = e % kBK;
+        const float* rp = rowp[m];
+        As[m][k] = (rp != nullptr && k0 + k < D) ? rp[k0 + k] : 0.f;
+      }
+#pragma unroll 4
+      for (int e = t; e < BN * kBK; e += 256) {
+        const int n = e / kBK, k = e % kBK;
+        Bs[n][k] = (c0 + n < C && k0 + k < D) ? W[static_cast<int64_t>(c0 + n) * D + k0 + k] : 0.f;
+      }
     }
     __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kBK; k += 4) {
+      float4 a[TM], b[TN];
 #pragma unroll
-    for (int k = 0; k < kBK; ++k) {
-      float a[TM], b[TN];
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(&As[ty + 16 * i][k]);
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+      for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(&Bs[tx + 16 * j][k]);
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) {
+          float c = acc[i][j];
+          c = fmaf(a[i].x, b[j].x, c);
+          c = fmaf(a[i].y, b[j].y, c);
+          c = fmaf(a[i].z, b[j].z, c);
+          c = fmaf(a[i].w, b[j].w, c);
+          acc[i][j] = c;
+        }
     }
     __syncthreads();
   }
   float* __restrict__ G = p.G + head * p.g_stride;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
-    const int64_t r = m0 + ty * TM + i;
+    const int64_t r = m0 + ty + 16 * i;
     if (r >= R) continue;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-      const int c = c0 + tx * TN + j;
+      const int c = c0 + tx + 16 * j;
       if (c < C) G[r * p.ldg + c] = acc[i][j];
     }
   }
@@ -224,6 +254,25 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   const int c0 = blockIdx.y * BM, d0 = blockIdx.x * BN;
   const int D = p.dim, C = p.n_classes;
   const float* __restrict__ G = p.G + head * p.g_stride;
+  float* __restrict__ W = p.W + head * p.head_stride;
+  float* __restrict__ Mo = p.m + head * p.head_stride;
+  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
+  const int d = d0 + tx * TN;
+  const bool vec = (D % 4 == 0) && (d + TN <= D);  // slabs are 16-byte aligned (checked by the launcher)
+  // The weights and optimizer state this thread will update are requested BEFORE the contraction: the kernel is bound
+  // by HBM (24 B per parameter against ~130 FLOP), so what matters is how many bytes each SM keeps in flight
+  float4 w4[TM], m4[TM], v4[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int c = c0 + ty * TM + i;
+    w4[i] = m4[i] = v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && c < C) {
+      const int64_t off = static_cast<int64_t>(c) * D + d;
+      w4[i] = *reinterpret_cast<const float4*>(W + off);
+      m4[i] = *reinterpret_cast<const float4*>(Mo + off);
+      if (Vo) v4[i] = *reinterpret_cast<const float4*>(Vo + off);
+    }
+  }
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -233,12 +282,12 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   for (int64_t r0 = 0; r0 < R; r0 += kBK) {
     if (t < kBK) rowp[t] = (r0 + t < R) ? row_ptr(p, head, r0 + t) : nullptr;
     __syncthreads();
-#pragma unroll
+#pragma unroll 4
     for (int e = t; e < BM * kBK; e += 256) {
       const int k = e / BM, m = e % BM;
       As[k][m] = (r0 + k < R && c0 + m < C) ? G[(r0 + k) * p.ldg + c0 + m] : 0.f;
     }
-#pragma unroll
+#pragma unroll 4
     for (int e = t; e < BN * kBK; e += 256) {
       const int k = e / BN, n = e % BN;
       const float* rp = rowp[k];
@@ -259,27 +308,19 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   }
 
   const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
-  float* __restrict__ W = p.W + head * p.head_stride;
-  float* __restrict__ Mo = p.m + head * p.head_stride;
-  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
-  const int d = d0 + tx * TN;
-  const bool vec = (D % 4 == 0) && (d + TN <= D);  // slabs are 16-byte aligned (checked by the launcher)
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int c = c0 + ty * TM + i;
     if (c >= C) continue;
     const int64_t off = static_cast<int64_t>(c) * D + d;
     if (vec) {
-      float4 w4 = *reinterpret_cast<const float4*>(W + off);
-      float4 m4 = *reinterpret_cast<const float4*>(Mo + off);
-      float4 v4 = Vo ? *reinterpret_cast<const float4*>(Vo + off) : make_float4(0.f, 0.f, 0.f, 0.f);
-      update_one(p, lr, step_size, decay, wd, w4.x, m4.x, v4.x, acc[i][0]);
-      update_one(p, lr, step_size, decay, wd, w4.y, m4.y, v4.y, acc[i][1]);
-      update_one(p, lr, step_size, decay, wd, w4.z, m4.z, v4.z, acc[i][2]);
-      update_one(p, lr, step_size, decay, wd, w4.w, m4.w, v4.w, acc[i][3]);
-      *reinterpret_cast<float4*>(W + off) = w4;
-      *reinterpret_cast<float4*>(Mo + off) = m4;
-      if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4;
+      update_one(p, lr, step_size, decay, wd, w4[i].x, m4[i].x, v4[i].x, acc[i][0]);
+      update_one(p, lr, step_size, decay, wd, w4[i].y, m4[i].y, v4[i].y, acc[i][1]);
+      update_one(p, lr, step_size, decay, wd, w4[i].z, m4[i].z, v4[i].z, acc[i][2]);
+      update_one(p, lr, step_size, decay, wd, w4[i].w, m4[i].w, v4[i].w, acc[i][3]);
+      *reinterpret_cast<float4*>(W + off) = w4[i];
+      *reinterpret_cast<float4*>(Mo + off) = m4[i];
+      if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4[i];
     } else {
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
@@ -371,6 +412,9 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
   p.dim = a->dim;
   p.n_classes = a->n_classes;
   p.active_mask = mask;
+  p.vec_rows = a->dim % 4 == 0;  // weight rows: covered by the slab alignment check above
+  for (int s = 0; s < 2; ++s)
+    if (a->bank[s] && ((reinterpret_cast<uintptr_t>(a->bank[s]) & 15) != 0 || a->bank_ld[s] % 4 != 0)) p.vec_rows = 0;
   p.kind = a->kind;
   p.beta1 = a->beta1;
   p.beta2 = a->beta2;
@@ -407,7 +451,7 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       p.step_size[k] = static_cast<float>(static_cast<double>(l) / bc1);
       p.decay[k] = static_cast<float>(1.0 - static_cast<double>(l) * static_cast<double>(a->weight_decay[k]));
     }
-    const unsigned rt = static_cast<unsigned>((R + 31) / 32), ct = static_cast<unsigned>((a->n_classes + 31) / 32);
+    const unsigned rt = static_cast<unsigned>((R + 63) / 64), ct = static_cast<unsigned>((a->n_classes + 63) / 64);
     const bool timed = i == n_steps - 1;
     auto mark = [&](int e) -> int {
       if (timed && a->ev[e]) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(a->ev[e]), st));
