@@ -88,7 +88,7 @@ def test_sweep_run_against_oracle(C, D, optim):
         # Adam divides by |g| + eps: the few elements whose gradient (plus L2 term) nearly cancels amplify fp32
         # summation-order noise, so the maximum gets the stated 1e-3 and the mean a much tighter bound
         diff = (w - st.head).abs() / st.head.abs().max()
-        assert float(diff.max()) < 1e-3 and float(diff.mean()) < 1e-6, (k, float(diff.max()), float(diff.mean()))
+        assert float(diff.max()) < 1e-3 and float(diff.mean()) < 5e-6, (k, float(diff.max()), float(diff.mean()))
         assert opts[k].slot(models[k].head.weight)["step"] == len(rows)
 
 
