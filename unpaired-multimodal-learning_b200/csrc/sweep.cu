@@ -12,6 +12,7 @@
 // own epoch permutation (device int64) at the common position `pos` - the heads share bank and batch sizes, so their
 // epochs turn over on the same steps.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -80,6 +81,18 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   for (int w = 0; w < (blockDim.x >> 5); ++w) r += sh[w];
   __syncthreads();
   return r;
+}
+
+
+// 16-byte asynchronous global -> shared copy (LDGSTS); `valid` false zero-fills the destination without reading
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -175,6 +188,99 @@ __global__ void __launch_bounds__(256) sweep_logits_kernel(const __grid_constant
   }
 }
 
+// The same tile with the k-tiles double-buffered through cp.async: the loads of tile i+1 are in flight while tile i is
+// multiplied (the synchronous version above exposes one L2/HBM round trip per k-tile).  Needs 16-byte aligned rows
+// (p.vec_rows); identical arithmetic, identical results.
+constexpr int kLogitsLd = 68;
+constexpr int kLogitsStageFloats = 2 * 64 * kLogitsLd;  // A tile + B tile
+constexpr int kLogitsSmemBytes = 2 * kLogitsStageFloats * 4;
+
+__global__ void __launch_bounds__(256) sweep_logits_async_kernel(const __grid_constant__ SweepDev p) {
+  constexpr int BM = 64, BN = 64, kBK = 64, LD = kLogitsLd, TM = 4, TN = 4;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ const float* rowp[BM];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t R = p.n0 + p.n1;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * BM;
+  const int c0 = blockIdx.x * BN;
+  const int D = p.dim, C = p.n_classes;
+  const float* __restrict__ W = p.W + head * p.head_stride;
+  if (t < BM) rowp[t] = (m0 + t < R) ? row_ptr(p, head, m0 + t) : nullptr;
+  __syncthreads();
+
+  auto load_stage = [&](int stage, int k0) {
+    float* As = dyn + stage * kLogitsStageFloats;
+    float* Bs = As + BM * LD;
+#pragma unroll
+    for (int f = t; f < BM * (kBK / 4); f += 256) {
+      const int m = f / (kBK / 4), kk = 4 * (f % (kBK / 4));
+      const float* rp = rowp[m];
+      const bool ok = rp != nullptr && k0 + kk < D;
+      cp_async16(As + m * LD + kk, ok ? rp + k0 + kk : W, ok);
+    }
+#pragma unroll
+    for (int f = t; f < BN * (kBK / 4); f += 256) {
+      const int n = f / (kBK / 4), kk = 4 * (f % (kBK / 4));
+      const bool ok = c0 + n < C && k0 + kk < D;
+      cp_async16(Bs + n * LD + kk, ok ? W + static_cast<int64_t>(c0 + n) * D + k0 + kk : W, ok);
+    }
+    cp_async_commit();
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  const int nk = (D + kBK - 1) / kBK;
+  load_stage(0, 0);
+  for (int it = 0; it < nk; ++it) {
+    if (it + 1 < nk) {
+      load_stage((it + 1) & 1, (it + 1) * kBK);
+      cp_async_wait<1>();  // everything but the newest group has landed: tile `it` is complete
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* As = dyn + (it & 1) * kLogitsStageFloats;
+    const float* Bs = As + BM * LD;
+#pragma unroll 4
+    for (int k = 0; k < kBK; k += 4) {
+      float4 a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + 16 * i) * LD + k);
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (tx + 16 * j) * LD + k);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          float c = acc[i][j];
+          c = fmaf(a[i].x, b[j].x, c);
+          c = fmaf(a[i].y, b[j].y, c);
+          c = fmaf(a[i].z, b[j].z, c);
+          c = fmaf(a[i].w, b[j].w, c);
+          acc[i][j] = c;
+        }
+    }
+    __syncthreads();  // the next iteration's loads overwrite this buffer's sibling only after everyone is done with it
+  }
+  float* __restrict__ G = p.G + head * p.g_stride;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t r = m0 + ty + 16 * i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int c = c0 + tx + 16 * j;
+      if (c < C) G[r * p.ldg + c] = acc[i][j];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // 2. per-row softmax / CE / argmax; the raw logits row becomes G = w s / n (softmax - onehot)   grid (rows, K)
 //    (F.cross_entropy x2 and the weighted sum, finetune.py:186-188; same arithmetic as simt.cu's row kernel)
@@ -254,25 +360,6 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   const int c0 = blockIdx.y * BM, d0 = blockIdx.x * BN;
   const int D = p.dim, C = p.n_classes;
   const float* __restrict__ G = p.G + head * p.g_stride;
-  float* __restrict__ W = p.W + head * p.head_stride;
-  float* __restrict__ Mo = p.m + head * p.head_stride;
-  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
-  const int d = d0 + tx * TN;
-  const bool vec = (D % 4 == 0) && (d + TN <= D);  // slabs are 16-byte aligned (checked by the launcher)
-  // The weights and optimizer state this thread will update are requested BEFORE the contraction: the kernel is bound
-  // by HBM (24 B per parameter against ~130 FLOP), so what matters is how many bytes each SM keeps in flight
-  float4 w4[TM], m4[TM], v4[TM];
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int c = c0 + ty * TM + i;
-    w4[i] = m4[i] = v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vec && c < C) {
-      const int64_t off = static_cast<int64_t>(c) * D + d;
-      w4[i] = *reinterpret_cast<const float4*>(W + off);
-      m4[i] = *reinterpret_cast<const float4*>(Mo + off);
-      if (Vo) v4[i] = *reinterpret_cast<const float4*>(Vo + off);
-    }
-  }
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
@@ -282,12 +369,12 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   for (int64_t r0 = 0; r0 < R; r0 += kBK) {
     if (t < kBK) rowp[t] = (r0 + t < R) ? row_ptr(p, head, r0 + t) : nullptr;
     __syncthreads();
-#pragma unroll 4
+#pragma unroll
     for (int e = t; e < BM * kBK; e += 256) {
       const int k = e / BM, m = e % BM;
       As[k][m] = (r0 + k < R && c0 + m < C) ? G[(r0 + k) * p.ldg + c0 + m] : 0.f;
     }
-#pragma unroll 4
+#pragma unroll
     for (int e = t; e < BN * kBK; e += 256) {
       const int k = e / BN, n = e % BN;
       const float* rp = rowp[k];
@@ -308,19 +395,27 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
   }
 
   const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
+  float* __restrict__ W = p.W + head * p.head_stride;
+  float* __restrict__ Mo = p.m + head * p.head_stride;
+  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
+  const int d = d0 + tx * TN;
+  const bool vec = (D % 4 == 0) && (d + TN <= D);  // slabs are 16-byte aligned (checked by the launcher)
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int c = c0 + ty * TM + i;
     if (c >= C) continue;
     const int64_t off = static_cast<int64_t>(c) * D + d;
     if (vec) {
-      update_one(p, lr, step_size, decay, wd, w4[i].x, m4[i].x, v4[i].x, acc[i][0]);
-      update_one(p, lr, step_size, decay, wd, w4[i].y, m4[i].y, v4[i].y, acc[i][1]);
-      update_one(p, lr, step_size, decay, wd, w4[i].z, m4[i].z, v4[i].z, acc[i][2]);
-      update_one(p, lr, step_size, decay, wd, w4[i].w, m4[i].w, v4[i].w, acc[i][3]);
-      *reinterpret_cast<float4*>(W + off) = w4[i];
-      *reinterpret_cast<float4*>(Mo + off) = m4[i];
-      if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4[i];
+      float4 w4 = *reinterpret_cast<const float4*>(W + off);
+      float4 m4 = *reinterpret_cast<const float4*>(Mo + off);
+      float4 v4 = Vo ? *reinterpret_cast<const float4*>(Vo + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      update_one(p, lr, step_size, decay, wd, w4.x, m4.x, v4.x, acc[i][0]);
+      update_one(p, lr, step_size, decay, wd, w4.y, m4.y, v4.y, acc[i][1]);
+      update_one(p, lr, step_size, decay, wd, w4.z, m4.z, v4.z, acc[i][2]);
+      update_one(p, lr, step_size, decay, wd, w4.w, m4.w, v4.w, acc[i][3]);
+      *reinterpret_cast<float4*>(W + off) = w4;
+      *reinterpret_cast<float4*>(Mo + off) = m4;
+      if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4;
     } else {
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
@@ -332,6 +427,99 @@ __global__ void __launch_bounds__(256) sweep_dw_update_kernel(const __grid_const
         if (Vo) Vo[off + j] = vv;
       }
     }
+  }
+}
+
+// The same launch with every memory request of a CTA issued up front: the G and feature tiles of ALL rows of the step
+// go to shared memory through cp.async while the weights and optimizer state the thread will update are already on
+// their way to registers; one wait, then the contraction, the update and the stores.  (The synchronous version pays a
+// load -> barrier -> multiply round per 32 rows and only then asks for W, m, v.)  Needs 16-byte aligned rows and
+// ldg % 4 == 0; identical arithmetic, identical results.
+__global__ void __launch_bounds__(256, 2) sweep_dw_update_async_kernel(const __grid_constant__ SweepDev p) {
+  constexpr int BM = 64, BN = 64, kR = 64, LD = 68, TM = 4, TN = 4;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  __shared__ __align__(16) float As[kR][LD];  // G tile   [row][class]
+  __shared__ __align__(16) float Bs[kR][LD];  // X tile   [row][dim]
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int64_t R = p.n0 + p.n1;
+  const int c0 = blockIdx.y * BM, d0 = blockIdx.x * BN;
+  const int D = p.dim, C = p.n_classes;
+  const float* __restrict__ G = p.G + head * p.g_stride;
+  float* __restrict__ W = p.W + head * p.head_stride;
+  float* __restrict__ Mo = p.m + head * p.head_stride;
+  float* __restrict__ Vo = p.kind == 3 ? nullptr : p.v + head * p.head_stride;
+  const int d = d0 + tx * TN;
+  const bool live = d < D;  // D % 4 == 0: d < D implies d + 4 <= D
+
+  auto load_rows = [&](int64_t r0) {
+#pragma unroll
+    for (int f = t; f < kR * (BM / 4); f += 256) {
+      const int k = f / (BM / 4), q = 4 * (f % (BM / 4));
+      const bool ok = r0 + k < R && c0 + q < C;  // ldg % 4 == 0 and ldg >= C: the 16 bytes stay inside the row
+      cp_async16(&As[k][q], ok ? G + (r0 + k) * p.ldg + c0 + q : G, ok);
+    }
+#pragma unroll
+    for (int f = t; f < kR * (BN / 4); f += 256) {
+      const int k = f / (BN / 4), q = 4 * (f % (BN / 4));
+      const bool ok = r0 + k < R && d0 + q < D;
+      cp_async16(&Bs[k][q], ok ? row_ptr(p, head, r0 + k) + d0 + q : G, ok);
+    }
+    cp_async_commit();
+  };
+
+  load_rows(0);
+  float4 w4[TM], m4[TM], v4[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int c = c0 + ty * TM + i;
+    w4[i] = m4[i] = v4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live && c < C) {
+      const int64_t off = static_cast<int64_t>(c) * D + d;
+      w4[i] = *reinterpret_cast<const float4*>(W + off);
+      m4[i] = *reinterpret_cast<const float4*>(Mo + off);
+      if (Vo) v4[i] = *reinterpret_cast<const float4*>(Vo + off);
+    }
+  }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int64_t r0 = 0; r0 < R; r0 += kR) {
+    if (r0 > 0) {
+      __syncthreads();  // everyone is done with the previous rows
+      load_rows(r0);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < kR; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * TM]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * TN]);
+      const float a[TM] = {a4.x, a4.y, a4.z, a4.w}, b[TN] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+
+  if (!live) return;
+  const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int c = c0 + ty * TM + i;
+    if (c >= C) continue;
+    const int64_t off = static_cast<int64_t>(c) * D + d;
+    update_one(p, lr, step_size, decay, wd, w4[i].x, m4[i].x, v4[i].x, acc[i][0]);
+    update_one(p, lr, step_size, decay, wd, w4[i].y, m4[i].y, v4[i].y, acc[i][1]);
+    update_one(p, lr, step_size, decay, wd, w4[i].z, m4[i].z, v4[i].z, acc[i][2]);
+    update_one(p, lr, step_size, decay, wd, w4[i].w, m4[i].w, v4[i].w, acc[i][3]);
+    *reinterpret_cast<float4*>(W + off) = w4[i];
+    *reinterpret_cast<float4*>(Mo + off) = m4[i];
+    if (Vo) *reinterpret_cast<float4*>(Vo + off) = v4[i];
   }
 }
 
@@ -415,6 +603,17 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
   p.vec_rows = a->dim % 4 == 0;  // weight rows: covered by the slab alignment check above
   for (int s = 0; s < 2; ++s)
     if (a->bank[s] && ((reinterpret_cast<uintptr_t>(a->bank[s]) & 15) != 0 || a->bank_ld[s] % 4 != 0)) p.vec_rows = 0;
+  // UML_SWEEP_ASYNC=1: the cp.async variants of the two GEMM launches (same results; need aligned rows)
+  static const bool want_async = [] {
+    const char* e = getenv("UML_SWEEP_ASYNC");
+    return e != nullptr && e[0] == '1';
+  }();
+  const bool use_async = want_async && p.vec_rows && a->ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(a->G) & 15) == 0;
+  if (use_async) {
+    static const cudaError_t attr = cudaFuncSetAttribute(sweep_logits_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         kLogitsSmemBytes);
+    UML_CUDA(attr);
+  }
   p.kind = a->kind;
   p.beta1 = a->beta1;
   p.beta2 = a->beta2;
@@ -458,13 +657,19 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       return 0;
     };
     if (mark(0)) return 1;
-    sweep_logits_kernel<<<dim3(ct, rt, K), 256, 0, st>>>(p);
+    if (use_async)
+      sweep_logits_async_kernel<<<dim3(ct, rt, K), 256, kLogitsSmemBytes, st>>>(p);
+    else
+      sweep_logits_kernel<<<dim3(ct, rt, K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
     if (mark(1) || mark(2)) return 1;
     sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
     if (mark(3) || mark(4)) return 1;
-    sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
+    if (use_async)
+      sweep_dw_update_async_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
+    else
+      sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
     if (mark(5) || mark(6)) return 1;
     sweep_stats_kernel<<<dim3(2, K), 256, 0, st>>>(p);
