@@ -104,3 +104,81 @@ def test_group_rejects_mixed_runs():
     od = build_optimizer(c.parameters(), "adamw", 1e-2, 0.01)
     assert sweep_mod.group_blockers([a, c], [oa, od], la, [None, None]) == []  # lr / wd may differ
     assert sweep_mod.group_blockers([a, c], [oa, od], [la[0], BankLoader(bank, 8, shuffle=True)], [None, None])
+
+
+def _sweep_args(tmp_path, **over):
+    import types
+    a = types.SimpleNamespace(device="cpu", savepath=str(tmp_path), use_clip=True, clip_encoder="synthetic", img_indim=16,
+                              nclasses=6, logit=3.0, hyperparams="clip_linear", modality="crossmodal", classifier_init="zeroshot",
+                              common_dim=0, text_indim=16, num_workers=0, alpha=0.5, eval_test=False, seed=3, overwrite=False,
+                              sweep_batched=True, dataset="synth", precision="fp32", vision_model="", dp_sampler="global")
+    a.__dict__.update(over)
+    return a
+
+
+def _sweep_datasets():
+    from oracle.synth import synth_banks
+    from uml_b200.engine.datasets.utils import FeatureBank, TextTensorDataset
+    xi, yi, xt, yt, xv, yv = synth_banks(2, 6, 16, 16, 60, 4, 30)
+    tds = TextTensorDataset(xt, yt, torch.zeros(len(yt), dtype=torch.int64))
+    return {"text_ds": tds, "text_bank": FeatureBank.from_text_dataset(tds, "cpu"), "img_tr_bank": FeatureBank(xi, yi, "cpu"),
+            "img_val_bank": FeatureBank(xv, yv, "cpu"), "img_te_bank": FeatureBank(xv, yv, "cpu")}
+
+
+def test_batched_sweep_orchestration(monkeypatch, tmp_path):
+    """finetune.sweep with --sweep-batched (setup_group): all four combinations of a 2 x 2 grid train as one group, write
+    their result files, and a second call finds them; the results are those of each combination trained alone with
+    its derived seed."""
+    import os
+    _patched(monkeypatch)
+    hp = dict(optim="adamw", lr=[1e-2, 1e-3], weight_decay=[0.0, 0.01], lr_scheduler="cosine", batch_size=8, max_iter=40,
+              warmup_iter=5, warmup_type="linear", warmup_min_lr=1e-5, dropout=0.0, learnable_temp=False, patience=3)
+    calls = []
+    real = ft.train_group
+    monkeypatch.setattr(ft, "train_group", lambda *a, **k: (calls.append(len(a[0])), real(*a, **k))[1])
+    monkeypatch.setattr(ft, "EVAL_FREQ", 10)
+    res, best_val, best_test = ft.sweep(_sweep_datasets(), hp, _sweep_args(tmp_path))
+    assert calls == [4] and len(res["val_acc"]) == 4 and best_val > 1.0 / 6
+    files = [os.path.join(r, f) for r, _, fs in os.walk(str(tmp_path)) for f in fs if f == "test_result.pth"]
+    assert len(files) == 4
+    # second call: nothing left to train
+    res2, _, _ = ft.sweep(_sweep_datasets(), hp, _sweep_args(tmp_path))
+    assert calls == [4] and res2["val_acc"] == res["val_acc"]
+    # combination n alone, same derived seed -> same result (the group does not couple its members)
+    tmp2 = tmp_path / "alone"
+    tmp2.mkdir()
+    hp1 = dict(hp, lr=[1e-3], weight_decay=[0.0])  # combination index 2 of the grid above
+    args = _sweep_args(tmp2, seed=3)
+    import uml_b200.finetune as F2
+    monkeypatch.setattr(F2, "setup_group", lambda ds, combos, a: real_setup_group_with_offset(ds, combos, a, 2))
+
+    def real_setup_group_with_offset(ds, combos, a, offset):
+        ctx = F2._prepare(ds, combos[0], a, rng=torch.Generator().manual_seed(a.seed * 1000003 + offset))
+        out = real([ctx["model"]], [ctx["image_loader"]], [ctx["text_loader"]], [ctx["val_loader"]], None, [ctx["optimizer"]],
+                   [ctx["scheduler"]], device=a.device, max_iters=combos[0]["max_iter"], alphas=a.alpha, eval_freq=10,
+                   patience=combos[0]["patience"])
+        return [F2._finish(ctx, out[0], a)]
+    res3, _, _ = ft.sweep(_sweep_datasets(), hp1, args)
+    assert res3["val_acc"][0] == res["val_acc"][2] and res3["test_acc"][0] == res["test_acc"][2]
+
+
+def test_setup_group_routes_unbatchable_runs_to_the_plain_loop(monkeypatch, tmp_path):
+    """Learnable-temperature combinations cannot share a HeadGroup: they go through train() one by one, the others
+    still train together."""
+    _patched(monkeypatch)
+    hp = dict(optim="adamw", lr=[1e-2, 1e-3], weight_decay=0.0, lr_scheduler="cosine", batch_size=8, max_iter=20,
+              warmup_iter=5, warmup_type="linear", warmup_min_lr=1e-5, dropout=0.0, learnable_temp=[False, True], patience=3)
+    groups, solos = [], []
+    real = ft.train_group
+    monkeypatch.setattr(ft, "train_group", lambda *a, **k: (groups.append(len(a[0])), real(*a, **k))[1])
+
+    def fake_train(model, *a, **k):
+        solos.append(bool(model.learnable_temp))
+        return {"iter": 0, "val_acc": 0.5, "val_loss": 1.0, "model": {k_: v.cpu() for k_, v in model.state_dict().items()}}
+    monkeypatch.setattr(ft, "train", fake_train)
+    monkeypatch.setattr(ft, "EVAL_FREQ", 10)
+    # image-only UML without adapter (common_dim 0): the head is batchable unless its temperatures are learnable
+    args = _sweep_args(tmp_path, use_clip=False, vision_model="synthetic", common_dim=0, modality="image",
+                       classifier_init="random")
+    res, _, _ = ft.sweep(_sweep_datasets(), hp, args)
+    assert groups == [2] and solos == [True, True] and len(res["val_acc"]) == 4
