@@ -144,22 +144,52 @@ def test_batched_sweep_orchestration(monkeypatch, tmp_path):
     # second call: nothing left to train
     res2, _, _ = ft.sweep(_sweep_datasets(), hp, _sweep_args(tmp_path))
     assert calls == [4] and res2["val_acc"] == res["val_acc"]
-    # combination n alone, same derived seed -> same result (the group does not couple its members)
+    # combination 2 of the grid trained alone with its derived seed: the same weights, bit for bit (the group does not
+    # couple its members)
     tmp2 = tmp_path / "alone"
     tmp2.mkdir()
-    hp1 = dict(hp, lr=[1e-3], weight_decay=[0.0])  # combination index 2 of the grid above
-    args = _sweep_args(tmp2, seed=3)
-    import uml_b200.finetune as F2
-    monkeypatch.setattr(F2, "setup_group", lambda ds, combos, a: real_setup_group_with_offset(ds, combos, a, 2))
+    a2 = _sweep_args(tmp2)
+    hp2 = dict(hp, lr=1e-3, weight_decay=0.0)
+    ctx = ft._prepare(_sweep_datasets(), hp2, a2, rng=torch.Generator().manual_seed(ft.run_seed(a2, 2)))
+    out = real([ctx["model"]], [ctx["image_loader"]], [ctx["text_loader"]], [ctx["val_loader"]], None, [ctx["optimizer"]],
+               [ctx["scheduler"]], device="cpu", max_iters=hp2["max_iter"], alphas=a2.alpha, eval_freq=10, patience=hp2["patience"])
+    alone = ft._finish(ctx, out[0], a2)
+    grouped = torch.load([f for f in files if "lr_0.001-wd_0.0-" in f][0])
+    assert grouped["iter"] == alone["iter"] and grouped["val_acc"] == alone["val_acc"]
+    assert torch.equal(grouped["model"]["head.weight"], alone["model"]["head.weight"])
 
-    def real_setup_group_with_offset(ds, combos, a, offset):
-        ctx = F2._prepare(ds, combos[0], a, rng=torch.Generator().manual_seed(a.seed * 1000003 + offset))
-        out = real([ctx["model"]], [ctx["image_loader"]], [ctx["text_loader"]], [ctx["val_loader"]], None, [ctx["optimizer"]],
-                   [ctx["scheduler"]], device=a.device, max_iters=combos[0]["max_iter"], alphas=a.alpha, eval_freq=10,
-                   patience=combos[0]["patience"])
-        return [F2._finish(ctx, out[0], a)]
-    res3, _, _ = ft.sweep(_sweep_datasets(), hp1, args)
-    assert res3["val_acc"][0] == res["val_acc"][2] and res3["test_acc"][0] == res["test_acc"][2]
+
+def test_sweep_alphas_trains_every_alpha_in_one_group(monkeypatch, tmp_path):
+    """sweep_alphas: alpha x grid combinations in lock step, result files per alpha where one main() per alpha would have
+    written them, and each alpha's results identical to its own batched sweep."""
+    import copy
+    import os
+    _patched(monkeypatch)
+    monkeypatch.setattr(ft, "EVAL_FREQ", 10)
+    hp = dict(optim="adamw", lr=[1e-2, 1e-3], weight_decay=0.0, lr_scheduler="cosine", batch_size=8, max_iter=30,
+              warmup_iter=5, warmup_type="linear", warmup_min_lr=1e-5, dropout=0.0, learnable_temp=False, patience=3)
+    sizes = []
+    real = ft.train_group
+    monkeypatch.setattr(ft, "train_group", lambda *a, **k: (sizes.append(len(a[0])), real(*a, **k))[1])
+    per_alpha = []
+    for al in (0.2, 1.0, 1.5):
+        d = tmp_path / f"alpha_{al}"
+        d.mkdir()
+        per_alpha.append(_sweep_args(d, alpha=al))
+    outs = ft.sweep_alphas(_sweep_datasets(), hp, per_alpha)
+    assert sizes == [6] and len(outs) == 3
+    for a, (res, best_val, best_test) in zip(per_alpha, outs):
+        assert len(res["val_acc"]) == 2
+        names = [f for _, _, fs in os.walk(a.savepath) for f in fs]
+        assert names.count("test_result.pth") == 2 and "results.pth" in names
+    # alpha = 1.0 on its own (fresh directory): same numbers and weights
+    d = tmp_path / "single"
+    d.mkdir()
+    res1, _, _ = ft.sweep(_sweep_datasets(), hp, _sweep_args(d, alpha=1.0))
+    assert res1["val_acc"] == outs[1][0]["val_acc"] and res1["test_acc"] == outs[1][0]["test_acc"]
+    pick = lambda root: sorted(os.path.join(r, f) for r, _, fs in os.walk(str(root)) for f in fs if f == "test_result.pth")
+    for fa, fb in zip(pick(per_alpha[1].savepath), pick(d)):
+        assert torch.equal(torch.load(fa)["model"]["head.weight"], torch.load(fb)["model"]["head.weight"])
 
 
 def test_setup_group_routes_unbatchable_runs_to_the_plain_loop(monkeypatch, tmp_path):
@@ -182,3 +212,21 @@ def test_setup_group_routes_unbatchable_runs_to_the_plain_loop(monkeypatch, tmp_
                        classifier_init="random")
     res, _, _ = ft.sweep(_sweep_datasets(), hp, args)
     assert groups == [2] and solos == [True, True] and len(res["val_acc"]) == 4
+
+
+def test_cli_groups_alpha_jobs_only_when_batched(monkeypatch, tmp_path):
+    """The YAML's alpha list becomes ONE job per remaining combination when sweep_batched is set, and stays one job per
+    alpha (the reference's behaviour, finetune.py:541-560) otherwise."""
+    import yaml
+    calls = []
+    monkeypatch.setattr(ft, "main", lambda args, alphas=None: calls.append((args.dataset, args.alpha, alphas)))
+    cfg = {"dataset": ["sun397", "food101"], "alpha": [0.2, 0.5, 1.0], "modality": "crossmodal", "hyperparams": "clip_linear"}
+    path = tmp_path / "sweep.yaml"
+    path.write_text(yaml.safe_dump(cfg, sort_keys=False))
+    ft.cli(["-c", str(path)])
+    assert [(d, a) for d, a, _ in calls] == [(d, a) for d in ("sun397", "food101") for a in (0.2, 0.5, 1.0)]
+    assert all(al is None for _, _, al in calls)
+    calls.clear()
+    path.write_text(yaml.safe_dump(dict(cfg, sweep_batched=True), sort_keys=False))
+    ft.cli(["-c", str(path)])
+    assert calls == [("sun397", 0.2, [0.2, 0.5, 1.0]), ("food101", 0.2, [0.2, 0.5, 1.0])]

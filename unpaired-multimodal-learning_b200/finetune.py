@@ -618,23 +618,35 @@ def setup(datasets, hparams, args):
     return _finish(ctx, result, args)
 
 
-def setup_group(datasets, combos, args):
+def run_seed(args, n):
+    """Sampler seed of combination ``n`` of a batched sweep: a function of --seed, --alpha and the combination's position
+    in the preset's grid only, so a combination's result does not depend on which others train with it."""
+    return args.seed * 1000003 + n + 7919 * int(round(float(args.alpha) * 1000))
+
+
+def setup_group(datasets, combos, args, positions=None):
     """``setup`` for several hyper-parameter combinations at once: the runs that can share a HeadGroup (same shapes,
     optimizer kind, batch size; no adapter, fixed temperatures) train in lock step (``train_group``), the rest one
-    after the other.  Run k's loaders draw from their own generator seeded ``args.seed * 1000003 + k`` (``k``: position
-    in ``combos``) - or from the global stream when ``args.seed < 0`` - so a combination's result does not depend
-    on which others run with it."""
+    after the other.  ``args`` is one namespace for all combinations or a list with one per combination (runs that
+    differ in --alpha and therefore in ``savepath``).  Run k's loaders draw from their own generator seeded
+    ``run_seed(args_k, positions[k])`` (``positions``: each combination's index in the preset's grid, default
+    0, 1, ...) - or from the global stream when ``args.seed < 0``."""
     from .engine.sweep import MAX_HEADS, group_blockers
 
+    per_run = list(args) if isinstance(args, (list, tuple)) else [args] * len(combos)
+    positions = list(positions) if positions is not None else list(range(len(combos)))
+    args = per_run[0]
     results = [None] * len(combos)
     ctxs = {}
     for n, hp in enumerate(combos):
-        print(f"=> Preparing {n + 1}/{len(combos)}: {hp}")
-        seed = args.seed * 1000003 + n if args.seed >= 0 else int(torch.empty((), dtype=torch.int64).random_().item())
-        ctx = _prepare(datasets, hp, args, rng=torch.Generator().manual_seed(seed))
+        a = per_run[n]
+        print(f"=> Preparing {n + 1}/{len(combos)}: alpha {a.alpha} {hp}")
+        seed = run_seed(a, positions[n]) if a.seed >= 0 else int(torch.empty((), dtype=torch.int64).random_().item())
+        ctx = _prepare(datasets, hp, a, rng=torch.Generator().manual_seed(seed))
         if "done" in ctx:
             results[n] = ctx["done"]
         else:
+            ctx["args"] = a
             ctxs[n] = ctx
     todo = sorted(ctxs)
     while todo:
@@ -655,34 +667,38 @@ def setup_group(datasets, combos, args):
             c = ctxs[first]
             outs = [train(c["model"], c["image_loader"], c["text_loader"], c["val_loader"],
                           c["test_loader"] if args.eval_test else None, c["optimizer"], c["scheduler"],
-                          device=args.device, max_iters=c["hparams"]["max_iter"], alpha=args.alpha,
-                          eval_freq=EVAL_FREQ, patience=c["hparams"]["patience"], args=args, logger=c["logger"])]
+                          device=args.device, max_iters=c["hparams"]["max_iter"], alpha=c["args"].alpha,
+                          eval_freq=EVAL_FREQ, patience=c["hparams"]["patience"], args=c["args"], logger=c["logger"])]
         else:
             print(f"=> Training {len(members)} combinations in lock step: {members}")
             outs = train_group(col("model"), col("image_loader"), col("text_loader"), col("val_loader"),
                                col("test_loader") if args.eval_test else None, col("optimizer"), col("scheduler"),
                                device=args.device, max_iters=[ctxs[c]["hparams"]["max_iter"] for c in members],
-                               alphas=args.alpha, eval_freq=EVAL_FREQ,
+                               alphas=[ctxs[c]["args"].alpha for c in members], eval_freq=EVAL_FREQ,
                                patience=[ctxs[c]["hparams"]["patience"] for c in members], loggers=col("logger"),
                                tags=[f"run {c + 1}" for c in members])
         for c, out in zip(members, outs):
-            results[c] = _finish(ctxs.pop(c), out, args)
+            ctx = ctxs.pop(c)
+            results[c] = _finish(ctx, out, ctx["args"])
     return results
 
 
-def sweep(datasets, hyperparams, args):
+def _grid(hyperparams):
     grid = {k: (v if isinstance(v, list) else [v]) for k, v in hyperparams.items()}
     keys = list(grid)
-    combos = list(product(*[grid[k] for k in keys]))
+    return [dict(zip(keys, combo)) for combo in product(*[grid[k] for k in keys])]
+
+
+def _collect(hps, outcomes, args):
+    """The bookkeeping of the reference's ``sweep`` (finetune.py:417-448) over finished runs: running best, results.pth,
+    the final summary."""
     results = {"test_acc": [], "val_acc": [], "hparams": [], "model_records": []}
     best_val = best_test = 0
     best_hp = None
-    hps = [dict(zip(keys, combo)) for combo in combos]
-    # --sweep-batched: the combinations train in lock step on one GPU (setup_group) instead of one after the other
-    pre = setup_group(datasets, hps, args) if getattr(args, "sweep_batched", False) else None
-    for n, hp in enumerate(hps):
-        print(f"=> Running {n + 1}/{len(combos)}: {hp}")
-        res = pre[n] if pre is not None else setup(datasets, hp, args)
+    for n, (hp, res) in enumerate(zip(hps, outcomes)):
+        print(f"=> Running {n + 1}/{len(hps)}: {hp}")
+        if callable(res):
+            res = res()
         results["test_acc"].append(res["test_acc"])
         results["val_acc"].append(res["val_acc"])
         results["hparams"].append(hp)
@@ -703,7 +719,32 @@ def sweep(datasets, hyperparams, args):
     return results, results["val_acc"][k], results["test_acc"][k]
 
 
-def main(args):
+def sweep(datasets, hyperparams, args):
+    hps = _grid(hyperparams)
+    if getattr(args, "sweep_batched", False):
+        # --sweep-batched: the combinations train in lock step on one GPU (setup_group) instead of one after the other
+        return _collect(hps, setup_group(datasets, hps, args), args)
+    return _collect(hps, [lambda hp=hp: setup(datasets, hp, args) for hp in hps], args)
+
+
+def sweep_alphas(datasets, hyperparams, args_per_alpha):
+    """``sweep`` for several values of --alpha at once.  The reference's YAML lists alpha (configs/finetune.yaml:17) and
+    runs ``main`` once per value over the same banks; here all alpha x hyper-parameter combinations (<= 32 per
+    HeadGroup) train in lock step.  ``args_per_alpha``: one namespace per alpha (own ``alpha`` and ``savepath``).
+    Result files land where one ``main`` per alpha would have put them; returns ``[sweep's return value per alpha]``."""
+    hps = _grid(hyperparams)
+    runs, owners = [], []
+    for a in args_per_alpha:
+        runs += hps
+        owners += [a] * len(hps)
+    outcomes = setup_group(datasets, runs, owners, positions=[n % len(hps) for n in range(len(runs))])
+    return [_collect(hps, outcomes[i * len(hps):(i + 1) * len(hps)], a) for i, a in enumerate(args_per_alpha)]
+
+
+def main(args, alphas=None):
+    """``alphas``: several --alpha values to train in ONE batched sweep over the banks loaded once (``sweep_alphas``; the
+    reference runs ``main`` once per alpha of its YAML list).  Returns ``sweep``'s triple, or a list of them (one per
+    alpha) when ``alphas`` is given."""
     if args.seed >= 0:
         print("=> Setting fixed seed: {}".format(args.seed))
         set_random_seed(args.seed)
@@ -718,12 +759,15 @@ def main(args):
         torch.distributed.init_process_group("nccl", device_id=torch.device(args.device))
     args.use_clip = args.vision_model == "" and args.language_model == ""
     encoder_name = args.clip_encoder if args.use_clip else f"{args.vision_model}-{args.language_model}"
-    args.savepath = savedir(args.result_dir, args.dataset, encoder_name, args.train_shot, args.seed, args.text_type,
-                            args.text_shot, args.image_augmentation, args.modality, args.classifier_init, args.alpha,
-                            getattr(args, "text_batch_size", 0), args.custom_name, args)
-    makedirs(args.savepath)
-    logfile = open(os.path.join(args.savepath, "log.txt"), "w")
-    sys.stdout = Tee(sys.__stdout__, logfile)
+    alpha_list = [float(a) for a in alphas] if alphas else [args.alpha]
+    savepaths = [savedir(args.result_dir, args.dataset, encoder_name, args.train_shot, args.seed, args.text_type,
+                         args.text_shot, args.image_augmentation, args.modality, args.classifier_init, a,
+                         getattr(args, "text_batch_size", 0), args.custom_name, args) for a in alpha_list]
+    args.savepath = savepaths[0]
+    for sp in savepaths:
+        makedirs(sp)
+    logfiles = [open(os.path.join(sp, "log.txt"), "w") for sp in dict.fromkeys(savepaths)]
+    sys.stdout = Tee(sys.__stdout__, *logfiles)
     try:
         print("=> Arguments:", args)
         text_encoder = args.clip_encoder if args.use_clip else args.language_model
@@ -756,13 +800,23 @@ def main(args):
             "text_ds": text_ds, "text_bank": FeatureBank.from_text_dataset(text_ds, dev),
             "img_tr_bank": tr_bank, "img_val_bank": val_bank, "img_te_bank": te_bank,
         }
-        results, best_val, best_test = sweep(datasets, HYPER_DICT[args.hyperparams], args)
+        if alphas:
+            import copy
+            per_alpha = []
+            for a, sp in zip(alpha_list, savepaths):
+                c = copy.copy(args)
+                c.alpha, c.savepath = a, sp
+                per_alpha.append(c)
+            out = sweep_alphas(datasets, HYPER_DICT[args.hyperparams], per_alpha)
+        else:
+            out = sweep(datasets, HYPER_DICT[args.hyperparams], args)
         del datasets
         print("Done!")
     finally:
         sys.stdout = sys.__stdout__
-        logfile.close()
-    return results, best_val, best_test
+        for f in logfiles:
+            f.close()
+    return out
 
 
 def cli(argv=None):
@@ -794,11 +848,26 @@ def cli(argv=None):
             print("Invalid SLURM_ARRAY_TASK_ID")
             sys.exit(1)
         combos = [combos[job]]
-    for i, c in enumerate(combos):
+    # sweep_batched: jobs that differ only in alpha share their banks, so they become ONE job whose alpha x
+    # hyper-parameter combinations train in lock step (main(args, alphas=[...]))
+    jobs = []
+    for c in combos:
+        rest_ = {k: v for k, v in c.items() if k != "alpha"}
+        mate = next((j for j in jobs if c.get("sweep_batched") and j[0] == rest_ and "alpha" in c), None)
+        if mate is not None:
+            mate[1].append(c["alpha"])
+        else:
+            jobs.append((rest_, [c["alpha"]] if "alpha" in c else []))
+    for i, (c, alphas_) in enumerate(jobs):
         print(f"=> Running job {i}")
+        if alphas_:
+            c = dict(c, alpha=alphas_[0])
         args = parser.parse_args([], argparse.Namespace(**c))
         args.overwrite = outer_args.overwrite
-        main(args)
+        if len(alphas_) > 1:
+            main(args, alphas=alphas_)
+        else:
+            main(args)
 
 
 if __name__ == "__main__":
