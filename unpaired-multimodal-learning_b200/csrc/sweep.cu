@@ -11,7 +11,11 @@
 // Layout in HBM: W, m, v are [K][C*D] slabs (head_stride apart); G is [K][rows][ldg] scratch; every head reads its
 // own epoch permutation (device int64) at the common position `pos` - the heads share bank and batch sizes, so their
 // epochs turn over on the same steps.
-#include <algorithm>
+//
+// Two GEMM-shaped launches exist in two forms with identical arithmetic: register-staged (any alignment) and cp.async
+// (16-byte aligned rows; the default - double-buffered k-tiles for the logits, all rows of the step plus the thread's
+// W, m, v requested up front for dW).  Measured on B200 with K = 30 heads of 1000 x 512: 0.219 ms per step of all heads
+// (logits 73 us, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7); register-staged 0.268 ms.
 #include <cstdlib>
 
 #include "common.cuh"
