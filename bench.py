@@ -27,7 +27,6 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
 import threading
 import time

@@ -162,7 +162,6 @@ def test_batched_sweep_orchestration(monkeypatch, tmp_path):
 def test_sweep_alphas_trains_every_alpha_in_one_group(monkeypatch, tmp_path):
     """sweep_alphas: alpha x grid combinations in lock step, result files per alpha where one main() per alpha would have
     written them, and each alpha's results identical to its own batched sweep."""
-    import copy
     import os
     _patched(monkeypatch)
     monkeypatch.setattr(ft, "EVAL_FREQ", 10)
