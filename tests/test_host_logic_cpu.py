@@ -372,3 +372,37 @@ def test_take_run_matches_batchwise_iteration():
                 x = next(ib)
             ref.append(x.host_idx)
         assert torch.equal(got, torch.cat(ref))
+
+
+def test_take_run_ragged_shapes_property():
+    """take_run against batch-wise iteration over many (bank rows, batch size, drop_last, num_workers, chunking) shapes:
+    banks shorter than a batch, exact multiples, one-row tails."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 70), bs=st.integers(1, 24), drop=st.booleans(), nw=st.sampled_from([0, 2]),
+           seed=st.integers(0, 2 ** 31), chunks=st.lists(st.integers(1, 9), min_size=3, max_size=8))
+    def check(n, bs, drop, nw, seed, chunks):
+        if drop and n < bs:
+            return  # such a loader yields nothing (len == 0), as the reference's DataLoader would
+        g1, g2 = torch.Generator().manual_seed(seed), torch.Generator().manual_seed(seed)
+        a = BankLoader(_bank(n), bs, shuffle=True, drop_last=drop, num_workers=nw, rng=g1)
+        b = BankLoader(_bank(n), bs, shuffle=True, drop_last=drop, num_workers=nw, rng=g2)
+        ia, ib = iter(a), iter(b)
+        for want in chunks:
+            if ia.batches_left() == 0:
+                ia = iter(a)
+            k = min(want, ia.batches_left())
+            perm, start, total = ia.take_run(k)
+            ref = []
+            for _ in range(k):
+                try:
+                    x = next(ib)
+                except StopIteration:
+                    ib = iter(b)
+                    x = next(ib)
+                ref.append(x.host_idx)
+            assert torch.equal(perm[start:start + total], torch.cat(ref))
+            assert g1.get_state().equal(g2.get_state())  # both consumed the same draws
+
+    check()
