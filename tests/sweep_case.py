@@ -28,7 +28,7 @@ def _unpad(a):
     return [row[row >= 0] for row in a]
 
 
-def run_group_case(ft, device, optim=None, modality=None):
+def run_group_case(ft, device, optim=None, modality=None, max_iters=None, num_workers=None, eval_freq=None):
     from uml_b200.engine.datasets.utils import BankLoader, FeatureBank, TextTensorDataset
     from uml_b200.engine.models.head import UMLClip
     from uml_b200.engine.optimizer.optim import build_optimizer
@@ -36,7 +36,12 @@ def run_group_case(ft, device, optim=None, modality=None):
 
     fx = np.load(os.path.join(GOLDEN, "train_clip.npz"), allow_pickle=False)
     cfg = ast.literal_eval(str(fx["cfg"]))
-    golden_exact = optim is None and modality is None
+    golden_exact = optim is None and modality is None and max_iters is None and num_workers is None and eval_freq is None
+    if num_workers is not None:
+        cfg["num_workers"] = num_workers
+    if eval_freq is not None:
+        cfg["eval_freq"] = eval_freq
+    iters = list(max_iters) if max_iters is not None else [cfg["steps"]] * len(HEADS)
     optim, modality = optim or cfg["optim"], modality or cfg["modality"]
     heads = [dict(h) for h in HEADS]
     heads[0].update(lr=cfg["lr"], wd=cfg["wd"], alpha=cfg["alpha"], patience=cfg["patience"], seed=1000 + cfg["seed"])
@@ -62,7 +67,7 @@ def run_group_case(ft, device, optim=None, modality=None):
         vls.append(BankLoader(vb, cfg["bs"], shuffle=False, rng=rng))
         traces.append({})
     torch.manual_seed(99)  # the global stream must not matter
-    outs = ft.train_group(models, ils, tls, vls, None, opts, schs, device=device, max_iters=cfg["steps"],
+    outs = ft.train_group(models, ils, tls, vls, None, opts, schs, device=device, max_iters=iters,
                           alphas=[h["alpha"] for h in heads], eval_freq=cfg["eval_freq"],
                           patience=[h["patience"] for h in heads], traces=traces)
 
@@ -92,12 +97,12 @@ def run_group_case(ft, device, optim=None, modality=None):
         want, wtr = O.train(st, (xi, yi) if modality != "text" else None,
                             (tds.input_tensor, tds.label_tensor) if modality != "image" else None, (xv, yv),
                             batch_size=cfg["bs"], optim=optim, lr=h["lr"], weight_decay=h["wd"],
-                            warmup_iter=cfg["warmup_iter"], sched_max_iter=cfg["sched_max"], max_iters=cfg["steps"],
+                            warmup_iter=cfg["warmup_iter"], sched_max_iter=cfg["sched_max"], max_iters=iters[k],
                             alpha=h["alpha"], eval_freq=cfg["eval_freq"], patience=h["patience"],
                             num_workers=cfg["num_workers"])
         out, tr = outs[k], traces[k]
         n = len(wtr.lr)
-        stopped_early.append(n < cfg["steps"])
+        stopped_early.append(n < iters[k])
         assert len(tr["stats"]) == n, (k, len(tr["stats"]), n)
         for name, ref in (("img_idx", wtr.img_idx), ("txt_idx", wtr.txt_idx)):
             if ref:

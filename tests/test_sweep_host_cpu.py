@@ -89,6 +89,13 @@ def test_group_text_only(monkeypatch):
     run_group_case(ft, "cpu", optim="adam", modality="text")
 
 
+def test_group_heads_with_different_lengths_and_worker_protocol(monkeypatch):
+    """Heads that end at different iterations (one in the middle of an evaluation interval), the num_workers > 0 sampler
+    protocol (seed drawn when the iterator is built) and an evaluation interval that does not divide the epochs."""
+    _patched(monkeypatch)
+    run_group_case(ft, "cpu", max_iters=[60, 33, 47], num_workers=2, eval_freq=7)
+
+
 def test_group_rejects_mixed_runs():
     from uml_b200.engine.datasets.utils import BankLoader, FeatureBank
     from uml_b200.engine.models.head import UML, UMLClip

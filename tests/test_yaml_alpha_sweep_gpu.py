@@ -144,3 +144,10 @@ def test_sweep_run_more_than_one_row_tile(bi, bt):
             assert abs(got["img_acc"][i][k] - stats["img_acc"]) < 1e-6 and abs(got["text_acc"][i][k] - stats["text_acc"]) < 1e-6
         diff = (models[k].head.weight.detach().cpu() - st.head).abs() / st.head.abs().max()
         assert float(diff.max()) < 1e-3 and float(diff.mean()) < 5e-6, (k, float(diff.max()), float(diff.mean()))
+
+
+def test_train_group_heads_of_different_lengths():
+    """Same body as test_sweep_gpu.py::test_train_group_matches_reference_and_oracle with heads that end at different
+    iterations, the num_workers > 0 sampler protocol and an evaluation interval of 7 (chunks cut at odd places)."""
+    from sweep_case import run_group_case
+    run_group_case(ft, "cuda:0", max_iters=[60, 33, 47], num_workers=2, eval_freq=7)
