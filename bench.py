@@ -480,6 +480,22 @@ def run_gaussian(args):
     t1 = time.perf_counter()
     O.gaussian_train(p, dx, dy, num_steps=200, batch_size=B, lr=1e-3, mode="xy")
     cpu = 200 * 2 * B / (time.perf_counter() - t1)
+    # The reference's loop also evaluates linear CKA and mutual 10-NN on the 2000-row validation embeddings after EVERY
+    # step (main.py:14-27 EVAL_EVERY = 1, :67-84) - diagnostics this implementation does not run.  Their CPU cost at
+    # those shapes (n x n kernel matrices), for context next to the bare step:
+    probes = None
+    try:
+        from oracle import metrics_oracle as MO
+        ga = torch.Generator().manual_seed(0)
+        ea, eb = torch.randn(2000, 10, generator=ga), torch.randn(2000, 10, generator=ga)
+        MO.cka_linear(ea, eb)
+        t2 = time.perf_counter()
+        for _ in range(3):
+            MO.cka_linear(ea, eb)
+            MO.mutual_knn(ea, eb, 10)
+        probes = (time.perf_counter() - t2) / 3
+    except Exception as e:  # context only
+        print(f"probe timing failed: {e}", file=sys.stderr)
     line = {"metric": "UML train samples/sec (img+text)", "value": K * 2 * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -491,7 +507,9 @@ def run_gaussian(args):
             "roofline": {"bound": "latency", "kernel": "gauss_fwd_bwd_kernel + gauss_update_kernel", "achieved": None, "peak": None,
                          "unit": "us/step", "frac": None, "traffic": None},
             "cpu_baseline": {"value": cpu, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "200 steps of the oracle port (fp32 torch ops on the host)"}}
+                             "sample": "200 steps of the oracle port (fp32 torch ops on the host)",
+                             "reference_probes_s_per_step": probes,
+                             "value_with_reference_probes": (2 * B / (2 * B / cpu + probes)) if probes else None}}
     print(json.dumps(line))
 
 
