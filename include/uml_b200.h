@@ -162,7 +162,11 @@ int uml_head_fwd_ce_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const u
                          uml_seg_stats* stats /* optional, with G: per-run {mean loss, dscale, hits, rows} written by
                                                  the fix-up launch (saves the uml_reduce_tile_stats launch)     */,
                          void* stream);
-#define UML_TILE_WS_FLOATS(n_rows) ((((n_rows) + 255) / 256) * 64 + (n_rows) * 16)
+#define UML_TILE_WS_FLOATS(n_rows) (16 + (((n_rows) + 255) / 256) * 264 + (n_rows) * 32)
+/* tile_ws must be ZERO-INITIALISED when it is allocated (the exchange flags of the forward kernel are keyed by a launch
+ * epoch kept in its first words).  1 when a forward launch on this workspace ever timed out waiting for a peer CTA pair
+ * (its results are undefined): synchronises, meant for flush / evaluation cadence.                              */
+int uml_fwd_x_failed(const float* tile_ws);
 /* per-run {mean loss, dscale, hits, rows} from the forward kernel's per-tile partials (fixed order)     */
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream);
 /* The same forward without its fix-up pass: G receives the unnormalised bf16 exp(l - m_running) and tile_ws the

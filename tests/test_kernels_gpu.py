@@ -424,9 +424,11 @@ def test_grad_diagnostics_match_autograd():
 
 @pytest.mark.parametrize("n_img,n_txt,d,c", [(300, 212, 256, 1000), (2048, 1500, 768, 1000), (129, 0, 512, 397), (1000, 1000, 512, 101),
                                              (4736, 4736, 768, 1000)])
-def test_dw_prologue_fixup_is_bit_identical_to_the_fixup_kernel(n_img, n_txt, d, c):
-    """The deferred softmax normalisation applied to the dW operand stages in shared memory (tc_gemm kFix) must give
-    exactly the partial sums of forward + g_fixup_kernel + plain dW, and the same per-run statistics."""
+def test_dw_prologue_fixup_matches_the_default_forward(n_img, n_txt, d, c):
+    """The deferred softmax normalisation applied to the dW operand stages in shared memory (tc_gemm kFix, an
+    experiment kept behind UML_FUSE_FIX=1) against the default path - the exchange forward kernel, whose G is final -
+    + plain dW: the same partial sums up to the bf16 rounding of G (the two paths round the rescaled probabilities
+    differently), the same hit counts, the same per-run statistics."""
     xi, yi, xt, yt, w, g = _mk(n_img + d + c, max(n_img, 1), max(n_txt, 1), d, d, c)
     x = torch.cat([xi[:n_img], xt[:n_txt]]).to(DEV)
     y = torch.cat([yi[:n_img], yt[:n_txt]]).to(DEV).to(torch.int32)
@@ -443,10 +445,10 @@ def test_dw_prologue_fixup_is_bit_identical_to_the_fixup_kernel(n_img, n_txt, d,
     ops.head_fwd_ce_deferred_bf16(x16, w16, y, segs, ws_b, n_rows=n)
     ops.head_bwd_dw_fix_bf16(ws_b, x16, n, c, pb, splits, segs, y, stats=st_b)
     torch.cuda.synchronize()
-    assert torch.equal(pa, pb)
+    assert (pa.sum(0) - pb.sum(0)).abs().max().item() <= 2e-3 * pa.sum(0).abs().max().item()
     k = len(rows)
     assert torch.equal(st_a.view(torch.int32)[:k, 2:], st_b.view(torch.int32)[:k, 2:])       # hits, rows
-    torch.testing.assert_close(st_a[:k, :2], st_b[:k, :2], rtol=1e-5, atol=1e-6)             # mean loss, dscale
+    torch.testing.assert_close(st_a[:k, :2], st_b[:k, :2], rtol=2e-4, atol=2e-5)             # mean loss, dscale
 
 
 def test_full_size_step_properties():

@@ -105,6 +105,7 @@ PROTOTYPES = {
     "uml_sum_partials": [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp],
     "uml_reduce_seg_stats": [c_vp, c_vp, c_vp, C.POINTER(c_i64), c_i32, c_vp, c_vp],
     "uml_reduce_tile_stats": [c_vp, c_i64, c_i32, c_vp, c_vp],
+    "uml_fwd_x_failed": [c_vp],
     "uml_linear_step": [C.POINTER(LinearStepArgs), c_vp],
     "uml_linear_run": [C.POINTER(LinearStepArgs), C.POINTER(RunStep), c_i32, c_vp],
     "uml_dp_unique_id": [c_vp],

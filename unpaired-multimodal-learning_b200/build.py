@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("UML_LIB_PATH") or os.path.join(LIB_DIR, "libuml_b200.so")
-SOURCES = ["lib.cu", "gather.cu", "simt.cu", "optim.cu", "tc_fwd.cu", "tc_gemm.cu", "step.cu", "dp.cu", "sampler.cu", "gauss.cu", "sweep.cu"]
+SOURCES = ["lib.cu", "gather.cu", "simt.cu", "optim.cu", "tc_fwd.cu", "tc_fwd2.cu", "tc_gemm.cu", "step.cu", "dp.cu", "sampler.cu", "gauss.cu", "sweep.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -41,7 +41,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = _nvcc()
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.environ.get("UML_OBJ_DIR") or os.path.join(HERE, "build")
     os.makedirs(obj_dir, exist_ok=True)
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("UML_NVCC_FLAGS", "").split()
 

@@ -143,6 +143,13 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
 int uml_head_bwd_dw_gated_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
                                float* partials, int32_t n_splits, const unsigned* done, int* failed, void* stream);  // tc_gemm.cu
 
+// tc_fwd2.cu / tc_gemm.cu: exchange forward kernel (G final after one pass) and the dW GEMM that reduces its statistics
+bool uml_fwd_x_eligible(int64_t n_rows, int32_t n_classes);
+void uml_fwd_x_partials(float* tile_ws, int64_t n_rows, int32_t n_classes, const float** part, int64_t* n_entries);
+int uml_head_bwd_dw_stats_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                               float* partials, int32_t n_splits, const float* part, int64_t part_entries, int32_t nseg,
+                               uml_seg_stats* stats, void* stream);
+
 float* uml_dp_p2p_input(int64_t n);   // dp.cu: this rank's exchange buffers of the peer-memory all-reduce (or NULL)
 float* uml_dp_p2p_output(int64_t n);
 
@@ -313,6 +320,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   const bool pregathered = hooks.pregathered;
   const cudaEvent_t operand_free = hooks.operand_free;
   Pipe* opipe = nullptr;  // set when this step's dW runs on the second stream, overlapping the fix-up launch
+  bool stats_in_dw = false;  // the forward's per-run statistics are reduced inside the dW kernel
   UML_REQUIRE(a != nullptr, "linear_step: null args");
   UML_REQUIRE(a->nseg >= 1 && a->nseg <= UML_MAX_SEGMENTS, "linear_step: 1..2 segments");
   UML_REQUIRE(a->W && a->G && a->row_loss && a->row_correct && a->stats, "linear_step: null buffers");
@@ -396,11 +404,15 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
         if (!after_fwd) after_fwd = opipe->fwd_done;
       }
       rec(a->ev[2], stream);
-      // ev[2]..ev[3] bracket the tensor-core kernel alone; the fix-up launch (which also reduces the per-run
-      // statistics) follows it
+      // ev[2]..ev[3] bracket the tensor-core kernel alone.  Exchange kernel (default): G is final when it ends and the
+      // per-run statistics are reduced by an idle warp of the dW GEMM - unless a learnable temperature needs them
+      // before that (then a small reduction launch follows the forward).  Chunk-sequential kernel (UML_FWD_IMPL=old):
+      // the fix-up launch, which also reduces the statistics, follows it.
+      stats_in_dw = !fuse_fix() && !opipe && uml_fwd_x_eligible(total, a->n_classes) && !a->scale_param[0] &&
+                    !a->scale_param[1];
       rc = uml_head_fwd_ce_bf16_ev(a->X16, total, a->dim, a->W16, a->n_classes, a->labels32, &ts,
                                    static_cast<uint16_t*>(a->G), a->ldg, nullptr, nullptr, nullptr, nullptr, a->tile_ws,
-                                   a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, after_fwd,
+                                   stats_in_dw ? nullptr : a->stats, a->ev[3], stream, fuse_fix() ? 1 : 0, after_fwd,
                                    fuse_fix() ? nullptr : hooks.merged, opipe ? &sig : nullptr);
       if (rc) return rc;
       if (opipe) {
@@ -485,6 +497,14 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     }
     rc = uml_head_bwd_dw_fix_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
                                   a->partials, splits, &ts2, a->labels32, a->tile_ws, a->stats, stream);
+  } else if (stats_in_dw) {
+    const float* part = nullptr;
+    int64_t entries = 0;
+    uml_fwd_x_partials(a->tile_ws, total, a->n_classes, &part, &entries);
+    int nseg_live = 0;
+    for (int i = 0; i < a->nseg; ++i) nseg_live += a->seg[i].n > 0 ? 1 : 0;
+    rc = uml_head_bwd_dw_stats_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
+                                    a->partials, splits, part, entries, nseg_live, a->stats, stream);
   } else {
     rc = uml_head_bwd_dw_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes, a->partials,
                               splits, stream);

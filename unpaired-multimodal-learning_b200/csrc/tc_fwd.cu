@@ -626,6 +626,13 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
                             void* ev_after_fwd, void* stream, int defer_fixup = 0, void* ev_after_fwd2 = nullptr,
                             const uml::GatherJob* job = nullptr, const uml::FixupSignal* sig = nullptr);
 int64_t uml_fwd_tiles(int64_t n_rows);
+// tc_fwd2.cu: the exchange kernel (class chunks of a row tile on different CTA pairs, G final after one pass)
+bool uml_fwd_x_eligible(int64_t n_rows, int32_t n_classes);
+int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const uint16_t* W, int32_t n_classes,
+                           const int32_t* labels, const uml_tc_segments* segs, uint16_t* G, int64_t ldg, float* row_loss,
+                           int32_t* row_pred, int32_t* row_correct, float* row_dscale, float* tile_ws, uml_seg_stats* stats,
+                           void* stream);
+int uml_fwd_x_reduce_stats(float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream);
 
 extern "C" {
 
@@ -662,6 +669,19 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
               "head_fwd_ce_bf16: ldg must be a multiple of 64 and >= n_classes");
   UML_REQUIRE(segs->nseg >= 1 && segs->nseg <= UML_MAX_SEGMENTS, "head_fwd_ce_bf16: 1..2 segments");
   if (n_rows == 0) return 0;
+  if (!defer_fixup && !sig && tile_ws && uml_fwd_x_eligible(n_rows, n_classes)) {
+    // default for anything larger than one 128-row tile: one kernel, G final, no fix-up launch
+    int rc = uml_head_fwd_ce_x_bf16(X, n_rows, dim, W, n_classes, labels, segs, G, ldg, row_loss, row_pred, row_correct,
+                                    row_dscale, tile_ws, stats, stream);
+    if (rc) return rc;
+    if (ev_after_fwd) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd), uml::as_stream(stream)));
+    if (ev_after_fwd2) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd2), uml::as_stream(stream)));
+    if (job && job->blocks > 0)  // (prefetch placement 3 rode in the fix-up launch: copy the rows directly instead)
+      rc = uml_gather2_rows_bf16_light(reinterpret_cast<const uint16_t*>(job->s0.bank), job->s0.labels, job->s0.idx, job->s0.n,
+                                       reinterpret_cast<const uint16_t*>(job->s1.bank), job->s1.labels, job->s1.idx, job->s1.n,
+                                       dim, reinterpret_cast<uint16_t*>(job->out), dim, job->out_labels, stream);
+    return rc;
+  }
   const int64_t n0 = segs->seg_rows[0], n1 = segs->nseg > 1 ? segs->seg_rows[1] : 0;
   UML_REQUIRE(n0 + n1 == n_rows, "head_fwd_ce_bf16: segment rows (%lld+%lld) != n_rows (%lld)", (long long)n0,
               (long long)n1, (long long)n_rows);
@@ -748,6 +768,7 @@ int uml_head_fwd_ce_deferred_bf16(const uint16_t* X, int64_t n_rows, int32_t dim
 int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream) {
   using namespace uml;
   UML_REQUIRE(tile_ws && stats && nseg >= 1 && nseg <= UML_MAX_SEGMENTS && n_rows >= 0, "reduce_tile_stats: bad arguments");
+  if (uml_fwd_x_eligible(n_rows, 1)) return uml_fwd_x_reduce_stats(const_cast<float*>(tile_ws), n_rows, nseg, stats, stream);
   const int cg = fwd_cta_group(n_rows);
   const int64_t tiles = ((n_rows + kFwdBlockM * cg - 1) / (kFwdBlockM * cg)) * cg;  // tiles the forward kernel wrote
   UML_CUDA(launch_kernel(tile_stats_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, true, tile_ws, tiles,

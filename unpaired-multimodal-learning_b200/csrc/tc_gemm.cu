@@ -60,6 +60,10 @@ struct FixArgs {
   const unsigned* wait_done;
   unsigned wait_expected[8];
   int* wait_failed;
+  // any instantiation: the exchange forward kernel's per-(tile, chunk, warp) partials (tc_fwd2.cu), reduced into
+  // `stats` by an idle warp of the first CTA - the forward's statistics cost no launch of their own
+  const float* part;
+  int64_t part_entries;
 };
 
 template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
@@ -205,6 +209,32 @@ __global__ void __launch_bounds__(256, 1)
       else umma_commit(tfull_bar);
     }
     __syncwarp();
+  } else if (!kFix && warp == 3) {
+    // ------------------------------------------------ per-run statistics of the exchange forward kernel -------
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && fix.stats && fix.part) {
+      for (int sgi = 0; sgi < fix.nseg; ++sgi) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int64_t i0 = 0; i0 < fix.part_entries; i0 += 128) {  // four independent 16-byte loads in flight per lane
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * 32 + lane;
+            v[u] = i < fix.part_entries ? __ldcg(reinterpret_cast<const float4*>(fix.part) + i * 2 + sgi)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) {
+          fix.stats[sgi].loss_mean = acc[3] > 0.f ? acc[0] / acc[3] : 0.f;
+          fix.stats[sgi].dscale = acc[1];
+          fix.stats[sgi].correct = static_cast<int32_t>(acc[2] + 0.5f);
+          fix.stats[sgi].n = static_cast<int32_t>(acc[3] + 0.5f);
+        }
+      }
+    }
   } else if (kFix && warp == 3) {
     // ------------------------------------------------ per-run statistics (one idle warp of one CTA) ---------
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && fix.stats) {
@@ -414,6 +444,11 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
   } else {
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, kGBlockK, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   }
+  if (fix && !fix->fac && !fix->wait_done) {  // statistics job only: plain dW kernel
+    UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: the statistics job is wired for the dW layout only");
+    return cg == 2 ? launch_tc_gemm<true, true, false, 2, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
+                   : launch_tc_gemm<true, true, false, 1, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);
+  }
   if (fix && !fix->fac) {  // wait-only: plain dW kernel whose splits are gated by the fix-up counters
     UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: split gating is wired for the dW layout only");
     return cg == 2 ? launch_tc_gemm<true, true, false, 2, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
@@ -454,6 +489,23 @@ int uml_head_bwd_dw_gated_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X
     const int64_t r_hi = r_hi_raw < n_rows ? r_hi_raw : n_rows;
     fx.wait_expected[sp] = r_hi > r_lo ? static_cast<unsigned>((r_hi - r_lo + 7) / 8) : 0u;
   }
+  return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
+}
+
+// dW that also reduces the exchange forward kernel's partial statistics (library-internal, step.cu)
+int uml_head_bwd_dw_stats_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                               float* partials, int32_t n_splits, const float* part, int64_t part_entries, int32_t nseg,
+                               uml_seg_stats* stats, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(G && X && partials && n_rows > 0 && n_splits >= 1 && part && stats && nseg >= 1 && nseg <= UML_MAX_SEGMENTS,
+              "dw_stats: bad arguments");
+  UML_REQUIRE(dim % 8 == 0 && ldg % 64 == 0 && ldg >= n_classes, "dw_stats: dim must be a multiple of 8 and ldg of 64");
+  FixArgs fx;
+  memset(&fx, 0, sizeof(fx));
+  fx.part = part;
+  fx.part_entries = part_entries;
+  fx.nseg = nseg;
+  fx.stats = stats;
   return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
 }
 

@@ -162,7 +162,8 @@ class HeadWorkspace:
         self.row_dscale = torch.empty(max_rows, device=device, dtype=torch.float32)
         self.stats = torch.zeros((2, 4), device=device, dtype=torch.float32)  # 2 x uml_seg_stats (16 B each)
         # UML_TILE_WS_FLOATS(max_rows): per-tile partial sums written by the tensor-core forward
-        self.fac = (torch.zeros(((max_rows + 255) // 256) * 64 + max_rows * 16, device=device, dtype=torch.float32)
+        # (zero-initialised: the forward kernel keeps its launch epoch and exchange flags in the first words)
+        self.fac = (torch.zeros(16 + ((max_rows + 255) // 256) * 264 + max_rows * 32, device=device, dtype=torch.float32)
                     if bf16 else None)
 
     def read_stats(self):
