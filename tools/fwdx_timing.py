@@ -14,8 +14,8 @@ w16 = ops.cast_bf16(W)
 labels = torch.randint(0, Cc, (N,), device=DEV, dtype=torch.int32)
 ws = ops.HeadWorkspace(N, Cc, DEV, bf16=True)
 segs = ops.tc_segments([N0, N1], [100.0, 100.0], [1.0, 0.5])
-names = ["epi_wait_tfull", "epi_wait_staging", "epi_pass1", "epi_half_combine", "epi_publish", "epi_flag_wait", "epi_recs",
-         "epi_pass2_store", "epi_row_stats", "mma_wait_tempty", "mma_wait_full", "mma_issue", "tma_wait_empty", "tma_issue", "-", "-"]
+names = ["epi_wait_tfull", "epi_first_ld", "epi_pass1+finish_prev", "epi_finish_rows", "epi_combine_publish", "epi_last_resolve", "epi_last_finish",
+         "-", "-", "mma_wait_tempty", "mma_wait_full", "mma_issue", "tma_wait_empty", "tma_issue", "-", "-"]
 for mode in ("train",):
     for _ in range(3):
         ops.head_fwd_ce_bf16(x16, w16, labels, segs, ws, None)

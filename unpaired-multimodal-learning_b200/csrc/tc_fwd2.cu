@@ -7,22 +7,25 @@
 //
 // tc_fwd.cu walks the (up to four) 256-class chunks of a row tile one after the other inside one CTA pair; a row's
 // final max / sum is then only known after its first chunks have left the SM, which cost a second pass over G
-// (g_fixup_kernel: 155 MB of traffic + a launch gap, a quarter of the step) and re-streamed the X tile per chunk.
+// (g_fixup_kernel: 155 MB of traffic + a launch gap, a quarter of the step).
 // Here the class chunks of a row tile are computed AT THE SAME TIME by different CTA pairs:
 //
 //   * CTA pair (cluster of 2, cta_group::2, M = 256) p owns class chunk p % n_chunks for good - and walks the 256-row
-//     units of group p / n_chunks.  X tile and the pair's half of the W chunk come by TMA (4 stages, SWIZZLE_128B),
+//     units of group p / n_chunks.  X tile and the pair's half of the W chunk come by TMA (6 stages, SWIZZLE_128B),
 //     accumulators live in TMEM, double buffered (2 x 256 columns): the MMA of unit i+1 overlaps the epilogue of unit i.
-//   * epilogue, 8 warps, one thread per (row, 128-column half): ONE sweep over the accumulator, 32 columns at a time
+//   * epilogue, 16 warps, one thread per (row, 64-column quarter): ONE sweep over the accumulator, 16 columns at a time
 //     with the next tcgen05.ld in flight: running max (in the raw-logit domain, so that the maximal element's
-//     exponential is exactly 1 and the cross entropy can never come out negative), exp(l - m_running) staged as
-//     bf16 in shared memory (the whole 128 x 256 tile, 64 KB, TMA-store layout).  The TMEM buffer is handed back
-//     to the MMA warp right after this sweep.
-//   * the pairs of a group exchange one 16-byte record per row - {max, sum, sum p*raw, argmax} - through L2
-//     (release/acquire flags keyed by a per-launch epoch: no memset, no cluster wider than the pair, every SM usable),
-//   * then every thread rescales ITS OWN staged half row by  exp(m_group - M) * coef / S  (two bf16x2 FMAs per pair
-//     with the factor split hi + lo, so the product carries fp32-level accuracy), patches the one-hot column and the
-//     warp's 32 x 64 boxes leave as TMA stores.  G is written once and is final.
+//     exponential is exactly 1 and the cross entropy can never come out negative), exp(l - m_running) kept as 32
+//     registers of bf16 pairs.  The TMEM buffer is handed back to the MMA warp right after this sweep.  Nothing of
+//     the epilogue goes through shared memory except one 32-byte record per thread: the operand stages' TMA
+//     writes and the tensor core's operand reads already use most of the SM's shared-memory bandwidth.
+//   * the four quarters of a row meet through shared memory, the pairs of a group exchange one 16-byte record per row -
+//     {max, sum, sum p*raw, argmax} - through L2 (release/acquire flags keyed by a per-launch epoch: no memset, no
+//     cluster wider than the pair, every SM usable),
+//   * then every thread rescales ITS OWN 64 columns in registers by  exp(m_group - M) * coef / S  (two bf16x2 FMAs per
+//     pair with the factor split hi + lo, so the product carries fp32-level accuracy) and writes its 128-byte line
+//     of G with four 256-bit stores; the one-hot column is patched by a 2-byte store of the same thread.  G is
+//     written once and is final.
 //   * the pair that owns a row's label column computes loss / hit / d(scale) for that row; per-(tile, chunk, warp)
 //     partial sums go to tile_part and are reduced in a fixed order by the next kernel of the step (the dW GEMM's
 //     idle warp) or by uml_reduce_tile_stats.
@@ -35,18 +38,35 @@
 
 namespace uml {
 
-constexpr int kXStages = 4;
+#ifndef UML_X_STAGES
+#define UML_X_STAGES 6
+#endif
+constexpr int kXStages = UML_X_STAGES;
 constexpr int kXABytes = 128 * 64 * 2;                 // X tile: 128 rows x 64 k
 constexpr int kXBBytes = 128 * 64 * 2;                 // this CTA's half of the W chunk: 128 classes x 64 k
 constexpr int kXStageBytes = kXABytes + kXBBytes;
-constexpr int kXBoxBytes = 32 * 128;                   // staging / TMA-store box: 32 rows x 64 bf16 columns
-constexpr int kXStagingBytes = 128 * 256 * 2;          // 16 boxes: [column group of 64][row quarter]
-constexpr int kXHalfFloats = 8;                        // record the two column halves of a row exchange
-constexpr int kXHxBytes = 2 * 2 * 128 * kXHalfFloats * 4;  // [tile parity][half][row]
-constexpr int kXSmemBytes = kXStages * kXStageBytes + kXStagingBytes + kXHxBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kXWarpAlloc = 8, kXWarpMma = 10, kXWarpTma = 11;
-constexpr int kXThreads = 384;
+constexpr int kXRecBytes = 32;                         // record the four column quarters of a row exchange
+#ifndef UML_X_SLICES
+#define UML_X_SLICES 2
+#endif
+constexpr int kXSlices = UML_X_SLICES;                 // column slices of a chunk, one epilogue thread per (row, slice)
+constexpr int kXSliceCols = 256 / kXSlices;
+#ifndef UML_X_GC
+#define UML_X_GC 32
+#endif
+constexpr int kXGC = UML_X_GC;                         // columns per group: one tcgen05.ld, one running-max step
+constexpr int kXGW = kXGC / 2;                         // ... and its registers of bf16 pairs
+constexpr int kXGroups = kXSliceCols / kXGC;           // groups per thread
+constexpr int kXHxBytes = 2 * kXSlices * 128 * kXRecBytes;  // [unit parity][column slice][row]
+constexpr int kXSmemBytes = kXStages * kXStageBytes + kXHxBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kXEpiWarps = 4 * kXSlices;               // warp e: TMEM lane quarter e & 3, column slice e >> 2
+constexpr int kXWarpMma = kXEpiWarps, kXWarpTma = kXEpiWarps + 1;  // (the TMA warp also owns the TMEM allocation)
+constexpr int kXThreads = (kXEpiWarps + 4) * 32;        // the producer warps form a warpgroup of their own (two of them idle): it
+                                                       // hands most of its registers to the epilogue warpgroups (setmaxnreg)
+constexpr int kXRegsProducer = 40, kXRegsEpilogue = kXSlices == 2 ? 232 : 112;
+constexpr int kXHalf = kXGroups / 2;                    // groups of a new unit that are made before the previous unit is finished
 constexpr int kXMaxChunks = 4;
+static_assert(kXSmemBytes <= 227 * 1024, "exchange forward kernel: shared memory");
 
 struct XSegs {
   int64_t n0;
@@ -82,9 +102,6 @@ __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint3
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
-__device__ __forceinline__ void sts_u16(uint32_t a, unsigned short x) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(x) : "memory");
-}
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
@@ -95,24 +112,50 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned short lds_u16(uint32_t a) {
-  unsigned short v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void tma_store_2d_s(const CUtensorMap* m, uint32_t smem_src, int32_t c0, int32_t c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_src), "r"(c0), "r"(c1)
+// one 32-byte sector of a G row (16 bf16) straight from registers
+__device__ __forceinline__ void stg256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
                : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-// makes the 32 registers of a tcgen05.ld "change" after the wait, so that no use can be scheduled above it
-__device__ __forceinline__ void pin32(uint32_t (&v)[32]) {
+// 32 lanes x 16 columns of fp32: thread i of the warp receives lane (base_lane + i), columns c..c+15
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld32(taddr, v); }
+// makes the registers of a tcgen05.ld "change" after the wait, so that no use can be scheduled above it
+template <int N>
+__device__ __forceinline__ void pin16(uint32_t (&v)[N]) {
 #pragma unroll
-  for (int i = 0; i < 32; i += 8)
+  for (int i = 0; i < N; i += 8)
     asm volatile("" : "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]),
                       "+r"(v[i + 6]), "+r"(v[i + 7]));
+}
+
+// packed fp32 pairs (sm_100): two fused multiply-adds / adds per issue slot
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 #ifdef UML_FWD_TIMING
@@ -128,23 +171,30 @@ __device__ long long g_fwdx_dbg[148 * 16];
 #define XDBG_FLUSH(base, n)
 #endif
 
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>());
+    static_for<B + 1, E>(f);
+  }
+}
+
 template <bool kPred, bool kDs>
 __global__ void __launch_bounds__(kXThreads, 1)
     head_fwd_ce_x_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                         const __grid_constant__ CUtensorMap tmap_g, int64_t n_rows, int dim, int n_classes, int n_groups,
-                         const int32_t* __restrict__ labels, XSegs segs, int write_g, int64_t ldg,
-                         float* __restrict__ row_loss, int32_t* __restrict__ row_pred, int32_t* __restrict__ row_correct,
-                         float* __restrict__ row_dscale, XWork wk) {
+                         int64_t n_rows, int dim, int n_classes, int n_groups, const int32_t* __restrict__ labels, XSegs segs,
+                         uint16_t* __restrict__ G, int64_t ldg, float* __restrict__ row_loss, int32_t* __restrict__ row_pred,
+                         int32_t* __restrict__ row_correct, float* __restrict__ row_dscale, XWork wk) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* staging = smem + kXStages * kXStageBytes;  // 1024-aligned
-  float* hx = reinterpret_cast<float*>(staging + kXStagingBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(hx) + kXHxBytes);
+  unsigned char* hx = smem + kXStages * kXStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(hx + kXHxBytes);
   uint64_t* empty_bar = full_bar + kXStages;
   uint64_t* tfull_bar = empty_bar + kXStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint32_t* epoch_slot = tmem_slot + 1;
+  float* run_scale = reinterpret_cast<float*>(epoch_slot + 1);  // [2]: the runs' logit scales
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -157,11 +207,11 @@ __global__ void __launch_bounds__(kXThreads, 1)
   const int n_valid = n_classes - col0 < 256 ? n_classes - col0 : 256;  // class columns of this chunk
   const int n_mma = ((n_valid + 15) / 16) * 16;                          // N of the pair's MMA
   const int64_t n_units = (n_rows + 255) / 256;
+  const bool write_g = G != nullptr;
 
   if (warp == kXWarpTma && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
-    if (write_g) tma_prefetch_desc(&tmap_g);
   }
   if (warp == kXWarpMma && lane == 0) {
     for (int s = 0; s < kXStages; ++s) {
@@ -170,17 +220,18 @@ __global__ void __launch_bounds__(kXThreads, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 16);  // one arrival per epilogue warp of both CTAs
+      mbar_init(&tempty_bar[b], 2 * kXEpiWarps);  // one arrival per epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == kXWarpAlloc) tmem_alloc_cg2(tmem_slot, 512);
+  if (warp == kXWarpTma) tmem_alloc_cg2(tmem_slot, 512);
   tc_fence_before();
   cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_trigger();
   pdl_wait();
+  if (threadIdx.x < 2) run_scale[threadIdx.x] = segs.scale_dev[threadIdx.x] ? __ldg(segs.scale_dev[threadIdx.x]) : segs.scale[threadIdx.x];
   if (threadIdx.x == 0) {
     *epoch_slot = *reinterpret_cast<volatile unsigned*>(wk.ctrl) + 1u;
     if (blockIdx.x == 0) wk.ctrl[3] = static_cast<unsigned>(n_units * 2 * n_chunks * 4);  // partial records per run
@@ -188,6 +239,8 @@ __global__ void __launch_bounds__(kXThreads, 1)
   __syncthreads();
   const unsigned epoch = *epoch_slot;
 
+  if (warp >= kXEpiWarps) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kXRegsProducer));
   if (warp == kXWarpTma) {
     // ------------------------------------------------ TMA producer ------------------------------
     if (lane == 0) {
@@ -204,8 +257,12 @@ __global__ void __launch_bounds__(kXThreads, 1)
           XDBG_ACC(0);
           unsigned char* a = smem + s * kXStageBytes;
           const uint32_t lead_bar = lead_bar0 + s * 8;
+#ifdef UML_X_HALFLOAD
+          if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kXBBytes);
+#else
           if (leader) mbar_arrive_expect_tx(&full_bar[s], 2 * kXStageBytes);
           tma_load_2d_cg2(a, &tmap_x, lead_bar, kb * 64, row0);
+#endif
           tma_load_2d_cg2(a + kXABytes, &tmap_w, lead_bar, kb * 64, wrow0);
           if (!leader) mbar_arrive_remote(lead_bar);
           XDBG_ACC(1);
@@ -249,331 +306,165 @@ __global__ void __launch_bounds__(kXThreads, 1)
       XDBG_FLUSH(9, 3);
     }
     __syncwarp();
-  } else if (warp < 8) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kXRegsEpilogue));
     // ------------------------------------------------ epilogue ----------------------------------
-    const int q = warp & 3;   // TMEM lane quarter = row quarter of the tile
-    const int h = warp >> 2;  // column half of the chunk: columns [h * 128, h * 128 + 128)
+    // Software-pipelined over the units: iteration i makes the exponentials of unit i (pass 1) and - interleaved with
+    // it, 16 columns at a time, so that one set of 32 registers serves both - the final G of unit i-1, whose row
+    // statistics the other class chunks published one unit ago: nobody ever waits on the exchange.
+    const int q = warp & 3;    // TMEM lane quarter = row quarter of the tile
+    const int cq = warp >> 2;  // column slice of the chunk: columns [cq * kXSliceCols, (cq + 1) * kXSliceCols)
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kMasked = -1.0e30f;  // padded class column: never the maximum, exponential exactly 0, 0 * it finite
+    constexpr bool kSecond = kPred || kDs;
     const int rloc = q * 32 + lane;
-    // this warp's two staging boxes (32 rows x 64 columns each): box j at + j * 4 * kXBoxBytes; this thread's row
-    const uint32_t box0 = smem_u32(staging) + ((h * 2) * 4 + q) * kXBoxBytes;
-    const uint32_t srow0 = box0 + lane * 128;
-    const uint32_t swz = static_cast<uint32_t>(lane & 7) << 4;  // 16-byte chunk c of row r sits at chunk c ^ (r & 7)
     const uint32_t hx_base = smem_u32(hx);
     const uint32_t tempty_remote0 = mapa_cta(smem_u32(&tempty_bar[0]), 0);
+    const int live_groups = !write_g ? 0 : static_cast<int>((ldg - col0 - cq * kXSliceCols) / kXGC);  // groups of this slice inside G's row (<= 0: none)
     uint32_t tile_it = 0;
     XDBG_DECL();
-    for (int64_t unit = group; unit < n_units; unit += n_groups, ++tile_it) {
-      const int64_t tile = unit * 2 + rank;
-      const int64_t row = tile * 128 + rloc;
-      const bool valid = row < n_rows;
-      const bool sg = valid && row >= segs.n0;
-      const float* sdev = sg ? segs.scale_dev[1] : segs.scale_dev[0];
-      const float scale = sdev ? __ldg(sdev) : (sg ? segs.scale[1] : segs.scale[0]);
-      const float dcoef = sg ? segs.dcoef[1] : segs.dcoef[0];
-      const float gcoef = dcoef * scale;
-      const bool neg = scale < 0.f;                     // (a learnable temperature may in principle go negative)
-      const float sgn = neg ? -1.f : 1.f;
-      const float sabs = fabsf(scale);
-      const float sl2 = sabs * kLog2e;                  // exponent per unit of (sign-adjusted) raw logit, in bits
-      const bool neg_any = __any_sync(0xffffffffu, neg);
-      const int label = valid ? labels[row] : -1;
-      const int lcol = label - col0 - h * 128;          // label position inside this thread's 128 columns
-      // running statistics of this thread's half row, in the raw (sign-adjusted) logit domain
-      float run_max = -INFINITY, run_sum = 0.f, run_pr = 0.f, max_before = -INFINITY, lab_raw = -INFINITY;
-      int arg = 0x7fffffff;
-      float gm0 = -INFINITY, gm1 = -INFINITY, gm2 = -INFINITY, gm3 = -INFINITY;  // running max each group was written against
 
-      const uint32_t b = tile_it & 1, aph = (tile_it >> 1) & 1;
-      XDBG_MARK();
-      mbar_wait(&tfull_bar[b], aph);
-      XDBG_ACC(0);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + h * 128;
-      if (write_g) {
-        if (lane == 0) bulk_wait_read<0>();  // the previous unit's TMA stores have read the staging boxes
-        __syncwarp();
-      }
-      XDBG_ACC(1);
-      uint32_t va[32], vb[32];
-      tmem_ld32(taddr, va);
-      tmem_ld_wait();
-      pin32(va);
+    // what a row needs from its run (image rows first, then text rows): hoisted, a row only selects
+    struct RowCtx {
+      float sl2, sabs, sgn, dcoef, gcoef;
+      bool valid, sg;
+    };
+    // (the two runs' temperatures sit in shared memory: a learnable one is read from the device once per CTA)
+    const float scale_a = run_scale[0], scale_b = run_scale[1];
+    const bool any_neg = scale_a < 0.f || scale_b < 0.f;  // (a learnable temperature may in principle go negative)
+    auto row_ctx = [&](int64_t row) {
+      RowCtx c;
+      c.valid = row < n_rows;
+      c.sg = c.valid && row >= segs.n0;
+      const float scale = c.sg ? run_scale[1] : run_scale[0];
+      c.dcoef = c.sg ? segs.dcoef[1] : segs.dcoef[0];
+      c.gcoef = c.dcoef * scale;
+      c.sgn = scale < 0.f ? -1.f : 1.f;
+      c.sabs = fabsf(scale);
+      c.sl2 = c.sabs * kLog2e;  // exponent per unit of (sign-adjusted) raw logit, in bits
+      return c;
+    };
 
-      // one 32-column group: running max, exponentials relative to it, bf16 staging.  Returns the max it was written against.
-      auto run_group = [&](uint32_t (&v)[32], const int g) -> float {
-        const int c0l = h * 128 + g * 32;  // first column of the group inside the chunk
-        if (c0l >= n_valid) {              // nothing but padding: G stays zero there
-          if (write_g && col0 + c0l < ldg) {
-            const uint32_t srow = srow0 + (g >> 1) * (4 * kXBoxBytes);
+    // ---- state of the unit whose G is still to be finished (the previous one) ----
+    uint32_t pk[kXSliceCols / 2];                       // exp(l - m_running) of this thread's columns, bf16 pairs
+    float p_gm[kXGroups];                               // running max each group was written against
 #pragma unroll
-            for (int j = 0; j < 4; ++j) sts128(srow + ((static_cast<uint32_t>((g & 1) * 4 + j) << 4) ^ swz), 0u, 0u, 0u, 0u);
+    for (int g = 0; g < kXGroups; ++g) p_gm[g] = 0.f;
+    float p_cm = 0.f, p_cs = 1.f, p_cpr = 0.f, p_before = 0.f, p_lraw = 0.f, p_lab_p = 0.f, p_lab_gm = 0.f;
+    int p_carg = 0, p_label = -1;
+    int p_tile = -1;
+    // resolved when the unit is finished: row maximum, factor coef / sum, the one-hot column's value
+    float f_M = 0.f, f_tc = 0.f, f_sl2 = 0.f;
+    unsigned short f_patch = 0;
+    bool f_store = false;
+    unsigned char* f_grow = nullptr;
+
+    // the other chunks' records of the previous unit: requested at the top of an iteration, looked at after the new
+    // unit's first group - the L2 round trip is covered by that group's work
+    uint4 r0[kXMaxChunks], r1[kXMaxChunks];
+    auto request_prev = [&]() {
+      const int64_t row = static_cast<int64_t>(p_tile) * 128 + rloc;
+      if (n_chunks > 1 && row < n_rows) {
+#pragma unroll
+        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          if (c2 < n_chunks && c2 != chunk) {
+            const uint4* rec = wk.recs + (row * n_chunks + c2) * 2;
+            r0[c2] = ld_volatile_v4(rec);
+            if (kSecond) r1[c2] = ld_volatile_v4(rec + 1);
           }
-          return run_max;
-        }
-        if (neg_any) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sgn);
-        }
-        if (c0l + 32 > n_valid) {  // padded class columns (or stale TMEM beyond the MMA's N)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0l + i >= n_valid) v[i] = __float_as_uint(kMasked);
-        }
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(v[i]));
-          m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-        }
-        const float bm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        // hit flag without an argmax index:  argmax == label  <=>  logit[label] == row max  and
-        // logit[label] > max over the columns before it  (torch.argmax returns the FIRST maximal index)
-        const int d = lcol - g * 32;
-        if (d >= 32) {
-          max_before = fmaxf(max_before, bm);
-        } else if (d >= 0) {
-          float b0 = -INFINITY, b1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float r0 = __uint_as_float(v[i]), r1 = __uint_as_float(v[i + 1]);
-            b0 = fmaxf(b0, i < d ? r0 : -INFINITY);
-            b1 = fmaxf(b1, i + 1 < d ? r1 : -INFINITY);
-            if (i == d) lab_raw = r0;
-            if (i + 1 == d) lab_raw = r1;
-          }
-          max_before = fmaxf(max_before, fmaxf(b0, b1));
-        }
-        if (kPred && bm > run_max) {  // first column holding the new maximum (columns are visited in order)
-#pragma unroll
-          for (int i = 31; i >= 0; --i)
-            if (__uint_as_float(v[i]) == bm) arg = col0 + c0l + i;
-        }
-        const float new_max = fmaxf(run_max, bm);
-        const float resc = x_exp2((run_max - new_max) * sl2);  // exp2(-inf) = 0 on the first group
-        run_sum *= resc;
-        if (kDs) run_pr *= resc;
-        run_max = new_max;
-        // exponentials relative to the running max: (raw - max) is exact for the maximal element -> p = 1
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-        const uint32_t srow = srow0 + (g >> 1) * (4 * kXBoxBytes);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // 8 columns -> one 16-byte chunk of the staged row
-          uint32_t w[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 8 * j + 2 * e;
-            const float r0 = __uint_as_float(v[i]), r1 = __uint_as_float(v[i + 1]);
-            const float p0 = x_exp2((r0 - new_max) * sl2);
-            const float p1 = x_exp2((r1 - new_max) * sl2);
-            if (e & 1) { s2 += p0; s3 += p1; if (kDs) { q2 = fmaf(p0, r0, q2); q3 = fmaf(p1, r1, q3); } }
-            else       { s0 += p0; s1 += p1; if (kDs) { q0 = fmaf(p0, r0, q0); q1 = fmaf(p1, r1, q1); } }
-            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-            w[e] = *reinterpret_cast<uint32_t*>(&hh);
-          }
-          if (write_g) sts128(srow + ((static_cast<uint32_t>((g & 1) * 4 + j) << 4) ^ swz), w[0], w[1], w[2], w[3]);
-        }
-        run_sum += (s0 + s1) + (s2 + s3);
-        if (kDs) run_pr += (q0 + q1) + (q2 + q3);
-        return new_max;
-      };
-      // one sweep, 32 columns at a time, the next tcgen05.ld in flight while a group is processed
-#pragma unroll 1
-      for (int gp = 0; gp < 2; ++gp) {
-        tmem_ld32(taddr + gp * 64 + 32, vb);
-        const float ma = run_group(va, gp * 2);
-        tmem_ld_wait();
-        pin32(vb);
-        if (gp == 0) tmem_ld32(taddr + 64, va);
-        const float mb = run_group(vb, gp * 2 + 1);
-        if (gp == 0) {
-          tmem_ld_wait();
-          pin32(va);
-          gm0 = ma; gm1 = mb;
-        } else {
-          gm2 = ma; gm3 = mb;
         }
       }
-      // accumulator buffer b may be overwritten by the (leader's) MMA warp now
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (!leader) mbar_arrive_remote(tempty_remote0 + b * 8);
-        else mbar_arrive(&tempty_bar[b]);
-      }
-      XDBG_ACC(2);
-
-      // ---- the two column halves of a row meet (shared memory) ---------------------------------------
-      const uint32_t mine = hx_base + ((((tile_it & 1) * 2 + h) * 128 + rloc) * kXHalfFloats) * 4;
-      const uint32_t other = hx_base + ((((tile_it & 1) * 2 + (h ^ 1)) * 128 + rloc) * kXHalfFloats) * 4;
-      sts128(mine, __float_as_uint(run_max), __float_as_uint(run_sum), __float_as_uint(run_pr), __float_as_uint(max_before));
-      sts64(mine + 16, __float_as_uint(lab_raw), static_cast<uint32_t>(arg));
-      named_bar_sync(1, 256);
-      const uint4 o4 = lds128(other);
-      const uint2 o2 = lds64(other + 16);
-      const float o_max = __uint_as_float(o4.x), o_sum = __uint_as_float(o4.y), o_pr = __uint_as_float(o4.z),
-                  o_before = __uint_as_float(o4.w), o_lab = __uint_as_float(o2.x);
-      const float cm = fmaxf(run_max, o_max);  // chunk-level statistics
-      const float e_me = x_exp2((run_max - cm) * sl2), e_ot = x_exp2((o_max - cm) * sl2);
-      const float cs = run_sum * e_me + o_sum * e_ot;
-      const float cpr = run_pr * e_me + o_pr * e_ot;
-      // max over the columns of this chunk that precede the label (meaningful when the label is in this chunk):
-      // label in half 0 -> half 0's max_before;  in half 1 -> max(all of half 0, half 1's max_before)
-      const int lc_chunk = label - col0;
-      const float m_h0 = h == 0 ? run_max : o_max, before_h0 = h == 0 ? max_before : o_before,
-                  before_h1 = h == 0 ? o_before : max_before;
-      const float before_loc = lc_chunk >= 128 ? fmaxf(m_h0, before_h1) : before_h0;
-      const float lraw = fmaxf(lab_raw, o_lab);  // exactly one half saw the label column (the other holds -inf)
-      int carg = arg;
-      if (kPred) {
-        const int oarg = static_cast<int>(o2.y);
-        // larger maximum wins; on equal maxima the lower column index (torch.argmax)
-        if (o_max > run_max || (o_max == run_max && oarg < arg)) carg = oarg;
-      }
-      XDBG_ACC(3);
-
-      // ---- the class chunks of a row meet (L2) -------------------------------------------------------
-      // Every value travels with the launch epoch in the same 8-byte word pair (which the memory system delivers whole):
-      // the reader spins until the epoch matches - no fence, no separate flag, one L2 round trip.
-      float M = cm, S = cs, PR = cpr, before_chunks = -INFINITY;
-      int garg = carg;
-      if (n_chunks > 1) {
-        constexpr bool kSecond = kPred || kDs;
-        if (h == 0 && valid) {
-          uint4* rec = wk.recs + (row * n_chunks + chunk) * 2;
-          st_volatile_v4(rec, __float_as_uint(cm), epoch, __float_as_uint(cs), epoch);
-          if (kSecond) st_volatile_v4(rec + 1, __float_as_uint(cpr), epoch, static_cast<uint32_t>(carg), epoch);
+    };
+    // ... -> row maximum / sum (polls only if a peer pair is a whole unit behind)
+    auto resolve_prev = [&]() {
+      const int64_t row = static_cast<int64_t>(p_tile) * 128 + rloc;
+      const RowCtx c = row_ctx(row);
+      float M = p_cm, S = p_cs, PR = p_cpr, before_chunks = -INFINITY;
+      int garg = p_carg;
+      if (n_chunks > 1 && c.valid) {
+        float om[kXMaxChunks], os[kXMaxChunks], opr[kXMaxChunks];
+        int oa[kXMaxChunks];
+#ifdef UML_X_NOEXCH
+#pragma unroll
+        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          r0[c2].y = r0[c2].w = epoch; r0[c2].x = __float_as_uint(p_cm); r0[c2].z = __float_as_uint(p_cs);
+          r1[c2].y = r1[c2].w = epoch;
         }
-        XDBG_ACC(4);
-        if (valid) {
-          float om[kXMaxChunks], os[kXMaxChunks], opr[kXMaxChunks];
-          int oa[kXMaxChunks];
+#endif
+        // a stale record (a peer pair most of a unit behind): ask again for all of them at once
+        for (unsigned polls = 0;; ++polls) {
+          bool fresh = true;
 #pragma unroll
           for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-            om[c2] = -INFINITY; os[c2] = 0.f; opr[c2] = 0.f; oa[c2] = 0x7fffffff;
             if (c2 < n_chunks && c2 != chunk) {
-              const uint4* rec = wk.recs + (row * n_chunks + c2) * 2;
-              uint4 r0 = ld_volatile_v4(rec);
-              long long t0 = 0;
-              while (r0.y != epoch || r0.w != epoch) {
-                if (t0 == 0) t0 = clock64();
-                else if (clock64() - t0 > 2000000000ll) {  // ~1 s: never hang the GPU; the host checks the flag
-                  atomicExch(wk.ctrl + 2, 1u);
-                  break;
-                }
-                r0 = ld_volatile_v4(rec);
-              }
-              om[c2] = __uint_as_float(r0.x); os[c2] = __uint_as_float(r0.z);
-              if (kSecond) {
-                uint4 r1 = ld_volatile_v4(rec + 1);
-                while (r1.y != epoch || r1.w != epoch) {
-                  if (t0 == 0) t0 = clock64();
-                  else if (clock64() - t0 > 2000000000ll) {
-                    atomicExch(wk.ctrl + 2, 1u);
-                    break;
-                  }
-                  r1 = ld_volatile_v4(rec + 1);
-                }
-                opr[c2] = __uint_as_float(r1.x); oa[c2] = static_cast<int>(r1.z);
-              }
+              fresh = fresh && r0[c2].y == epoch && r0[c2].w == epoch;
+              if (kSecond) fresh = fresh && r1[c2].y == epoch && r1[c2].w == epoch;
             }
           }
-          XDBG_ACC(5);
-#pragma unroll
-          for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-            M = fmaxf(M, om[c2]);
-            if (c2 < chunk) before_chunks = fmaxf(before_chunks, om[c2]);
+          if (fresh) break;
+          if (polls > (1u << 20)) {  // ~ a second: never hang the GPU; the host checks the flag
+            atomicExch(wk.ctrl + 2, 1u);
+            break;
           }
-          const float e_c = x_exp2((cm - M) * sl2);
-          S = cs * e_c;
-          PR = cpr * e_c;
+          request_prev();
+        }
 #pragma unroll
-          for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-            const float e = x_exp2((om[c2] - M) * sl2);  // 0 for the absent chunks (-inf)
-            S = fmaf(os[c2], e, S);
-            if (kDs) PR = fmaf(opr[c2], e, PR);
-          }
-          if (kPred) {
-            float bestm = cm;
-            int bestc = chunk;
-#pragma unroll
-            for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-              if (c2 < n_chunks && c2 != chunk && (om[c2] > bestm || (om[c2] == bestm && c2 < bestc))) {
-                bestm = om[c2]; bestc = c2; garg = oa[c2];
-              }
-            }
+        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          om[c2] = -INFINITY; os[c2] = 0.f; opr[c2] = 0.f; oa[c2] = 0x7fffffff;
+          if (c2 < n_chunks && c2 != chunk) {
+            om[c2] = __uint_as_float(r0[c2].x); os[c2] = __uint_as_float(r0[c2].z);
+            if (kSecond) { opr[c2] = __uint_as_float(r1[c2].x); oa[c2] = static_cast<int>(r1[c2].z); }
           }
         }
-        __syncwarp();
-      }
-      XDBG_ACC(6);
-
-      // ---- rescale the staged half row, patch the one-hot column, store -------------------------------
-      const float inv_sum = 1.f / S;
-      if (write_g) {
-        const float tc = inv_sum * gcoef;
-        // the one-hot column, from the ORIGINAL staged element in fp32 (G = p * f - coef, one rounding): computed
-        // before the sweep below overwrites it, written after
-        const bool patch = lcol >= 0 && lcol < 128;
-        uint32_t patch_addr = 0;
-        __nv_bfloat16 patch_val = __float2bfloat16_rn(0.f);
-        if (patch) {
-          const int gl = lcol >> 5;
-          const float gmx = gl == 0 ? gm0 : gl == 1 ? gm1 : gl == 2 ? gm2 : gm3;
-          const float f = x_exp2((gmx - M) * sl2) * tc;
-          patch_addr = srow0 + (lcol >> 6) * (4 * kXBoxBytes) + ((static_cast<uint32_t>((lcol & 63) >> 3) << 4) ^ swz) + (lcol & 7) * 2;
-          const float pf = __uint_as_float(static_cast<uint32_t>(lds_u16(patch_addr)) << 16);
-          patch_val = __float2bfloat16_rn(fmaf(pf, f, -gcoef));
+#pragma unroll
+        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          M = fmaxf(M, om[c2]);
+          if (c2 < chunk) before_chunks = fmaxf(before_chunks, om[c2]);
         }
-#pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
-          if (col0 + h * 128 + j * 64 >= ldg) break;
-          const uint32_t srow = srow0 + j * (4 * kXBoxBytes);
+        const float offM = __fmul_rn(M, c.sl2);
+        const float e_c = x_exp2(__fmul_rn(p_cm, c.sl2) - offM);
+        S = p_cs * e_c;
+        PR = p_cpr * e_c;
 #pragma unroll
-          for (int gg = 0; gg < 2; ++gg) {
-            const float gmx = j == 0 ? (gg == 0 ? gm0 : gm1) : (gg == 0 ? gm2 : gm3);
-            const float f = x_exp2((gmx - M) * sl2) * tc;
-            const __nv_bfloat16 fh = __float2bfloat16_rn(f);
-            const __nv_bfloat16 fl = __float2bfloat16_rn(f - __bfloat162float(fh));
-            const __nv_bfloat162 fh2 = __halves2bfloat162(fh, fh), fl2 = __halves2bfloat162(fl, fl);
+        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          const float e = x_exp2(__fmul_rn(om[c2], c.sl2) - offM);  // 0 for the absent chunks (-inf)
+          S = fmaf(os[c2], e, S);
+          if (kDs) PR = fmaf(opr[c2], e, PR);
+        }
+        if (kPred) {
+          float bestm = p_cm;
+          int bestc = chunk;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t addr = srow + ((static_cast<uint32_t>(gg * 4 + k) << 4) ^ swz);
-              const uint4 in = lds128(addr);
-              uint32_t wi[4] = {in.x, in.y, in.z, in.w}, wo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(&wi[e]);
-                const __nv_bfloat162 r = __hfma2(pv, fh2, __hmul2(pv, fl2));
-                wo[e] = *reinterpret_cast<const uint32_t*>(&r);
-              }
-              sts128(addr, wo[0], wo[1], wo[2], wo[3]);
+          for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+            if (c2 < n_chunks && c2 != chunk && (om[c2] > bestm || (om[c2] == bestm && c2 < bestc))) {
+              bestm = om[c2]; bestc = c2; garg = oa[c2];
             }
-          }
-          if (patch && (lcol >> 6) == j) sts_u16(patch_addr, __bfloat16_as_ushort(patch_val));
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {  // the warp's 32 x 64 box leaves as ONE coalesced TMA store
-            tma_store_2d_s(&tmap_g, box0 + j * (4 * kXBoxBytes), col0 + h * 128 + j * 64,
-                           static_cast<int32_t>(tile * 128 + q * 32));
-            bulk_commit();
           }
         }
       }
-      XDBG_ACC(7);
-
-      // ---- per-row results: the (chunk, half 0) thread that owns the row's label column ----------------
-      if (h == 0) {
-        const bool own = valid && lc_chunk >= 0 && lc_chunk < 256;
+      f_M = __fmul_rn(M, c.sl2);  // the row's exponent offset, in bits: off(m) = m * sl2 rounded once, everywhere
+      f_sl2 = c.sl2;
+      f_tc = __fdividef(c.gcoef, S);
+      f_store = c.valid && live_groups > 0;
+      f_grow = reinterpret_cast<unsigned char*>(G) + (row * ldg + col0 + cq * kXSliceCols) * 2;
+      {
+        // the one-hot column from the staged element in fp32 (G = p * f - coef, one rounding); stored after the row's
+        // vector stores (a later store of the same thread to the same address is ordered after them)
+        const float f = x_exp2(__fmul_rn(p_lab_gm, c.sl2) - f_M) * f_tc;
+        f_patch = __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(p_lab_p, f, -c.gcoef)));
+      }
+      if (cq == 0) {  // per-row results: the (chunk, quarter 0) thread that owns the row's label column
+        const int lc_chunk = p_label - col0;
+        const bool own = c.valid && lc_chunk >= 0 && lc_chunk < 256;
         float loss = 0.f, dsc = 0.f;
         int hit = 0;
         if (own) {
-          loss = logf(S) + (M - lraw) * sabs;  // lraw == M for a correctly classified row: loss = log S >= 0
-          if (kDs) dsc = (PR * inv_sum - lraw) * sgn * dcoef;
-          hit = (lraw == M && lraw > fmaxf(before_chunks, before_loc)) ? 1 : 0;
+          // ln S - ln 2 * (u_label - offset), the label's exponent taken exactly as pass 1 took it: S >= 2^that up to the
+          // 2^-22 of ex2.approx, so the cross entropy is >= -3e-7 before the clamp (torch's is never negative)
+          loss = fmaxf(fmaf(__log2f(S), 0.6931471805599453f, -0.6931471805599453f * fmaf(p_lraw, c.sl2, -f_M)), 0.f);
+          if (kDs) dsc = (__fdividef(PR, S) - p_lraw) * c.sgn * c.dcoef;
+          hit = (p_lraw == M && p_lraw > fmaxf(before_chunks, p_before)) ? 1 : 0;
           if (row_loss) row_loss[row] = loss;
           if (kPred && row_pred) row_pred[row] = garg;
           if (row_correct) row_correct[row] = hit;
@@ -581,20 +472,318 @@ __global__ void __launch_bounds__(kXThreads, 1)
         }
         if (wk.tile_part) {
           // deterministic per-(tile, chunk, warp, run) partial sums; the statistics kernel adds them in a fixed order
+          const bool any1 = __any_sync(0xffffffffu, c.sg), all1 = __all_sync(0xffffffffu, c.sg || !c.valid);
 #pragma unroll
           for (int s2 = 0; s2 < 2; ++s2) {
-            const bool mn = own && (static_cast<int>(sg) == s2);
-            const float a = warp_sum(mn ? loss : 0.f), dd = kDs ? warp_sum(mn ? dsc : 0.f) : 0.f;
-            const int hh = warp_sum_i(mn ? hit : 0), cnt = warp_sum_i(mn ? 1 : 0);
-            if (lane == 0)
-              *reinterpret_cast<float4*>(wk.tile_part + (((tile * n_chunks + chunk) * 4 + q) * 2 + s2) * 4) =
-                  make_float4(a, dd, static_cast<float>(hh), static_cast<float>(cnt));
+            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s2 == 0 ? !all1 || !any1 : any1) {  // (a warp's rows nearly always belong to one run)
+              const bool mn = own && (static_cast<int>(c.sg) == s2);
+              const float a = warp_sum(mn ? loss : 0.f), dd = kDs ? warp_sum(mn ? dsc : 0.f) : 0.f;
+              const int hh = warp_sum_i(mn ? hit : 0), cnt = warp_sum_i(mn ? 1 : 0);
+              out = make_float4(a, dd, static_cast<float>(hh), static_cast<float>(cnt));
+            }
+            if (lane == 0) *reinterpret_cast<float4*>(wk.tile_part + (((static_cast<int64_t>(p_tile) * n_chunks + chunk) * 4 + q) * 2 + s2) * 4) = out;
           }
         }
       }
-      XDBG_ACC(8);
+    };
+    // final G of 16 columns of the previous unit: p_final * coef / S = p_staged * exp(m_staged - M) * coef / S; the factor
+    // split hi + lo so that the product of two bf16x2 operations carries fp32-level accuracy before the one rounding
+    auto finish_group = [&](auto gc) {
+      constexpr int g = decltype(gc)::value;
+      if (!f_store || g >= live_groups) return;
+      const float gmx = p_gm[g];
+      const float f = x_exp2(__fmul_rn(gmx, f_sl2) - f_M) * f_tc;
+      const __nv_bfloat16 fh = __float2bfloat16_rn(f);
+      const __nv_bfloat16 fl = __float2bfloat16_rn(f - __bfloat162float(fh));
+      const __nv_bfloat162 fh2 = __halves2bfloat162(fh, fh), fl2 = __halves2bfloat162(fl, fl);
+      uint32_t o[kXGW];
+#pragma unroll
+      for (int j = 0; j < kXGW; ++j) {
+        const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(&pk[g * kXGW + j]);
+        const __nv_bfloat162 r = __hfma2(pv, fh2, __hmul2(pv, fl2));
+        o[j] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+#ifdef UML_X_NOSTORE
+      if (f_M == 12345.678f)
+#endif
+#pragma unroll
+      for (int j = 0; j < kXGW; j += 8) stg256(f_grow + g * (2 * kXGC) + j * 4, o + j);
+    };
+    // the one-hot column of the previous unit
+    auto finish_rows = [&]() {
+      const int lcol = p_label - col0 - cq * kXSliceCols;
+      if (f_store && lcol >= 0 && lcol < kXSliceCols) *reinterpret_cast<volatile unsigned short*>(f_grow + lcol * 2) = f_patch;
+    };
+
+    int next_label = -1;
+    {
+      const int64_t frow = (static_cast<int64_t>(group) * 2 + rank) * 128 + rloc;
+      if (group < n_units && frow < n_rows) next_label = __ldg(labels + frow);
     }
-    if (write_g && lane == 0) bulk_wait<0>();  // this warp's TMA stores have landed before the kernel ends
+    for (int unit = group; unit < static_cast<int>(n_units); unit += n_groups, ++tile_it) {
+      const int tile = unit * 2 + static_cast<int>(rank);
+      const int64_t row = static_cast<int64_t>(tile) * 128 + rloc;
+      const RowCtx c = row_ctx(row);
+      const float sl2 = c.sl2, sgn = c.sgn;
+      const int label = next_label;
+      {  // the next unit's label: its load is in flight for a whole unit
+        const int64_t nrow = (static_cast<int64_t>(unit + n_groups) * 2 + rank) * 128 + rloc;
+        next_label = nrow < n_rows ? __ldg(labels + nrow) : -1;
+      }
+#ifdef UML_X_NOLABEL
+      const int lcol = -1000000;
+#else
+      const int lcol = label - col0 - cq * kXSliceCols;  // label position inside this thread's columns
+#endif
+      // running statistics of this thread's quarter row, in the raw (sign-adjusted) logit domain
+      float run_max = -INFINITY, run_sum = 0.f, run_pr = 0.f, max_before = -INFINITY, lab_raw = -INFINITY;
+      float lab_p = 0.f, lab_gm = 0.f;                  // the label column's staged exponential and the max it was taken against
+      int arg = 0x7fffffff;
+      float gm[kXGroups];
+      const bool have_prev = p_tile >= 0;
+
+      const uint32_t b = tile_it & 1, aph = (tile_it >> 1) & 1;
+      XDBG_MARK();
+      mbar_wait(&tfull_bar[b], aph);
+      XDBG_ACC(0);
+      tc_fence_after();
+#ifdef UML_X_NOEPI
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (!leader) mbar_arrive_remote(tempty_remote0 + b * 8);
+        else mbar_arrive(&tempty_bar[b]);
+      }
+      continue;
+#endif
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + cq * kXSliceCols;
+      uint32_t v[kXGC];
+      uint32_t nk[kXGW * kXHalf];  // the new unit's first four groups: live beside the previous unit's registers until those are stored
+
+      // one 16-column group: running max, exponentials relative to it, packed as bf16 pairs into out[0..8).
+      // kPlain: every column of the chunk is a class and no temperature is negative (all but the last chunk's tail)
+      const uint64_t sl2x2 = pack2(sl2, sl2);
+      auto run_group = [&](uint32_t* out, auto gc) -> float {
+        constexpr int g = decltype(gc)::value;
+        const int c0l = cq * kXSliceCols + g * kXGC;  // first column of the group inside the chunk
+        if (c0l + kXGC > n_valid || any_neg) {  // (uniform; only the last chunk's tail - or a negative temperature)
+          if (c0l >= n_valid) {            // nothing but padding (or TMEM columns beyond the MMA's N): G stays zero there
+#pragma unroll
+            for (int j = 0; j < kXGW; ++j) out[j] = 0u;
+            return run_max;
+          }
+          if (any_neg) {
+#pragma unroll
+            for (int i = 0; i < kXGC; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * sgn);
+          }
+          if (c0l + kXGC > n_valid) {  // padded class columns
+#pragma unroll
+            for (int i = 0; i < kXGC; ++i)
+              if (c0l + i >= n_valid) v[i] = __float_as_uint(kMasked);
+          }
+        }
+        float m0 = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), m1 = fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3]));
+#pragma unroll
+        for (int i = 4; i < kXGC; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+        }
+        const float bm = fmaxf(m0, m1);
+        // hit flag without an argmax index:  argmax == label  <=>  logit[label] == row max  and
+        // logit[label] > max over the columns before it  (torch.argmax returns the FIRST maximal index)
+        const int d = lcol - g * kXGC;
+        const bool lab_here = static_cast<unsigned>(d) < static_cast<unsigned>(kXGC);
+        if (d >= kXGC) max_before = fmaxf(max_before, bm);
+        if (lab_here) {  // (divergent: one lane in thirty)
+          // v[d] by a select tree, then the columns before d only if the label can still be the first maximum
+          float t[kXGC / 2];
+#pragma unroll
+          for (int i = 0; i < kXGC / 2; ++i) t[i] = (d & (kXGC / 2)) ? __uint_as_float(v[i + kXGC / 2]) : __uint_as_float(v[i]);
+#pragma unroll
+          for (int w = kXGC / 4; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int i = 0; i < w; ++i) t[i] = (d & w) ? t[i + w] : t[i];
+          }
+          lab_raw = t[0];
+          if (lab_raw == bm) {
+            float b0 = -INFINITY, b1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < kXGC; i += 2) {
+              b0 = fmaxf(b0, i < d ? __uint_as_float(v[i]) : -INFINITY);
+              b1 = fmaxf(b1, i + 1 < d ? __uint_as_float(v[i + 1]) : -INFINITY);
+            }
+            max_before = fmaxf(max_before, fmaxf(b0, b1));
+          } else {
+            max_before = fmaxf(max_before, bm);  // something in this group beats the label: any such value says "no hit"
+          }
+        }
+        if (kPred && bm > run_max) {  // first column holding the new maximum (columns are visited in order)
+#pragma unroll
+          for (int i = kXGC - 1; i >= 0; --i)
+            if (__uint_as_float(v[i]) == bm) arg = col0 + c0l + i;
+        }
+        // exponent offsets are off(m) = m * sl2 rounded ONCE (never fused), differences of offsets are exact: rescaling
+        // a sum from one running maximum to the next telescopes, and the label's term of the final sum is exactly the
+        // 2^(u_label - off(M)) the loss subtracts
+        const float new_max = fmaxf(run_max, bm);
+        const float noff = -__fmul_rn(new_max, sl2);
+        const float resc = x_exp2(__fmul_rn(run_max, sl2) + noff);  // exp2(-inf) = 0 on the first group
+        run_sum *= resc;
+        if (kDs) run_pr *= resc;
+        run_max = new_max;
+        const uint64_t noffx2 = pack2(noff, noff);
+        uint64_t sx2 = pack2(0.f, 0.f), sy2 = pack2(0.f, 0.f);
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kXGW; ++j) {
+          const float r0 = __uint_as_float(v[2 * j]), r1 = __uint_as_float(v[2 * j + 1]);
+          float t0, t1;
+          unpack2(ffma2(pack2(r0, r1), sl2x2, noffx2), t0, t1);  // u - off(max), one rounding
+          const float p0 = x_exp2(t0), p1 = x_exp2(t1);
+          if (j & 1) sy2 = fadd2(sy2, pack2(p0, p1));
+          else sx2 = fadd2(sx2, pack2(p0, p1));
+          if (kDs) {
+            q0 = fmaf(p0, r0, q0);
+            q1 = fmaf(p1, r1, q1);
+          }
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          out[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        float s0, s1;
+        unpack2(fadd2(sx2, sy2), s0, s1);
+        run_sum += s0 + s1;
+        if (kDs) run_pr += q0 + q1;
+        if (lab_here) {  // the label column's staged value, as it was rounded
+          uint32_t w4[kXGW / 2];
+          const int dw = d >> 1;
+#pragma unroll
+          for (int i = 0; i < kXGW / 2; ++i) w4[i] = (dw & (kXGW / 2)) ? out[i + kXGW / 2] : out[i];
+#pragma unroll
+          for (int w = kXGW / 4; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int i = 0; i < w; ++i) w4[i] = (dw & w) ? w4[i + w] : w4[i];
+          }
+          lab_p = __uint_as_float((d & 1) ? (w4[0] & 0xffff0000u) : (w4[0] << 16));
+          lab_gm = new_max;
+        }
+        return new_max;
+      };
+
+      // ---- the first half of the new unit goes to registers of its own: the other chunks publish the previous unit's
+      //      row statistics at the END of their iteration, so looking at them half a unit later (nearly) never finds them
+      //      missing - CTA pairs of a group may drift by a good part of a unit without anybody waiting. ----
+      tmem_ldg(taddr, v);
+      static_for<0, kXHalf>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        tmem_ld_wait();
+        pin16(v);
+        if (g == 0) XDBG_ACC(1);
+        gm[g] = run_group(nk + kXGW * g, gc);
+        tmem_ldg(taddr + kXGC * (g + 1), v);
+        if (g == (kXHalf > 2 ? 1 : 0) && have_prev) request_prev();  // (the L2 round trip is covered by the next groups)
+      });
+      if (have_prev) {
+        resolve_prev();
+        static_for<0, kXHalf + 1>([&](auto gc) { finish_group(gc); });
+      }
+#pragma unroll
+      for (int j = 0; j < kXGW * kXHalf; ++j) pk[j] = nk[j];
+      // ---- then group g of the new unit takes the registers group g of the previous unit has just left ----
+      static_for<kXHalf, kXGroups - 1>([&](auto gc) {
+        constexpr int g = decltype(gc)::value;
+        tmem_ld_wait();
+        pin16(v);
+        gm[g] = run_group(pk + kXGW * g, gc);
+        tmem_ldg(taddr + kXGC * (g + 1), v);
+        if (have_prev) finish_group(std::integral_constant<int, g + 1>());
+      });
+      tmem_ld_wait();
+      pin16(v);
+      // accumulator buffer b may be overwritten by the (leader's) MMA warp now
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (!leader) mbar_arrive_remote(tempty_remote0 + b * 8);
+        else mbar_arrive(&tempty_bar[b]);
+      }
+      gm[kXGroups - 1] = run_group(pk + kXGW * (kXGroups - 1), std::integral_constant<int, kXGroups - 1>());
+      XDBG_ACC(2);
+      if (have_prev) finish_rows();
+      XDBG_ACC(3);
+
+      // ---- the four column quarters of a row meet (shared memory) -------------------------------------
+      const uint32_t hx_par = hx_base + (tile_it & 1) * (kXSlices * 128 * kXRecBytes);
+      const uint32_t mine = hx_par + (cq * 128 + rloc) * kXRecBytes;
+      sts128(mine, __float_as_uint(run_max), __float_as_uint(run_sum), __float_as_uint(max_before), __float_as_uint(lab_raw));
+      if (kSecond) sts64(mine + 16, __float_as_uint(run_pr), static_cast<uint32_t>(arg));
+      named_bar_sync(1 + q, 32 * kXSlices);
+      float cm = run_max, before_loc = max_before, lraw = lab_raw;
+      constexpr int kOthers = kXSlices - 1;
+      float o_max[kOthers], o_sum[kOthers], o_pr[kOthers];
+      int carg = arg;
+#pragma unroll
+      for (int k = 0; k < kOthers; ++k) {
+        const int oq = (cq + 1 + k) % kXSlices;
+        const uint32_t other = hx_par + (oq * 128 + rloc) * kXRecBytes;
+        const uint4 o4 = lds128(other);
+        o_max[k] = __uint_as_float(o4.x);
+        o_sum[k] = __uint_as_float(o4.y);
+        cm = fmaxf(cm, o_max[k]);
+        before_loc = fmaxf(before_loc, __uint_as_float(o4.z));  // quarters before the label's hold their whole max, later ones -inf
+        lraw = fmaxf(lraw, __uint_as_float(o4.w));               // exactly one quarter saw the label column (the others hold -inf)
+        o_pr[k] = kDs ? __uint_as_float(lds64(other + 16).x) : 0.f;
+      }
+      float cs, cpr = 0.f;
+      {
+        const float offc = __fmul_rn(cm, sl2);
+        const float e_me = x_exp2(__fmul_rn(run_max, sl2) - offc);
+        cs = run_sum * e_me;
+        if (kDs) cpr = run_pr * e_me;
+#pragma unroll
+        for (int k = 0; k < kOthers; ++k) {
+          const float e = x_exp2(__fmul_rn(o_max[k], sl2) - offc);
+          cs = fmaf(o_sum[k], e, cs);
+          if (kDs) cpr = fmaf(o_pr[k], e, cpr);
+        }
+      }
+      if (kPred) {
+        // the chunk's first maximal column: the lowest quarter among those that hold the chunk maximum
+        float bmx = run_max;
+        int cbest = cq;
+#pragma unroll
+        for (int k = 0; k < kOthers; ++k) {
+          const int oq = (cq + 1 + k) % kXSlices;
+          if (o_max[k] > bmx || (o_max[k] == bmx && oq < cbest)) {
+            bmx = o_max[k];
+            cbest = oq;
+          }
+        }
+        if (cbest != cq) carg = static_cast<int>(lds64(hx_par + (cbest * 128 + rloc) * kXRecBytes + 16).y);
+      }
+      // ---- ... and go to the other class chunks of the row (L2).  Every value travels with the launch epoch in the
+      //      same 8-byte word pair (which the memory system delivers whole): a reader checks the epoch - no fence, no flag.
+      if (n_chunks > 1 && cq == 0 && c.valid) {
+        uint4* rec = wk.recs + (row * n_chunks + chunk) * 2;
+        st_volatile_v4(rec, __float_as_uint(cm), epoch, __float_as_uint(cs), epoch);
+        if (kSecond) st_volatile_v4(rec + 1, __float_as_uint(cpr), epoch, static_cast<uint32_t>(carg), epoch);
+      }
+      XDBG_ACC(4);
+      // this unit becomes the previous one
+#pragma unroll
+      for (int g = 0; g < kXGroups; ++g) p_gm[g] = gm[g];
+      p_cm = cm; p_cs = cs; p_cpr = cpr; p_before = before_loc; p_lraw = lraw; p_lab_p = lab_p; p_lab_gm = lab_gm;
+      p_carg = carg; p_label = label; p_tile = tile;
+    }
+    if (p_tile >= 0) {  // the last unit
+      XDBG_MARK();
+      request_prev();
+      resolve_prev();
+      XDBG_ACC(5);
+      static_for<0, kXGroups>([&](auto gc) { finish_group(gc); });
+      finish_rows();
+      XDBG_ACC(6);
+    }
 #ifdef UML_FWD_TIMING
     if (warp == 0 && lane == 0) XDBG_FLUSH(0, 9);
 #endif
@@ -602,7 +791,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
 
   tc_fence_before();
   cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the last commit
-  if (warp == kXWarpAlloc) tmem_dealloc_cg2(tmem_base, 512);
+  if (warp == kXWarpTma) tmem_dealloc_cg2(tmem_base, 512);
   if (threadIdx.x == 0) {
     // the last CTA of the grid closes the launch: flags written with `epoch` can never match a later launch
     __threadfence();
@@ -727,19 +916,13 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
   const int64_t n0 = segs->seg_rows[0], n1 = segs->nseg > 1 ? segs->seg_rows[1] : 0;
   UML_REQUIRE(n0 + n1 == n_rows, "head_fwd_ce_x: segment rows (%lld+%lld) != n_rows (%lld)", (long long)n0, (long long)n1,
               (long long)n_rows);
-  CUtensorMap tx, tw, tg;
+  CUtensorMap tx, tw;
   if (make_tmap_2d(&tx, X, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim, n_rows, static_cast<uint64_t>(dim) * 2, 64, 128,
                    CU_TENSOR_MAP_SWIZZLE_128B))
     return 1;
   if (make_tmap_2d(&tw, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim, n_classes, static_cast<uint64_t>(dim) * 2, 64, 128,
                    CU_TENSOR_MAP_SWIZZLE_128B))
     return 1;
-  memset(&tg, 0, sizeof(tg));
-  if (G) {
-    if (make_tmap_2d(&tg, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, static_cast<uint64_t>(ldg), n_rows,
-                     static_cast<uint64_t>(ldg) * 2, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B))
-      return 1;
-  }
   XSegs fs;
   fs.n0 = segs->nseg > 1 ? n0 : INT64_MAX;
   bool learnable = false;
@@ -752,8 +935,8 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
     learnable = learnable || segs->scale_dev[j] != nullptr;
   }
   const bool ds = learnable || row_dscale != nullptr;  // the sum p * raw is only needed for d loss / d scale
-  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, int64_t, int, int, int, const int32_t*, XSegs, int, int64_t,
-                        float*, int32_t*, int32_t*, float*, XWork);
+  using Kern = void (*)(CUtensorMap, CUtensorMap, int64_t, int, int, int, const int32_t*, XSegs, uint16_t*, int64_t, float*,
+                        int32_t*, int32_t*, float*, XWork);
   const int slot = (row_pred ? 2 : 0) + (ds ? 1 : 0);
   const Kern kerns[4] = {head_fwd_ce_x_kernel<false, false>, head_fwd_ce_x_kernel<false, true>,
                          head_fwd_ce_x_kernel<true, false>, head_fwd_ce_x_kernel<true, true>};
@@ -773,9 +956,9 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
   wk.recs = l.recs;
   wk.ctrl = l.ctrl;
   const dim3 grid(static_cast<unsigned>(n_groups * n_chunks * 2));
-  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, true, tx, tw, tg, n_rows,
-                         static_cast<int>(dim), static_cast<int>(n_classes), static_cast<int>(n_groups), labels, fs,
-                         G ? 1 : 0, ldg, row_loss, row_pred, row_correct, row_dscale, wk));
+  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, true, tx, tw, n_rows,
+                         static_cast<int>(dim), static_cast<int>(n_classes), static_cast<int>(n_groups), labels, fs, G, ldg,
+                         row_loss, row_pred, row_correct, row_dscale, wk));
   if (stats)
     UML_CUDA(launch_kernel(x_tile_stats_kernel, dim3(segs->nseg), dim3(1024), 0, as_stream(stream), 1, true,
                            static_cast<const float*>(l.tile_part), l.part_entries, stats));
