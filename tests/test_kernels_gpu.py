@@ -440,7 +440,8 @@ def test_dw_prologue_fixup_matches_the_default_forward(n_img, n_txt, d, c):
     ws_a, ws_b = ops.HeadWorkspace(n, c, DEV, bf16=True), ops.HeadWorkspace(n, c, DEV, bf16=True)
     pa, pb = torch.zeros(splits, c, d, device=DEV), torch.zeros(splits, c, d, device=DEV)
     st_a, st_b = torch.zeros(2, 4, device=DEV), torch.zeros(2, 4, device=DEV)
-    ops.head_fwd_ce_bf16(x16, w16, y, segs, ws_a, None, n_rows=n, stats=st_a)
+    # (row_dscale asks the exchange kernel for d loss / d scale, which it otherwise only computes for a learnable temperature)
+    ops.head_fwd_ce_bf16(x16, w16, y, segs, ws_a, None, n_rows=n, stats=st_a, row_dscale=ws_a.row_dscale)
     ops.head_bwd_dw_bf16(ws_a.G, ws_a.ldg, x16, n, c, pa, splits)
     ops.head_fwd_ce_deferred_bf16(x16, w16, y, segs, ws_b, n_rows=n)
     ops.head_bwd_dw_fix_bf16(ws_b, x16, n, c, pb, splits, segs, y, stats=st_b)

@@ -45,7 +45,11 @@ void set_error(const char* fmt, ...);
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached multiprocessor count of the current device
-bool pdl_enabled();  // programmatic dependent launch between the kernels of a step (env UML_PDL=0 disables)
+// Programmatic dependent launch between the kernels of a step: a launch site takes part when its bit is set in the mask
+// (env UML_PDL, default kPdlDefault): the dependent's CTAs may become resident - and run their prologue up to
+// griddepcontrol.wait - while the kernel before it drains.
+enum : int { kPdlFwd = 1, kPdlDw = 2, kPdlUpdate = 4, kPdlGather = 8, kPdlStats = 16, kPdlFwdOld = 32 };
+int pdl_mask();
 
 // Launch with optional thread-block cluster and programmatic stream serialization (PDL).  A kernel launched
 // with `pdl` MUST execute pdl_wait() before touching anything an earlier kernel on the stream produced (or
@@ -53,7 +57,7 @@ bool pdl_enabled();  // programmatic dependent launch between the kernels of a s
 // transitive along the stream.
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
-                                 bool pdl, Args... args) {
+                                 int pdl_site, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -69,7 +73,7 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
-  if (pdl && pdl_enabled()) {
+  if (pdl_site & pdl_mask()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

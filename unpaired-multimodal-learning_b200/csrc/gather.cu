@@ -298,7 +298,7 @@ int uml_gather2_rows_bf16(const uint16_t* bank0, const int64_t* labels0, const i
   const int grid = static_cast<int>(std::min<int64_t>(groups, sm_count()));
   CopySeg a{reinterpret_cast<const unsigned char*>(bank0), idx0, labels0, n0};
   CopySeg b{reinterpret_cast<const unsigned char*>(bank1), idx1, labels1, n1};
-  UML_CUDA(launch_kernel(gather_copy2_kernel<kCopyStagesFull>, dim3(grid), dim3(32), smem, as_stream(stream), 1, true, a, b,
+  UML_CUDA(launch_kernel(gather_copy2_kernel<kCopyStagesFull>, dim3(grid), dim3(32), smem, as_stream(stream), 1, kPdlGather, a, b,
                          row_bytes, rows, reinterpret_cast<unsigned char*>(out), ld_out * 2, out_labels));
   return 0;
 }

@@ -28,16 +28,15 @@ int sm_count() {
   return cached[dev];
 }
 
-bool pdl_enabled() {
+int pdl_mask() {
   static int cached = -1;
   if (cached < 0) {
-    // OFF unless UML_PDL=1.  Measured on B200 (round 1): with every kernel of the step triggering its dependents
-    // at entry the 50-step bench got SLOWER (0.266 vs 0.214 ms/step - early-resident dependents compete with the
-    // running kernel) and the end-to-end arm (memcpys interleaved with the kernels) hung; kept for experiments.
+    // Round 1 measured "every site on" as SLOWER (0.266 vs 0.214 ms/step: early-resident dependents compete with the
+    // running kernel) and the end-to-end arm hung; the sites are now selectable one by one (UML_PDL=<bit mask>).
     const char* e = getenv("UML_PDL");
-    cached = (e && e[0] == '1') ? 1 : 0;
+    cached = e ? atoi(e) : 0;
   }
-  return cached != 0;
+  return cached;
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

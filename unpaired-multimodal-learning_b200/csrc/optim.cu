@@ -107,10 +107,10 @@ static int launch_adam(float* p, const float* parts, int n_parts, int64_t stride
   const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
   __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
   if (vec)
-    UML_CUDA(launch_kernel(adam_kernel<true>, dim3(grid), dim3(256), 0, st, 1, true, p, parts, n_parts, stride, g2, w2, m, v, n,
+    UML_CUDA(launch_kernel(adam_kernel<true>, dim3(grid), dim3(256), 0, st, 1, kPdlUpdate, p, parts, n_parts, stride, g2, w2, m, v, n,
                            a, sh, g_out));
   else
-    UML_CUDA(launch_kernel(adam_kernel<false>, dim3(grid), dim3(256), 0, st, 1, true, p, parts, n_parts, stride, g2, w2, m, v, n,
+    UML_CUDA(launch_kernel(adam_kernel<false>, dim3(grid), dim3(256), 0, st, 1, kPdlUpdate, p, parts, n_parts, stride, g2, w2, m, v, n,
                            a, sh, g_out));
   return 0;
 }

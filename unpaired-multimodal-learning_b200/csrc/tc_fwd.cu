@@ -724,7 +724,7 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
   // workspace layout: per-tile partial sums, then the per-row normalisation factors
   float* fac = tile_ws ? tile_ws + units * cg * 32 : nullptr;
   const dim3 grid(static_cast<unsigned>((units < max_clusters ? units : max_clusters) * cg));
-  UML_CUDA(launch_kernel(kern, grid, dim3(kFwdThreads), kFwdSmemBytes, as_stream(stream), cg, true, tx, tw, tg, n_rows,
+  UML_CUDA(launch_kernel(kern, grid, dim3(kFwdThreads), kFwdSmemBytes, as_stream(stream), cg, kPdlFwdOld, tx, tw, tg, n_rows,
                          static_cast<int>(dim), static_cast<int>(n_classes), labels, fs, reinterpret_cast<__nv_bfloat16*>(G), ldg,
                          row_loss, row_pred, row_correct, row_dscale, tile_ws, fac));
   if (ev_after_fwd) UML_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(ev_after_fwd), as_stream(stream)));
@@ -740,7 +740,7 @@ int uml_head_fwd_ce_bf16_ev(const uint16_t* X, int64_t n_rows, int32_t dim, cons
     memset(&fsig, 0, sizeof(fsig));
     if (sig) fsig = *sig;
     UML_CUDA(launch_kernel(g_fixup_kernel, dim3(static_cast<unsigned>(row_blocks + stat_blocks + gj.blocks)), dim3(256), 0,
-                           as_stream(stream), 1, true, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels,
+                           as_stream(stream), 1, kPdlFwdOld, reinterpret_cast<__nv_bfloat16*>(G), ldg, n_rows, labels,
                            static_cast<const float*>(fac), fs, static_cast<const float*>(tile_ws), units * cg, row_blocks,
                            stat_blocks, stats, gj, fsig));
   }
@@ -771,7 +771,7 @@ int uml_reduce_tile_stats(const float* tile_ws, int64_t n_rows, int32_t nseg, um
   if (uml_fwd_x_eligible(n_rows, 1)) return uml_fwd_x_reduce_stats(const_cast<float*>(tile_ws), n_rows, nseg, stats, stream);
   const int cg = fwd_cta_group(n_rows);
   const int64_t tiles = ((n_rows + kFwdBlockM * cg - 1) / (kFwdBlockM * cg)) * cg;  // tiles the forward kernel wrote
-  UML_CUDA(launch_kernel(tile_stats_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, true, tile_ws, tiles,
+  UML_CUDA(launch_kernel(tile_stats_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, kPdlStats, tile_ws, tiles,
                          static_cast<int>(nseg), stats));
   return 0;
 }

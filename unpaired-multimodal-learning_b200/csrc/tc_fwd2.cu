@@ -956,11 +956,11 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
   wk.recs = l.recs;
   wk.ctrl = l.ctrl;
   const dim3 grid(static_cast<unsigned>(n_groups * n_chunks * 2));
-  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, true, tx, tw, n_rows,
+  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, kPdlFwd, tx, tw, n_rows,
                          static_cast<int>(dim), static_cast<int>(n_classes), static_cast<int>(n_groups), labels, fs, G, ldg,
                          row_loss, row_pred, row_correct, row_dscale, wk));
   if (stats)
-    UML_CUDA(launch_kernel(x_tile_stats_kernel, dim3(segs->nseg), dim3(1024), 0, as_stream(stream), 1, true,
+    UML_CUDA(launch_kernel(x_tile_stats_kernel, dim3(segs->nseg), dim3(1024), 0, as_stream(stream), 1, kPdlStats,
                            static_cast<const float*>(l.tile_part), l.part_entries, stats));
   return 0;
 }
@@ -969,7 +969,7 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
 int uml_fwd_x_reduce_stats(float* tile_ws, int64_t n_rows, int32_t nseg, uml_seg_stats* stats, void* stream) {
   using namespace uml;
   const XLayout l = x_layout(tile_ws, n_rows, 1);  // (the offsets do not depend on the class count)
-  UML_CUDA(launch_kernel(x_tile_stats_dev_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, true,
+  UML_CUDA(launch_kernel(x_tile_stats_dev_kernel, dim3(nseg), dim3(1024), 0, as_stream(stream), 1, kPdlStats,
                          static_cast<const float*>(l.tile_part), static_cast<const unsigned*>(l.ctrl), stats));
   return 0;
 }

@@ -418,7 +418,7 @@ static int launch_tc_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int64_t 
   }
   const dim3 grid(static_cast<unsigned>((M + Cfg::kTileM - 1) / Cfg::kTileM) * kCG,
                   static_cast<unsigned>((N + Cfg::kTileN - 1) / Cfg::kTileN), static_cast<unsigned>(n_splits));
-  UML_CUDA(launch_kernel(kern, grid, dim3(256), Cfg::kSmemBytes, st, kCG, true, ta, tb, M, N, K, n_splits, out, ldo, fix));
+  UML_CUDA(launch_kernel(kern, grid, dim3(256), Cfg::kSmemBytes, st, kCG, kPdlDw, ta, tb, M, N, K, n_splits, out, ldo, fix));
   return 0;
 }
 
