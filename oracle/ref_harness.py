@@ -1,10 +1,10 @@
 """TEST INFRASTRUCTURE — drives the *unmodified* reference on CPU.
 
-This module is only usable where ``/root/reference`` exists (the build container);
-it never travels to the GPU box and nothing in the product imports it.  It is the
-tool that *pins* ``oracle/uml_oracle.py``: ``tests/golden/make_golden.py`` calls it
-to produce the committed golden traces, and ``tests/test_oracle_vs_reference.py``
-cross-checks the restatement against it live when the reference tree is present.
+Usable where the reference tree exists: ``/root/reference`` (the build container) or its byte-for-byte copy
+``oracle/_ref`` made by ``oracle/build_ref.py`` (git-ignored; travels to the GPU box with the repo snapshot).
+Nothing in the product imports this module.  It is the tool that *pins* ``oracle/uml_oracle.py``:
+``tests/golden/make_golden.py`` calls it to produce the committed golden traces, and ``bench.py --impl reference``
+times the reference's own ``finetune.train`` through it.
 
 Recipe: the reference imports ``timm`` and ``ftfy`` which are not in
 this image, so both are replaced by stub modules *before* the reference is imported;
@@ -20,7 +20,13 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("UML_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    if os.path.isfile("/root/reference/vision_language/finetune.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("UML_REFERENCE_ROOT") or _default_root()
 _VL = os.path.join(REFERENCE_ROOT, "vision_language")
 _GAUSS = os.path.join(REFERENCE_ROOT, "Gaussian_experiment")
 

@@ -18,7 +18,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 3 and line["gpu_launches"] == 0 and line["vs_baseline"] is None
     cb, e2e = line["cpu_baseline"], line["e2e"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert e2e == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
 

@@ -240,8 +240,10 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     a.X16 = xbuf[b];
     a.labels32 = lbuf[b];
     if (i == 0) {
+      rec(a.ev[0], stream);
       const int rc = shadow_gather(&a, xbuf[0], lbuf[0], false, stream);
       if (rc) return rc;
+      rec(a.ev[1], stream);
     } else if (prefetch_placement() != 3 || fuse_fix()) {
       UML_CUDA(cudaStreamWaitEvent(main_st, pipe->ready[b], 0));
     }
@@ -290,6 +292,10 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
           hooks.merged = &gjob;
         }
       }
+      if (next.have) {  // (the merged copy has no launch of its own to bracket)
+        rec(next.nx.ev[0], stream);
+        rec(next.nx.ev[1], stream);
+      }
       next.have = false;  // nothing for the side stream to do
     }
     hooks.mid_arg = &next;
@@ -300,8 +306,10 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
       if (n->record_mid) UML_CUDA(cudaEventRecord(n->pipe->mid, n->main_st));
       UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_a, 0));
       UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_b, 0));
+      rec(n->nx.ev[0], n->pipe->aux);  // ev[0]..ev[1] bracket the gather where it really runs: on the side stream
       const int rc = shadow_gather(&n->nx, n->x, n->l, true, n->pipe->aux);
       if (rc) return rc;
+      rec(n->nx.ev[1], n->pipe->aux);
       UML_CUDA(cudaEventRecord(n->ready, n->pipe->aux));
       return 0;
     };
@@ -350,7 +358,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     memset(&ts, 0, sizeof(ts));
     ts.nseg = 0;
     int64_t off = 0;
-    rec(a->ev[0], stream);
+    if (!pregathered) rec(a->ev[0], stream);  // (a pre-gathered step's ev[0]..ev[1] were recorded around its gather)
     const bool shadow = pregathered || shadow_gatherable(a);
     if (shadow && !pregathered) {
       rc = shadow_gather(a, a->X16, a->labels32, false, stream);
@@ -383,7 +391,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
       ts.nseg++;
       off += s.n;
     }
-    rec(a->ev[1], stream);
+    if (!pregathered) rec(a->ev[1], stream);
     if (hooks.mid && prefetch_placement() == 0) {
       rc = hooks.mid(hooks.mid_arg);
       if (rc) return rc;
