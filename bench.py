@@ -346,8 +346,10 @@ def run_ours(args, wl, rank, world, dev):
     # ---------------- device-resident arm: CUDA events around K steps ----------------------------
     model, opt, sch = make_model(wl, dev, init_bank)
     engine = StepEngine(model, opt, dev, B, BT, log_slots=64, precision=args.precision, world_size=world)
-    il = BankLoader(img_bank, B, shuffle=True, upload="epoch", shard_of=shard)
-    tl = BankLoader(txt_bank, BT, shuffle=True, upload="epoch", shard_of=shard)
+    # per-rank shards (world > 1) drop their ragged last batch: a 3742-row text shard would otherwise end every epoch
+    # with a 158-row batch and the per-GPU work of a step would no longer be fixed (weak scaling)
+    il = BankLoader(img_bank, B, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1)
+    tl = BankLoader(txt_bank, BT, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1)
     torch.manual_seed(2)
     ii, ti = iter(il), iter(tl)
 
@@ -478,8 +480,8 @@ def run_ours(args, wl, rank, world, dev):
         memory, the step, and the D2H copy of its loss record, read on the host before the clock stops."""
         m2, o2, s2 = make_model(wl, dev, init_bank)
         m2.precision = args.precision
-        il2 = BankLoader(img_bank, B, shuffle=True, upload="step", shard_of=shard)
-        tl2 = BankLoader(txt_bank, BT, shuffle=True, upload="step", shard_of=shard)
+        il2 = BankLoader(img_bank, B, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1)
+        tl2 = BankLoader(txt_bank, BT, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1)
         vl2 = BankLoader(val_bank, 512, shuffle=False)
         torch.manual_seed(2)
         tr = {"timing": {"warmup": warm}, "indices": False}

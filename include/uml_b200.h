@@ -267,8 +267,13 @@ int uml_dp_shutdown(void);
  * uml_dp_p2p_open; from then on a data-parallel step sums dW with ONE kernel per rank (peer loads of 1/world of
  * the data, peer stores of the reduced slice, two flag round trips) instead of ncclAllReduce.  Deterministic and
  * bit-identical on all ranks.  uml_dp_allreduce_p2p sums the ranks' input halves of the blocks into every rank's
- * output half; uml_dp_p2p_failed() != 0 after a peer stopped answering (2 s watchdog, no hang).             */
+ * output half.  A peer that stops answering for UML_DP_TIMEOUT_S (default 20) seconds makes the kernel give up instead
+ * of hanging: it then performs NO reduction and NO update (weights, moments and bf16 shadow keep their values) and
+ * uml_dp_p2p_failed() returns 1 from then on - the engine polls it whenever it reads its statistics log and raises.
+ * Re-sizing: uml_dp_p2p_close_peers on every rank, a barrier between the ranks, then uml_dp_p2p_alloc / _open again
+ * (an exported block must not be freed while a peer still has it mapped).                                     */
 int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes /*host*/);
+int uml_dp_p2p_close_peers(void);
 int uml_dp_p2p_open(const void* handles /*host: world x 64 bytes, rank order*/, int32_t rank, int32_t world);
 int uml_dp_allreduce_p2p(int64_t n, void* stream);
 /* the whole data-parallel tail of a step in ONE kernel per rank: split-K sum of the local dW partials -> exchange

@@ -118,6 +118,7 @@ PROTOTYPES = {
     "uml_dp_fused_adam_update": [c_vp, c_i32, c_i64, c_i64, c_vp, c_vp, c_vp, c_f64, c_f64, c_f64, c_f64, c_f64, c_i64, c_i32,
                                  c_vp, c_vp],
     "uml_dp_p2p_failed": [],
+    "uml_dp_p2p_close_peers": [],
     "uml_gauss_param_count": [c_i32, c_i32, c_i32],
     "uml_gauss_workspace_floats": [c_i32, c_i32, c_i32, c_i64],
     "uml_gauss_step": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i32, c_f32, c_f32,

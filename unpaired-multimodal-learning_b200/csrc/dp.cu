@@ -5,6 +5,8 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "optim.cuh"
 
@@ -80,7 +82,9 @@ struct ArPtrs {
   uint32_t* flags[kMaxRanks];  // [2][kMaxRanks] per rank
 };
 
-__device__ __forceinline__ void wait_flags(const volatile uint32_t* f, int world, uint32_t epoch, int* failed) {
+// Returns false when a peer did not answer within `timeout` clock cycles (a peer died, or its host stalled for that
+// long: UML_DP_TIMEOUT_S, default 20 s) - the caller then leaves the weights untouched and the host raises.
+__device__ __forceinline__ bool wait_flags(const volatile uint32_t* f, int world, uint32_t epoch, int* failed, long long timeout) {
   // one warp polls: lane p watches rank p's flag
   const int lane = threadIdx.x & 31;
   const long long t0 = clock64();
@@ -88,12 +92,13 @@ __device__ __forceinline__ void wait_flags(const volatile uint32_t* f, int world
   while (!ok) {
     const uint32_t v = lane < world ? f[lane] : epoch;
     ok = __all_sync(0xffffffffu, static_cast<int32_t>(v - epoch) >= 0);
-    if (!ok && clock64() - t0 > 4000000000ll) {  // ~2 s: a peer died - give up instead of hanging the GPU
+    if (!ok && (clock64() - t0 > timeout || *reinterpret_cast<volatile int*>(failed) != 0)) {
       *failed = 1;
       break;
     }
   }
   __threadfence_system();
+  return ok;
 }
 
 // Arguments of the optional stages fused around the exchange.
@@ -111,10 +116,11 @@ struct FusedUpdate {
 // counters[0]: blocks past phase A, counters[1]: blocks past phase B (each reset by its last block)
 __global__ void __launch_bounds__(kArThreads)
     p2p_allreduce_kernel(ArPtrs P, int rank, int world, int64_t n4, uint32_t epoch, unsigned int* counters, int* failed,
-                         FusedUpdate F) {
+                         long long timeout, FusedUpdate F) {
   using uml::adam_one;
   uint32_t* my_flags = P.flags[rank];
   __shared__ bool last;
+  __shared__ bool alive;
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
   // ---- phase A: this rank's local gradient sum (fixed split order) into its exchange buffer
@@ -146,8 +152,12 @@ __global__ void __launch_bounds__(kArThreads)
       reinterpret_cast<volatile uint32_t*>(P.flags[threadIdx.x])[rank] = epoch;
     }
   }
-  if (threadIdx.x < 32) wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags), world, epoch, failed);
+  if (threadIdx.x < 32) {
+    const bool ok = wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags), world, epoch, failed, timeout);
+    if (threadIdx.x == 0) alive = ok;
+  }
   __syncthreads();
+  if (!alive) return;  // a peer is gone: no reduction from stale buffers, no update - weights, moments and shadow stay as they were
   // ---- phase B: reduce my slice in rank order (peer loads), deliver it to every rank's rbuf (peer stores)
   const int64_t per = (n4 + world - 1) / world, lo = per * rank, hi = lo + per < n4 ? lo + per : n4;
   for (int64_t i = lo + tid; i < hi; i += nth) {
@@ -175,8 +185,12 @@ __global__ void __launch_bounds__(kArThreads)
     }
   }
   // ---- every rank's slice has landed in my rbuf
-  if (threadIdx.x < 32) wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags + kMaxRanks), world, epoch, failed);
+  if (threadIdx.x < 32) {
+    const bool ok = wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags + kMaxRanks), world, epoch, failed, timeout);
+    if (threadIdx.x == 0) alive = ok;
+  }
   __syncthreads();
+  if (!alive) return;  // (every block of this rank sees the same failure: the flag is sticky and polled by all of them)
   // ---- phase D: the optimizer update, identical on every rank (replicated weights)
   if (F.w) {
     const float4* r = reinterpret_cast<const float4*>(P.r[rank]);
@@ -217,9 +231,11 @@ int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are expected to be 64 bytes");
   UML_REQUIRE(max_floats > 0 && handle_out_64_bytes, "dp_p2p_alloc: bad arguments");
   max_floats = (max_floats + 3) / 4 * 4;
-  if (p2p.local) {  // re-sizing: unmap the peers' blocks, free ours
-    for (int p = 0; p < p2p.world; ++p)
-      if (p2p.ready && p != p2p.rank && p2p.peer[p]) cudaIpcCloseMemHandle(p2p.peer[p]);
+  // Re-sizing frees an IPC-exported block: every importer must have closed its mapping first (CUDA leaves freeing an
+  // exported allocation that a peer still has open undefined).  The caller runs uml_dp_p2p_close_peers on every rank,
+  // then a barrier, then this.
+  UML_REQUIRE(!p2p.ready, "dp_p2p_alloc: peers are still mapped - call uml_dp_p2p_close_peers on every rank and synchronise the ranks first");
+  if (p2p.local) {
     cudaFree(p2p.local);
     p2p = P2P();
   }
@@ -230,6 +246,19 @@ int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes) {
   UML_CUDA(cudaIpcGetMemHandle(&p2p.handle, p2p.local));
   p2p.max_floats = max_floats;
   memcpy(handle_out_64_bytes, &p2p.handle, 64);
+  return 0;
+}
+
+// Unmaps every peer's block (first half of a re-size; a no-op when nothing is mapped).  Synchronises the device.
+int uml_dp_p2p_close_peers(void) {
+  if (!p2p.ready) return 0;
+  UML_CUDA(cudaDeviceSynchronize());
+  for (int p = 0; p < p2p.world; ++p)
+    if (p != p2p.rank && p2p.peer[p]) {
+      cudaIpcCloseMemHandle(p2p.peer[p]);
+      p2p.peer[p] = nullptr;
+    }
+  p2p.ready = false;
   return 0;
 }
 
@@ -268,8 +297,14 @@ static int p2p_launch(int64_t n, const FusedUpdate& F, void* stream) {
   unsigned int* counters = my + 2 * kMaxRanks;
   int* failed = reinterpret_cast<int*>(my + 2 * kMaxRanks + 2);
   ++p2p.epoch;
+  static long long timeout = 0;
+  if (timeout == 0) {
+    const char* e = getenv("UML_DP_TIMEOUT_S");
+    const double sec = e ? atof(e) : 20.0;
+    timeout = static_cast<long long>((sec > 0.01 ? sec : 0.01) * 2.0e9);  // clock64 ticks at ~2 GHz
+  }
   p2p_allreduce_kernel<<<kArBlocks, kArThreads, 0, uml::as_stream(stream)>>>(P, p2p.rank, p2p.world, n / 4, p2p.epoch, counters,
-                                                                              failed, F);
+                                                                              failed, timeout, F);
   UML_CUDA(cudaGetLastError());
   return 0;
 }

@@ -455,6 +455,8 @@ class _BankIter:
             self._draw()
         start = self.pos
         total = min(k * l.batch_size, self.n - start)
+        if l.drop_last:
+            total -= total % l.batch_size
         if self.perm is not None:
             self.perm.wait(start + total)
         host = self.perm_host[start:start + total]

@@ -98,6 +98,10 @@ def ensure_dp_p2p(max_floats: int):
     rank, world = dist.get_rank(), dist.get_world_size()
     if world > 16:
         return
+    # re-sizing (a later job of the same process with a larger head): every rank unmaps its peers, THEN - after a
+    # barrier - frees its own exported block; freeing while a peer still has the block open is undefined in CUDA IPC
+    check(load().uml_dp_p2p_close_peers())
+    dist.barrier()
     h = (C.c_ubyte * 64)()
     check(load().uml_dp_p2p_alloc(int(max_floats), h))
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -234,7 +238,8 @@ class StepEngine:
             raise ValueError("at least one modality per step")
         n_i, n_t = (img.n if img else 0), (txt.n if txt else 0)
         slot %= self.log_slots
-        self.slot_modalities[slot] = (img is not None, txt is not None)
+        # (a rank's local slice of a modality can be empty in a data-parallel run: only runs that are launched write a record)
+        self.slot_modalities[slot] = (n_i > 0, n_t > 0)
         wi, wt = dp_loss_weights(n_i, n_t, alpha, global_img_rows, global_txt_rows)
         bf16 = self._use_bf16(n_i + n_t)
         if self.adapter and bf16:
@@ -396,7 +401,7 @@ class StepEngine:
                     st["step"] += 1
                     rs.scale_step[jj] = st["step"]
                 slot = (slot0 + m) % self.log_slots
-                self.slot_modalities[slot] = (ig is not None, tg is not None)
+                self.slot_modalities[slot] = (ig is not None and ig.n > 0, tg is not None and tg.n > 0)
                 rs.stats = self.stats_log[slot].data_ptr()
                 if self.profile is not None:
                     names = ("gather_bf16", "head_fwd_ce_bf16" if bf16 else "head_fwd_ce_f32",
@@ -674,6 +679,10 @@ class StepEngine:
     def read_log(self, slots, from_host_ring=False):
         """Per-step stats for the given slots: one synchronising D2H of the device log, or - when every
         step already pushed its record with ``copy_slot_to_host`` - a stream sync and a host read."""
+        from .._lib import load as _load_lib
+        if self.world > 1 and _P2P_FLOATS and _load_lib().uml_dp_p2p_failed():
+            raise RuntimeError("data-parallel step: a peer rank stopped answering the NVLink gradient exchange (UML_DP_TIMEOUT_S); "
+                               "the affected steps applied no update - the replicas may no longer agree, restart from a checkpoint")
         if from_host_ring and self.host_log is not None:
             torch.cuda.current_stream().synchronize()
             raw = self.host_log.clone()

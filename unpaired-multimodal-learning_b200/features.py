@@ -226,7 +226,8 @@ def load_feature_bank(v1_path, device="cuda", split=None):
     (``<stem>.bank2[.split]``, written by ``convert_bank``; the bf16 shadow comes along), else from the v1 dict."""
     from .engine.datasets.utils import FeatureBank
     v2 = os.path.splitext(v1_path)[0] + ".bank2" + (f".{split}" if split else "")
-    if os.path.exists(v2):
+    # a v1 file regenerated after the conversion wins over the stale v2 cache
+    if os.path.exists(v2) and (not os.path.exists(v1_path) or os.path.getmtime(v2) >= os.path.getmtime(v1_path)):
         t, _, meta = load_bank_v2(v2, device, sections=("features", "features_bf16", "labels"))
         bank = FeatureBank.__new__(FeatureBank)
         bank.features, bank.labels = t["features"], t["labels"]

@@ -116,8 +116,12 @@ def validate_enqueue(model, val_loader):
     row_pred = torch.empty(n, device=dev, dtype=torch.int32)
     W = model.head.weight.data
     adapter = model.img_proj is not None
-    use_tc = (getattr(model, "precision", "auto") != "fp32" and n >= 4096 and W.shape[1] % 8 == 0
-              and W.shape[0] <= 1024 and bank.dim % 8 == 0)
+    # The reference evaluates in fp32.  The bf16 tensor-core forward is used only where the model is trained through the
+    # bf16 path as well (precision "bf16", or "auto" with a throughput-sized training batch - train() notes that on the
+    # model): a run that trains on the exact path also reports fp32 accuracies and takes its early-stopping decisions on them.
+    prec = getattr(model, "precision", "auto")
+    want_tc = prec == "bf16" or (prec == "auto" and getattr(model, "_trained_bf16", False))
+    use_tc = (want_tc and n >= 4096 and W.shape[1] % 8 == 0 and W.shape[0] <= 1024 and bank.dim % 8 == 0)
     if use_tc:
         x16 = bank.bf16()
         if adapter:  # Z = X Wp^T on the tensor cores
@@ -180,6 +184,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
     engine = StepEngine(model, optimizer, device, per_rank(image_loader, bs_i), per_rank(text_loader, bs_t),
                         log_slots=min(max(int(eval_freq), 1), int(max_iters)) + 1, precision=precision,
                         dist_group=None, world_size=world)
+    model._trained_bf16 = bool(engine._use_bf16(engine.max_rows))  # validate() follows the training path's precision
     if trace is not None:
         trace["engine"] = engine
         if trace.get("profile"):
@@ -767,7 +772,8 @@ def main(args, alphas=None):
     for sp in savepaths:
         makedirs(sp)
     logfiles = [open(os.path.join(sp, "log.txt"), "w") for sp in dict.fromkeys(savepaths)]
-    sys.stdout = Tee(sys.__stdout__, *logfiles)
+    prev_stdout = sys.stdout  # (the caller's redirection - pytest capture, a notebook, an outer Tee - stays in the chain)
+    sys.stdout = Tee(prev_stdout, *logfiles)
     try:
         print("=> Arguments:", args)
         text_encoder = args.clip_encoder if args.use_clip else args.language_model
@@ -813,7 +819,7 @@ def main(args, alphas=None):
         del datasets
         print("Done!")
     finally:
-        sys.stdout = sys.__stdout__
+        sys.stdout = prev_stdout
         for f in logfiles:
             f.close()
     return out
