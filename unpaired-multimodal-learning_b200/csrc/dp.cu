@@ -53,13 +53,24 @@ int load_nccl() {
 // ---------------------------------------------------------------------------------------------------------
 // Two-shot all-reduce over NVLink peer memory (one node, NVSwitch): every rank owns one cudaMalloc'd exchange
 // block, opened by all peers through CUDA IPC.
-//   [ xbuf: max_floats | rbuf: max_floats | flags: 2 x kMaxRanks u32 | counter ]
-// One kernel per rank and call:  signal "my xbuf is complete" to every peer -> wait for all peers -> reduce MY
-// slice over all ranks' xbuf in rank order (peer loads) and store it into EVERY rank's rbuf (peer stores) ->
-// last block signals "my slice is delivered" -> wait for all peers' deliveries.  Each element is summed by
-// exactly one rank in a fixed order, so the result is deterministic and bit-identical on all ranks.  NCCL needed
-// 38-50 us for this 3 MB message on 8 B200s (85 us inside the step); the message is latency bound, and two
-// flag round trips plus one peer read and one peer write of 1/N of the data is all it takes.
+//   [ xbuf: max_floats | out: max_floats | recv: flagged slots | rll: flagged slots | failed ]
+// One kernel per rank and call.  No grid-wide step, no fence and no separate flag inside it: block b of every rank
+// owns chunk b of the message from the first load to the optimizer update, and the data carries its own validity -
+// it travels in 16-byte SLOTS of three floats and the call's epoch, each written by one 16-byte vector store of one
+// thread (the memory system delivers such a store whole - the LL protocol of NCCL, at 16 instead of 8 bytes: 75 %
+// payload), so a reader that finds the epoch in a slot has the slot's data.  A thread moves UNITS of three float4
+// (twelve floats = four slots).
+//   push   : block b sums its chunk of the local gradient and stores sub-slice j of it, as slots, straight into rank
+//            j's recv area (peer stores);
+//   reduce : block b polls the world copies of ITS sub-slice (local loads) unit by unit, adds them in rank order and
+//            stores the sum, as slots again, into EVERY rank's rll area (peer stores);
+//   update : block b polls the units of chunk b in its rll area and applies Adam as they arrive.
+// Two one-way NVLink hops per chunk.  (Round 1's kernel: grid-wide "last block" hand-offs, system fences, separate
+// flags and pulled loads - two flag round trips plus a load round trip, +31 us over the single-GPU update at any rank
+// count; a push version with fences and per-block flags still needed 20 us for the exchange alone, as NCCL does; 128-
+// byte lines with one flag per line - LL128 - delivered torn lines here: parity failed.)
+// Each element is summed by exactly one rank in a fixed order, so the result is deterministic and bit-identical on
+// all ranks.
 namespace {
 
 constexpr int kMaxRanks = 16;
@@ -77,140 +88,155 @@ struct P2P {
 P2P p2p;
 
 struct ArPtrs {
-  const float* x[kMaxRanks];
-  float* r[kMaxRanks];
-  uint32_t* flags[kMaxRanks];  // [2][kMaxRanks] per rank
+  const float* x;              // this rank's local gradient sum (when no split-K partials are given)
+  float* out;                  // this rank's plain result (exchange-only calls)
+  uint4* recv[kMaxRanks];      // per rank: [source rank][block][unit][4] slots
+  uint4* rll[kMaxRanks];       // per rank: [owner rank][block][unit][4] slots
 };
-
-// Returns false when a peer did not answer within `timeout` clock cycles (a peer died, or its host stalled for that
-// long: UML_DP_TIMEOUT_S, default 20 s) - the caller then leaves the weights untouched and the host raises.
-__device__ __forceinline__ bool wait_flags(const volatile uint32_t* f, int world, uint32_t epoch, int* failed, long long timeout) {
-  // one warp polls: lane p watches rank p's flag
-  const int lane = threadIdx.x & 31;
-  const long long t0 = clock64();
-  bool ok = false;
-  while (!ok) {
-    const uint32_t v = lane < world ? f[lane] : epoch;
-    ok = __all_sync(0xffffffffu, static_cast<int32_t>(v - epoch) >= 0);
-    if (!ok && (clock64() - t0 > timeout || *reinterpret_cast<volatile int*>(failed) != 0)) {
-      *failed = 1;
-      break;
-    }
-  }
-  __threadfence_system();
-  return ok;
-}
 
 // Arguments of the optional stages fused around the exchange.
 struct FusedUpdate {
-  const float* partials;   // phase A: xbuf = sum over n_parts split-K partials (nullptr: xbuf was written by an earlier kernel)
+  const float* partials;   // push: chunk = sum over n_parts split-K partials (nullptr: the local sum is in xbuf)
   int n_parts;
   int64_t stride;
-  float* w;                // phase D: Adam(W) on every element from rbuf (nullptr: exchange only)
+  float* w;                // update: Adam(W) on every element (nullptr: exchange only, plain result in `out`)
   float* m;
   float* v;
   __nv_bfloat16* shadow;
   uml::AdamArgs adam;
 };
 
-// counters[0]: blocks past phase A, counters[1]: blocks past phase B (each reset by its last block)
-__global__ void __launch_bounds__(kArThreads)
-    p2p_allreduce_kernel(ArPtrs P, int rank, int world, int64_t n4, uint32_t epoch, unsigned int* counters, int* failed,
-                         long long timeout, FusedUpdate F) {
-  using uml::adam_one;
-  uint32_t* my_flags = P.flags[rank];
-  __shared__ bool last;
-  __shared__ bool alive;
-  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  // ---- phase A: this rank's local gradient sum (fixed split order) into its exchange buffer
-  if (F.partials) {
-    float4* x = const_cast<float4*>(reinterpret_cast<const float4*>(P.x[rank]));
-    for (int64_t i = tid; i < n4; i += nth) {
-      float4 g = reinterpret_cast<const float4*>(F.partials)[i];
-      for (int sp = 1; sp < F.n_parts; ++sp) {
-        const float4 q = reinterpret_cast<const float4*>(F.partials + sp * F.stride)[i];
-        g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+struct Unit {
+  float4 a, b, c;
+};
+
+__device__ __forceinline__ void st_slot(uint4* p, float x, float y, float z, uint32_t e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(__float_as_uint(x)), "r"(__float_as_uint(y)),
+               "r"(__float_as_uint(z)), "r"(e)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ld_slot(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// The four slots of unit kk of a region sit 32 slots apart, at (kk & ~31) * 4 + part * 32 + (kk & 31): the 32 units of
+// a warp then fill 512 contiguous bytes with each store instruction (full lines on NVLink instead of 16-byte packets).
+__device__ __forceinline__ int64_t unit_slot(int64_t kk) { return (kk & ~int64_t(31)) * 4 + (kk & 31); }
+__device__ __forceinline__ void st_unit(uint4* p, const Unit& u, uint32_t e) {
+  st_slot(p, u.a.x, u.a.y, u.a.z, e);
+  st_slot(p + 32, u.a.w, u.b.x, u.b.y, e);
+  st_slot(p + 64, u.b.z, u.b.w, u.c.x, e);
+  st_slot(p + 96, u.c.y, u.c.z, u.c.w, e);
+}
+// Polls the four slots of a unit until all carry `epoch`.  false: the peer did not deliver within `timeout` clock
+// cycles (it died, or its host stalled that long: UML_DP_TIMEOUT_S, default 20 s) - the kernel then leaves the
+// weights untouched and the host raises.
+__device__ __forceinline__ bool ld_unit(const uint4* p, uint32_t epoch, Unit& u, int* failed, long long timeout) {
+  unsigned polls = 0;
+  long long t0 = 0;
+  for (;;) {
+    const uint4 s0 = ld_slot(p), s1 = ld_slot(p + 32), s2 = ld_slot(p + 64), s3 = ld_slot(p + 96);
+    if (s0.w == epoch && s1.w == epoch && s2.w == epoch && s3.w == epoch) {
+      u.a = make_float4(__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z), __uint_as_float(s1.x));
+      u.b = make_float4(__uint_as_float(s1.y), __uint_as_float(s1.z), __uint_as_float(s2.x), __uint_as_float(s2.y));
+      u.c = make_float4(__uint_as_float(s2.z), __uint_as_float(s3.x), __uint_as_float(s3.y), __uint_as_float(s3.z));
+      return true;
+    }
+    if ((++polls & 255u) == 0) {
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > timeout || *reinterpret_cast<volatile int*>(failed) != 0) {
+        *failed = 1;
+        return false;
       }
-      x[i] = g;
-    }
-    // device-scope fence per block; the block that signals the peers issues the system-scope fence (fences are
-    // cumulative: what it observed through the counter is ordered before its flag stores)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(&counters[0], 1u) == gridDim.x - 1;
-    __syncthreads();
-  } else {
-    if (threadIdx.x == 0) last = blockIdx.x == 0;  // xbuf complete by stream order: one block signals right away
-    __syncthreads();
-  }
-  // ---- "my xbuf is complete" -> every rank; then wait until everyone's is
-  if (last) {
-    if (threadIdx.x == 0 && F.partials) counters[0] = 0;
-    if (threadIdx.x < world) {
-      __threadfence_system();
-      reinterpret_cast<volatile uint32_t*>(P.flags[threadIdx.x])[rank] = epoch;
     }
   }
-  if (threadIdx.x < 32) {
-    const bool ok = wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags), world, epoch, failed, timeout);
-    if (threadIdx.x == 0) alive = ok;
-  }
-  __syncthreads();
-  if (!alive) return;  // a peer is gone: no reduction from stale buffers, no update - weights, moments and shadow stay as they were
-  // ---- phase B: reduce my slice in rank order (peer loads), deliver it to every rank's rbuf (peer stores)
-  const int64_t per = (n4 + world - 1) / world, lo = per * rank, hi = lo + per < n4 ? lo + per : n4;
-  for (int64_t i = lo + tid; i < hi; i += nth) {
-    float4 v[kMaxRanks];
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
+__global__ void __launch_bounds__(kArThreads)
+    p2p_allreduce_kernel(ArPtrs P, int rank, int world, int64_t n4, int64_t sub, uint32_t epoch, int* failed, long long timeout,
+                         FusedUpdate F) {
+  using uml::adam_one;
+  const int b = blockIdx.x;
+  const int64_t lo = sub * world * b;                // first unit of chunk b; unit u covers float4 [3u, 3u + 3)
+  const int64_t sub32 = (sub + 31) & ~int64_t(31);   // a sub-slice's region holds whole warps of units
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- push: local gradient sum of chunk b (fixed split order), sub-slice j -> rank j, as flagged slots
+  {
+    const float4* src = reinterpret_cast<const float4*>(F.partials ? F.partials : P.x);
+    for (int64_t k = threadIdx.x; k < sub32 * world; k += blockDim.x) {
+      const int j = static_cast<int>(k / sub32);
+      const int64_t kk = k - j * sub32, i0 = (lo + j * sub + kk) * 3;
+      if (kk >= sub || i0 >= n4) continue;
+      Unit u;
+      float4* part[3] = {&u.a, &u.b, &u.c};
 #pragma unroll
-    for (int p = 0; p < kMaxRanks; ++p)
-      if (p < world) v[p] = __ldcv(reinterpret_cast<const float4*>(P.x[p]) + i);  // all peer loads in flight at once
-    float4 acc = v[0];
-#pragma unroll
-    for (int p = 1; p < kMaxRanks; ++p)
-      if (p < world) { acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w; }
-#pragma unroll
-    for (int p = 0; p < kMaxRanks; ++p)
-      if (p < world) reinterpret_cast<float4*>(P.r[p])[i] = acc;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(&counters[1], 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (last) {
-    if (threadIdx.x == 0) counters[1] = 0;
-    if (threadIdx.x < world) {
-      __threadfence_system();
-      reinterpret_cast<volatile uint32_t*>(P.flags[threadIdx.x])[kMaxRanks + rank] = epoch;
+      for (int e = 0; e < 3; ++e) {
+        float4 g = zero;
+        if (i0 + e < n4) {
+          g = F.partials ? src[i0 + e] : __ldcv(src + i0 + e);
+          for (int sp = 1; F.partials && sp < F.n_parts; ++sp) add4(g, reinterpret_cast<const float4*>(F.partials + sp * F.stride)[i0 + e]);
+        }
+        *part[e] = g;
+      }
+      st_unit(P.recv[j] + (static_cast<int64_t>(rank) * kArBlocks + b) * sub32 * 4 + unit_slot(kk), u, epoch);
     }
   }
-  // ---- every rank's slice has landed in my rbuf
-  if (threadIdx.x < 32) {
-    const bool ok = wait_flags(reinterpret_cast<const volatile uint32_t*>(my_flags + kMaxRanks), world, epoch, failed, timeout);
-    if (threadIdx.x == 0) alive = ok;
+  // ---- reduce: my sub-slice of chunk b, summed in rank order from the copies the ranks pushed here -> everyone's rll
+  for (int64_t kk = threadIdx.x; kk < sub; kk += blockDim.x) {
+    if ((lo + sub * rank + kk) * 3 >= n4) break;
+    Unit acc, v;
+    for (int p = 0; p < world; ++p) {
+      if (!ld_unit(P.recv[rank] + (static_cast<int64_t>(p) * kArBlocks + b) * sub32 * 4 + unit_slot(kk), epoch, v, failed, timeout)) return;
+      if (p == 0) {
+        acc = v;
+      } else {
+        add4(acc.a, v.a); add4(acc.b, v.b); add4(acc.c, v.c);
+      }
+    }
+    for (int q = 0; q < world; ++q) st_unit(P.rll[q] + (static_cast<int64_t>(rank) * kArBlocks + b) * sub32 * 4 + unit_slot(kk), acc, epoch);
   }
-  __syncthreads();
-  if (!alive) return;  // (every block of this rank sees the same failure: the flag is sticky and polled by all of them)
-  // ---- phase D: the optimizer update, identical on every rank (replicated weights)
-  if (F.w) {
-    const float4* r = reinterpret_cast<const float4*>(P.r[rank]);
-    for (int64_t i = tid; i < n4; i += nth) {
-      const float4 g = __ldcv(r + i);
-      float4 w = reinterpret_cast<float4*>(F.w)[i];
-      float4 mm = reinterpret_cast<float4*>(F.m)[i], vv = reinterpret_cast<float4*>(F.v)[i];
-      w.x = adam_one(F.adam, w.x, g.x, mm.x, vv.x);
-      w.y = adam_one(F.adam, w.y, g.y, mm.y, vv.y);
-      w.z = adam_one(F.adam, w.z, g.z, mm.z, vv.z);
-      w.w = adam_one(F.adam, w.w, g.w, mm.w, vv.w);
-      reinterpret_cast<float4*>(F.w)[i] = w;
-      reinterpret_cast<float4*>(F.m)[i] = mm;
-      reinterpret_cast<float4*>(F.v)[i] = vv;
-      if (F.shadow) reinterpret_cast<uint2*>(F.shadow)[i] = uml::pack_bf16x4(w);
+  // ---- update: chunk b of the reduced gradient arrives unit by unit from its owners; the optimizer step is identical
+  //      on every rank (replicated weights)
+  for (int64_t k = threadIdx.x; k < sub32 * world; k += blockDim.x) {
+    const int q = static_cast<int>(k / sub32);
+    const int64_t kk = k - q * sub32, i0 = (lo + q * sub + kk) * 3;
+    if (kk >= sub || i0 >= n4) continue;
+    Unit u;
+    if (!ld_unit(P.rll[rank] + (static_cast<int64_t>(q) * kArBlocks + b) * sub32 * 4 + unit_slot(kk), epoch, u, failed, timeout)) return;
+    const float4 gs[3] = {u.a, u.b, u.c};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int64_t i = i0 + e;
+      if (i >= n4) break;
+      const float4 g = gs[e];
+      if (F.w) {
+        float4 w = reinterpret_cast<float4*>(F.w)[i];
+        float4 mm = reinterpret_cast<float4*>(F.m)[i], vv = reinterpret_cast<float4*>(F.v)[i];
+        w.x = adam_one(F.adam, w.x, g.x, mm.x, vv.x);
+        w.y = adam_one(F.adam, w.y, g.y, mm.y, vv.y);
+        w.z = adam_one(F.adam, w.z, g.z, mm.z, vv.z);
+        w.w = adam_one(F.adam, w.w, g.w, mm.w, vv.w);
+        reinterpret_cast<float4*>(F.w)[i] = w;
+        reinterpret_cast<float4*>(F.m)[i] = mm;
+        reinterpret_cast<float4*>(F.v)[i] = vv;
+        if (F.shadow) reinterpret_cast<uint2*>(F.shadow)[i] = uml::pack_bf16x4(w);
+      } else {
+        reinterpret_cast<float4*>(P.out)[i] = g;
+      }
     }
   }
 }
 
-inline int64_t flags_offset(int64_t max_floats) { return 2 * max_floats * static_cast<int64_t>(sizeof(float)); }
+// layout of an exchange block (bytes): xbuf, out, recv slots, rll slots, failed word
+inline int64_t ll_slots(int64_t max_floats) { return (max_floats / 3 + 4) + 4 * 33 * static_cast<int64_t>(kArBlocks) * kMaxRanks + 64; }
+inline int64_t recv_offset(int64_t max_floats) { return 2 * max_floats * static_cast<int64_t>(sizeof(float)); }
+inline int64_t rll_offset(int64_t max_floats) { return recv_offset(max_floats) + ll_slots(max_floats) * 16; }
+constexpr int64_t kFlagWords = 0;  // (the slots carry their own flags) then: the sticky "failed" word
+inline int64_t flags_offset(int64_t max_floats) { return rll_offset(max_floats) + ll_slots(max_floats) * 16; }
 
 }  // namespace
 
@@ -239,7 +265,7 @@ int uml_dp_p2p_alloc(int64_t max_floats, void* handle_out_64_bytes) {
     cudaFree(p2p.local);
     p2p = P2P();
   }
-  const size_t bytes = static_cast<size_t>(flags_offset(max_floats)) + 4096;
+  const size_t bytes = static_cast<size_t>(flags_offset(max_floats)) + kFlagWords * sizeof(uint32_t) + 4096;
   UML_CUDA(cudaMalloc(&p2p.local, bytes));
   UML_CUDA(cudaMemset(p2p.local, 0, bytes));
   UML_CUDA(cudaDeviceSynchronize());
@@ -288,14 +314,14 @@ static int p2p_launch(int64_t n, const FusedUpdate& F, void* stream) {
   UML_REQUIRE(p2p.ready && n > 0 && n % 4 == 0 && n <= p2p.max_floats, "dp_allreduce_p2p: not initialised or bad size");
   ArPtrs P;
   memset(&P, 0, sizeof(P));
+  P.x = reinterpret_cast<const float*>(p2p.local);
+  P.out = reinterpret_cast<float*>(p2p.local) + p2p.max_floats;
   for (int p = 0; p < p2p.world; ++p) {
-    P.x[p] = reinterpret_cast<const float*>(p2p.peer[p]);
-    P.r[p] = reinterpret_cast<float*>(p2p.peer[p]) + p2p.max_floats;
-    P.flags[p] = reinterpret_cast<uint32_t*>(p2p.peer[p] + flags_offset(p2p.max_floats));
+    P.recv[p] = reinterpret_cast<uint4*>(p2p.peer[p] + recv_offset(p2p.max_floats));
+    P.rll[p] = reinterpret_cast<uint4*>(p2p.peer[p] + rll_offset(p2p.max_floats));
   }
   uint32_t* my = reinterpret_cast<uint32_t*>(p2p.local + flags_offset(p2p.max_floats));
-  unsigned int* counters = my + 2 * kMaxRanks;
-  int* failed = reinterpret_cast<int*>(my + 2 * kMaxRanks + 2);
+  int* failed = reinterpret_cast<int*>(my + kFlagWords);
   ++p2p.epoch;
   static long long timeout = 0;
   if (timeout == 0) {
@@ -303,8 +329,12 @@ static int p2p_launch(int64_t n, const FusedUpdate& F, void* stream) {
     const double sec = e ? atof(e) : 20.0;
     timeout = static_cast<long long>((sec > 0.01 ? sec : 0.01) * 2.0e9);  // clock64 ticks at ~2 GHz
   }
-  p2p_allreduce_kernel<<<kArBlocks, kArThreads, 0, uml::as_stream(stream)>>>(P, p2p.rank, p2p.world, n / 4, p2p.epoch, counters,
-                                                                              failed, timeout, F);
+  // block b owns units [b * sub * world, (b + 1) * sub * world) of the message (a unit = three float4), rank j reduces
+  // its j-th sub-slice
+  const int64_t n4 = n / 4, units = (n4 + 2) / 3;
+  const int64_t sub = (units + static_cast<int64_t>(kArBlocks) * p2p.world - 1) / (static_cast<int64_t>(kArBlocks) * p2p.world);
+  p2p_allreduce_kernel<<<kArBlocks, kArThreads, 0, uml::as_stream(stream)>>>(P, p2p.rank, p2p.world, n4, sub, p2p.epoch, failed,
+                                                                              timeout, F);
   UML_CUDA(cudaGetLastError());
   return 0;
 }
@@ -343,7 +373,7 @@ int uml_dp_p2p_failed(void) {
   if (!p2p.ready) return 0;
   int f = 0;
   const uint32_t* my = reinterpret_cast<const uint32_t*>(p2p.local + flags_offset(p2p.max_floats));
-  if (cudaMemcpy(&f, my + 2 * kMaxRanks + 2, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (cudaMemcpy(&f, my + kFlagWords, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   return f != 0;
 }
 

@@ -7,6 +7,7 @@
 // bf16 shadow of the weights (B operand of the next tcgen05 forward) is refreshed here, so neither
 // costs an extra trip through HBM.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "optim.cuh"
@@ -104,7 +105,12 @@ static int launch_adam(float* p, const float* parts, int n_parts, int64_t stride
                    (!g_out || al16(g_out));
   const int64_t work = vec ? n / 4 : n;
   // a multiple of the SM count; 8 CTAs of 256 threads keep 64 warps resident per SM
-  const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * 8));
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    const char* e = getenv("UML_ADAM_CTAS_PER_SM");
+    ctas_per_sm = e && atoi(e) > 0 ? atoi(e) : 8;
+  }
+  const int grid = static_cast<int>(std::min<int64_t>((work + 255) / 256, static_cast<int64_t>(sm_count()) * ctas_per_sm));
   __nv_bfloat16* sh = reinterpret_cast<__nv_bfloat16*>(shadow);
   if (vec)
     UML_CUDA(launch_kernel(adam_kernel<true>, dim3(grid), dim3(256), 0, st, 1, kPdlUpdate, p, parts, n_parts, stride, g2, w2, m, v, n,
