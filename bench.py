@@ -583,6 +583,105 @@ def run_gaussian(args):
     print(json.dumps(line))
 
 
+def run_eval(args):
+    """--workload eval: the evaluation sweep (a-11 / K7; reference finetune.py:291-315 `validate`) over test banks of the
+    named shapes, through the public ``finetune.validate`` call.  Unit = bank rows per second.  Three banks:
+      imagenet : 50 000 x 768, C = 1000  - the logits GEMM dominates -> tensor roofline (bf16 path)
+      sun397   : 19 850 x 512, C = 397   | the bank read dominates on the tensor-core path -> HBM roofline
+      food101  : 25 250 x 512, C = 101   |
+    each on the bf16 tensor-core path (what a model trained on that path uses) and on the exact fp32 path (what a run at the
+    reference's batch sizes uses).  ``value``: imagenet / bf16, device time of the K7 launches (CUDA events, L2 flushed
+    between repetitions); ``e2e``: wall clock of validate() calls including the read-back of (loss, hits)."""
+    from oracle import uml_oracle as O
+    import uml_b200  # noqa: F401
+    from uml_b200 import _lib, finetune as ft
+    from uml_b200.engine.datasets.utils import BankLoader, FeatureBank
+    from uml_b200.engine.models.head import UMLClip
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    peaks = measured_peaks()
+    K, Wm = args.steps, max(args.warmup, 3)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    g = torch.Generator().manual_seed(3)
+    cases, sampler = [], ClockSampler(0)
+    shapes = (("imagenet", 50_000, 768, 1000), ("sun397", 19_850, 512, 397), ("food101", 25_250, 512, 101))
+    first = True
+    for name, n, D, C in shapes:
+        x = torch.randn(n, D, generator=g)
+        x = x / x.norm(dim=1, keepdim=True)
+        y = torch.randint(0, C, (n,), generator=g)
+        bank = FeatureBank(x, y, dev)
+        model = UMLClip(f"synthetic:{D}", C, logit_scale_init=LOGIT).to(dev)
+        w = torch.randn(C, D, generator=g)
+        model.head.weight.data.copy_((w / w.norm(dim=1, keepdim=True)).to(dev))
+        loader = BankLoader(bank, 512, shuffle=False)
+        for prec in ("bf16", "fp32"):
+            model.precision = prec
+            for _ in range(Wm):
+                ft.validate(model, loader, device=dev)
+            n0 = _lib.LAUNCH_COUNT[0]
+            if first:
+                sampler.start()
+            ts = []
+            for _ in range(K):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ft.validate_enqueue(model, loader)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            launches = _lib.LAUNCH_COUNT[0] - n0
+            clocks = sampler.stop() if first else None
+            first = False
+            t0 = time.perf_counter()
+            for _ in range(K):
+                loss, acc = ft.validate(model, loader, device=dev)
+            wall = (time.perf_counter() - t0) / K
+            ms = sorted(ts)[len(ts) // 2]
+            flops, bytes_ = 2.0 * n * D * C, n * (D * (2 if prec == "bf16" else 4) + 8)
+            if prec == "bf16" and C >= 512:
+                roof = {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s"}
+            elif prec == "bf16":
+                roof = {"bound": "hbm", "achieved": bytes_ / (ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s"}
+            else:  # exact path: fp32 FMA pipe (148 SMs x 128 lanes x 2 flop x 1.965 GHz = 74.4 TFLOP/s nominal), not a measured peak
+                roof = {"bound": "fp32-fma (nominal)", "achieved": flops / (ms * 1e-3) / 1e12, "peak": 74.4, "unit": "TFLOP/s"}
+            roof["frac"] = roof["achieved"] / roof["peak"]
+            cases.append({"bank": name, "rows": n, "dim": D, "classes": C, "path": prec, "device_ms": ms, "rows_per_s": n / (ms * 1e-3),
+                          "e2e_ms": wall * 1e3, "e2e_rows_per_s": n / wall, "val_loss": loss, "val_acc": acc, "roofline": roof,
+                          "launches_per_call": launches / K, "clocks": clocks})
+        del bank, model
+    # CPU port on a sample of the imagenet bank
+    n_s = 4096
+    xs = torch.randn(n_s, 768, generator=g)
+    ys = torch.randint(0, 1000, (n_s,), generator=g)
+    st = O.HeadState(head=torch.randn(1000, 768, generator=g), img_scale=math.exp(LOGIT), txt_scale=math.exp(LOGIT))
+    torch.set_num_threads(os.cpu_count() or 1)
+    O.validate(st, xs, ys, 512)
+    t0, reps = time.perf_counter(), 0
+    while time.perf_counter() - t0 < min(args.cpu_seconds, 10.0):
+        O.validate(st, xs, ys, 512)
+        reps += 1
+    cpu = reps * n_s / (time.perf_counter() - t0)
+    head = cases[0]
+    line = {"metric": "UML eval rows/sec (validate over a test bank)", "value": head["rows_per_s"], "unit": "rows/s", "n_gpus": 1,
+            "steps": K, "warmup": Wm, "ms_per_step": head["device_ms"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "eval: validate() over test banks - imagenet 50000x768 C=1000 (headline, bf16 path), sun397 "
+                                   "19850x512 C=397, food101 25250x512 C=101; each on the bf16 tensor-core and the exact fp32 path",
+                       "l2_policy": "256 MB written between repetitions (the 77 MB bf16 shadow of the largest bank would otherwise sit in L2)"},
+            "clocks": head["clocks"], "e2e": {"value": head["e2e_rows_per_s"], "unit": "rows/s", "h2d_bytes_per_step": 0,
+                                              "d2h_bytes_per_step": 8, "note": "the bank is resident; per call the host reads (loss, hits)"},
+            "gpu_launches": int(sum(c["launches_per_call"] for c in cases) * K),
+            "roofline": dict(head["roofline"], kernel="head_fwd_ce_x (evaluation mode) + eval_reduce", traffic=None),
+            "cpu_baseline": {"value": cpu, "unit": "rows/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"oracle validate() on a {n_s}-row sample of the imagenet bank shape, repeated for 10 s"},
+            "eval_cases": [{k: v for k, v in c.items() if k != "clocks"} for c in cases]}
+    sampler.close()
+    print(json.dumps(line))
+
+
 def run_sweep(args):
     """--workload cfg2_sweep: the reference's real few-shot workload - the hyper-parameter sweep of preset `clip_linear`
     (lr x weight decay, engine/optimizer/default.py:17-31) times its alpha sweep over the SAME cfg2 banks - with
@@ -733,7 +832,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1", "cfg2_sweep"])
+    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1", "cfg2_sweep", "eval"])
     ap.add_argument("--heads", type=int, default=30, help="cfg2_sweep: hyper-parameter combinations trained in lock step (<= 32)")
     ap.add_argument("--ref-device", type=str, default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: 'cuda' times the same port as eager PyTorch on one GPU (collate on the host, "
@@ -742,6 +841,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload == "eval":
+        if args.impl == "reference":
+            raise SystemExit("bench.py --workload eval runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
+        return run_eval(args)
     if args.workload == "cfg1":
         if args.impl == "reference" or not torch.cuda.is_available():
             raise SystemExit("bench.py --workload cfg1 runs the GPU arm only (its line carries the CPU port as cpu_baseline)")

@@ -135,6 +135,18 @@ int uml_eval_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t 
 int uml_eval_reduce(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
                     int64_t batch_size, float* out_loss /*[1]*/, int32_t* out_correct /*[1]*/, void* stream);
 
+/* The same for the heads of a sweep group over ONE bank in one launch each (the reference's sweep loop calls validate once
+ * per combination, finetune.py:406-448 + 291-315): head h reads its weights at W + head_ids[h] * w_stride (floats) and
+ * fills rows [h * n_rows, (h + 1) * n_rows) of row_loss / row_pred; uml_eval_reduce_group writes out_loss[h] /
+ * out_correct[h].  head_ids / scales: HOST arrays of n_heads <= 32 entries.                              */
+int uml_eval_group_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t n_rows, int32_t dim, const float* W,
+                       int64_t w_stride, const int32_t* head_ids /*host*/, const float* scales /*host*/, int32_t n_heads,
+                       int32_t n_classes, float* row_loss /*[n_heads, n_rows]*/, int32_t* row_pred /*[n_heads, n_rows]*/,
+                       void* stream);
+int uml_eval_reduce_group(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
+                          int64_t batch_size, int32_t n_heads, float* out_loss /*[n_heads]*/,
+                          int32_t* out_correct /*[n_heads]*/, void* stream);
+
 /* ---- K8  gradient diagnostics (finetune.py:200-206): out = {dot, |a|^2, |b|^2, sign agreement} */
 #define UML_DIAG_BLOCKS 296
 int uml_grad_diag(const float* a, const float* b, int64_t n, float* workspace /* >= 4*UML_DIAG_BLOCKS floats */,

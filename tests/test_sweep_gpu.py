@@ -142,3 +142,43 @@ def test_sweep_run_matches_single_head_engine():
         assert o1["iter"] == o2["iter"]
         a, b = o1["model"]["head.weight"], o2["model"]["head.weight"]
         assert float((a - b).abs().max() / a.abs().max()) < 1e-4
+
+
+def test_batched_group_evaluation_matches_per_head_validate():
+    """validate_group_enqueue (one logits + argmax launch and one reduction launch for all running heads of a group over
+    the same bank) against validate_enqueue head by head: identical losses and hit counts (same kernel, same order)."""
+    import torch
+    from uml_b200 import finetune as ft, ops
+    from uml_b200.engine.datasets.utils import BankLoader, FeatureBank
+
+    class _Head:
+        def __init__(self, w, s):
+            self.head = type("H", (), {})()
+            self.head.weight = torch.nn.Parameter(w, requires_grad=False)
+            self.img_proj = None
+            self.precision = "fp32"
+            self._s = s
+
+        def scales(self):
+            return self._s, self._s
+
+    class _Group:
+        pass
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(9)
+    n, D, C, K = 1234, 96, 37, 5
+    bank = FeatureBank(torch.randn(n, D, generator=g), torch.randint(0, C, (n,), generator=g), dev)
+    stride = (C * D + 3) // 4 * 4
+    grp = _Group()
+    grp.W = torch.randn(K, stride, generator=g).to(dev)
+    grp.C, grp.D = C, D
+    models = [_Head(grp.W[k, :C * D].view(C, D), 3.0 + k) for k in range(K)]
+    loaders = [BankLoader(bank, 100, shuffle=False) for _ in range(K)]
+    heads = [0, 2, 3]
+    got = ft.validate_group_enqueue(grp, models, heads, lambda k: loaders[k])
+    for (loss, hits, rows), k in zip(got, heads):
+        l1, h1, n1 = ft.validate_enqueue(models[k], loaders[k])
+        assert rows == n1 == n
+        assert float(loss.item()) == float(l1.item())
+        assert int(hits.item()) == int(h1.item())

@@ -329,11 +329,23 @@ __device__ __forceinline__ void merge(RowStat& a, const RowStat& b) {
   a.lab += b.lab;
 }
 
+// Heads of a sweep group evaluated over the same bank in one launch (blockIdx.y): head h reads its weights at
+// W + id[h] * w_stride and writes rows [h * n_rows, (h + 1) * n_rows) of the outputs.  A single head is {n = 1, id = {0}}.
+struct EvalHeads {
+  int n;
+  int id[UML_SWEEP_MAX_HEADS];
+  float scale[UML_SWEEP_MAX_HEADS];
+};
+
 __global__ void __launch_bounds__(256)
     eval_kernel(const float* __restrict__ X, int64_t ldx, const int64_t* __restrict__ labels, int64_t n_rows, int D,
-                const float* __restrict__ W, int C, float scale, float* __restrict__ row_loss,
-                int32_t* __restrict__ row_pred) {
+                const float* __restrict__ W0, int64_t w_stride, int C, EvalHeads heads, float* __restrict__ row_loss0,
+                int32_t* __restrict__ row_pred0) {
   constexpr int BM = 32, BN = 64, TM = 2, TN = 4, kBK = 16;
+  const float* __restrict__ W = W0 + heads.id[blockIdx.y] * w_stride;
+  const float scale = heads.scale[blockIdx.y];
+  float* __restrict__ row_loss = row_loss0 + blockIdx.y * n_rows;
+  int32_t* __restrict__ row_pred = row_pred0 + blockIdx.y * n_rows;
   __shared__ float Xs[kBK][BM + 4];
   __shared__ float Ws[kBK][BN + 4];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -424,6 +436,10 @@ __global__ void __launch_bounds__(256)
                        const int64_t* __restrict__ labels, int64_t n_rows, int64_t bs, float* __restrict__ out_loss,
                        int32_t* __restrict__ out_correct) {
   __shared__ float sh[8];
+  row_loss += blockIdx.x * n_rows;  // (one CTA per head of a group)
+  row_pred += blockIdx.x * n_rows;
+  out_loss += blockIdx.x;
+  out_correct += blockIdx.x;
   const int64_t n_batches = (n_rows + bs - 1) / bs;
   float acc = 0.f;
   int hits = 0;
@@ -594,8 +610,45 @@ int uml_eval_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t 
   UML_REQUIRE(feats && labels && W && row_loss && row_pred && dim > 0 && n_classes > 0 && n_rows >= 0,
               "eval_f32: bad arguments");
   if (n_rows == 0) return 0;
+  EvalHeads h;
+  memset(&h, 0, sizeof(h));
+  h.n = 1;
+  h.scale[0] = scale;
   eval_kernel<<<static_cast<unsigned>((n_rows + 31) / 32), 256, 0, as_stream(stream)>>>(
-      feats, ld, labels, n_rows, dim, W, n_classes, scale, row_loss, row_pred);
+      feats, ld, labels, n_rows, dim, W, 0, n_classes, h, row_loss, row_pred);
+  UML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uml_eval_group_f32(const float* feats, int64_t ld, const int64_t* labels, int64_t n_rows, int32_t dim, const float* W,
+                       int64_t w_stride, const int32_t* head_ids, const float* scales, int32_t n_heads, int32_t n_classes,
+                       float* row_loss, int32_t* row_pred, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(feats && labels && W && head_ids && scales && row_loss && row_pred && dim > 0 && n_classes > 0 && n_rows >= 0 &&
+                  n_heads >= 1 && n_heads <= UML_SWEEP_MAX_HEADS && w_stride >= static_cast<int64_t>(dim) * n_classes,
+              "eval_group_f32: bad arguments");
+  if (n_rows == 0) return 0;
+  EvalHeads h;
+  memset(&h, 0, sizeof(h));
+  h.n = n_heads;
+  for (int i = 0; i < n_heads; ++i) {
+    UML_REQUIRE(head_ids[i] >= 0, "eval_group_f32: negative head id");
+    h.id[i] = head_ids[i];
+    h.scale[i] = scales[i];
+  }
+  eval_kernel<<<dim3(static_cast<unsigned>((n_rows + 31) / 32), static_cast<unsigned>(n_heads)), 256, 0, as_stream(stream)>>>(
+      feats, ld, labels, n_rows, dim, W, w_stride, n_classes, h, row_loss, row_pred);
+  UML_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int uml_eval_reduce_group(const float* row_loss, const int32_t* row_pred, const int64_t* labels, int64_t n_rows,
+                          int64_t batch_size, int32_t n_heads, float* out_loss, int32_t* out_correct, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(row_loss && row_pred && out_loss && out_correct && n_rows > 0 && batch_size > 0 && n_heads >= 1,
+              "eval_reduce_group: bad arguments");
+  eval_reduce_kernel<<<static_cast<unsigned>(n_heads), 256, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size,
+                                                                                  out_loss, out_correct);
   UML_CUDA(cudaGetLastError());
   return 0;
 }

@@ -130,7 +130,10 @@ def validate_enqueue(model, val_loader):
             x16 = z16
         segs = ops.tc_segments([n], [s_img], [1.0])
         # hit flags instead of predicted classes: the kernel needs no index tracking for them
-        ops.head_fwd_ce_bf16(x16, ops.cast_bf16(W), bank.labels32(), segs, None, row_loss, row_correct=row_pred)
+        tws = getattr(bank, "_eval_tile_ws", None)  # scratch of the exchange forward kernel, kept with the bank
+        if tws is None or tws.numel() < 16 + ((n + 255) // 256) * 264 + n * 32:
+            tws = bank._eval_tile_ws = ops.tile_workspace(n, dev)
+        ops.head_fwd_ce_bf16(x16, ops.cast_bf16(W), bank.labels32(), segs, None, row_loss, row_correct=row_pred, tile_ws=tws)
         hit_labels = None
     else:
         hit_labels = bank.labels
@@ -140,6 +143,34 @@ def validate_enqueue(model, val_loader):
     out_hits = torch.empty(1, device=dev, dtype=torch.int32)
     ops.eval_reduce(row_loss, row_pred, hit_labels, bs, out_loss, out_hits)
     return out_loss, out_hits, n
+
+
+def validate_group_enqueue(group, models, heads, val_loader_of):
+    """``validate_enqueue`` for the running heads of a sweep group (``engine/sweep.py`` HeadGroup): heads whose
+    loaders share one bank and batch size are evaluated by ONE logits + argmax launch and ONE reduction launch (the head is
+    a grid dimension, the weights are read straight from the group's slab) instead of two launches per head.  Returns one
+    ``(loss, hits, n_rows)`` triple per head, in the order of ``heads``; the tensors are views of per-bank result vectors
+    that are read back together by the caller."""
+    out = [None] * len(heads)
+    by_bank = {}
+    for pos, k in enumerate(heads):
+        ld = val_loader_of(k)
+        iter(ld)  # every DataLoader iterator draws a base seed from its generator: keep each head's stream aligned
+        by_bank.setdefault((id(ld.bank), ld.batch_size), []).append((pos, k, ld))
+    for (_, bs), members in by_bank.items():
+        bank = members[0][2].bank
+        n, dev = len(bank), bank.device
+        ids = [k for _, k, _ in members]
+        scales = [float(models[k].scales()[0]) for k in ids]
+        row_loss = torch.empty((len(ids), n), device=dev)
+        row_pred = torch.empty((len(ids), n), device=dev, dtype=torch.int32)
+        ops.eval_group_f32(bank.features, bank.labels, group.W, group.W.stride(0), ids, scales, group.C, row_loss, row_pred)
+        out_loss = torch.empty(len(ids), device=dev)
+        out_hits = torch.empty(len(ids), device=dev, dtype=torch.int32)
+        ops.eval_reduce_group(row_loss, row_pred, bank.labels, bs, out_loss, out_hits)
+        for j, (pos, _, _) in enumerate(members):
+            out[pos] = (out_loss[j:j + 1], out_hits[j:j + 1], n)
+    return out
 
 
 def validate(model, val_loader, device="cuda"):
@@ -474,8 +505,11 @@ def train_group(models, image_loaders, text_loaders, val_loaders, test_loaders, 
             flush()
             heads = [k for k in range(K) if running[k]]
             # every head's evaluation is enqueued before anything is read back: one synchronisation per round
-            results = [validate_enqueue(models[k], val_loaders[k]) for k in heads]
-            tests = [validate_enqueue(models[k], test_loaders[k]) if test_loaders[k] is not None else None for k in heads]
+            # the same draw order per head as the sequential loop (val, then test): each head has its own generator
+            results = validate_group_enqueue(group, models, heads, lambda k: val_loaders[k])
+            with_test = [k for k in heads if test_loaders[k] is not None]
+            t_res = dict(zip(with_test, validate_group_enqueue(group, models, with_test, lambda k: test_loaders[k]))) if with_test else {}
+            tests = [t_res.get(k) for k in heads]
             snaps = group.W.clone()
             losses = torch.cat([r[0] for r in results]).cpu().tolist()
             hits = torch.cat([r[1] for r in results]).cpu().tolist()

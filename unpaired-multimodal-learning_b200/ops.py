@@ -267,6 +267,28 @@ def eval_reduce(row_loss, row_pred, labels, batch_size, out_loss, out_correct):
                                       int(batch_size), out_loss.data_ptr(), out_correct.data_ptr(), _stream()))
 
 
+def eval_group_f32(feats, labels, W_slab, w_stride, head_ids, scales, n_classes, row_loss, row_pred):
+    """Evaluation of several heads of a sweep group over one bank in ONE launch: head h's weights at
+    ``W_slab.data_ptr() + head_ids[h] * w_stride`` floats; ``row_loss`` / ``row_pred``: [n_heads, n_rows]."""
+    import ctypes as C
+    _need(feats, torch.float32, "feats")
+    _need(labels, torch.int64, "labels")
+    _need(W_slab, torch.float32, "W")
+    k = len(head_ids)
+    ids = (C.c_int32 * k)(*[int(h) for h in head_ids])
+    sc = (C.c_float * k)(*[float(x) for x in scales])
+    check(_lib.load().uml_eval_group_f32(feats.data_ptr(), feats.stride(0), labels.data_ptr(), feats.shape[0], feats.shape[1],
+                                         W_slab.data_ptr(), int(w_stride), ids, sc, k, int(n_classes), row_loss.data_ptr(),
+                                         row_pred.data_ptr(), _stream()))
+
+
+def eval_reduce_group(row_loss, row_pred, labels, batch_size, out_loss, out_correct):
+    """row_loss / row_pred: [n_heads, n_rows] -> out_loss / out_correct: [n_heads]."""
+    check(_lib.load().uml_eval_reduce_group(row_loss.data_ptr(), row_pred.data_ptr(), _ptr(labels), row_loss.shape[1],
+                                            int(batch_size), row_loss.shape[0], out_loss.data_ptr(), out_correct.data_ptr(),
+                                            _stream()))
+
+
 def grad_diag(a, b, workspace, out4):
     check(_lib.load().uml_grad_diag(a.data_ptr(), b.data_ptr(), a.numel(), workspace.data_ptr(), out4.data_ptr(),
                                     _stream()))
@@ -284,15 +306,21 @@ def tc_segments(rows: Sequence[int], scales: Sequence[float], weights: Sequence[
     return s
 
 
+def tile_workspace(max_rows: int, device):
+    """Zero-initialised UML_TILE_WS_FLOATS(max_rows) scratch of the tensor-core forward (launch epoch, exchange records)."""
+    return torch.zeros(16 + ((max_rows + 255) // 256) * 264 + max_rows * 32, device=device, dtype=torch.float32)
+
+
 def head_fwd_ce_bf16(X, W_bf16, labels_i32, segs: TcSegments, ws: Optional[HeadWorkspace], row_loss=None, row_pred=None,
-                     row_correct=None, row_dscale=None, n_rows: Optional[int] = None, stats=None):
-    """``stats`` (optional, training mode only): [nseg, 4] fp32 record the fix-up launch fills with the per-run
-    statistics, instead of a separate reduce_tile_stats launch."""
+                     row_correct=None, row_dscale=None, n_rows: Optional[int] = None, stats=None, tile_ws=None):
+    """``stats`` (optional, training mode only): [nseg, 4] fp32 record of the per-run statistics.  ``ws=None`` is the
+    evaluation mode (no G); with ``tile_ws`` (``tile_workspace(n_rows)``) it runs the exchange kernel, else the
+    chunk-sequential one."""
     _need(X, torch.bfloat16, "X")
     _need(W_bf16, torch.bfloat16, "W")
     _need(labels_i32, torch.int32, "labels")
     n_rows = X.shape[0] if n_rows is None else n_rows
-    G, ldg, fac = (ws.G.data_ptr(), ws.ldg, ws.fac.data_ptr()) if ws is not None else (None, 0, None)
+    G, ldg, fac = (ws.G.data_ptr(), ws.ldg, ws.fac.data_ptr()) if ws is not None else (None, 0, _ptr(tile_ws))
     check(_lib.load().uml_head_fwd_ce_bf16(X.data_ptr(), n_rows, X.shape[1], W_bf16.data_ptr(), W_bf16.shape[0],
                                            labels_i32.data_ptr(), C.byref(segs), G, ldg, _ptr(row_loss),
                                            _ptr(row_pred), _ptr(row_correct), _ptr(row_dscale), fac,
