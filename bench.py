@@ -826,13 +826,108 @@ def run_sweep(args):
     print(json.dumps(line))
 
 
+def run_ratio(args):
+    """--workload cfg5: BASELINE config 5, the text:image conversion-ratio sweep (configs/ratio_sweep_sun397.yaml) on
+    ViT-B/16-shaped (512-d) few-shot banks: SUN397 (397 classes) and Food101 (101 classes), 4 image shots per class,
+    text:image ratios 0 (image only), 1, 2, 4 and 7.5 (text_shot 0 / 4 / 8 / 16 / 30 of the 30 prompts per class, selected by
+    ``TextTensorDataset(n_shots=...)`` like the reference, engine/datasets/utils.py:55-98), preset ``clip_linear``'s six
+    lr x wd combinations per point, batch 32 per modality.  Every point is ONE public ``train_group()`` call (sweep-level
+    batching); value = rows consumed by all heads of all points per second of those calls' timed regions (wall clock,
+    stream-synchronised: sampler, permutation uploads and the statistics read-back included - the same number is the e2e
+    figure, there is no separate device-resident arm)."""
+    import contextlib
+    import io
+    import uml_b200  # noqa: F401
+    from uml_b200 import _lib, finetune as ft
+    from uml_b200.engine.datasets.utils import BankLoader, FeatureBank, TextTensorDataset
+    from uml_b200.engine.models.head import UMLClip, get_zero_shot_weights
+    from uml_b200.engine.optimizer.optim import build_optimizer
+    from uml_b200.engine.optimizer.scheduler import build_lr_scheduler
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks = measured_peaks()
+    K, W = args.steps, max(args.warmup, 3)
+    D, B, shots = 512, 32, 4
+    grid = [(lr, wd) for lr in (1e-3, 1e-4) for wd in (0.0, 0.01, 0.001)]
+    H = len(grid)
+    g = torch.Generator().manual_seed(5)
+    points, rows_total, secs_total, launches0 = [], 0, 0.0, _lib.LAUNCH_COUNT[0]
+    sampler = ClockSampler(0)
+    sampler.start()
+    for name, C in (("sun397", 397), ("food101", 101)):
+        xi = torch.randn(C * shots, D, generator=g)
+        yi = torch.arange(C * shots) % C
+        xt_all = torch.randn(C * 30, D, generator=g)
+        yt_all = torch.arange(C * 30) % C
+        xv, yv = torch.randn(C * 4, D, generator=g), torch.arange(C * 4) % C
+        img_bank, val_bank = FeatureBank(xi, yi, dev), FeatureBank(xv, yv, dev)
+        for text_shot in (0, 4, 8, 16, 30):
+            with contextlib.redirect_stdout(io.StringIO()):
+                torch.manual_seed(1)
+                tds = TextTensorDataset(xt_all, yt_all, torch.zeros(C * 30, dtype=torch.int64), n_shots=max(text_shot, 1))
+                txt_bank = FeatureBank.from_text_dataset(tds, dev)
+                W0 = get_zero_shot_weights(txt_bank, C, D)
+                ms_, os_, ss, il, tl, vl = [], [], [], [], [], []
+                for k, (lr, wd) in enumerate(grid):
+                    m = UMLClip(f"synthetic:{D}", C, logit_scale_init=LOGIT)
+                    m.precision = "fp32"
+                    m.load_state_dict({"head.weight": W0.clone()})
+                    m.to(dev)
+                    o = build_optimizer(m.parameters(), "adamw", lr, wd)
+                    rng = torch.Generator().manual_seed(100 + k)
+                    ms_.append(m); os_.append(o)
+                    ss.append(build_lr_scheduler(o, "cosine", 50, 12800, warmup_type="linear", warmup_lr=1e-5))
+                    il.append(BankLoader(img_bank, B, shuffle=True, rng=rng))
+                    tl.append(BankLoader(txt_bank, B, shuffle=True, rng=rng) if text_shot else None)
+                    vl.append(BankLoader(val_bank, 32, shuffle=False, rng=rng))
+                trs = [None] * H
+                trs[0] = {"indices": False, "timing": {"warmup": W}}
+                ft.train_group(ms_, il, tl if text_shot else None, vl, None, os_, ss, device=dev, max_iters=W + K,
+                               alphas=[1.0] * H, eval_freq=10 ** 9, patience=5, traces=trs)
+            t = trs[0]["timing"]
+            rows = H * t["iters"] * (B + (B if text_shot else 0))
+            rows_total += rows
+            secs_total += t["seconds"]
+            points.append({"dataset": name, "classes": C, "train_shot": shots, "text_shot": text_shot, "ratio": text_shot / shots,
+                           "text_bank_rows": len(txt_bank) if text_shot else 0, "heads": H, "ms_per_step_of_all_heads": t["seconds"] / t["iters"] * 1e3,
+                           "samples_per_s": rows / t["seconds"]})
+    clocks = sampler.stop()
+    sampler.close()
+    launches = _lib.LAUNCH_COUNT[0] - launches0
+    value = rows_total / secs_total
+    # whole-step algorithmic HBM bytes of a head-step: W, m, v read and written (24 B / parameter) + G and rows once
+    bytes_total = sum(p["heads"] * K * (24.0 * p["classes"] * D + 4.0 * (B + (B if p["text_shot"] else 0)) * (p["classes"] + D)) for p in points)
+    roof = {"bound": "hbm", "kernel": "whole step (4 launches per step of a group)", "achieved": bytes_total / secs_total / 1e9,
+            "peak": peaks["hbm"], "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
+            "note": "six 0.2-0.8 MB heads per group: the whole working set sits in L2 and a step is launch-latency bound"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    line = {"metric": "UML train samples/sec (img+text)", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": K, "warmup": W,
+            "ms_per_step": secs_total / (len(points) * K) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5: SUN397 / Food101 conversion-ratio sweep (text:image 0-7.5x) on ViT-B/16-shaped 512-d few-shot "
+                                   "banks, preset clip_linear (6 combinations per point in lock step), batch 32 per modality",
+                       "points": len(points), "heads_per_point": H, "l2_policy": "working set fits L2 (few-shot banks)"},
+            "clocks": clocks,
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": H * 2 * 16,
+                    "note": "value IS the end-to-end figure here: public train_group() calls, wall clock"},
+            "gpu_launches": launches, "roofline": roof, "ratio_points": points}
+    try:
+        r = cpu_reference_run(dict(WORKLOADS["cfg2"], classes=397, n_img=397 * shots, n_txt=397 * 30), 10 ** 6, 1, budget_s=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"] + " (sun397 shapes, one combination)"}
+    except Exception as e:
+        line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1", "cfg2_sweep", "eval"])
+    ap.add_argument("--workload", type=str, default="cfg3", choices=sorted(WORKLOADS) + ["cfg1", "cfg2_sweep", "cfg5", "eval"])
     ap.add_argument("--heads", type=int, default=30, help="cfg2_sweep: hyper-parameter combinations trained in lock step (<= 32)")
     ap.add_argument("--ref-device", type=str, default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: 'cuda' times the same port as eager PyTorch on one GPU (collate on the host, "
@@ -845,6 +940,10 @@ def main():
         if args.impl == "reference":
             raise SystemExit("bench.py --workload eval runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
         return run_eval(args)
+    if args.workload == "cfg5":
+        if args.impl == "reference" or not torch.cuda.is_available():
+            raise SystemExit("bench.py --workload cfg5 runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
+        return run_ratio(args)
     if args.workload == "cfg1":
         if args.impl == "reference" or not torch.cuda.is_available():
             raise SystemExit("bench.py --workload cfg1 runs the GPU arm only (its line carries the CPU port as cpu_baseline)")

@@ -406,3 +406,48 @@ def test_take_run_ragged_shapes_property():
             assert g1.get_state().equal(g2.get_state())  # both consumed the same draws
 
     check()
+
+
+def test_text_selection_through_the_class_index_matches_the_mask_per_class_form(tmp_path):
+    """n-shot selection and class averaging walk the class-sorted row index (computed here, or read from a v2 bank
+    file - SURVEY 8f-2) and must pick exactly the rows the reference's mask-per-class loops pick
+    (engine/datasets/utils.py:76-98), with the same RNG draws, classes without rows included."""
+    import torch
+    from uml_b200 import features as F
+    from uml_b200.engine.datasets.utils import TextTensorDataset
+
+    g = torch.Generator().manual_seed(4)
+    n, d, c = 700, 24, 41
+    labels = torch.randint(0, c, (n,), generator=g)
+    labels[labels == 7] = 8      # a class id without rows
+    labels[labels == 40] = 3     # ... and the largest one
+    feats = torch.randn(n, d, generator=g)
+    eot = torch.randint(0, 77, (n,), generator=g)
+
+    def reference_select(k):
+        out = []
+        for cls in torch.unique(labels):
+            inds = (labels == cls).nonzero(as_tuple=True)[0]
+            out.append(inds[torch.randperm(inds.size(0))[: min(k, inds.size(0))]])
+        return torch.cat(out)
+
+    path = str(tmp_path / "text.bank2")
+    F.write_bank_v2(path, feats, labels, eot_indices=eot)
+    t, _, _ = F.load_bank_v2(path, "cpu")
+    for k in (1, 3, 64):
+        torch.manual_seed(11)
+        want = reference_select(k)
+        state_after = torch.random.get_rng_state()
+        for kw in ({}, {"class_order": t["class_order"], "class_starts": t["class_starts"]}):
+            torch.manual_seed(11)
+            ds = TextTensorDataset(feats, labels, eot, n_shots=k, **kw)
+            assert torch.equal(ds.label_tensor, labels[want]) and torch.equal(ds.input_tensor, feats[want])
+            assert torch.equal(ds.eot_indices, eot[want])
+            assert torch.equal(torch.random.get_rng_state(), state_after)   # the same number of draws
+    for kw in ({}, {"class_order": t["class_order"], "class_starts": t["class_starts"]}):
+        ds = TextTensorDataset(feats, labels, eot, n_shots="average", **kw)
+        classes = torch.unique(labels)
+        assert torch.equal(ds.label_tensor, classes)
+        want_mean = torch.stack([feats[labels == cls].mean(0) for cls in classes])
+        torch.testing.assert_close(ds.input_tensor, want_mean, rtol=1e-5, atol=1e-6)
+        assert torch.equal(ds.eot_indices, torch.stack([eot[labels == cls][0] for cls in classes]))

@@ -30,44 +30,66 @@ class TextTensorDataset(torch.utils.data.Dataset):
     ``randperm`` per class, classes in ``torch.unique`` order), ``'average'`` replaces each class by
     its mean row.  Exposes ``input_tensor``, ``label_tensor``, ``eot_indices``."""
 
-    def __init__(self, input_tensor, label_tensor, eot_indices, n_shots=None):
+    def __init__(self, input_tensor, label_tensor, eot_indices, n_shots=None, class_order=None, class_starts=None):
+        """``class_order`` / ``class_starts`` (optional): the class-sorted row index a v2 bank file carries
+        (``features.write_bank_v2``: row ids sorted by class, stable; offsets per class id).  Selection and averaging
+        walk that index - one pass over the rows - instead of building a boolean mask per class; without it the index is
+        computed here once.  The rows themselves may live on the device: they are gathered / reduced there."""
         if n_shots is None:
             picked = (input_tensor, label_tensor, eot_indices)
         elif isinstance(n_shots, int) and not isinstance(n_shots, bool):
-            picked = self._subsample(input_tensor, label_tensor, eot_indices, n_shots)
+            picked = self._subsample(input_tensor, label_tensor, eot_indices, n_shots, class_order, class_starts)
             print(f"=> Using {n_shots} text shots per class, with total of {picked[1].shape[0]} samples")
         elif isinstance(n_shots, str) and n_shots.lower() == "average":
-            picked = self._class_means(input_tensor, label_tensor, eot_indices)
+            picked = self._class_means(input_tensor, label_tensor, eot_indices, class_order, class_starts)
             print(f"=> Averaging text features per class, with total of {picked[1].shape[0]} samples")
         else:
             raise ValueError("n_shots must be an int, None, or 'average'")
         self.input_tensor, self.label_tensor, self.eot_indices = picked
 
     @staticmethod
-    def _subsample(feats, labels, eot, k):
+    def _class_index(labels, class_order, class_starts):
+        """(order, starts) on the host: ``order[starts[c]:starts[c + 1]]`` = the rows of class c in ascending row order -
+        what ``(labels == c).nonzero()`` yields in the reference (engine/datasets/utils.py:78-79)."""
+        if class_order is not None and class_starts is not None:
+            return class_order.to("cpu", torch.int64), class_starts.to("cpu", torch.int64)
+        lab = labels.to("cpu", torch.int64)
+        n_classes = int(lab.max()) + 1 if lab.numel() else 0
+        starts = torch.zeros(n_classes + 1, dtype=torch.int64)
+        if lab.numel():
+            starts[1:] = torch.cumsum(torch.bincount(lab, minlength=n_classes), 0)
+        return torch.argsort(lab, stable=True), starts
+
+    @staticmethod
+    def _subsample(feats, labels, eot, k, class_order=None, class_starts=None):
+        order, starts = TextTensorDataset._class_index(labels, class_order, class_starts)
+        counts = (starts[1:] - starts[:-1]).tolist()
+        lo = starts.tolist()
         chosen = []
-        for cls in torch.unique(labels):
-            members = torch.nonzero(labels == cls, as_tuple=True)[0]
-            order = torch.randperm(members.numel())  # global generator, like the reference
-            chosen.append(members[order[: min(k, members.numel())]])
-        chosen = torch.cat(chosen)
+        for cls, cnt in enumerate(counts):  # classes in ascending id = torch.unique order; absent classes draw nothing
+            if cnt == 0:
+                continue
+            perm = torch.randperm(cnt)      # global generator, one draw per present class - the reference's RNG protocol
+            chosen.append(order[lo[cls]:lo[cls] + cnt][perm[: min(k, cnt)]])
+        chosen = torch.cat(chosen) if chosen else torch.zeros(0, dtype=torch.int64)
         if isinstance(feats, list):
             feats = [feats[i] for i in chosen.tolist()]
         else:
-            feats = feats[chosen]
-        return feats, labels[chosen], eot[chosen]
+            feats = feats[chosen.to(feats.device)]  # a device-resident bank is gathered on the device
+        return feats, labels[chosen.to(labels.device)], eot[chosen.to(eot.device)]
 
     @staticmethod
-    def _class_means(feats, labels, eot):
-        classes = torch.unique(labels)
-        # one sorted pass instead of a boolean mask per class
-        order = torch.argsort(labels, stable=True)
-        sorted_labels = labels[order]
-        counts = torch.bincount(sorted_labels, minlength=int(classes.max()) + 1)[classes]
-        sums = torch.zeros(int(classes.max()) + 1, feats.shape[1], dtype=feats.dtype).index_add_(0, labels, feats)
-        means = sums[classes] / counts.unsqueeze(1).to(feats.dtype)
-        first = order[torch.cumsum(counts, 0) - counts]
-        return means, classes, eot[first]
+    def _class_means(feats, labels, eot, class_order=None, class_starts=None):
+        order, starts = TextTensorDataset._class_index(labels, class_order, class_starts)
+        counts = starts[1:] - starts[:-1]
+        classes = torch.nonzero(counts > 0, as_tuple=True)[0]
+        dev = feats.device
+        lab_dev = labels.to(dev, torch.int64)
+        # one segmented sum over the rows (on the device when the bank lives there) instead of a boolean mask per class
+        sums = torch.zeros(counts.numel(), feats.shape[1], dtype=feats.dtype, device=dev).index_add_(0, lab_dev, feats)
+        means = sums[classes.to(dev)] / counts[classes].to(dev).unsqueeze(1).to(feats.dtype)
+        first = order[starts[:-1][classes]]
+        return means, classes.to(labels.device).to(labels.dtype), eot[first.to(eot.device)]
 
     def __getitem__(self, i):
         return self.input_tensor[i], self.label_tensor[i], self.eot_indices[i]

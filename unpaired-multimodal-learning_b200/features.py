@@ -46,6 +46,17 @@ def _check_rows(d, what):
 
 
 def load_text_bank(path):
+    """The text bank dict of the reference's layout (features.py:152-184 there).  When a fresh v2 file sits next to it
+    (``<stem>.bank2``, ``convert_bank``) the rows come from that file - no unpickling - together with its class-sorted row
+    index (``class_order`` / ``class_starts``), which ``TextTensorDataset`` consumes for n-shot selection / averaging."""
+    v2 = os.path.splitext(path)[0] + ".bank2"
+    if os.path.exists(v2) and (not os.path.exists(path) or os.path.getmtime(v2) >= os.path.getmtime(path)):
+        t, _, meta = load_bank_v2(v2, "cpu", sections=("features", "labels", "eot_indices", "class_order", "class_starts"))
+        d = dict(meta or {})
+        d.update(t)
+        if "eot_indices" not in d:
+            d["eot_indices"] = torch.zeros(d["labels"].shape[0], dtype=torch.int64)
+        return _check_rows(d, v2)
     d = torch.load(path, map_location="cpu")
     for k in ("features", "labels", "eot_indices"):
         if k not in d:

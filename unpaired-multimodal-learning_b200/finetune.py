@@ -817,7 +817,10 @@ def main(args, alphas=None):
         shots = args.text_shot
         if shots is not None and shots != "average":
             shots = int(shots)
-        text_ds = TextTensorDataset(tf["features"], tf["labels"], tf["eot_indices"], n_shots=shots)
+        # a v2 file next to the v1 text bank (features.convert_bank) carries the class-sorted row index: the per-class
+        # selection / averaging then walks it instead of masking the labels once per class
+        text_ds = TextTensorDataset(tf["features"], tf["labels"], tf["eot_indices"], n_shots=shots,
+                                    class_order=tf.get("class_order"), class_starts=tf.get("class_starts"))
 
         image_encoder = args.clip_encoder if args.use_clip else args.vision_model
         tr_path = img_outdir(args.feature_dir, image_encoder, args.dataset, args.image_augmentation, args.train_shot,
