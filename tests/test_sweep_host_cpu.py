@@ -68,9 +68,15 @@ def torch_validate_enqueue(model, val_loader):
     return torch.tensor([loss]), torch.tensor([int(round(acc * len(bank)))], dtype=torch.int32), len(bank)
 
 
+def torch_validate_group_enqueue(group, models, heads, val_loader_of):
+    """Stand-in of the batched evaluation launch: head by head through the oracle (same draw order per head)."""
+    return [torch_validate_enqueue(models[k], val_loader_of(k)) for k in heads]
+
+
 def _patched(monkeypatch):
     monkeypatch.setattr(sweep_mod, "HeadGroup", TorchGroup)
     monkeypatch.setattr(ft, "validate_enqueue", torch_validate_enqueue)
+    monkeypatch.setattr(ft, "validate_group_enqueue", torch_validate_group_enqueue)
 
 
 def test_group_of_three_heads_matches_reference_and_oracle(monkeypatch):

@@ -430,33 +430,48 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// mean over reference batches of the batch-mean loss, and total hits; one CTA, fixed order
-__global__ void __launch_bounds__(256)
+// mean over reference batches of the batch-mean loss, and total hits; one CTA per head, fixed order: a warp per
+// reference batch (lanes stride over its rows, shuffle tree), the batch means added up in batch order by the warps'
+// partial sums in warp order - the result does not depend on timing
+__global__ void __launch_bounds__(1024)
     eval_reduce_kernel(const float* __restrict__ row_loss, const int32_t* __restrict__ row_pred,
                        const int64_t* __restrict__ labels, int64_t n_rows, int64_t bs, float* __restrict__ out_loss,
                        int32_t* __restrict__ out_correct) {
-  __shared__ float sh[8];
+  __shared__ float sh_loss[32];
+  __shared__ int sh_hits[32];
   row_loss += blockIdx.x * n_rows;  // (one CTA per head of a group)
   row_pred += blockIdx.x * n_rows;
   out_loss += blockIdx.x;
   out_correct += blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   const int64_t n_batches = (n_rows + bs - 1) / bs;
   float acc = 0.f;
   int hits = 0;
-  for (int64_t b = threadIdx.x; b < n_batches; b += blockDim.x) {
+  for (int64_t b = warp; b < n_batches; b += n_warps) {
     const int64_t beg = b * bs, end = min(n_rows, beg + bs);
     float s = 0.f;
-    for (int64_t i = beg; i < end; ++i) {
+    for (int64_t i = beg + lane; i < end; i += 32) {
       s += row_loss[i];
       hits += labels ? (row_pred[i] == static_cast<int32_t>(labels[i])) : (row_pred[i] != 0);
     }
+    s = uml::warp_sum(s);
     acc += s / static_cast<float>(end - beg);
   }
-  const float tot = block_reduce_sum(acc, sh);
-  const float h = block_reduce_sum(static_cast<float>(hits), sh);
+  hits = uml::warp_sum_i(hits);
+  if (lane == 0) {
+    sh_loss[warp] = acc;
+    sh_hits[warp] = hits;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    float tot = 0.f;
+    int h = 0;
+    for (int w = 0; w < n_warps; ++w) {
+      tot += sh_loss[w];
+      h += sh_hits[w];
+    }
     out_loss[0] = tot / static_cast<float>(n_batches);
-    out_correct[0] = static_cast<int32_t>(h + 0.5f);
+    out_correct[0] = h;
   }
 }
 
@@ -647,7 +662,7 @@ int uml_eval_reduce_group(const float* row_loss, const int32_t* row_pred, const 
   using namespace uml;
   UML_REQUIRE(row_loss && row_pred && out_loss && out_correct && n_rows > 0 && batch_size > 0 && n_heads >= 1,
               "eval_reduce_group: bad arguments");
-  eval_reduce_kernel<<<static_cast<unsigned>(n_heads), 256, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size,
+  eval_reduce_kernel<<<static_cast<unsigned>(n_heads), 1024, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size,
                                                                                   out_loss, out_correct);
   UML_CUDA(cudaGetLastError());
   return 0;
@@ -658,7 +673,7 @@ int uml_eval_reduce(const float* row_loss, const int32_t* row_pred, const int64_
   using namespace uml;
   UML_REQUIRE(row_loss && row_pred && out_loss && out_correct && n_rows > 0 && batch_size > 0,
               "eval_reduce: bad arguments");
-  eval_reduce_kernel<<<1, 256, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size, out_loss,
+  eval_reduce_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_loss, row_pred, labels, n_rows, batch_size, out_loss,
                                                        out_correct);
   UML_CUDA(cudaGetLastError());
   return 0;
