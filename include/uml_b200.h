@@ -319,6 +319,23 @@ int uml_gauss_eval(const float* params, int32_t dim_obs, int32_t dim_common, int
                    const float* data_y, int64_t n_rows, float* workspace /* >= 2*ceil(n_rows/16) floats */,
                    float* loss_out, void* stream);
 
+/* ---- f-3  alignment probes (diagnostics logged beside the loops: metrics.py:55-119,252-285 of the reference, called at
+ * Gaussian_experiment/main.py:67-84 and vision_language/finetune.py:209-233) --------------------------------------
+ * uml_cka_linear_f32: out[0] = linear CKA with the biased HSIC estimator of A [n, da] and B [n, db] (row pitches lda /
+ *   ldb floats), in its O(n d^2) form (squared Frobenius norms of the centred Gram blocks; no n x n matrix).
+ *   ws: uml_cka_workspace_doubles(da, db) doubles.
+ * uml_mutual_knn_f32: out[0] = mean over rows of |kNN_A(i) & kNN_B(i)| / topk, neighbours by inner product, self
+ *   excluded (its similarity set to -1e8), ties -> lower index.  ws: 2 * n * topk + 1 int32.
+ * uml_gauss_embed: emb = shared_encoder(in_head(row)) of the Gaussian autoencoder (model.py:51-60) for the given
+ *   modalities (data_x / data_y may be NULL), [n_rows, dim_latent] each.                                      */
+int64_t uml_cka_workspace_doubles(int32_t da, int32_t db);
+int uml_cka_linear_f32(const float* A, int64_t lda, int32_t da, const float* B, int64_t ldb, int32_t db, int64_t n, double* ws,
+                       float* out /*[1]*/, void* stream);
+int uml_mutual_knn_f32(const float* A, int64_t lda, int32_t da, const float* B, int64_t ldb, int32_t db, int64_t n, int32_t topk,
+                       int32_t* ws, float* out /*[1]*/, void* stream);
+int uml_gauss_embed(const float* params, int32_t dim_obs, int32_t dim_common, int32_t dim_latent, const float* data_x,
+                    const float* data_y, int64_t n_rows, float* emb_x, float* emb_y, void* stream);
+
 /* ---- sweep-level batching: the lr x weight-decay (x alpha) combinations that
  * finetune.py:406-448 (`sweep`) and engine/optimizer/default.py:17-31 (`HYPER_DICT`) train one after the other over the
  * SAME banks advance here in lock step - K heads with their own weights, optimizer state, sampler stream, lr, weight

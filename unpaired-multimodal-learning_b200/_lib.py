@@ -90,6 +90,10 @@ PROTOTYPES = {
     "uml_sgd_step": [c_vp, c_vp, c_vp, c_f32, c_vp, c_i64, c_f64, c_f64, c_f64, c_i64, c_vp, c_vp],
     "uml_eval_f32": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_f32, c_vp, c_vp, c_vp],
     "uml_eval_reduce": [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp],
+    "uml_cka_workspace_doubles": [c_i32, c_i32],
+    "uml_cka_linear_f32": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_vp],
+    "uml_mutual_knn_f32": [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp],
+    "uml_gauss_embed": [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
     "uml_eval_group_f32": [c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp],
     "uml_eval_reduce_group": [c_vp, c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp],
     "uml_grad_diag": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp],
@@ -144,7 +148,7 @@ KERNELS_PER_CALL = {
     "uml_gather_rows_f32": 1, "uml_gather_rows_bf16": 1, "uml_gather_labels_i32": 1, "uml_cast_f32_to_bf16": 1,
     "uml_gather_rows_labels_bf16": 1, "uml_gather2_rows_bf16": 1, "uml_gather2_rows_bf16_light": 1, "uml_gauss_step": 2, "uml_gauss_eval": 2, "uml_head_fwd_ce_deferred_bf16": 1, "uml_head_bwd_dw_fix_bf16": 1,
     "uml_head_fwd_ce_f32": 3, "uml_head_bwd_dw_f32": 1, "uml_gemm_nt_f32": 1, "uml_gemm_nn_f32": 1,
-    "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1, "uml_eval_group_f32": 1, "uml_eval_reduce_group": 1,
+    "uml_gemm_tn_f32": 1, "uml_adamw_step": 1, "uml_sgd_step": 1, "uml_eval_f32": 1, "uml_eval_reduce": 1, "uml_eval_group_f32": 1, "uml_eval_reduce_group": 1, "uml_cka_linear_f32": 3, "uml_mutual_knn_f32": 4, "uml_gauss_embed": 1,
     "uml_grad_diag": 2, "uml_head_fwd_ce_bf16": 2, "uml_reduce_tile_stats": 1, "uml_head_bwd_dw_bf16": 1, "uml_gemm_bf16": 1, "uml_adamw_step_partials": 1,
     "uml_sum_partials": 1, "uml_reduce_seg_stats": 1,
 }  # uml_linear_step is counted by the caller (its kernel count depends on the path)

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.environ.get("UML_LIB_PATH") or os.path.join(LIB_DIR, "libuml_b200.so")
-SOURCES = ["lib.cu", "gather.cu", "simt.cu", "optim.cu", "tc_fwd.cu", "tc_fwd2.cu", "tc_gemm.cu", "step.cu", "dp.cu", "sampler.cu", "gauss.cu", "sweep.cu"]
+SOURCES = ["lib.cu", "gather.cu", "simt.cu", "optim.cu", "tc_fwd.cu", "tc_fwd2.cu", "tc_gemm.cu", "step.cu", "dp.cu", "sampler.cu", "gauss.cu", "sweep.cu", "probes.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -173,6 +173,32 @@ def validate_group_enqueue(group, models, heads, val_loader_of):
     return out
 
 
+def alignment_probe(model, image_rows, image_labels, text_rows, n_classes, topk=10):
+    """The feature probes the reference computes beside its loop when ``capture_features_during_training`` is set
+    (finetune.py:209-233), on feature rows and on the device: the image rows go through ``model.extract_features`` (the
+    adapter, or nothing for a CLIP head), then
+      * ``cka``: linear CKA between the per-class means of those features and ``text_rows`` (one text row per class:
+        ``text_rows.shape[0] == n_classes``),
+      * ``mknn``: mutual 10-NN accuracy between the features and ``text_rows`` (when the two have the same number of rows),
+      * ``inclass_distance``: mean over classes of the mean distance of a class's features to their mean.
+    Returns a dict of floats (one read-back); a probe whose row counts do not match is left out."""
+    feats = model.extract_features(image_rows.to(torch.float32)).contiguous()
+    labels = image_labels.to(feats.device, torch.int64)
+    counts = torch.bincount(labels, minlength=n_classes).clamp_min(1).to(feats.dtype)
+    means = torch.zeros(n_classes, feats.shape[1], device=feats.device, dtype=feats.dtype).index_add_(0, labels, feats) / counts[:, None]
+    dist = (feats - means[labels]).norm(dim=1)
+    inclass = (torch.zeros(n_classes, device=feats.device).index_add_(0, labels, dist) / counts).mean().view(1)
+    text = text_rows.to(feats.device, torch.float32).contiguous()
+    parts, names = [inclass], ["inclass_distance"]
+    if text.shape[0] == n_classes:
+        parts.append(ops.cka_linear(means, text))
+        names.append("cka")
+    if text.shape[0] == feats.shape[0]:
+        parts.append(ops.mutual_knn(feats, text, topk))
+        names.append("mknn")
+    return dict(zip(names, torch.cat(parts).tolist()))
+
+
 def validate(model, val_loader, device="cuda"):
     """(val_loss, val_acc) over the loader's bank: accuracy over all rows, loss = mean over the
     loader's batches of the batch-mean CE (the reference's weighting, finetune.py:310-312).  One logit +
@@ -341,6 +367,13 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
                 trace.setdefault("evals", []).append((last_step, val_loss, val_acc))
             if logger is not None:
                 logger.log({"val/val_loss": val_loss, "val/val_acc": val_acc, "iter": last_step})
+            probe = (trace or {}).get("alignment") or getattr(args, "alignment_samples", None)
+            if probe:  # {"image": (rows, labels), "text": rows}: the reference's feature probes, at evaluation cadence
+                al = alignment_probe(model, probe["image"][0], probe["image"][1], probe["text"], model.head.weight.shape[0])
+                if trace is not None:
+                    trace.setdefault("alignment_log", []).append((last_step, al))
+                if logger is not None:
+                    logger.log(dict({f"train/{k}": v for k, v in al.items()}, iter=last_step))
             if rank == 0:
                 print(f"Iter {last_step} | Img Loss: {last['image_loss']:.4f} | Text Loss: {last['text_loss']:.4f} | "
                       f"Img Acc: {last['img_acc']:.4f} | Text Acc: {last['text_acc']:.4f} | Val Loss: {val_loss:.4f} | "

@@ -150,10 +150,40 @@ def validate(model: SharedAutoencoder, val_data_x: torch.Tensor, val_data_y: tor
     return lx, ly
 
 
+def get_embeddings(model: SharedAutoencoder, x=None, y=None):
+    """``model.get_embeddings`` of the reference (model.py:51-60): latent = shared_encoder(in_head(rows)) per modality,
+    ``[n, dim_latent]`` device tensors (None for an absent modality)."""
+    def prep(t):
+        return None if t is None else t.to(device=model.device, dtype=torch.float32).contiguous()
+    x, y = prep(x), prep(y)
+    if x is None and y is None:
+        return None, None
+    n = (x if x is not None else y).shape[0]
+    if x is not None and y is not None and x.shape[0] != y.shape[0]:
+        raise ValueError("get_embeddings: x and y must have the same number of rows")
+    ex = torch.empty((n, model.dim_latent), device=model.device) if x is not None else None
+    ey = torch.empty((n, model.dim_latent), device=model.device) if y is not None else None
+    check(_lib.load().uml_gauss_embed(model.flat.data_ptr(), model.dim_obs, model.dim_common, model.dim_latent,
+                                      x.data_ptr() if x is not None else None, y.data_ptr() if y is not None else None, n,
+                                      ex.data_ptr() if ex is not None else None, ey.data_ptr() if ey is not None else None,
+                                      torch.cuda.current_stream().cuda_stream))
+    return ex, ey
+
+
+def alignment(model: SharedAutoencoder, val_data_x, val_data_y, topk: int = 10):
+    """(cka, mknn) of the two modalities' validation embeddings - the probes main.py:21-29,78-83 logs as val/cka and
+    val/mknn - computed on the device (``csrc/probes.cu``); one read-back of two floats."""
+    from . import ops
+    ex, ey = get_embeddings(model, val_data_x, val_data_y)
+    both = torch.cat([ops.cka_linear(ex, ey), ops.mutual_knn(ex, ey, topk)]).tolist()
+    return both[0], both[1]
+
+
 def train_model_steps(model: SharedAutoencoder, data_loader: BankLoader, optimizer: Adam, num_steps: int,
                       val_data_x=None, val_data_y=None, device="cuda", args=None, eval_every: int = 0, trace=None):
     """``main.train_model_steps`` (main.py:31-86).  ``args`` carries ``mode`` ('xy' | 'x'), ``alpha_x``, ``alpha_y``.
-    Returns ``{'loss_x': [...], 'loss_y': [...], 'loss': [...], 'val': [(step, val_x, val_y), ...]}``; the
+    Returns ``{'loss_x': [...], 'loss_y': [...], 'loss': [...], 'val': [(step, val_x, val_y), ...], 'align': [(step, cka,
+    mknn), ...]}``; the
     training losses are read back from the device log once, after the last step (or at validation points)."""
     mode = getattr(args, "mode", "xy")
     alpha_x, alpha_y = float(getattr(args, "alpha_x", 1.0)), float(getattr(args, "alpha_y", 1.0))
@@ -167,7 +197,7 @@ def train_model_steps(model: SharedAutoencoder, data_loader: BankLoader, optimiz
     stream = torch.cuda.current_stream().cuda_stream
     import ctypes as C
     it = iter(data_loader)
-    out = {"loss_x": [], "loss_y": [], "loss": [], "val": []}
+    out = {"loss_x": [], "loss_y": [], "loss": [], "val": [], "align": []}
     chunk_max = 32  # steps enqueued per library call (a Python round trip per step costs more than the step's kernels)
     step = 0
     while step < num_steps:
@@ -194,6 +224,8 @@ def train_model_steps(model: SharedAutoencoder, data_loader: BankLoader, optimiz
         step += n
         if eval_every and val_data_x is not None and step % eval_every == 0:
             out["val"].append((step - 1,) + validate(model, val_data_x, val_data_y))
+            # val/cka and val/mknn of the validation embeddings, as the reference logs them at every evaluation point
+            out["align"].append((step - 1,) + alignment(model, val_data_x, val_data_y))
     host = log.cpu()
     out["loss_x"], out["loss_y"] = host[:, 0].tolist(), host[:, 1].tolist()
     out["loss"] = [(alpha_x * a + alpha_y * b) if mode == "xy" else a for a, b in zip(out["loss_x"], out["loss_y"])]

@@ -289,6 +289,36 @@ def eval_reduce_group(row_loss, row_pred, labels, batch_size, out_loss, out_corr
                                             _stream()))
 
 
+def cka_linear(a, b):
+    """Linear CKA (biased HSIC) of two feature sets with the same number of rows - reference ``metrics.py:96-119`` with
+    ``kernel_metric='ip'`` - as a one-element device tensor.  O(n d^2): no n x n kernel matrices."""
+    _need(a, torch.float32, "a", contiguous=False)
+    _need(b, torch.float32, "b", contiguous=False)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[0] != b.shape[0] or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("cka_linear: expected [n, da] and [n, db] with contiguous rows")
+    lib = _lib.load()
+    ws = torch.empty(int(lib.uml_cka_workspace_doubles(a.shape[1], b.shape[1])), device=a.device, dtype=torch.float64)
+    out = torch.empty(1, device=a.device)
+    check(lib.uml_cka_linear_f32(a.data_ptr(), a.stride(0), a.shape[1], b.data_ptr(), b.stride(0), b.shape[1], a.shape[0],
+                                 ws.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
+def mutual_knn(a, b, topk: int = 10):
+    """Mutual k-nearest-neighbour accuracy (reference ``metrics.py:55-86``, ``topk=10`` at both call sites) as a one-element
+    device tensor: mean over rows of the overlap of the row's top-k inner-product neighbours in the two feature spaces."""
+    _need(a, torch.float32, "a", contiguous=False)
+    _need(b, torch.float32, "b", contiguous=False)
+    if a.dim() != 2 or b.dim() != 2 or a.shape[0] != b.shape[0] or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("mutual_knn: expected [n, da] and [n, db] with contiguous rows")
+    n = a.shape[0]
+    ws = torch.empty(2 * n * topk + 1, device=a.device, dtype=torch.int32)
+    out = torch.empty(1, device=a.device)
+    check(_lib.load().uml_mutual_knn_f32(a.data_ptr(), a.stride(0), a.shape[1], b.data_ptr(), b.stride(0), b.shape[1], n, int(topk),
+                                         ws.data_ptr(), out.data_ptr(), _stream()))
+    return out
+
+
 def grad_diag(a, b, workspace, out4):
     check(_lib.load().uml_grad_diag(a.data_ptr(), b.data_ptr(), a.numel(), workspace.data_ptr(), out4.data_ptr(),
                                     _stream()))
