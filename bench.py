@@ -45,8 +45,8 @@ WORKLOADS = {
     "cfg3_sym": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, batch_txt=18944, n_val=4096,
                      desc="cfg3 with 18944 rows per modality per GPU (text epochs of two steps)"),
     # DINOv2 ViT-g (1536-d) image bank + OpenLLaMA-3B (3200-d) text bank, linear adapter img_proj 1536 -> 3200 + shared
-    # head, learnable temperatures (preset "linear"), throughput batch; a 200 k-row sample of the image bank
-    "cfg4": dict(n_img=200_000, n_txt=29_940, dim=3200, dv=1536, classes=1000, batch=8192, batch_txt=8192, n_val=4096,
+    # head, learnable temperatures (preset "linear"), throughput batch; the full 1.28 M-row image bank (7.9 GB fp32 + 3.9 GB bf16)
+    "cfg4": dict(n_img=1_281_167, n_txt=29_940, dim=3200, dv=1536, classes=1000, batch=8192, batch_txt=8192, n_val=4096,
                  desc="DINOv2 ViT-g 1536-d image + OpenLLaMA-3B 3200-d text features, adapter + shared head, throughput batch"),
     "cfg2": dict(n_img=16_000, n_txt=29_940, dim=512, classes=1000, batch=32, batch_txt=32, n_val=4000,
                  desc="ImageNet 16-shot CLIP ViT-B/16 512-d features + CUPL text, linear head, reference batch 32"),

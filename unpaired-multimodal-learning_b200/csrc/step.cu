@@ -63,13 +63,17 @@ Pipe* get_pipe() {
 // start / after fix-up / after the forward kernel (default 2).  Placement 3 needs no side stream: the copy of step
 // i+1's rows rides in step i's fix-up launch as extra, interleaved CTAs - measured 0.1936 ms/step against 0.1862 for
 // placement 2 (two bandwidth-bound jobs in one launch just add up: 49.7 us for the launch instead of 24.5 us).
+// Placement 4: after the dW GEMM, i.e. under the step's data-parallel tail (that kernel waits on NVLink most of the time).
+static bool g_dp_step = false;  // set by linear_run for the step being enqueued
 int prefetch_placement() {
-  static int cached = -1;
-  if (cached < 0) {
+  static int cached = -2;
+  if (cached == -2) {
     const char* e = getenv("UML_PREFETCH_AT");
-    cached = (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+    cached = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : -1;
   }
-  return cached;
+  if (cached >= 0) return cached;
+  (void)g_dp_step;  // measured on 2 B200s: placement 4 0.1627 ms/step, placement 2 0.1618 - no gain, 2 stays the default
+  return 2;
 }
 
 // UML_FUSE_FIX=1: the deferred softmax normalisation is applied in the dW prologue (tc_gemm kFix: each G stage is
@@ -228,6 +232,7 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
   cudaStream_t main_st = as_stream(stream);
   if (pipe) UML_CUDA(cudaEventRecord(pipe->start, main_st));  // everything enqueued so far may still read buffer 1
 
+  g_dp_step = base->dp_allreduce != 0;
   for (int i = 0; i < n_steps; ++i) {
     patch(a, steps[i]);
     if (i > 0 && a.precision == 1) a.w16_valid = 1;  // the optimizer kernel of the previous step refreshed the shadow
@@ -443,7 +448,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
                                        reinterpret_cast<uint16_t*>(j.out), a->dim, j.out_labels, stream);
       if (rc) return rc;
     }
-    if (hooks.mid && prefetch_placement() != 0) {
+    if (hooks.mid && prefetch_placement() != 0 && prefetch_placement() != 4) {
       rc = hooks.mid(hooks.mid_arg);
       if (rc) return rc;
     }
@@ -468,6 +473,10 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   }
 
   const int64_t np_all = static_cast<int64_t>(a->n_classes) * a->dim;
+  if (total == 0 && a->precision == 1 && hooks.mid && prefetch_placement() == 4) {  // (no dW launch to follow on this rank)
+    rc = hooks.mid(hooks.mid_arg);
+    if (rc) return rc;
+  }
   if (total == 0 && !dp) return 0;
   if (total == 0) {  // a rank without rows still takes part in the all-reduce, contributing zeros
     UML_CUDA(cudaMemsetAsync(dp_local_sum_target(a, np_all), 0, np_all * sizeof(float), as_stream(stream)));
@@ -521,6 +530,10 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   rec(a->ev[5], stream);
   }
   if (operand_free) UML_CUDA(cudaEventRecord(operand_free, as_stream(stream)));  // X16 / labels32 may be overwritten
+  if (a->precision == 1 && hooks.mid && prefetch_placement() == 4) {  // the next step's gather starts when dW has finished
+    rc = hooks.mid(hooks.mid_arg);
+    if (rc) return rc;
+  }
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
   if (!fused) {
     if (dp && a->upd.kind != 3 && uml_dp_p2p_input(np)) {

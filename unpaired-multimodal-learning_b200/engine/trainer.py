@@ -131,7 +131,7 @@ class StepEngine:
             raise RuntimeError("StepEngine: the model must live on a CUDA device (no CPU path)")
         if self.world > 1:
             ensure_dp_comm()
-            ensure_dp_p2p(self.W.numel())
+            ensure_dp_p2p(max(p.numel() for p in model.parameters()))  # the head, or the larger adapter
             # replicas must start from identical bits (they apply identical updates and are never re-synchronised)
             for prm in model.parameters():
                 torch.distributed.broadcast(prm.data, src=0)
@@ -470,9 +470,16 @@ class StepEngine:
             rows, _, idx = self._view(img)
             Wp = self.model.img_proj.weight
             if self.world > 1:
-                raise NotImplementedError("data-parallel adapter training is not wired yet")
-            ops.gemm_tn(self.dZ, rows, None, k=n_i, m=self.D, n=self.Dv, b_row_idx=idx, P=Wp.data,
-                        update=self.opt.update_struct(Wp), ldc=Wp.data.stride(0))
+                # data parallel on the exact path: this rank's dWp = dZ^T X_img (no fused update), summed over the ranks,
+                # then the optimizer step - the same order of operations as the head's gradient above
+                if getattr(self, "dWp", None) is None:
+                    self.dWp = torch.empty_like(Wp.data)
+                ops.gemm_tn(self.dZ, rows, self.dWp, k=n_i, m=self.D, n=self.Dv, b_row_idx=idx)
+                torch.distributed.all_reduce(self.dWp, group=self.dist_group)
+                self.opt.apply(Wp, self.dWp)
+            else:
+                ops.gemm_tn(self.dZ, rows, None, k=n_i, m=self.D, n=self.Dv, b_row_idx=idx, P=Wp.data,
+                            update=self.opt.update_struct(Wp), ldc=Wp.data.stride(0))
         self._w16_valid = False
 
     def _apply_scalar(self, param, grad_view):
@@ -605,6 +612,17 @@ class StepEngine:
         data-parallel all-reduce in between when there is more than one rank."""
         g, st = self.opt.group_of(param), self.opt.slot(param)
         data = param.data
+        if self.world > 1 and self.opt.name != "sgd" and _P2P_FLOATS >= data.numel() and data.numel() % 4 == 0:
+            # the data-parallel tail in ONE kernel per rank: split-K sum -> exchange over NVLink peer memory -> Adam(W) +
+            # bf16 shadow (csrc/dp.cu), for the head and for the adapter alike
+            from .._lib import check, load
+            st["step"] += 1
+            check(load().uml_dp_fused_adam_update(partials.data_ptr(), int(splits), data.numel(), data.numel(), data.data_ptr(),
+                                                  st["m"].data_ptr(), st["v"].data_ptr(), g["lr"], g["betas"][0], g["betas"][1],
+                                                  g["eps"], g["weight_decay"], st["step"], int(self.opt.name == "adamw"),
+                                                  shadow.data_ptr() if shadow is not None else None,
+                                                  torch.cuda.current_stream().cuda_stream))
+            return
         if self.world > 1 or self.opt.name == "sgd":
             buf = getattr(self, buf_name, None)
             if buf is None:
