@@ -489,6 +489,17 @@ class StepEngine:
             grad_view = g
         self.opt.apply(param, grad_view)
 
+    def _apply_scalars(self, pairs):
+        """Optimizer steps of several scalar parameters (the learnable temperatures) with ONE all-reduce for all of them."""
+        if self.world > 1 and len(pairs) > 1:
+            g = torch.cat([v.reshape(1) for _, v in pairs])
+            torch.distributed.all_reduce(g, group=self.dist_group)
+            for i, (prm, _) in enumerate(pairs):
+                self.opt.apply(prm, g[i:i + 1])
+            return
+        for prm, v in pairs:
+            self._apply_scalar(prm, v)
+
     # ------------------------------------------------------------------------------------ bf16
     def _alloc_bf16(self):
         dev = self.device
@@ -591,20 +602,38 @@ class StepEngine:
         self._timed("head_fwd_ce_bf16", ops.head_fwd_ce_bf16, self.X16, self.W16, self.labels32, segs, ws, None, n_rows=n,
                     stats=stats)  # the fix-up launch also reduces the per-run statistics
         if self.learnable:
-            k = 0
+            k, pairs = 0, []
             if n_i:
-                self._apply_scalar(self.model.img_scale, stats[k, 1:2]); k += 1
+                pairs.append((self.model.img_scale, stats[k, 1:2])); k += 1
             if n_t:
-                self._apply_scalar(self.model.txt_scale, stats[k, 1:2])
+                pairs.append((self.model.txt_scale, stats[k, 1:2]))
+            self._apply_scalars(pairs)
         if n_i:
             # dZ = G_img W with the head BEFORE its update (W16 is refreshed by the optimizer kernel below)
             ops.gemm_bf16(ws.G, self.W16, self.dZ16, n_i, D, C, b_mn=True)
         splits = min(self.max_splits, max(1, ops.tc_dw_splits(n, D, C)))
         ops.head_bwd_dw_bf16(ws.G, ws.ldg, self.X16, n, C, self.partials, splits)
-        self._apply_partials(self.W, self.partials, splits, self.W16, "dW")
+        side = None
+        if self.world > 1 and n_i and _P2P_FLOATS >= max(self.W.numel(), Wp.numel()):
+            # data parallel: the head's exchange + update (a kernel that mostly waits on NVLink) runs on a side stream
+            # under the adapter's dWp GEMM; the adapter's own exchange follows both (the ranks' exchange blocks are shared)
+            if getattr(self, "_dp_stream", None) is None:
+                self._dp_stream = torch.cuda.Stream(device=dev)
+                self._dp_ev = (torch.cuda.Event(), torch.cuda.Event())
+            main = torch.cuda.current_stream(dev)
+            self._dp_ev[0].record(main)
+            side = self._dp_stream
+            with torch.cuda.stream(side):
+                side.wait_event(self._dp_ev[0])
+                self._apply_partials(self.W, self.partials, splits, self.W16, "dW")
+                self._dp_ev[1].record(side)
+        else:
+            self._apply_partials(self.W, self.partials, splits, self.W16, "dW")
         if n_i:
             ps = min(self.proj_splits, max(1, ops.gemm_bf16_splits(D, Dv, n_i)))
             ops.gemm_bf16(self.dZ16, self.Xi16, self.partials_p, D, Dv, n_i, a_mn=True, b_mn=True, n_splits=ps)
+            if side is not None:
+                torch.cuda.current_stream(dev).wait_event(self._dp_ev[1])
             self._apply_partials(Wp, self.partials_p, ps, self.Wp16, "dWp")
 
     def _apply_partials(self, param, partials, splits, shadow, buf_name):
