@@ -6,20 +6,22 @@
 Metric (BASELINE.json): UML train samples/sec (image + text rows consumed per second).
 Workload at N=1 (``config.workload``): cfg3 = ImageNet full-data shapes, "ViT-L/14" 768-d features,
 1000-class shared linear head + unpaired text bank, preset ``clip_linear`` arithmetic (logit scale
-exp(4.60517), AdamW) at the THROUGHPUT batch of 34304 image + 3584 text rows per GPU and step (296 tiles of 128 rows
-= two waves over 148 SMs; the text batch is sized so that 8 GPUs still fit the 29940-row text bank; SURVEY.md
-section 8d; the reference's own batch of 32 is a latency-bound regime reported separately by --workload cfg2).
+exp(4.60517), AdamW) at the THROUGHPUT batch of 70144 image + 3584 text rows per GPU and step (288 row units of 256
+= 16 per CTA-pair group of the forward kernel; the text batch is sized so that 8 GPUs still fit the 29940-row text
+bank; --workload cfg3_r1 is round 1's 34304 + 3584; the reference's own batch of 32 is a
+latency-bound regime reported separately by --workload cfg2).
 Synthetic seeded banks, random-init/zero-shot-init head.  One "step" = one full UML iteration:
 gather(img) + gather(txt) -> shared head forward -> logit scale + softmax CE -> dW -> AdamW.
 
 ``value``  device-resident: banks and the K steps' index batches already in HBM, K steps timed with CUDA events
-           (gather from the banks, forward, fix-up, dW, update all inside the timed region).
+           (gather from the banks, forward, dW, update all inside the timed region).
 ``e2e``    the same K steps through the public ``uml_b200.finetune.train`` call with index batches copied
            from pinned host memory every step and every step's loss record copied back to the host.
 ``roofline`` dominant kernel (head forward/CE/G, tcgen05) timed with CUDA events inside the run.
 ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference step on the host cores.
+``--impl reference``: the UNMODIFIED reference's finetune.train() on the host cores (oracle/_ref, see oracle/build_ref.py).
 Multi-GPU (torchrun): data-parallel, fixed per-GPU batch (weak scaling), banks row-sharded over the ranks with a
-per-rank sampler, one NCCL all-reduce of dW per step issued from inside the step launcher.
+per-rank sampler, dW summed over the ranks by the step's last kernel (NVLink peer memory, csrc/dp.cu).
 """
 from __future__ import annotations
 
@@ -37,11 +39,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # batch / batch_txt: rows per modality per GPU and step.  cfg3: 34304 image + 3584 text rows = 296 forward tiles of
-    # 128 rows = exactly two waves over 148 SMs; the text batch is sized so that 8 GPUs together (28672 rows) still
-    # fit the 29940-row CUPL text bank - per-GPU work stays fixed from 1 to 8 GPUs (weak scaling).
-    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=34304, batch_txt=3584, n_val=4096,
+    # batch / batch_txt: rows per modality per GPU and step.  cfg3: 70144 image + 3584 text rows = 288 row units of 256 =
+    # exactly 16 per CTA-pair group of the forward kernel (18 groups x 4 class chunks x 2 CTAs = 144 SMs); the text batch is
+    # sized so that 8 GPUs together (28672 rows) still fit the 29940-row CUPL text bank - per-GPU work stays fixed from 1
+    # to 8 GPUs (weak scaling).  The batch is a free parameter of a throughput run (the reference trains at 32): per-step
+    # costs that do not grow with it (update, launch gaps, pipeline fill of the two GEMM kernels: ~30 us) weigh 21 % at
+    # round 1's 37888 rows, 13 % here; DESIGN.md lists the measured series 36864 / 73728 / 147456 rows.
+    "cfg3": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=70144, batch_txt=3584, n_val=4096,
                  desc="ImageNet full-data CLIP ViT-L/14 768-d features + CUPL text, linear head, throughput batch"),
+    # round 1's throughput batch (34304 + 3584 rows = 296 tiles of 128 = two waves over 148 SMs of the round-1 forward kernel)
+    "cfg3_r1": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=34304, batch_txt=3584, n_val=4096,
+                    desc="cfg3 at round 1's batch (34304 image + 3584 text rows per GPU and step)"),
     "cfg3_sym": dict(n_img=1_281_167, n_txt=29_940, dim=768, classes=1000, batch=18944, batch_txt=18944, n_val=4096,
                      desc="cfg3 with 18944 rows per modality per GPU (text epochs of two steps)"),
     # DINOv2 ViT-g (1536-d) image bank + OpenLLaMA-3B (3200-d) text bank, linear adapter img_proj 1536 -> 3200 + shared
@@ -953,6 +961,8 @@ def main():
             raise SystemExit("bench.py --workload cfg2_sweep runs the GPU arm only (its line carries the CPU port as cpu_baseline)")
         return run_sweep(args)
     wl = WORKLOADS[args.workload]
+    if os.environ.get("UML_BENCH_BATCH"):  # experiments: image rows per GPU and step
+        wl = dict(wl, batch=int(os.environ["UML_BENCH_BATCH"]))
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     peaks = measured_peaks()
     D, C, B, BT = wl["dim"], wl["classes"], wl["batch"], wl["batch_txt"]
@@ -966,7 +976,7 @@ def main():
                          "per-rank shard permutation (DistributedSampler-style, equal strided shards); dW summed over the ranks by "
                          "the step's last kernel (split-K sum + two-shot all-reduce over NVLink peer memory + Adam, csrc/dp.cu)",
               "l2_policy": "inputs larger than L2: every step gathers fresh rows from a 3.9 GB bank and rewrites a "
-                           "67 MB gradient-logit matrix" if args.workload != "cfg2" else "working set fits L2 (few-shot)"}
+                           "gradient-logit matrix of 2 KB per row" if args.workload != "cfg2" else "working set fits L2 (few-shot)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -1021,7 +1031,7 @@ def main():
                     # committed `ncu --set full` capture profiles/r02_fwd_exchange.md (63.1 MB read + 32.2 MB written;
                     # algorithmic: 58 MB of bf16 rows + 1.5 MB of weights read, 78 MB of G written, part of which is
                     # still in L2 when the kernel ends)
-                    "traffic": 9.5e7 if (D, C) == (768, 1000) and abs(rows_per_gpu - 37888) < 4000 else None,
+                    "traffic": 9.5e7 * rows_per_gpu / 36864.0 if (D, C) == (768, 1000) else None,
                     "traffic_unit": "bytes per launch",
                     "peak_source": f"{peaks['src']} bf16 burst (the timed region is {res['ms']:.1f} ms long)",
                     "frac_of_sustained_peak": flops / (kms * 1e-3) / 1e12 / peaks["tf_sustained"]}

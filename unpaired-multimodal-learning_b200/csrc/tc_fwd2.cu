@@ -63,8 +63,15 @@ constexpr int kXEpiWarps = 4 * kXSlices;               // warp e: TMEM lane quar
 constexpr int kXWarpMma = kXEpiWarps, kXWarpTma = kXEpiWarps + 1;  // (the TMA warp also owns the TMEM allocation)
 constexpr int kXThreads = (kXEpiWarps + 4) * 32;        // the producer warps form a warpgroup of their own (two of them idle): it
                                                        // hands most of its registers to the epilogue warpgroups (setmaxnreg)
-constexpr int kXRegsProducer = 40, kXRegsEpilogue = kXSlices == 2 ? 232 : 112;
-constexpr int kXHalf = kXGroups / 2;                    // groups of a new unit that are made before the previous unit is finished
+// setmaxnreg moves registers inside the CTA's launch-time budget (threads x launch registers): what the epilogue
+// warpgroups gain must not exceed what the producer warpgroup gives up, or the last warpgroup to ask waits for ever.
+//   2 slices: 384 threads x 168 -> producers 40 (frees 128 x 128 = 16384), epilogue 232 (takes 256 x 64 = 16384)
+//   4 slices: 640 threads x  96 -> producers 24 (frees 128 x  72 =  9216), epilogue 112 (takes 512 x 16 =  8192)
+constexpr int kXRegsProducer = kXSlices == 2 ? 40 : 24, kXRegsEpilogue = kXSlices == 2 ? 232 : 112;
+#ifndef UML_X_HALF
+#define UML_X_HALF (kXGroups > 2 ? kXGroups - 1 : kXGroups / 2)   // measured: 3 of 4 groups first 68.6 us, 2 of 4 70.4 us
+#endif
+constexpr int kXHalf = UML_X_HALF;                     // groups of a new unit that are made before the previous unit is finished
 constexpr int kXMaxChunks = 4;
 static_assert(kXSmemBytes <= 227 * 1024, "exchange forward kernel: shared memory");
 
@@ -681,7 +688,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
         if (g == 0) XDBG_ACC(1);
         gm[g] = run_group(nk + kXGW * g, gc);
         tmem_ldg(taddr + kXGC * (g + 1), v);
-        if (g == (kXHalf > 2 ? 1 : 0) && have_prev) request_prev();  // (the L2 round trip is covered by the next groups)
+        if (g == 0 && have_prev) request_prev();  // (the L2 round trip is covered by the next groups)
       });
       if (have_prev) {
         resolve_prev();
