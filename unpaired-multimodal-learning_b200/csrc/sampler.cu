@@ -79,6 +79,57 @@ inline uint32_t mt_next(PermState& s) {
   return y;
 }
 
+// ---- the draw stage in bulk (helper thread of uml_randperm_run): tempered MT words by the block, remainders without the
+// integer divider.  x % d for 32-bit x, d through one double division: q = floor(x / d) is exact in double (the true
+// quotient is at least 1 / d >= 2^-32 away from the next integer in relative terms 2^-32 >> 2^-53), r = x - q * d.  Four
+// to eight quotients per divide instruction with AVX2 / AVX-512 against one 25-cycle `div` each - the draws were the
+// slower stage of the two-thread pipeline.
+inline void mt_fill(PermState& s, uint32_t* dst, int64_t cnt) {
+  while (cnt > 0) {
+    if (s.next >= 624) {
+      mt_twist(s.mt);
+      s.next = 0;
+    }
+    const int64_t take = cnt < 624 - s.next ? cnt : 624 - s.next;
+    const uint32_t* src = s.mt + s.next;
+    for (int64_t j = 0; j < take; ++j) {
+      uint32_t y = src[j];
+      y ^= y >> 11;
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= y >> 18;
+      dst[j] = y;
+    }
+    s.next += static_cast<int32_t>(take);
+    dst += take;
+    cnt -= take;
+  }
+}
+
+#define UML_MOD_BLOCK_BODY                                                                                       \
+  for (int64_t k = 0; k < cnt; ++k) {                                                                            \
+    const uint32_t x = y[k], d = d0 - static_cast<uint32_t>(k);                                                  \
+    /* unsigned -> double through the signed conversion the vector units have */                                 \
+    const double xd = static_cast<double>(static_cast<int32_t>(x ^ 0x80000000u)) + 2147483648.0;                 \
+    const double dd = static_cast<double>(static_cast<int32_t>(d));  /* d < 2^31: n < 2^32 / 20 */               \
+    const uint32_t q = static_cast<uint32_t>(static_cast<int64_t>(xd / dd));                                     \
+    z[k] = x - q * d;                                                                                            \
+  }
+
+__attribute__((target("avx2"))) void mod_block_avx2(const uint32_t* __restrict__ y, uint32_t* __restrict__ z, int64_t cnt, uint32_t d0) {
+  UML_MOD_BLOCK_BODY
+}
+void mod_block_generic(const uint32_t* __restrict__ y, uint32_t* __restrict__ z, int64_t cnt, uint32_t d0) {
+  UML_MOD_BLOCK_BODY
+}
+#undef UML_MOD_BLOCK_BODY
+
+inline void mod_block(const uint32_t* y, uint32_t* z, int64_t cnt, uint32_t d0) {
+  static const bool avx2 = __builtin_cpu_supports("avx2");
+  if (avx2) mod_block_avx2(y, z, cnt, d0);
+  else mod_block_generic(y, z, cnt, d0);
+}
+
 // draw the z of iteration s.made (the draws happen strictly in iteration order, as in torch) and prefetch its target
 inline void draw_one(PermState& s) {
   const uint32_t z = mt_next(s) % static_cast<uint32_t>(s.n - s.made);
@@ -201,7 +252,9 @@ int uml_randperm_run(void* state, uint64_t seed, int64_t n, int64_t* out, int64_
       while (b - consumed.load(std::memory_order_acquire) >= kRing) sched_yield();
       uint32_t* z = ring.data() + (b % kRing) * kBlk;
       const int64_t i0 = b * kBlk, cnt = m - i0 < kBlk ? m - i0 : kBlk;
-      for (int64_t k = 0; k < cnt; ++k) z[k] = mt_next(s) % static_cast<uint32_t>(n - (i0 + k));
+      uint32_t y[kBlk];
+      mt_fill(s, y, cnt);
+      mod_block(y, z, cnt, static_cast<uint32_t>(n - i0));  // z[k] = y[k] % (n - (i0 + k))
       produced.store(b + 1, std::memory_order_release);
     }
   });
