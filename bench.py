@@ -356,8 +356,9 @@ def run_ours(args, wl, rank, world, dev):
     engine = StepEngine(model, opt, dev, B, BT, log_slots=64, precision=args.precision, world_size=world)
     # per-rank shards (world > 1) drop their ragged last batch: a 3742-row text shard would otherwise end every epoch
     # with a 158-row batch and the per-GPU work of a step would no longer be fixed (weak scaling)
-    il = BankLoader(img_bank, B, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1)
-    tl = BankLoader(txt_bank, BT, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1)
+    # (a shard shorter than the batch - cfg4's 8192-row text batch on 8 GPUs - is one ragged batch per epoch instead)
+    il = BankLoader(img_bank, B, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1 and len(img_bank) >= B)
+    tl = BankLoader(txt_bank, BT, shuffle=True, upload="epoch", shard_of=shard, drop_last=world > 1 and len(txt_bank) >= BT)
     torch.manual_seed(2)
     ii, ti = iter(il), iter(tl)
 
@@ -488,8 +489,8 @@ def run_ours(args, wl, rank, world, dev):
         memory, the step, and the D2H copy of its loss record, read on the host before the clock stops."""
         m2, o2, s2 = make_model(wl, dev, init_bank)
         m2.precision = args.precision
-        il2 = BankLoader(img_bank, B, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1)
-        tl2 = BankLoader(txt_bank, BT, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1)
+        il2 = BankLoader(img_bank, B, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1 and len(img_bank) >= B)
+        tl2 = BankLoader(txt_bank, BT, shuffle=True, upload="step", shard_of=shard, drop_last=world > 1 and len(txt_bank) >= BT)
         vl2 = BankLoader(val_bank, 512, shuffle=False)
         torch.manual_seed(2)
         tr = {"timing": {"warmup": warm}, "indices": False}
@@ -1027,11 +1028,11 @@ def main():
             # beside it for reference).
             roof = {"bound": "tensor", "kernel": kname, "achieved": flops / (kms * 1e-3) / 1e12,
                     "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch at this shape, from the
-                    # committed `ncu --set full` capture profiles/r02_fwd_exchange.md (63.1 MB read + 32.2 MB written;
-                    # algorithmic: 58 MB of bf16 rows + 1.5 MB of weights read, 78 MB of G written, part of which is
-                    # still in L2 when the kernel ends)
-                    "traffic": 9.5e7 * rows_per_gpu / 36864.0 if (D, C) == (768, 1000) else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch at the cfg3 shape, from the
+                    # committed `ncu --set full` capture profiles/r02_fwd_exchange.md (73728 rows: 124.6 MB read + 116.7 MB
+                    # written; algorithmic: 113 MB of bf16 rows + 1.5 MB of weights read, 151 MB of G written, part of
+                    # which is still in L2 when the kernel ends), scaled by the rows of the step
+                    "traffic": 2.414e8 * rows_per_gpu / 73728.0 if (D, C) == (768, 1000) else None,
                     "traffic_unit": "bytes per launch",
                     "peak_source": f"{peaks['src']} bf16 burst (the timed region is {res['ms']:.1f} ms long)",
                     "frac_of_sustained_peak": flops / (kms * 1e-3) / 1e12 / peaks["tf_sustained"]}
