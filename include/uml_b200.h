@@ -246,6 +246,9 @@ typedef struct {
    * does not use) on a side stream while step i's GEMMs run                                                  */
   uint16_t*     X16_alt;  int32_t* labels32_alt;
   int64_t       g_capacity_rows;            /* rows the G workspace has room for (fp32 path: split-K planes); 0 = rows */
+  /* optional third operand buffers: the gather then runs two steps ahead, and no forward kernel waits for an event
+   * of the side stream that is signalled at the last moment (UML_PREFETCH_DEPTH=1 keeps one step ahead)              */
+  uint16_t*     X16_alt2;  int32_t* labels32_alt2;
 } uml_linear_step_args;
 
 int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);

@@ -6,7 +6,8 @@ import uml_b200
 from uml_b200 import ops, _lib
 lib = C.CDLL(_lib.LIB_PATH)
 DEV = "cuda:0"
-N0, N1, D, Cc = 34304, 3584, 768, 1000
+N0, N1 = (int(v) for v in os.environ.get('FW_SHAPE', '34304+3584').split('+'))
+D, Cc = 768, 1000
 N = N0 + N1
 x16 = torch.randn(N, D, device=DEV).to(torch.bfloat16)
 W = torch.randn(Cc, D, device=DEV); W = W / W.norm(dim=1, keepdim=True)

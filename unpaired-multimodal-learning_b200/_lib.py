@@ -44,7 +44,8 @@ class LinearStepArgs(C.Structure):
                 ("X16", c_vp), ("W16", c_vp), ("labels32", c_vp), ("partials", c_vp), ("tile_ws", c_vp),
                 ("max_splits", c_i32), ("w16_valid", c_i32), ("dW_out", c_vp), ("dW_scratch", c_vp),
                 ("scale_param", c_vp * 2), ("scale_m", c_vp * 2), ("scale_v", c_vp * 2), ("scale_step", c_i64 * 2),
-                ("ev", c_vp * 8), ("dp_allreduce", c_i32), ("X16_alt", c_vp), ("labels32_alt", c_vp), ("g_capacity_rows", c_i64)]
+                ("ev", c_vp * 8), ("dp_allreduce", c_i32), ("X16_alt", c_vp), ("labels32_alt", c_vp), ("g_capacity_rows", c_i64),
+                ("X16_alt2", c_vp), ("labels32_alt2", c_vp)]
 
 
 class RunStep(C.Structure):

@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "optim.cuh"
 #include "gather.cuh"
 
 namespace {
@@ -20,7 +21,7 @@ struct Pipe {
   cudaStream_t aux2 = nullptr;          // the dW GEMM when it overlaps the fix-up launch
   cudaEvent_t dw_done = nullptr, fwd_done = nullptr;
   unsigned* split_done = nullptr;       // [8] fix-up CTAs finished per dW split, then one int: watchdog flag
-  cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr}, start = nullptr, mid = nullptr;
+  cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr}, start = nullptr, mid = nullptr;
   bool ok = false;
 };
 
@@ -37,9 +38,11 @@ Pipe* get_pipe() {
     int lo = 0, hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
     // lowest priority: the prefetch must never delay a kernel of the step it hides under
-    if (cudaStreamCreateWithPriority(&p.aux, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    const char* pe = getenv("UML_AUX_PRIORITY");  // experiments: "hi" = the GEMMs' priority class and above
+    const int aux_prio = (pe && pe[0] == 'h') ? hi : lo;
+    if (cudaStreamCreateWithPriority(&p.aux, cudaStreamNonBlocking, aux_prio) != cudaSuccess) return nullptr;
     bool good = true;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       good = good && cudaEventCreateWithFlags(&p.ready[i], cudaEventDisableTiming) == cudaSuccess;
       good = good && cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -65,6 +68,19 @@ Pipe* get_pipe() {
 // placement 2 (two bandwidth-bound jobs in one launch just add up: 49.7 us for the launch instead of 24.5 us).
 // Placement 4: after the dW GEMM, i.e. under the step's data-parallel tail (that kernel waits on NVLink most of the time).
 static bool g_dp_step = false;  // set by linear_run for the step being enqueued
+// UML_UPDATE_IN_DW=1: the split-K sum and AdamW run in the tail of the dW GEMM instead of a launch of their own.
+// Measured on B200 (cfg3, 73 728 rows): 0.2376 ms/step against 0.2319 with the separate launch - every CTA waits for the
+// slowest split of its tile with the whole SM in hand, and its share of the update (21 rows x 256 columns, nine
+// arrays) is latency-bound, while the separate kernel spreads the same bytes over 750 CTAs.  Off by default.
+bool update_in_dw_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("UML_UPDATE_IN_DW");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
+}
+
 int prefetch_placement() {
   static int cached = -2;
   if (cached == -2) {
@@ -154,6 +170,11 @@ int uml_head_bwd_dw_stats_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X
                                float* partials, int32_t n_splits, const float* part, int64_t part_entries, int32_t nseg,
                                uml_seg_stats* stats, void* stream);
 
+int uml_head_bwd_dw_update_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                                float* partials, int32_t n_splits, const float* part, int64_t part_entries, int32_t nseg,
+                                uml_seg_stats* stats, float* W, float* m, float* v, uint16_t* W16, const uml::AdamArgs* adam,
+                                unsigned* failed, void* stream);
+
 float* uml_dp_p2p_input(int64_t n);   // dp.cu: this rank's exchange buffers of the peer-memory all-reduce (or NULL)
 float* uml_dp_p2p_output(int64_t n);
 
@@ -227,10 +248,20 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     }
     if (all) pipe = get_pipe();
   }
-  uint16_t* xbuf[2] = {base->X16, base->X16_alt};
-  int32_t* lbuf[2] = {base->labels32, base->labels32_alt};
+  // With a third operand buffer the gather runs TWO steps ahead: step i + 2's rows are copied while step i's dW and
+  // update run and may spill into step i + 1 - no forward kernel ever waits for an event that is signalled at the last
+  // moment (one step ahead, the gather of step i + 1 ended about when the update did, and the cross-stream hand-over
+  // put ~9 us between the update and the next forward kernel).
+  int nb = 2;
+  if (pipe && base->X16_alt2 && base->labels32_alt2 && n_steps > 2 && prefetch_placement() != 3) {
+    const char* e = getenv("UML_PREFETCH_DEPTH");
+    if (!(e && e[0] == '1')) nb = 3;
+  }
+  const int depth = nb - 1;
+  uint16_t* xbuf[3] = {base->X16, base->X16_alt, base->X16_alt2};
+  int32_t* lbuf[3] = {base->labels32, base->labels32_alt, base->labels32_alt2};
   cudaStream_t main_st = as_stream(stream);
-  if (pipe) UML_CUDA(cudaEventRecord(pipe->start, main_st));  // everything enqueued so far may still read buffer 1
+  if (pipe) UML_CUDA(cudaEventRecord(pipe->start, main_st));  // everything enqueued so far may still read the other buffers
 
   g_dp_step = base->dp_allreduce != 0;
   for (int i = 0; i < n_steps; ++i) {
@@ -241,39 +272,51 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
       if (rc) return rc;
       continue;
     }
-    const int b = i & 1;
+    const int b = i % nb;
     a.X16 = xbuf[b];
     a.labels32 = lbuf[b];
     if (i == 0) {
+      // the first step's rows in line; with two steps of look-ahead the first step's hook (after its forward kernel)
+      // starts BOTH the second and the third step's gathers: beside the first forward kernel a gather would only have
+      // the SMs that kernel leaves free (4 of 148) and hold up the second step
       rec(a.ev[0], stream);
-      const int rc = shadow_gather(&a, xbuf[0], lbuf[0], false, stream);
-      if (rc) return rc;
+      const int rc0 = shadow_gather(&a, xbuf[0], lbuf[0], false, stream);
+      if (rc0) return rc0;
       rec(a.ev[1], stream);
     } else if (prefetch_placement() != 3 || fuse_fix()) {
       UML_CUDA(cudaStreamWaitEvent(main_st, pipe->ready[b], 0));
     }
-    struct Next {
-      Pipe* pipe;
+    struct Job {
       uml_linear_step_args nx;
       uint16_t* x;
       int32_t* l;
-      cudaEvent_t wait_a, wait_b, ready;
+      cudaEvent_t wait_a, ready;
+    };
+    struct Next {
+      Pipe* pipe;
+      Job job[2];
+      int n_jobs;
+      cudaEvent_t wait_b;
       cudaStream_t main_st;
       bool have, record_mid;
     } next;
     next.pipe = pipe;
-    next.have = i + 1 < n_steps;
+    next.n_jobs = 0;
     next.record_mid = prefetch_placement() != 2;
-    if (next.have) {
-      next.nx = a;
-      patch(next.nx, steps[i + 1]);
-      next.x = xbuf[b ^ 1];
-      next.l = lbuf[b ^ 1];
-      next.wait_a = i == 0 ? pipe->start : pipe->freed[b ^ 1];  // the dW kernel that last read that buffer
-      next.wait_b = pipe->mid;
-      next.ready = pipe->ready[b ^ 1];
-      next.main_st = main_st;
+    next.wait_b = pipe->mid;
+    next.main_st = main_st;
+    // step i's hook starts the gather of step i + depth (the first step's: of every step up to `depth`)
+    for (int t = (i == 0 ? 1 : i + depth); t <= i + depth && t < n_steps; ++t) {
+      const int tb = t % nb;  // last read by the dW kernel of step t - nb (never, when that is before this call)
+      Job& j = next.job[next.n_jobs++];
+      j.nx = a;
+      patch(j.nx, steps[t]);
+      j.x = xbuf[tb];
+      j.l = lbuf[tb];
+      j.wait_a = t < nb ? pipe->start : pipe->freed[tb];
+      j.ready = pipe->ready[tb];
     }
+    next.have = next.n_jobs > 0;
     StepHooks hooks;
     hooks.pregathered = true;
     hooks.operand_free = pipe->freed[b];
@@ -284,22 +327,22 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
       if (next.have) {
         const uml_segment* g[2] = {nullptr, nullptr};
         int ng = 0;
-        for (int k = 0; k < next.nx.nseg; ++k)
-          if (next.nx.seg[k].n > 0) g[ng++] = &next.nx.seg[k];
+        for (int k = 0; k < next.job[0].nx.nseg; ++k)
+          if (next.job[0].nx.seg[k].n > 0) g[ng++] = &next.job[0].nx.seg[k];
         if (ng > 0) {
           gjob.s0 = CopySeg{reinterpret_cast<const unsigned char*>(g[0]->rows16), g[0]->idx, g[0]->labels, g[0]->n};
           if (ng > 1) gjob.s1 = CopySeg{reinterpret_cast<const unsigned char*>(g[1]->rows16), g[1]->idx, g[1]->labels, g[1]->n};
           gjob.vec_per_row = a.dim / 8;
-          gjob.out = reinterpret_cast<uint4*>(next.x);
+          gjob.out = reinterpret_cast<uint4*>(next.job[0].x);
           gjob.out_pitch_vec = a.dim / 8;
-          gjob.out_labels = next.l;
+          gjob.out_labels = next.job[0].l;
           gjob.blocks = 4 * sm_count();
           hooks.merged = &gjob;
         }
       }
       if (next.have) {  // (the merged copy has no launch of its own to bracket)
-        rec(next.nx.ev[0], stream);
-        rec(next.nx.ev[1], stream);
+        rec(next.job[0].nx.ev[0], stream);
+        rec(next.job[0].nx.ev[1], stream);
       }
       next.have = false;  // nothing for the side stream to do
     }
@@ -309,13 +352,16 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
       Next* n = static_cast<Next*>(p);
       if (!n->have) return 0;
       if (n->record_mid) UML_CUDA(cudaEventRecord(n->pipe->mid, n->main_st));
-      UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_a, 0));
-      UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_b, 0));
-      rec(n->nx.ev[0], n->pipe->aux);  // ev[0]..ev[1] bracket the gather where it really runs: on the side stream
-      const int rc = shadow_gather(&n->nx, n->x, n->l, true, n->pipe->aux);
-      if (rc) return rc;
-      rec(n->nx.ev[1], n->pipe->aux);
-      UML_CUDA(cudaEventRecord(n->ready, n->pipe->aux));
+      for (int k = 0; k < n->n_jobs; ++k) {
+        Job& j = n->job[k];
+        UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, j.wait_a, 0));
+        UML_CUDA(cudaStreamWaitEvent(n->pipe->aux, n->wait_b, 0));
+        rec(j.nx.ev[0], n->pipe->aux);  // ev[0]..ev[1] bracket the gather where it really runs: on the side stream
+        const int rc = shadow_gather(&j.nx, j.x, j.l, true, n->pipe->aux);
+        if (rc) return rc;
+        rec(j.nx.ev[1], n->pipe->aux);
+        UML_CUDA(cudaEventRecord(j.ready, n->pipe->aux));
+      }
       return 0;
     };
     const int rc = linear_step_impl(&a, stream, hooks);
@@ -494,6 +540,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   }
   int splits = uml_tc_dw_splits(total, a->dim, a->n_classes);
   if (splits > a->max_splits) splits = a->max_splits;
+  const bool update_in_dw = fused && !dp && a->upd.kind != 3 && a->W16 && splits <= 8 && a->dim % 4 == 0 && update_in_dw_enabled();
   if (opipe) {
     UML_CUDA(cudaStreamWaitEvent(as_stream(stream), opipe->dw_done, 0));  // the GEMM was launched with the forward
     rc = 0;
@@ -514,6 +561,18 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     }
     rc = uml_head_bwd_dw_fix_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
                                   a->partials, splits, &ts2, a->labels32, a->tile_ws, a->stats, stream);
+  } else if (stats_in_dw && update_in_dw) {
+    // single GPU, AdamW: statistics, split-K sum and the update all run inside the dW launch (no update launch)
+    const float* part = nullptr;
+    int64_t entries = 0;
+    uml_fwd_x_partials(a->tile_ws, total, a->n_classes, &part, &entries);
+    int nseg_live = 0;
+    for (int i = 0; i < a->nseg; ++i) nseg_live += a->seg[i].n > 0 ? 1 : 0;
+    const uml::AdamArgs adam = uml::make_adam(a->upd.lr, a->upd.beta1, a->upd.beta2, a->upd.eps, a->upd.weight_decay, a->upd.step,
+                                              a->upd.kind == 1);
+    rc = uml_head_bwd_dw_update_bf16(static_cast<const uint16_t*>(a->G), a->ldg, a->X16, total, a->dim, a->n_classes,
+                                     a->partials, splits, part, entries, nseg_live, a->stats, a->W, a->upd.m, a->upd.v, a->W16,
+                                     &adam, reinterpret_cast<unsigned*>(a->tile_ws) + 2, stream);
   } else if (stats_in_dw) {
     const float* part = nullptr;
     int64_t entries = 0;
@@ -535,6 +594,11 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     if (rc) return rc;
   }
   const int64_t np = static_cast<int64_t>(a->n_classes) * a->dim;
+  if (stats_in_dw && update_in_dw) {  // (the events of the update bracket nothing: it ran inside the dW kernel)
+    rec(a->ev[6], stream);
+    rec(a->ev[7], stream);
+    return 0;
+  }
   if (!fused) {
     if (dp && a->upd.kind != 3 && uml_dp_p2p_input(np)) {
       // data parallel over NVLink peer memory: split-K sum + exchange + Adam in ONE kernel per rank

@@ -19,16 +19,16 @@
 //     registers of bf16 pairs.  The TMEM buffer is handed back to the MMA warp right after this sweep.  Nothing of
 //     the epilogue goes through shared memory except one 32-byte record per thread: the operand stages' TMA
 //     writes and the tensor core's operand reads already use most of the SM's shared-memory bandwidth.
-//   * the four quarters of a row meet through shared memory, the pairs of a group exchange one 16-byte record per row -
-//     {max, sum, sum p*raw, argmax} - through L2 (release/acquire flags keyed by a per-launch epoch: no memset, no
-//     cluster wider than the pair, every SM usable),
-//   * then every thread rescales ITS OWN 64 columns in registers by  exp(m_group - M) * coef / S  (two bf16x2 FMAs per
-//     pair with the factor split hi + lo, so the product carries fp32-level accuracy) and writes its 128-byte line
-//     of G with four 256-bit stores; the one-hot column is patched by a 2-byte store of the same thread.  G is
-//     written once and is final.
-//   * the pair that owns a row's label column computes loss / hit / d(scale) for that row; per-(tile, chunk, warp)
-//     partial sums go to tile_part and are reduced in a fixed order by the next kernel of the step (the dW GEMM's
-//     idle warp) or by uml_reduce_tile_stats.
+//   * the column slices of a row meet in slice 0's thread through shared memory (the other slices drop a record, arrive
+//     on an mbarrier and go on: nobody but slice 0 ever waits), the pairs of a group exchange one 16-byte record per row -
+//     {max, sum, sum p*raw, argmax} - through L2 (value + launch-epoch word pairs: no memset, no fence, no cluster wider
+//     than the pair, every SM usable),
+//   * then every thread rescales ITS OWN columns in registers by  exp(m_group - M) * coef / S  (two bf16x2 FMAs per
+//     pair with the factor split hi + lo, so the product carries fp32-level accuracy) and writes them with 256-bit
+//     stores; the one-hot column is patched by a 2-byte store of the same thread.  G is written once and is final.
+//   * the pair that owns a row's label column computes loss / hit / d(scale) for that row; each thread keeps the sums of
+//     its rows, one warp reduction per CTA at the end puts per-(CTA, row quarter, run) partial sums into tile_part, and
+//     the next kernel of the step (the dW GEMM's idle warp) or uml_reduce_tile_stats adds them in a fixed order.
 // All CTAs of the grid (<= one per SM) are co-resident, which the flag exchange relies on; a watchdog turns a
 // missing peer into an error flag (uml_fwd_x_failed) instead of a hang.
 #include <cstdlib>
@@ -38,8 +38,15 @@
 
 namespace uml {
 
+#ifndef UML_X_TMAST
+#define UML_X_TMAST 1
+#endif
+// G leaves through shared memory and TMA stores (32 rows x 64 B boxes, two per epilogue warp) instead of 32-byte register
+// stores: a warp's direct store instruction touches 32 rows = 32 separate sectors, and those 4.7 M small write requests
+// per launch cost the kernel 20 us of 120 (measured with the stores switched off); the staging boxes take one TMA stage
+constexpr bool kXTmaStore = UML_X_TMAST != 0;
 #ifndef UML_X_STAGES
-#define UML_X_STAGES 6
+#define UML_X_STAGES (UML_X_TMAST ? 5 : 6)
 #endif
 constexpr int kXStages = UML_X_STAGES;
 constexpr int kXABytes = 128 * 64 * 2;                 // X tile: 128 rows x 64 k
@@ -55,10 +62,18 @@ constexpr int kXSliceCols = 256 / kXSlices;
 #define UML_X_GC 32
 #endif
 constexpr int kXGC = UML_X_GC;                         // columns per group: one tcgen05.ld, one running-max step
+#ifndef UML_X_DB
+#define UML_X_DB 0
+#endif
+constexpr bool kXDoubleBuf = UML_X_DB != 0;            // the next group's tcgen05.ld is in flight while this group is worked on
 constexpr int kXGW = kXGC / 2;                         // ... and its registers of bf16 pairs
 constexpr int kXGroups = kXSliceCols / kXGC;           // groups per thread
-constexpr int kXHxBytes = 2 * kXSlices * 128 * kXRecBytes;  // [unit parity][column slice][row]
-constexpr int kXSmemBytes = kXStages * kXStageBytes + kXHxBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kXHxSlots = 4;                           // a record is read at most two units after it was written
+constexpr int kXHxBytes = kXHxSlots * (kXSlices - 1) * 128 * kXRecBytes;  // [unit & 3][column slice - 1][row]
+constexpr int kXEpiWarpsC = 4 * kXSlices;
+constexpr int kXSbufWarp = 2 * 2048;                       // per epilogue warp: two boxes of 32 rows x 32 bf16, SWIZZLE_64B
+constexpr int kXSbufBytes = kXTmaStore ? kXEpiWarpsC * kXSbufWarp : 0;
+constexpr int kXSmemBytes = kXStages * kXStageBytes + kXSbufBytes + kXHxBytes + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kXEpiWarps = 4 * kXSlices;               // warp e: TMEM lane quarter e & 3, column slice e >> 2
 constexpr int kXWarpMma = kXEpiWarps, kXWarpTma = kXEpiWarps + 1;  // (the TMA warp also owns the TMEM allocation)
 constexpr int kXThreads = (kXEpiWarps + 4) * 32;        // the producer warps form a warpgroup of their own (two of them idle): it
@@ -67,12 +82,25 @@ constexpr int kXThreads = (kXEpiWarps + 4) * 32;        // the producer warps fo
 // warpgroups gain must not exceed what the producer warpgroup gives up, or the last warpgroup to ask waits for ever.
 //   2 slices: 384 threads x 168 -> producers 40 (frees 128 x 128 = 16384), epilogue 232 (takes 256 x 64 = 16384)
 //   4 slices: 640 threads x  96 -> producers 24 (frees 128 x  72 =  9216), epilogue 112 (takes 512 x 16 =  8192)
-constexpr int kXRegsProducer = kXSlices == 2 ? 40 : 24, kXRegsEpilogue = kXSlices == 2 ? 232 : 112;
+#ifndef UML_X_REGS_P
+#define UML_X_REGS_P (kXSlices == 2 ? 40 : 24)
+#define UML_X_REGS_E (kXSlices == 2 ? 232 : 112)
+#endif
+constexpr int kXRegsProducer = UML_X_REGS_P, kXRegsEpilogue = UML_X_REGS_E;
+static_assert((kXThreads - 128) * (kXRegsEpilogue - 168) <= 128 * (168 - kXRegsProducer) || kXSlices != 2, "setmaxnreg: the epilogue asks for more than the producers free");
 #ifndef UML_X_HALF
 #define UML_X_HALF (kXGroups > 2 ? kXGroups - 1 : kXGroups / 2)   // measured: 3 of 4 groups first 68.6 us, 2 of 4 70.4 us
 #endif
 constexpr int kXHalf = UML_X_HALF;                     // groups of a new unit that are made before the previous unit is finished
 constexpr int kXMaxChunks = 4;
+// the previous unit's records are asked for after this group of the new unit and looked at after group kXHalf - 1.  Asked
+// for after group 0, nine units in ten found a record of a slower pair still stale and paid a second, exposed L2 round trip
+// (ncu: the re-request loads ran 0.91 + 0.49 times per unit); a group later the pairs of a row may drift by ~2 us
+#ifndef UML_X_REQ_AFTER
+#define UML_X_REQ_AFTER 0
+#endif
+constexpr int kXReqAfter = UML_X_REQ_AFTER;
+static_assert(kXHalf >= 1 && kXHalf <= kXGroups && kXReqAfter < kXHalf, "the records must be requested before they are resolved");
 static_assert(kXSmemBytes <= 227 * 1024, "exchange forward kernel: shared memory");
 
 struct XSegs {
@@ -82,7 +110,7 @@ struct XSegs {
 };
 
 struct XWork {
-  float* tile_part;      // [(tile * n_chunks + chunk) * 8 + q * 2 + seg] x 4 floats
+  float* tile_part;      // [(CTA * 4 + row quarter) * 2 + run] x 4 floats: loss sum, d loss / d scale, hits, rows
   uint4* recs;           // [(row * n_chunks + chunk) * 2 + {0, 1}]: {max, epoch, sum, epoch}, {sum p*raw, epoch, argmax, epoch}
   unsigned* ctrl;        // [0] epoch of the last finished launch, [1] finished CTAs, [2] watchdog flag, [3] partial records
 };
@@ -178,6 +206,25 @@ __device__ long long g_fwdx_dbg[148 * 16];
 #define XDBG_FLUSH(base, n)
 #endif
 
+// v[d] for a run-time d: a switch whose cases cannot be turned into selects
+template <int N>
+__device__ __forceinline__ float pick_col(const uint32_t (&v)[N], int d) {
+  uint32_t r = 0;
+#define UML_PICK(i) \
+  case i:           \
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v[(i) < N ? (i) : 0])); \
+    break;
+  switch (d) {
+    UML_PICK(0) UML_PICK(1) UML_PICK(2) UML_PICK(3) UML_PICK(4) UML_PICK(5) UML_PICK(6) UML_PICK(7)
+    UML_PICK(8) UML_PICK(9) UML_PICK(10) UML_PICK(11) UML_PICK(12) UML_PICK(13) UML_PICK(14) UML_PICK(15)
+    UML_PICK(16) UML_PICK(17) UML_PICK(18) UML_PICK(19) UML_PICK(20) UML_PICK(21) UML_PICK(22) UML_PICK(23)
+    UML_PICK(24) UML_PICK(25) UML_PICK(26) UML_PICK(27) UML_PICK(28) UML_PICK(29) UML_PICK(30) UML_PICK(31)
+    default: break;
+  }
+#undef UML_PICK
+  return __uint_as_float(r);
+}
+
 template <int B, int E, class F>
 __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (B < E) {
@@ -189,17 +236,20 @@ __device__ __forceinline__ void static_for(F&& f) {
 template <bool kPred, bool kDs>
 __global__ void __launch_bounds__(kXThreads, 1)
     head_fwd_ce_x_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const __grid_constant__ CUtensorMap tmap_g,
                          int64_t n_rows, int dim, int n_classes, int n_groups, const int32_t* __restrict__ labels, XSegs segs,
                          uint16_t* __restrict__ G, int64_t ldg, float* __restrict__ row_loss, int32_t* __restrict__ row_pred,
                          int32_t* __restrict__ row_correct, float* __restrict__ row_dscale, XWork wk) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* hx = smem + kXStages * kXStageBytes;
+  unsigned char* sbuf = smem + kXStages * kXStageBytes;  // (1024-byte aligned: the stages are 32 KB each)
+  unsigned char* hx = sbuf + kXSbufBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(hx + kXHxBytes);
   uint64_t* empty_bar = full_bar + kXStages;
   uint64_t* tfull_bar = empty_bar + kXStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* xbar = tempty_bar + 2;                     // [row quarter]: the other column slices' records of a unit are in place
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xbar + 4);
   uint32_t* epoch_slot = tmem_slot + 1;
   float* run_scale = reinterpret_cast<float*>(epoch_slot + 1);  // [2]: the runs' logit scales
 
@@ -219,6 +269,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
   if (warp == kXWarpTma && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    if (kXTmaStore && write_g) tma_prefetch_desc(&tmap_g);
   }
   if (warp == kXWarpMma && lane == 0) {
     for (int s = 0; s < kXStages; ++s) {
@@ -229,6 +280,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 2 * kXEpiWarps);  // one arrival per epilogue warp of both CTAs
     }
+    for (int qq = 0; qq < 4; ++qq) mbar_init(&xbar[qq], kXSlices - 1);
     fence_barrier_init();
   }
   if (warp == kXWarpTma) tmem_alloc_cg2(tmem_slot, 512);
@@ -241,7 +293,7 @@ __global__ void __launch_bounds__(kXThreads, 1)
   if (threadIdx.x < 2) run_scale[threadIdx.x] = segs.scale_dev[threadIdx.x] ? __ldg(segs.scale_dev[threadIdx.x]) : segs.scale[threadIdx.x];
   if (threadIdx.x == 0) {
     *epoch_slot = *reinterpret_cast<volatile unsigned*>(wk.ctrl) + 1u;
-    if (blockIdx.x == 0) wk.ctrl[3] = static_cast<unsigned>(n_units * 2 * n_chunks * 4);  // partial records per run
+    if (blockIdx.x == 0) wk.ctrl[3] = gridDim.x * 4u;  // partial records per run: one per CTA and row quarter
   }
   __syncthreads();
   const unsigned epoch = *epoch_slot;
@@ -358,53 +410,48 @@ __global__ void __launch_bounds__(kXThreads, 1)
     float p_gm[kXGroups];                               // running max each group was written against
 #pragma unroll
     for (int g = 0; g < kXGroups; ++g) p_gm[g] = 0.f;
-    float p_cm = 0.f, p_cs = 1.f, p_cpr = 0.f, p_before = 0.f, p_lraw = 0.f, p_lab_p = 0.f, p_lab_gm = 0.f;
-    int p_carg = 0, p_label = -1;
+    float p_before = 0.f, p_lraw = 0.f, p_lab_p = 0.f, p_lab_gm = 0.f;
+    int p_label = -1;
     int p_tile = -1;
+    const uint4* p_rec = wk.recs;                       // the row's records, one per class chunk
     // resolved when the unit is finished: row maximum, factor coef / sum, the one-hot column's value
     float f_M = 0.f, f_tc = 0.f, f_sl2 = 0.f;
     unsigned short f_patch = 0;
     bool f_store = false;
     unsigned char* f_grow = nullptr;
+    // per-run sums of the rows this thread owns (slice 0, label column inside the chunk): reduced over the warp ONCE, when
+    // the CTA has done all its units
+    float acc_loss[2] = {0.f, 0.f}, acc_ds[2] = {0.f, 0.f};
+    int acc_hit[2] = {0, 0}, acc_cnt[2] = {0, 0};
 
-    // the other chunks' records of the previous unit: requested at the top of an iteration, looked at after the new
-    // unit's first group - the L2 round trip is covered by that group's work
+    // the class chunks' records of the previous unit (this pair's own among them: slice 0 published it, the other slices
+    // never saw the combined values): requested after the new unit's first group, looked at two groups later - the
+    // L2 round trip is covered by those groups' work
     uint4 r0[kXMaxChunks], r1[kXMaxChunks];
     auto request_prev = [&]() {
-      const int64_t row = static_cast<int64_t>(p_tile) * 128 + rloc;
-      if (n_chunks > 1 && row < n_rows) {
+      if (static_cast<int64_t>(p_tile) * 128 + rloc < n_rows) {
 #pragma unroll
         for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-          if (c2 < n_chunks && c2 != chunk) {
-            const uint4* rec = wk.recs + (row * n_chunks + c2) * 2;
-            r0[c2] = ld_volatile_v4(rec);
-            if (kSecond) r1[c2] = ld_volatile_v4(rec + 1);
+          if (c2 < n_chunks) {
+            r0[c2] = ld_volatile_v4(p_rec + c2 * 2);
+            if (kSecond) r1[c2] = ld_volatile_v4(p_rec + c2 * 2 + 1);
           }
         }
       }
     };
-    // ... -> row maximum / sum (polls only if a peer pair is a whole unit behind)
+    // ... -> row maximum / sum (polls only if a pair is most of a unit behind)
     auto resolve_prev = [&]() {
       const int64_t row = static_cast<int64_t>(p_tile) * 128 + rloc;
       const RowCtx c = row_ctx(row);
-      float M = p_cm, S = p_cs, PR = p_cpr, before_chunks = -INFINITY;
-      int garg = p_carg;
-      if (n_chunks > 1 && c.valid) {
-        float om[kXMaxChunks], os[kXMaxChunks], opr[kXMaxChunks];
-        int oa[kXMaxChunks];
-#ifdef UML_X_NOEXCH
-#pragma unroll
-        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-          r0[c2].y = r0[c2].w = epoch; r0[c2].x = __float_as_uint(p_cm); r0[c2].z = __float_as_uint(p_cs);
-          r1[c2].y = r1[c2].w = epoch;
-        }
-#endif
-        // a stale record (a peer pair most of a unit behind): ask again for all of them at once
+      float M = -INFINITY, S = 0.f, PR = 0.f, before_chunks = -INFINITY;
+      int garg = 0x7fffffff;
+      if (c.valid) {
+        // a stale record (a pair most of a unit behind): ask again for all of them at once
         for (unsigned polls = 0;; ++polls) {
           bool fresh = true;
 #pragma unroll
           for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-            if (c2 < n_chunks && c2 != chunk) {
+            if (c2 < n_chunks) {
               fresh = fresh && r0[c2].y == epoch && r0[c2].w == epoch;
               if (kSecond) fresh = fresh && r1[c2].y == epoch && r1[c2].w == epoch;
             }
@@ -416,36 +463,28 @@ __global__ void __launch_bounds__(kXThreads, 1)
           }
           request_prev();
         }
+        float om[kXMaxChunks], os[kXMaxChunks];
 #pragma unroll
         for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-          om[c2] = -INFINITY; os[c2] = 0.f; opr[c2] = 0.f; oa[c2] = 0x7fffffff;
-          if (c2 < n_chunks && c2 != chunk) {
-            om[c2] = __uint_as_float(r0[c2].x); os[c2] = __uint_as_float(r0[c2].z);
-            if (kSecond) { opr[c2] = __uint_as_float(r1[c2].x); oa[c2] = static_cast<int>(r1[c2].z); }
-          }
-        }
-#pragma unroll
-        for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
+          om[c2] = c2 < n_chunks ? __uint_as_float(r0[c2].x) : -INFINITY;
+          os[c2] = c2 < n_chunks ? __uint_as_float(r0[c2].z) : 0.f;
           M = fmaxf(M, om[c2]);
           if (c2 < chunk) before_chunks = fmaxf(before_chunks, om[c2]);
         }
         const float offM = __fmul_rn(M, c.sl2);
-        const float e_c = x_exp2(__fmul_rn(p_cm, c.sl2) - offM);
-        S = p_cs * e_c;
-        PR = p_cpr * e_c;
 #pragma unroll
         for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
           const float e = x_exp2(__fmul_rn(om[c2], c.sl2) - offM);  // 0 for the absent chunks (-inf)
           S = fmaf(os[c2], e, S);
-          if (kDs) PR = fmaf(opr[c2], e, PR);
+          if (kDs) PR = fmaf(c2 < n_chunks ? __uint_as_float(r1[c2].x) : 0.f, e, PR);
         }
-        if (kPred) {
-          float bestm = p_cm;
-          int bestc = chunk;
+        if (kPred) {  // the first chunk that holds the row maximum (chunks in class order)
+          float bestm = -INFINITY;
 #pragma unroll
           for (int c2 = 0; c2 < kXMaxChunks; ++c2) {
-            if (c2 < n_chunks && c2 != chunk && (om[c2] > bestm || (om[c2] == bestm && c2 < bestc))) {
-              bestm = om[c2]; bestc = c2; garg = oa[c2];
+            if (c2 < n_chunks && om[c2] > bestm) {
+              bestm = om[c2];
+              garg = static_cast<int>(r1[c2].z);
             }
           }
         }
@@ -461,36 +500,20 @@ __global__ void __launch_bounds__(kXThreads, 1)
         const float f = x_exp2(__fmul_rn(p_lab_gm, c.sl2) - f_M) * f_tc;
         f_patch = __bfloat16_as_ushort(__float2bfloat16_rn(fmaf(p_lab_p, f, -c.gcoef)));
       }
-      if (cq == 0) {  // per-row results: the (chunk, quarter 0) thread that owns the row's label column
+      if (cq == 0) {  // per-row results: the (chunk, slice 0) thread of the chunk that holds the row's label column
         const int lc_chunk = p_label - col0;
-        const bool own = c.valid && lc_chunk >= 0 && lc_chunk < 256;
-        float loss = 0.f, dsc = 0.f;
-        int hit = 0;
-        if (own) {
+        if (c.valid && lc_chunk >= 0 && lc_chunk < 256) {
           // ln S - ln 2 * (u_label - offset), the label's exponent taken exactly as pass 1 took it: S >= 2^that up to the
           // 2^-22 of ex2.approx, so the cross entropy is >= -3e-7 before the clamp (torch's is never negative)
-          loss = fmaxf(fmaf(__log2f(S), 0.6931471805599453f, -0.6931471805599453f * fmaf(p_lraw, c.sl2, -f_M)), 0.f);
-          if (kDs) dsc = (__fdividef(PR, S) - p_lraw) * c.sgn * c.dcoef;
-          hit = (p_lraw == M && p_lraw > fmaxf(before_chunks, p_before)) ? 1 : 0;
+          const float loss = fmaxf(fmaf(__log2f(S), 0.6931471805599453f, -0.6931471805599453f * fmaf(p_lraw, c.sl2, -f_M)), 0.f);
+          const float dsc = kDs ? (__fdividef(PR, S) - p_lraw) * c.sgn * c.dcoef : 0.f;
+          const int hit = (p_lraw == M && p_lraw > fmaxf(before_chunks, p_before)) ? 1 : 0;
           if (row_loss) row_loss[row] = loss;
           if (kPred && row_pred) row_pred[row] = garg;
           if (row_correct) row_correct[row] = hit;
           if (kDs && row_dscale) row_dscale[row] = dsc;
-        }
-        if (wk.tile_part) {
-          // deterministic per-(tile, chunk, warp, run) partial sums; the statistics kernel adds them in a fixed order
-          const bool any1 = __any_sync(0xffffffffu, c.sg), all1 = __all_sync(0xffffffffu, c.sg || !c.valid);
-#pragma unroll
-          for (int s2 = 0; s2 < 2; ++s2) {
-            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s2 == 0 ? !all1 || !any1 : any1) {  // (a warp's rows nearly always belong to one run)
-              const bool mn = own && (static_cast<int>(c.sg) == s2);
-              const float a = warp_sum(mn ? loss : 0.f), dd = kDs ? warp_sum(mn ? dsc : 0.f) : 0.f;
-              const int hh = warp_sum_i(mn ? hit : 0), cnt = warp_sum_i(mn ? 1 : 0);
-              out = make_float4(a, dd, static_cast<float>(hh), static_cast<float>(cnt));
-            }
-            if (lane == 0) *reinterpret_cast<float4*>(wk.tile_part + (((static_cast<int64_t>(p_tile) * n_chunks + chunk) * 4 + q) * 2 + s2) * 4) = out;
-          }
+          if (c.sg) { acc_loss[1] += loss; acc_ds[1] += dsc; acc_hit[1] += hit; acc_cnt[1] += 1; }
+          else { acc_loss[0] += loss; acc_ds[0] += dsc; acc_hit[0] += hit; acc_cnt[0] += 1; }
         }
       }
     };
@@ -517,8 +540,53 @@ __global__ void __launch_bounds__(kXThreads, 1)
 #pragma unroll
       for (int j = 0; j < kXGW; j += 8) stg256(f_grow + g * (2 * kXGC) + j * 4, o + j);
     };
+    // the same through shared memory: the warp's 32 rows x 32 columns go into one of its two staging boxes (16-byte chunk
+    // c of row r at chunk c ^ ((r >> 1) & 3): SWIZZLE_64B, conflict-free for a row per lane), the one-hot column is
+    // patched there, and one TMA store writes the box - rows past n_rows are clipped by the tensor map
+    const uint32_t sbuf_w = smem_u32(sbuf) + warp * kXSbufWarp;
+    auto finish_group_tma = [&](auto gc) {
+      constexpr int g = decltype(gc)::value;
+      static_assert(!kXTmaStore || kXGC == 32, "the staging boxes are 32 columns wide");
+      if (g >= live_groups) return;  // (warp-uniform)
+      const float gmx = p_gm[g];
+      const float f = x_exp2(__fmul_rn(gmx, f_sl2) - f_M) * f_tc;
+      const __nv_bfloat16 fh = __float2bfloat16_rn(f);
+      const __nv_bfloat16 fl = __float2bfloat16_rn(f - __bfloat162float(fh));
+      const __nv_bfloat162 fh2 = __halves2bfloat162(fh, fh), fl2 = __halves2bfloat162(fl, fl);
+      uint32_t o[kXGW];
+#pragma unroll
+      for (int j = 0; j < kXGW; ++j) {
+        const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(&pk[g * kXGW + j]);
+        const __nv_bfloat162 r = __hfma2(pv, fh2, __hmul2(pv, fl2));
+        o[j] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+      const uint32_t box = sbuf_w + (g & 1) * 2048, rowb = box + lane * 64, sw = (lane >> 1) & 3;
+      if (lane == 0) bulk_wait_read<1>();  // the store that last used this box (two stores ago) has read it
+      __syncwarp();
+#pragma unroll
+      for (int j4 = 0; j4 < kXGW / 4; ++j4) sts128(rowb + ((j4 ^ sw) << 4), o[4 * j4], o[4 * j4 + 1], o[4 * j4 + 2], o[4 * j4 + 3]);
+      const int lc = p_label - col0 - cq * kXSliceCols - g * kXGC;
+      if (static_cast<unsigned>(lc) < static_cast<unsigned>(kXGC))
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(rowb + (((lc >> 3) ^ sw) << 4) + (lc & 7) * 2), "h"(f_patch) : "memory");
+      fence_proxy_async();
+      __syncwarp();
+#ifndef UML_X_NOSTORE
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                         reinterpret_cast<uint64_t>(&tmap_g)),
+                     "r"(box), "r"(col0 + cq * kXSliceCols + g * kXGC), "r"(p_tile * 128 + q * 32)
+                     : "memory");
+        bulk_commit();
+      }
+#endif
+    };
+    auto finish_any = [&](auto gc) {
+      if constexpr (kXTmaStore) finish_group_tma(gc);
+      else finish_group(gc);
+    };
     // the one-hot column of the previous unit
     auto finish_rows = [&]() {
+      if (kXTmaStore) return;  // (patched in the staging box)
       const int lcol = p_label - col0 - cq * kXSliceCols;
       if (f_store && lcol >= 0 && lcol < kXSliceCols) *reinterpret_cast<volatile unsigned short*>(f_grow + lcol * 2) = f_patch;
     };
@@ -565,13 +633,13 @@ __global__ void __launch_bounds__(kXThreads, 1)
       continue;
 #endif
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 256 + cq * kXSliceCols;
-      uint32_t v[kXGC];
+      uint32_t vv[kXDoubleBuf ? 2 : 1][kXGC];
       uint32_t nk[kXGW * kXHalf];  // the new unit's first four groups: live beside the previous unit's registers until those are stored
 
       // one 16-column group: running max, exponentials relative to it, packed as bf16 pairs into out[0..8).
       // kPlain: every column of the chunk is a class and no temperature is negative (all but the last chunk's tail)
       const uint64_t sl2x2 = pack2(sl2, sl2);
-      auto run_group = [&](uint32_t* out, auto gc) -> float {
+      auto run_group = [&](uint32_t (&v)[kXGC], uint32_t* out, auto gc) -> float {
         constexpr int g = decltype(gc)::value;
         const int c0l = cq * kXSliceCols + g * kXGC;  // first column of the group inside the chunk
         if (c0l + kXGC > n_valid || any_neg) {  // (uniform; only the last chunk's tail - or a negative temperature)
@@ -603,16 +671,9 @@ __global__ void __launch_bounds__(kXThreads, 1)
         const bool lab_here = static_cast<unsigned>(d) < static_cast<unsigned>(kXGC);
         if (d >= kXGC) max_before = fmaxf(max_before, bm);
         if (lab_here) {  // (divergent: one lane in thirty)
-          // v[d] by a select tree, then the columns before d only if the label can still be the first maximum
-          float t[kXGC / 2];
-#pragma unroll
-          for (int i = 0; i < kXGC / 2; ++i) t[i] = (d & (kXGC / 2)) ? __uint_as_float(v[i + kXGC / 2]) : __uint_as_float(v[i]);
-#pragma unroll
-          for (int w = kXGC / 4; w >= 1; w >>= 1) {
-#pragma unroll
-            for (int i = 0; i < w; ++i) t[i] = (d & w) ? t[i + w] : t[i];
-          }
-          lab_raw = t[0];
+          // v[d] by a jump (one or two lanes of the warp are here: a branch per lane beats a select tree run by all),
+          // then the columns before d only if the label can still be the first maximum
+          lab_raw = pick_col(v, d);
           if (lab_raw == bm) {
             float b0 = -INFINITY, b1 = -INFINITY;
 #pragma unroll
@@ -661,17 +722,8 @@ __global__ void __launch_bounds__(kXThreads, 1)
         unpack2(fadd2(sx2, sy2), s0, s1);
         run_sum += s0 + s1;
         if (kDs) run_pr += q0 + q1;
-        if (lab_here) {  // the label column's staged value, as it was rounded
-          uint32_t w4[kXGW / 2];
-          const int dw = d >> 1;
-#pragma unroll
-          for (int i = 0; i < kXGW / 2; ++i) w4[i] = (dw & (kXGW / 2)) ? out[i + kXGW / 2] : out[i];
-#pragma unroll
-          for (int w = kXGW / 4; w >= 1; w >>= 1) {
-#pragma unroll
-            for (int i = 0; i < w; ++i) w4[i] = (dw & w) ? w4[i + w] : w4[i];
-          }
-          lab_p = __uint_as_float((d & 1) ? (w4[0] & 0xffff0000u) : (w4[0] << 16));
+        if (lab_here) {  // the label column's staged value, as it was rounded (the same three operations as in the loop)
+          lab_p = __bfloat162float(__float2bfloat16_rn(x_exp2(__fmaf_rn(lab_raw, sl2, noff))));
           lab_gm = new_max;
         }
         return new_max;
@@ -680,116 +732,139 @@ __global__ void __launch_bounds__(kXThreads, 1)
       // ---- the first half of the new unit goes to registers of its own: the other chunks publish the previous unit's
       //      row statistics at the END of their iteration, so looking at them half a unit later (nearly) never finds them
       //      missing - CTA pairs of a group may drift by a good part of a unit without anybody waiting. ----
-      tmem_ldg(taddr, v);
-      static_for<0, kXHalf>([&](auto gc) {
+      // (double-buffered: wait for group g, start the load of group g + 1 into the other register set, then work on
+      //  g - measured slower, off.)  Groups 0 .. kXHalf-1 of the new unit go to registers of their own (nk) - the
+      //  previous unit still sits in pk; after group kXHalf-1 its records are looked at, it is finished, and from then
+      //  on group g of the new unit takes the registers group g of the previous unit has just left.
+      constexpr int kB = kXDoubleBuf ? 1 : 0;  // buffer of group g: g & kB
+      tmem_ldg(taddr, vv[0]);
+      static_for<0, kXGroups>([&](auto gc) {
         constexpr int g = decltype(gc)::value;
+        constexpr bool last = g == kXGroups - 1;
         tmem_ld_wait();
-        pin16(v);
+        pin16(vv[g & kB]);
         if (g == 0) XDBG_ACC(1);
-        gm[g] = run_group(nk + kXGW * g, gc);
-        tmem_ldg(taddr + kXGC * (g + 1), v);
-        if (g == 0 && have_prev) request_prev();  // (the L2 round trip is covered by the next groups)
-      });
-      if (have_prev) {
-        resolve_prev();
-        static_for<0, kXHalf + 1>([&](auto gc) { finish_group(gc); });
-      }
+        if (last) {
+          // accumulator buffer b may be overwritten by the (leader's) MMA warp now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!leader) mbar_arrive_remote(tempty_remote0 + b * 8);
+            else mbar_arrive(&tempty_bar[b]);
+          }
+        } else if (kXDoubleBuf) {
+          tmem_ldg(taddr + kXGC * (g + 1), vv[(g + 1) & kB]);
+        }
+        gm[g] = run_group(vv[g & kB], g < kXHalf ? nk + kXGW * g : pk + kXGW * g, gc);
+        if (!last && !kXDoubleBuf) tmem_ldg(taddr + kXGC * (g + 1), vv[0]);
+        if (g == kXReqAfter && have_prev) request_prev();  // (the L2 round trip is covered by the next groups)
+        if (g == kXHalf - 1) {
+          if (have_prev) {
+            resolve_prev();
+            static_for<0, (kXHalf + 1 < kXGroups ? kXHalf + 1 : kXGroups)>([&](auto fc) { finish_any(fc); });
+          }
 #pragma unroll
-      for (int j = 0; j < kXGW * kXHalf; ++j) pk[j] = nk[j];
-      // ---- then group g of the new unit takes the registers group g of the previous unit has just left ----
-      static_for<kXHalf, kXGroups - 1>([&](auto gc) {
-        constexpr int g = decltype(gc)::value;
-        tmem_ld_wait();
-        pin16(v);
-        gm[g] = run_group(pk + kXGW * g, gc);
-        tmem_ldg(taddr + kXGC * (g + 1), v);
-        if (have_prev) finish_group(std::integral_constant<int, g + 1>());
+          for (int j = 0; j < kXGW * kXHalf; ++j) pk[j] = nk[j];
+        } else if (g >= kXHalf && !last) {
+          if (have_prev) finish_any(std::integral_constant<int, g + 1>());
+        }
       });
-      tmem_ld_wait();
-      pin16(v);
-      // accumulator buffer b may be overwritten by the (leader's) MMA warp now
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (!leader) mbar_arrive_remote(tempty_remote0 + b * 8);
-        else mbar_arrive(&tempty_bar[b]);
-      }
-      gm[kXGroups - 1] = run_group(pk + kXGW * (kXGroups - 1), std::integral_constant<int, kXGroups - 1>());
       XDBG_ACC(2);
       if (have_prev) finish_rows();
       XDBG_ACC(3);
 
-      // ---- the four column quarters of a row meet (shared memory) -------------------------------------
-      const uint32_t hx_par = hx_base + (tile_it & 1) * (kXSlices * 128 * kXRecBytes);
-      const uint32_t mine = hx_par + (cq * 128 + rloc) * kXRecBytes;
-      sts128(mine, __float_as_uint(run_max), __float_as_uint(run_sum), __float_as_uint(max_before), __float_as_uint(lab_raw));
-      if (kSecond) sts64(mine + 16, __float_as_uint(run_pr), static_cast<uint32_t>(arg));
-      named_bar_sync(1 + q, 32 * kXSlices);
-      float cm = run_max, before_loc = max_before, lraw = lab_raw;
-      constexpr int kOthers = kXSlices - 1;
-      float o_max[kOthers], o_sum[kOthers], o_pr[kOthers];
-      int carg = arg;
+      // ---- the column slices of a row meet in slice 0's thread (shared memory): the other slices drop their record and
+      //      go on - they never wait; slice 0 (nearly always the last to get here: it also owns the per-row results)
+      //      combines and publishes the chunk's record to the other class chunks of the row (L2).  Every value travels
+      //      with the launch epoch in the same 8-byte word pair (which the memory system delivers whole): a reader
+      //      checks the epoch - no fence, no flag.  Slot reuse: a slot is written again four units later, which needs
+      //      the accumulator of two units later, which slice 0 frees after it has read this slot.
+      const uint32_t hx_slot = hx_base + (tile_it & (kXHxSlots - 1)) * ((kXSlices - 1) * 128 * kXRecBytes);
+      const uint4* rec_row = wk.recs + row * n_chunks * 2;
+      if (cq != 0) {
+        const uint32_t mine = hx_slot + ((cq - 1) * 128 + rloc) * kXRecBytes;
+        sts128(mine, __float_as_uint(run_max), __float_as_uint(run_sum), __float_as_uint(max_before), __float_as_uint(lab_raw));
+        if (kSecond) sts64(mine + 16, __float_as_uint(run_pr), static_cast<uint32_t>(arg));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xbar[q]);
+      } else {
+        mbar_wait(&xbar[q], tile_it & 1);
+        float cm = run_max, before_loc = max_before, lraw = lab_raw;
+        constexpr int kOthers = kXSlices - 1;
+        float o_max[kOthers], o_sum[kOthers], o_pr[kOthers];
+        int o_arg[kOthers];
 #pragma unroll
-      for (int k = 0; k < kOthers; ++k) {
-        const int oq = (cq + 1 + k) % kXSlices;
-        const uint32_t other = hx_par + (oq * 128 + rloc) * kXRecBytes;
-        const uint4 o4 = lds128(other);
-        o_max[k] = __uint_as_float(o4.x);
-        o_sum[k] = __uint_as_float(o4.y);
-        cm = fmaxf(cm, o_max[k]);
-        before_loc = fmaxf(before_loc, __uint_as_float(o4.z));  // quarters before the label's hold their whole max, later ones -inf
-        lraw = fmaxf(lraw, __uint_as_float(o4.w));               // exactly one quarter saw the label column (the others hold -inf)
-        o_pr[k] = kDs ? __uint_as_float(lds64(other + 16).x) : 0.f;
-      }
-      float cs, cpr = 0.f;
-      {
+        for (int k = 0; k < kOthers; ++k) {
+          const uint32_t other = hx_slot + (k * 128 + rloc) * kXRecBytes;
+          const uint4 o4 = lds128(other);
+          o_max[k] = __uint_as_float(o4.x);
+          o_sum[k] = __uint_as_float(o4.y);
+          cm = fmaxf(cm, o_max[k]);
+          before_loc = fmaxf(before_loc, __uint_as_float(o4.z));  // slices before the label's hold their whole max, later ones -inf
+          lraw = fmaxf(lraw, __uint_as_float(o4.w));               // exactly one slice saw the label column (the others hold -inf)
+          o_pr[k] = 0.f;
+          o_arg[k] = 0;
+          if (kSecond) {
+            const uint2 o2 = lds64(other + 16);
+            o_pr[k] = __uint_as_float(o2.x);
+            o_arg[k] = static_cast<int>(o2.y);
+          }
+        }
         const float offc = __fmul_rn(cm, sl2);
         const float e_me = x_exp2(__fmul_rn(run_max, sl2) - offc);
-        cs = run_sum * e_me;
-        if (kDs) cpr = run_pr * e_me;
+        float cs = run_sum * e_me, cpr = kDs ? run_pr * e_me : 0.f;
 #pragma unroll
         for (int k = 0; k < kOthers; ++k) {
           const float e = x_exp2(__fmul_rn(o_max[k], sl2) - offc);
           cs = fmaf(o_sum[k], e, cs);
           if (kDs) cpr = fmaf(o_pr[k], e, cpr);
         }
-      }
-      if (kPred) {
-        // the chunk's first maximal column: the lowest quarter among those that hold the chunk maximum
-        float bmx = run_max;
-        int cbest = cq;
+        int carg = arg;
+        if (kPred) {  // the chunk's first maximal column: the lowest slice among those that hold the chunk maximum
+          float bmx = run_max;
 #pragma unroll
-        for (int k = 0; k < kOthers; ++k) {
-          const int oq = (cq + 1 + k) % kXSlices;
-          if (o_max[k] > bmx || (o_max[k] == bmx && oq < cbest)) {
-            bmx = o_max[k];
-            cbest = oq;
+          for (int k = 0; k < kOthers; ++k) {
+            if (o_max[k] > bmx) {
+              bmx = o_max[k];
+              carg = o_arg[k];
+            }
           }
         }
-        if (cbest != cq) carg = static_cast<int>(lds64(hx_par + (cbest * 128 + rloc) * kXRecBytes + 16).y);
-      }
-      // ---- ... and go to the other class chunks of the row (L2).  Every value travels with the launch epoch in the
-      //      same 8-byte word pair (which the memory system delivers whole): a reader checks the epoch - no fence, no flag.
-      if (n_chunks > 1 && cq == 0 && c.valid) {
-        uint4* rec = wk.recs + (row * n_chunks + chunk) * 2;
-        st_volatile_v4(rec, __float_as_uint(cm), epoch, __float_as_uint(cs), epoch);
-        if (kSecond) st_volatile_v4(rec + 1, __float_as_uint(cpr), epoch, static_cast<uint32_t>(carg), epoch);
+        if (c.valid) {
+          uint4* rec = const_cast<uint4*>(rec_row) + chunk * 2;
+          st_volatile_v4(rec, __float_as_uint(cm), epoch, __float_as_uint(cs), epoch);
+          if (kSecond) st_volatile_v4(rec + 1, __float_as_uint(cpr), epoch, static_cast<uint32_t>(carg), epoch);
+        }
+        p_before = before_loc;
+        p_lraw = lraw;
       }
       XDBG_ACC(4);
       // this unit becomes the previous one
 #pragma unroll
       for (int g = 0; g < kXGroups; ++g) p_gm[g] = gm[g];
-      p_cm = cm; p_cs = cs; p_cpr = cpr; p_before = before_loc; p_lraw = lraw; p_lab_p = lab_p; p_lab_gm = lab_gm;
-      p_carg = carg; p_label = label; p_tile = tile;
+      p_lab_p = lab_p; p_lab_gm = lab_gm;
+      p_label = label; p_tile = tile; p_rec = rec_row;
     }
     if (p_tile >= 0) {  // the last unit
       XDBG_MARK();
       request_prev();
       resolve_prev();
       XDBG_ACC(5);
-      static_for<0, kXGroups>([&](auto gc) { finish_group(gc); });
+      static_for<0, kXGroups>([&](auto gc) { finish_any(gc); });
       finish_rows();
       XDBG_ACC(6);
+    }
+    if (kXTmaStore && lane == 0) bulk_wait<0>();  // this warp's G stores are complete (and have left its staging boxes)
+    if (cq == 0 && wk.tile_part) {
+      // deterministic per-(CTA, row quarter, run) partial sums; the statistics kernel adds them in a fixed order
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const float a = warp_sum(acc_loss[s2]), dd = kDs ? warp_sum(acc_ds[s2]) : 0.f;
+        const int hh = warp_sum_i(acc_hit[s2]), cnt = warp_sum_i(acc_cnt[s2]);
+        if (lane == 0)
+          *reinterpret_cast<float4*>(wk.tile_part + ((static_cast<int64_t>(blockIdx.x) * 4 + q) * 2 + s2) * 4) =
+              make_float4(a, dd, static_cast<float>(hh), static_cast<float>(cnt));
+      }
     }
 #ifdef UML_FWD_TIMING
     if (warp == 0 && lane == 0) XDBG_FLUSH(0, 9);
@@ -872,12 +947,13 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
-// workspace carving (UML_TILE_WS_FLOATS): [ctrl 16 u32][(unused) units*8][tile_part units*2*4*32 f][recs n_rows*4*8 f]
+// workspace carving (UML_TILE_WS_FLOATS): [ctrl 16 u32][(unused) units*8][tile_part units*256 f][recs n_rows*4*8 f]
 struct XLayout {
   unsigned* ctrl;
   float* tile_part;
   uint4* recs;
-  int64_t part_entries;  // (tile, chunk, warp) partial records per run
+  int64_t part_entries;  // (CTA, row quarter) partial records per run
+  int64_t n_groups;      // CTA-pair groups of the launch: grid = n_groups * n_chunks * 2
 };
 static XLayout x_layout(float* tile_ws, int64_t n_rows, int n_classes) {
   const int64_t units = (n_rows + 255) / 256;
@@ -886,7 +962,9 @@ static XLayout x_layout(float* tile_ws, int64_t n_rows, int n_classes) {
   l.ctrl = reinterpret_cast<unsigned*>(tile_ws);
   l.tile_part = tile_ws + 16 + units * 8;
   l.recs = reinterpret_cast<uint4*>(l.tile_part + units * 256);
-  l.part_entries = units * 2 * n_chunks * 4;
+  l.n_groups = (sm_count() / 2) / n_chunks;
+  if (l.n_groups > units) l.n_groups = units;
+  l.part_entries = l.n_groups * n_chunks * 2 * 4;  // (<= units * 32: fits the units * 256 floats set aside for them)
   return l;
 }
 
@@ -930,6 +1008,11 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
   if (make_tmap_2d(&tw, W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dim, n_classes, static_cast<uint64_t>(dim) * 2, 64, 128,
                    CU_TENSOR_MAP_SWIZZLE_128B))
     return 1;
+  CUtensorMap tg = tx;  // (prediction mode: never used)
+  if (kXTmaStore && G &&
+      make_tmap_2d(&tg, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, static_cast<uint64_t>(ldg), n_rows, static_cast<uint64_t>(ldg) * 2, 32, 32,
+                   CU_TENSOR_MAP_SWIZZLE_64B))
+    return 1;
   XSegs fs;
   fs.n0 = segs->nseg > 1 ? n0 : INT64_MAX;
   bool learnable = false;
@@ -942,7 +1025,7 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
     learnable = learnable || segs->scale_dev[j] != nullptr;
   }
   const bool ds = learnable || row_dscale != nullptr;  // the sum p * raw is only needed for d loss / d scale
-  using Kern = void (*)(CUtensorMap, CUtensorMap, int64_t, int, int, int, const int32_t*, XSegs, uint16_t*, int64_t, float*,
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, int64_t, int, int, int, const int32_t*, XSegs, uint16_t*, int64_t, float*,
                         int32_t*, int32_t*, float*, XWork);
   const int slot = (row_pred ? 2 : 0) + (ds ? 1 : 0);
   const Kern kerns[4] = {head_fwd_ce_x_kernel<false, false>, head_fwd_ce_x_kernel<false, true>,
@@ -953,17 +1036,15 @@ int uml_head_fwd_ce_x_bf16(const uint16_t* X, int64_t n_rows, int32_t dim, const
     attr_set[slot] = true;
   }
   const int n_chunks = (n_classes + 255) / 256;
-  const int64_t units = (n_rows + 255) / 256;
-  int64_t n_groups = (sm_count() / 2) / n_chunks;
-  if (n_groups > units) n_groups = units;
-  UML_REQUIRE(n_groups >= 1, "head_fwd_ce_x: the device has too few SMs for %d class chunks", n_chunks);
   const XLayout l = x_layout(tile_ws, n_rows, n_classes);
+  const int64_t n_groups = l.n_groups;
+  UML_REQUIRE(n_groups >= 1, "head_fwd_ce_x: the device has too few SMs for %d class chunks", n_chunks);
   XWork wk;
   wk.tile_part = l.tile_part;
   wk.recs = l.recs;
   wk.ctrl = l.ctrl;
   const dim3 grid(static_cast<unsigned>(n_groups * n_chunks * 2));
-  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, kPdlFwd, tx, tw, n_rows,
+  UML_CUDA(launch_kernel(kerns[slot], grid, dim3(kXThreads), kXSmemBytes, as_stream(stream), 2, kPdlFwd, tx, tw, tg, n_rows,
                          static_cast<int>(dim), static_cast<int>(n_classes), static_cast<int>(n_groups), labels, fs, G, ldg,
                          row_loss, row_pred, row_correct, row_dscale, wk));
   if (stats)

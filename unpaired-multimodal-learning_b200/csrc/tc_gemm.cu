@@ -19,6 +19,11 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "optim.cuh"
+
+#ifndef UML_DW_UPD_UNROLL
+#define UML_DW_UPD_UNROLL 1  // float4 elements per thread and trip of the fused update (registers: 32 per element)
+#endif
 
 int64_t uml_fwd_tiles(int64_t n_rows);  // tc_fwd.cu: 128-row tiles the forward kernel writes partials for
 
@@ -64,9 +69,27 @@ struct FixArgs {
   // `stats` by an idle warp of the first CTA - the forward's statistics cost no launch of their own
   const float* part;
   int64_t part_entries;
+  // fp32 split-K output only (single-GPU step): when upd_p is set the kernel also finishes the step - every CTA signals
+  // its partial tile, waits for the tile's other splits (all CTAs of the grid are co-resident or become so without
+  // anybody's help) and then sums ITS share of the tile's rows over the splits, in split order, and applies AdamW to
+  // them: W, m, v and the bf16 shadow of W leave this kernel final, no update launch follows (ldo == N: the output
+  // tile is laid out like W)
+  float* upd_p;
+  float* upd_m;
+  float* upd_v;
+  __nv_bfloat16* upd_shadow;
+  AdamArgs upd;
+  unsigned* upd_cnt;     // [2 per CTA tile]: arrived, departed (both 0 between launches)
+  unsigned* upd_failed;  // set when a split never arrived (the update of that tile is then skipped)
 };
 
-template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false, bool kUpd = false>
 __global__ void __launch_bounds__(256, 1)
     tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int64_t M,
                    int64_t N, int64_t K, int n_splits, void* __restrict__ out_v, int64_t ldo, FixArgs fix) {
@@ -385,6 +408,89 @@ __global__ void __launch_bounds__(256, 1)
     if (kCG == 2) tmem_dealloc_cg2(tmem_base, 256);
     else tmem_dealloc(tmem_base, 256);
   }
+  if constexpr (kUpd && !kOutBf16) {
+    if (fix.upd_p != nullptr) {
+      // ------------------------------------------------ split-K sum + AdamW of this CTA's share of its tile ----------
+      __shared__ int upd_ok;
+      unsigned* arrived = fix.upd_cnt + 2 * (blockIdx.x * gridDim.y + blockIdx.y);
+      __threadfence();  // the epilogue warps' partial rows are visible device-wide before the arrival below
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        atomicAdd(arrived, 1u);
+        bool ok = true;
+        for (unsigned polls = 0; ld_acquire_u32(arrived) < static_cast<unsigned>(n_splits); ++polls) {
+          if (polls > (1u << 22)) {  // ~ a second: never hang the GPU; the host checks the flag
+            atomicExch(fix.upd_failed, 1u);
+            ok = false;
+            break;
+          }
+        }
+        upd_ok = ok ? 1 : 0;
+      }
+      __syncthreads();
+      if (upd_ok) {
+        const float* parts = static_cast<const float*>(out_v);
+        const int64_t plane = M * ldo;
+        const int r_lo = (128 * split) / n_splits, r_hi = (128 * (split + 1)) / n_splits;
+        const int64_t n_base = static_cast<int64_t>(n_tile) * Cfg::kTileN;
+        const int cols4 = static_cast<int>(((N - n_base < Cfg::kTileN ? N - n_base : Cfg::kTileN) + 3) / 4);
+        const int total4 = (r_hi - r_lo) * cols4;
+        constexpr int kU = UML_DW_UPD_UNROLL, kMaxSplits = 8;
+#pragma unroll 1
+        for (int e0 = threadIdx.x; e0 < total4; e0 += 256 * kU) {
+          float4 q[kMaxSplits][kU], w[kU], mm[kU], vv[kU];
+          int64_t off[kU];
+          bool on[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            const int e = e0 + u * 256, r = e / cols4;
+            const int64_t m = m_cta + r_lo + r;
+            on[u] = e < total4 && m < M;
+            off[u] = m * ldo + n_base + (e - r * cols4) * 4;
+          }
+#pragma unroll
+          for (int sp = 0; sp < kMaxSplits; ++sp) {
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+              if (sp < n_splits && on[u]) q[sp][u] = __ldcg(reinterpret_cast<const float4*>(parts + sp * plane + off[u]));
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            if (on[u]) {
+              w[u] = *reinterpret_cast<const float4*>(fix.upd_p + off[u]);
+              mm[u] = *reinterpret_cast<const float4*>(fix.upd_m + off[u]);
+              vv[u] = *reinterpret_cast<const float4*>(fix.upd_v + off[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            if (!on[u]) continue;
+            float4 g = q[0][u];
+#pragma unroll
+            for (int sp = 1; sp < kMaxSplits; ++sp) {
+              if (sp < n_splits) { g.x += q[sp][u].x; g.y += q[sp][u].y; g.z += q[sp][u].z; g.w += q[sp][u].w; }
+            }
+            float4 o = w[u];
+            o.x = adam_one(fix.upd, o.x, g.x, mm[u].x, vv[u].x);
+            o.y = adam_one(fix.upd, o.y, g.y, mm[u].y, vv[u].y);
+            o.z = adam_one(fix.upd, o.z, g.z, mm[u].z, vv[u].z);
+            o.w = adam_one(fix.upd, o.w, g.w, mm[u].w, vv[u].w);
+            *reinterpret_cast<float4*>(fix.upd_p + off[u]) = o;
+            *reinterpret_cast<float4*>(fix.upd_m + off[u]) = mm[u];
+            *reinterpret_cast<float4*>(fix.upd_v + off[u]) = vv[u];
+            if (fix.upd_shadow) *reinterpret_cast<uint2*>(fix.upd_shadow + off[u]) = pack_bf16x4(o);
+          }
+        }
+      }
+      if (threadIdx.x == 0) {  // the last split to leave puts the tile's counters back to zero for the next launch
+        const unsigned d = atomicAdd(arrived + 1, 1u);
+        if (d == static_cast<unsigned>(n_splits) - 1u) {
+          atomicExch(arrived, 0u);
+          atomicExch(arrived + 1, 0u);
+        }
+      }
+    }
+  }
 }
 
 static int cta_group_for(int64_t M) {
@@ -406,11 +512,11 @@ static int gemm_splits(int64_t M, int64_t N, int64_t K, int cg) {
   return static_cast<int>(s);
 }
 
-template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false>
+template <bool kAMn, bool kBMn, bool kOutBf16, int kCG, bool kFix = false, bool kUpd = false>
 static int launch_tc_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int64_t M, int64_t N, int64_t K, int n_splits,
                           void* out, int64_t ldo, cudaStream_t st, const FixArgs& fix = FixArgs()) {
   using Cfg = GemmCfg<kCG>;
-  auto kern = tc_gemm_kernel<kAMn, kBMn, kOutBf16, kCG, kFix>;
+  auto kern = tc_gemm_kernel<kAMn, kBMn, kOutBf16, kCG, kFix, kUpd>;
   static bool attr_set = false;
   if (!attr_set) {
     UML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -443,6 +549,11 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, ldb * 2, 64, kGBlockK, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
   } else {
     if (make_tmap_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, N, ldb * 2, kGBlockK, 256 / cg, CU_TENSOR_MAP_SWIZZLE_128B)) return 1;
+  }
+  if (fix && !fix->fac && !fix->wait_done && fix->upd_p) {  // dW kernel with the update in its tail (an instantiation of its own:
+    UML_REQUIRE(a_mn && b_mn && !out_bf16 && ldo == N, "tc_gemm: the fused update is wired for the dW layout only");  // its registers)
+    return cg == 2 ? launch_tc_gemm<true, true, false, 2, false, true>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
+                   : launch_tc_gemm<true, true, false, 1, false, true>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);
   }
   if (fix && !fix->fac && !fix->wait_done) {  // statistics job only: plain dW kernel
     UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: the statistics job is wired for the dW layout only");
@@ -506,6 +617,44 @@ int uml_head_bwd_dw_stats_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X
   fx.part_entries = part_entries;
   fx.nseg = nseg;
   fx.stats = stats;
+  return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
+}
+
+// dW + forward statistics + split-K sum + AdamW in one launch (library-internal, step.cu; single-GPU bf16 step)
+int uml_head_bwd_dw_update_bf16(const uint16_t* G, int64_t ldg, const uint16_t* X, int64_t n_rows, int32_t dim, int32_t n_classes,
+                                float* partials, int32_t n_splits, const float* part, int64_t part_entries, int32_t nseg,
+                                uml_seg_stats* stats, float* W, float* m, float* v, uint16_t* W16, const uml::AdamArgs* adam,
+                                unsigned* failed, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(G && X && partials && n_rows > 0 && n_splits >= 1 && n_splits <= 8 && W && m && v && adam && failed,
+              "dw_update: bad arguments");
+  UML_REQUIRE(dim % 8 == 0 && ldg % 64 == 0 && ldg >= n_classes, "dw_update: dim must be a multiple of 8 and ldg of 64");
+  // counters of the tiles' splits: one small device buffer per device, zero between launches (the kernel resets them)
+  static unsigned* cnt[64] = {nullptr};
+  int dev = 0;
+  UML_CUDA(cudaGetDevice(&dev));
+  UML_REQUIRE(dev >= 0 && dev < 64, "dw_update: device index");
+  constexpr int kCntWords = 2 * 1024;
+  if (!cnt[dev]) {
+    UML_CUDA(cudaMalloc(&cnt[dev], kCntWords * sizeof(unsigned)));
+    UML_CUDA(cudaMemset(cnt[dev], 0, kCntWords * sizeof(unsigned)));
+  }
+  const int cg = cta_group_for(n_classes);
+  const int64_t tiles = ((n_classes + 128 * cg - 1) / (128 * cg)) * cg * ((dim + 255) / 256);
+  UML_REQUIRE(tiles * 2 <= kCntWords, "dw_update: too many output tiles (%lld)", (long long)tiles);
+  FixArgs fx;
+  memset(&fx, 0, sizeof(fx));
+  fx.part = part;
+  fx.part_entries = part_entries;
+  fx.nseg = nseg;
+  fx.stats = part ? stats : nullptr;
+  fx.upd_p = W;
+  fx.upd_m = m;
+  fx.upd_v = v;
+  fx.upd_shadow = reinterpret_cast<__nv_bfloat16*>(W16);
+  fx.upd = *adam;
+  fx.upd_cnt = cnt[dev];
+  fx.upd_failed = failed;
   return tc_gemm(G, ldg, true, X, dim, true, n_classes, dim, n_rows, partials, dim, false, n_splits, as_stream(stream), &fx);
 }
 

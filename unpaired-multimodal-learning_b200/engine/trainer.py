@@ -149,7 +149,7 @@ class StepEngine:
         self._event_pool = []
         self.profile_only = None
         self.prefetch = True      # uml_linear_run gathers step i+1's rows on a side stream during step i
-        self.X16_alt = self.labels32_alt = None
+        self.X16_alt = self.labels32_alt = self.X16_alt2 = self.labels32_alt2 = None
         self.shadow_banks = True  # keep a bf16 copy of each bank in HBM (+50% bank memory) for the tensor-core path
         self._args = None
         self.single_call = True  # False: dispatch every kernel from Python (debugging)
@@ -298,9 +298,12 @@ class StepEngine:
                 if self.X16_alt is None:  # second operand buffer: the next step's rows are gathered while this one runs
                     self.X16_alt = torch.empty_like(self.X16)
                     self.labels32_alt = torch.empty_like(self.labels32)
+                    self.X16_alt2 = torch.empty_like(self.X16)   # third: the gather runs two steps ahead (step.cu)
+                    self.labels32_alt2 = torch.empty_like(self.labels32)
                 a.X16_alt, a.labels32_alt = self.X16_alt.data_ptr(), self.labels32_alt.data_ptr()
+                a.X16_alt2, a.labels32_alt2 = self.X16_alt2.data_ptr(), self.labels32_alt2.data_ptr()
             else:
-                a.X16_alt = a.labels32_alt = None
+                a.X16_alt = a.labels32_alt = a.X16_alt2 = a.labels32_alt2 = None
         need_dw = self.world > 1 or (bf16 and self.opt.name == "sgd")
         if need_dw and self.dW is None:
             self.dW = torch.empty_like(W)
@@ -735,6 +738,9 @@ class StepEngine:
             raw = self.host_log.clone()
         else:
             raw = self.stats_log.cpu()
+        if self.ws16 is not None and _load_lib().uml_fwd_x_failed(self.ws16.fac.data_ptr()):
+            raise RuntimeError("tensor-core step: a CTA waited a second for its peers (forward statistics exchange or the dW "
+                               "kernel's split-K update); the affected step's results are undefined - restart from a checkpoint")
         ints = raw.view(torch.int32)
         out = []
         for s in slots:
