@@ -342,7 +342,7 @@ def _stage(msg):
 def run_ours(args, wl, rank, world, dev):
     import uml_b200  # noqa: F401
     from uml_b200 import _lib, finetune as ft
-    from uml_b200.engine.datasets.utils import BankLoader
+    from uml_b200.engine.datasets.utils import BankLoader, mark_ready
     from uml_b200.engine.trainer import StepEngine
 
     dist = torch.distributed if world > 1 else None
@@ -390,6 +390,8 @@ def run_ours(args, wl, rank, world, dev):
         for j in range(n):
             img, txt, lr = draw(i0 + j)
             img.idx, txt.idx = img.idx.clone(), txt.idx.clone()
+            mark_ready(img)   # the clones are what the steps read: vouch for them (IndexBatch.ready), as the loaders do
+            mark_ready(txt)   # for their uploads
             staged.append((img, txt, lr))
 
     def step(i, n=1):

@@ -249,9 +249,16 @@ typedef struct {
   /* optional third operand buffers: the gather then runs two steps ahead, and no forward kernel waits for an event
    * of the side stream that is signalled at the last moment (UML_PREFETCH_DEPTH=1 keeps one step ahead)              */
   uint16_t*     X16_alt2;  int32_t* labels32_alt2;
+  /* optional cudaEvent_t after which every index batch of the call is valid in device memory (recorded by whoever
+   * uploaded them).  With it - and the three operand buffers - uml_linear_run keeps its gather pipeline running through
+   * the call boundaries: the first steps' rows are gathered beside the previous call's last steps.  NULL: every call
+   * starts with a gather on `stream`.                                                                             */
+  void*         idx_ready;
 } uml_linear_step_args;
 
 int uml_linear_step(const uml_linear_step_args* args /*host*/, void* stream);
+/* call after anything else has used the operand buffers (X16, X16_alt, X16_alt2): the next uml_linear_run starts cold */
+int uml_linear_run_reset(void);
 
 /* Several consecutive iterations enqueued by one call (the host stays well ahead of the GPU: Python
  * dispatch, not the kernels, limited throughput when every step was a separate call).  `base` describes

@@ -45,7 +45,7 @@ class LinearStepArgs(C.Structure):
                 ("max_splits", c_i32), ("w16_valid", c_i32), ("dW_out", c_vp), ("dW_scratch", c_vp),
                 ("scale_param", c_vp * 2), ("scale_m", c_vp * 2), ("scale_v", c_vp * 2), ("scale_step", c_i64 * 2),
                 ("ev", c_vp * 8), ("dp_allreduce", c_i32), ("X16_alt", c_vp), ("labels32_alt", c_vp), ("g_capacity_rows", c_i64),
-                ("X16_alt2", c_vp), ("labels32_alt2", c_vp)]
+                ("X16_alt2", c_vp), ("labels32_alt2", c_vp), ("idx_ready", c_vp)]
 
 
 class RunStep(C.Structure):
@@ -114,6 +114,7 @@ PROTOTYPES = {
     "uml_reduce_tile_stats": [c_vp, c_i64, c_i32, c_vp, c_vp],
     "uml_fwd_x_failed": [c_vp],
     "uml_linear_step": [C.POINTER(LinearStepArgs), c_vp],
+    "uml_linear_run_reset": [],
     "uml_linear_run": [C.POINTER(LinearStepArgs), C.POINTER(RunStep), c_i32, c_vp],
     "uml_dp_unique_id": [c_vp],
     "uml_dp_init": [c_vp, c_i32, c_i32],

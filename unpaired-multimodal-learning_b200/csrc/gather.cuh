@@ -55,7 +55,7 @@ __device__ __forceinline__ void gather_rows_by_warp(const CopySeg& s0, const Cop
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int v = v0 + j * 32 + lane;
-        if (v < vec_per_row) dst[v] = x[j];
+        if (v < vec_per_row) __stcs(dst + v, x[j]);  // read again a step or two later, after 0.5 GB of other traffic: not worth L2
       }
     }
   }

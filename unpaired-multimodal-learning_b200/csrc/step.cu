@@ -22,11 +22,26 @@ struct Pipe {
   cudaEvent_t dw_done = nullptr, fwd_done = nullptr;
   unsigned* split_done = nullptr;       // [8] fix-up CTAs finished per dW split, then one int: watchdog flag
   cudaEvent_t ready[3] = {nullptr, nullptr, nullptr}, freed[3] = {nullptr, nullptr, nullptr}, start = nullptr, mid = nullptr;
+  // the pipeline of uml_linear_run survives the call boundary when the caller vouches for its index batches (idx_ready):
+  bool warm = false;                    // freed[] / fwd_mid[] describe the last steps of the previous call
+  int phase = 0;                        // operand buffer of the next step
+  unsigned gstep = 0;                   // steps enqueued so far (fwd_mid[gstep & 1] is recorded after step gstep's forward)
+  const void* bufs[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fwd_mid[2] = {nullptr, nullptr};
   bool ok = false;
 };
 
+// any other user of the operand buffers (single-step calls, Python-side kernels) makes the next run start cold
+void pipe_invalidate();
+
+static Pipe g_pipes[64];
+void pipe_invalidate() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) g_pipes[dev].warm = false;
+}
+
 Pipe* get_pipe() {
-  static Pipe pipes[64];
+  Pipe* pipes = g_pipes;
   static bool tried[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
@@ -47,6 +62,7 @@ Pipe* get_pipe() {
       good = good && cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming) == cudaSuccess;
     }
     good = good && cudaEventCreateWithFlags(&p.start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2; ++i) good = good && cudaEventCreateWithFlags(&p.fwd_mid[i], cudaEventDisableTiming) == cudaSuccess;
     good = good && cudaEventCreateWithFlags(&p.mid, cudaEventDisableTiming) == cudaSuccess;
     good = good && cudaEventCreateWithFlags(&p.dw_done, cudaEventDisableTiming) == cudaSuccess;
     good = good && cudaEventCreateWithFlags(&p.fwd_done, cudaEventDisableTiming) == cudaSuccess;
@@ -216,6 +232,107 @@ static int dp_reduce_and_update(const uml_linear_step_args* a, int64_t np, void*
   return rc;
 }
 
+
+static bool continuous_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("UML_PREFETCH_CONTINUOUS");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+static int linear_run_continuous(const uml_linear_step_args* base, const uml_run_step* steps, int32_t n_steps, void* stream,
+                                 Pipe* pipe) {
+  using namespace uml;
+  constexpr int kNb = 3, kDepth = 2;
+  uml_linear_step_args a = *base;
+  auto patch = [&](uml_linear_step_args& t, const uml_run_step& s) {
+    for (int k = 0; k < t.nseg; ++k) {
+      t.seg[k].idx = s.idx[k];
+      t.seg[k].n = s.n[k];
+      t.seg[k].loss_weight = s.loss_weight[k];
+      t.scale_step[k] = s.scale_step[k];
+    }
+    t.upd.lr = s.lr;
+    t.upd.step = s.opt_step;
+    t.stats = s.stats;
+    for (int k = 0; k < 8; ++k) t.ev[k] = s.ev[k];
+  };
+  uint16_t* xbuf[kNb] = {base->X16, base->X16_alt, base->X16_alt2};
+  int32_t* lbuf[kNb] = {base->labels32, base->labels32_alt, base->labels32_alt2};
+  cudaStream_t main_st = as_stream(stream);
+  const cudaEvent_t idx_ready = static_cast<cudaEvent_t>(base->idx_ready);
+  if (!(pipe->warm && pipe->bufs[0] == xbuf[0] && pipe->bufs[1] == xbuf[1] && pipe->bufs[2] == xbuf[2])) {
+    // cold: everything enqueued so far may still read the buffers
+    pipe->warm = false;
+    pipe->phase = 0;
+    for (int k = 0; k < kNb; ++k) pipe->bufs[k] = xbuf[k];
+    UML_CUDA(cudaEventRecord(pipe->start, main_st));
+  }
+  const bool warm = pipe->warm;
+  const int phase = pipe->phase;
+  const unsigned g0 = pipe->gstep;
+
+  // the gather of step t of this call -> side stream.  `after_fwd`: the forward kernel it follows (so that it shares the
+  // machine with a dW GEMM and an update, never - but for its tail - with a forward kernel)
+  auto launch_gather = [&](int t, cudaEvent_t after_fwd) -> int {
+    const int tb = (phase + t) % kNb;
+    uml_linear_step_args g = a;
+    patch(g, steps[t]);
+    UML_CUDA(cudaStreamWaitEvent(pipe->aux, idx_ready, 0));
+    // the dW kernel that last read this buffer: step t - 3 of this call, or of the previous one (warm), else `start`
+    UML_CUDA(cudaStreamWaitEvent(pipe->aux, (t >= kNb || warm) ? pipe->freed[tb] : pipe->start, 0));
+    if (after_fwd) UML_CUDA(cudaStreamWaitEvent(pipe->aux, after_fwd, 0));
+    rec(g.ev[0], pipe->aux);
+    const int rc = shadow_gather(&g, xbuf[tb], lbuf[tb], true, pipe->aux);
+    if (rc) return rc;
+    rec(g.ev[1], pipe->aux);
+    UML_CUDA(cudaEventRecord(pipe->ready[tb], pipe->aux));
+    return 0;
+  };
+  for (int t = 0; t < kDepth && t < n_steps; ++t) {
+    // inside one long call step t's gather would have followed the forward kernel of step t - 2: steps -2 and -1 are the
+    // previous call's last two
+    const int rc = launch_gather(t, warm ? pipe->fwd_mid[(g0 + t) & 1u] : nullptr);  // (g0 + t - 2) & 1
+    if (rc) return rc;
+  }
+
+  g_dp_step = base->dp_allreduce != 0;
+  for (int i = 0; i < n_steps; ++i) {
+    patch(a, steps[i]);
+    if (i > 0) a.w16_valid = 1;  // the optimizer kernel of the previous step refreshed the shadow
+    const int b = (phase + i) % kNb;
+    a.X16 = xbuf[b];
+    a.labels32 = lbuf[b];
+    UML_CUDA(cudaStreamWaitEvent(main_st, pipe->ready[b], 0));
+    struct Next {
+      decltype(launch_gather)* launch;
+      int t;
+      cudaEvent_t mid;
+      cudaStream_t main_st;
+    } next{&launch_gather, i + kDepth < n_steps ? i + kDepth : -1, pipe->fwd_mid[(g0 + i) & 1u], main_st};
+    StepHooks hooks;
+    hooks.pregathered = true;
+    hooks.operand_free = pipe->freed[b];
+    hooks.mid_arg = &next;
+    hooks.after_fwd_kernel = next.mid;  // recorded right after the forward kernel, also for the next call's first gathers
+    hooks.mid = [](void* p) -> int {
+      Next* n = static_cast<Next*>(p);
+      return n->t >= 0 ? (*n->launch)(n->t, n->mid) : 0;
+    };
+    const int rc = linear_step_impl(&a, stream, hooks);
+    if (rc) {
+      pipe->warm = false;
+      return rc;
+    }
+  }
+  pipe->phase = (phase + n_steps) % kNb;
+  pipe->gstep = g0 + static_cast<unsigned>(n_steps);
+  pipe->warm = true;
+  return 0;
+}
+
 extern "C" {
 
 int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, int32_t n_steps, void* stream) {
@@ -248,6 +365,23 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
     }
     if (all) pipe = get_pipe();
   }
+  // ---- continuous mode: three operand buffers and an event that vouches for the index batches (idx_ready) ----------
+  // The gather pipeline then runs through the call boundaries: the first two steps' gathers go to the side stream at once,
+  // ordered after the index upload, after the dW kernel that last read their buffer and after the forward kernel of the
+  // step they would have followed inside one long call - when the host is a chunk ahead of the GPU (it normally is) they
+  // run beside the previous call's last steps, and a call costs no gather on the main stream at all.
+  if (a.precision == 1 && base->X16_alt && base->labels32_alt && base->X16_alt2 && base->labels32_alt2 && base->idx_ready &&
+      n_steps >= 1 && prefetch_placement() == 2 && !fuse_fix() && continuous_enabled()) {
+    bool all = true;
+    for (int i = 0; i < n_steps && all; ++i) {
+      uml_linear_step_args t = a;
+      patch(t, steps[i]);
+      all = shadow_gatherable(&t);
+    }
+    Pipe* cp = all ? get_pipe() : nullptr;
+    if (cp) return linear_run_continuous(base, steps, n_steps, stream, cp);
+  }
+  pipe_invalidate();
   // With a third operand buffer the gather runs TWO steps ahead: step i + 2's rows are copied while step i's dW and
   // update run and may spill into step i + 1 - no forward kernel ever waits for an event that is signalled at the last
   // moment (one step ahead, the gather of step i + 1 ended about when the update did, and the cross-stream hand-over
@@ -370,7 +504,16 @@ int uml_linear_run(const uml_linear_step_args* base, const uml_run_step* steps, 
   return 0;
 }
 
-int uml_linear_step(const uml_linear_step_args* a, void* stream) { return linear_step_impl(a, stream, StepHooks()); }
+int uml_linear_step(const uml_linear_step_args* a, void* stream) {
+  pipe_invalidate();  // (it gathers into the first operand buffer on the main stream)
+  return linear_step_impl(a, stream, StepHooks());
+}
+
+// the operand buffers were used by something the library did not see (Python-side kernels on them): start cold next time
+int uml_linear_run_reset(void) {
+  pipe_invalidate();
+  return 0;
+}
 
 }  // extern "C"
 

@@ -21,6 +21,16 @@
 #include "common.cuh"
 #include "optim.cuh"
 
+// order in which a split walks the contraction (plain kernel only; the kFix prologue keeps contiguous ascending):
+//   0 contiguous slice per split, ascending   1 contiguous, descending   2 k-blocks split, split + S, ... descending
+// The dW GEMM contracts over the batch rows, and the forward kernel has just written G in ascending row order: the
+// newest rows are the ones still in L2.
+// Measured on B200 inside the cfg3 step (73 728 rows, 6 splits): 0.2246-0.2270 ms/step with order 0, the same with 1,
+// 0.2228-0.2232 with 2 - every CTA then reads neighbouring k-blocks at the same time (the 3 + 8 CTAs that share a block
+// of G or X meet in L2) and the sweep starts where G is still resident.
+#ifndef UML_DW_KORDER
+#define UML_DW_KORDER 2
+#endif
 #ifndef UML_DW_UPD_UNROLL
 #define UML_DW_UPD_UNROLL 1  // float4 elements per thread and trip of the fused update (registers: 32 per element)
 #endif
@@ -110,8 +120,11 @@ __global__ void __launch_bounds__(256, 1)
   const int64_t m_cta = static_cast<int64_t>(m_tile) * Cfg::kTileM + rank * 128;   // first output row of this CTA
   const int64_t n_cta = static_cast<int64_t>(n_tile) * Cfg::kTileN + rank * Cfg::kCtaN;  // first B column staged here
   const int num_kb = static_cast<int>((K + kGBlockK - 1) / kGBlockK);
-  const int kb_lo = static_cast<int>((static_cast<int64_t>(num_kb) * split) / n_splits);
-  const int kb_hi = static_cast<int>((static_cast<int64_t>(num_kb) * (split + 1)) / n_splits);
+  constexpr int kOrder = kFix ? 0 : UML_DW_KORDER;
+  // (kOrder 2: kb_lo .. kb_hi only count this split's k-blocks; block j of the walk is split + n_splits * (count - 1 - j))
+  const int kb_lo = kOrder == 2 ? 0 : static_cast<int>((static_cast<int64_t>(num_kb) * split) / n_splits);
+  const int kb_hi = kOrder == 2 ? (num_kb - split + n_splits - 1) / n_splits
+                                : static_cast<int>((static_cast<int64_t>(num_kb) * (split + 1)) / n_splits);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -165,7 +178,8 @@ __global__ void __launch_bounds__(256, 1)
         mbar_wait(&empty_bar[s], ph ^ 1);
         unsigned char* a = smem + s * Cfg::kStageBytes;
         unsigned char* b = a + Cfg::kABytes;
-        const int32_t k0 = kb * kGBlockK;
+        const int kbe = kOrder == 0 ? kb : kOrder == 1 ? kb_hi - 1 - (kb - kb_lo) : split + n_splits * (kb_hi - 1 - kb);
+        const int32_t k0 = kbe * kGBlockK;
         if (kCG == 1 || kFix) {
           mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
           if (kAMn) {
@@ -561,6 +575,7 @@ static int tc_gemm(const uint16_t* A, int64_t lda, bool a_mn, const uint16_t* B,
                    : launch_tc_gemm<true, true, false, 1, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);
   }
   if (fix && !fix->fac) {  // wait-only: plain dW kernel whose splits are gated by the fix-up counters
+    UML_REQUIRE(UML_DW_KORDER == 0, "tc_gemm: split gating needs every split to own a contiguous row range");
     UML_REQUIRE(a_mn && b_mn && !out_bf16, "tc_gemm: split gating is wired for the dW layout only");
     return cg == 2 ? launch_tc_gemm<true, true, false, 2, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix)
                    : launch_tc_gemm<true, true, false, 1, false>(ta, tb, M, N, K, n_splits, out, ldo, st, *fix);

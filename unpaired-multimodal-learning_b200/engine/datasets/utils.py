@@ -150,6 +150,11 @@ class IndexBatch:
     start: int = 0
     host_idx: Optional[torch.Tensor] = None  # the same indices on the host (tests / tracing)
     global_n: Optional[int] = None           # set by per-rank (sharded) loaders: rows of the step over ALL ranks
+    # a CUDA event recorded (on the stream the indices were uploaded on) after ``idx`` became valid in device memory, and
+    # its position in the process-wide order of such events: with it the step launcher may read ``idx`` from another
+    # stream without waiting for everything else that was enqueued before the call (uml_linear_step_args.idx_ready)
+    ready: Optional[object] = None
+    ready_seq: int = 0
 
 
 def local_slice(batch: "IndexBatch", rank: int, world: int) -> "IndexBatch":
@@ -159,7 +164,39 @@ def local_slice(batch: "IndexBatch", rank: int, world: int) -> "IndexBatch":
     lo, hi = (batch.n * rank) // world, (batch.n * (rank + 1)) // world
     idx = batch.idx[lo:hi] if batch.idx is not None else None
     host = batch.host_idx[lo:hi] if batch.host_idx is not None else None
-    return IndexBatch(batch.bank, idx, hi - lo, batch.start + lo, host)
+    return IndexBatch(batch.bank, idx, hi - lo, batch.start + lo, host, ready=batch.ready, ready_seq=batch.ready_seq)
+
+
+_READY_SEQ = [0]
+
+
+class _ReadyRing:
+    """Events that vouch for uploaded index ranges (IndexBatch.ready), recycled: an event that is recorded again while an
+    older batch still points at it only makes that batch's consumer wait for a LATER point of the same stream."""
+
+    def __init__(self, n=32):
+        self.events, self.pos, self.n = [], 0, n
+
+    def mark(self):
+        if not torch.cuda.is_available():
+            return None, 0
+        if len(self.events) < self.n:
+            self.events.append(torch.cuda.Event())
+        ev = self.events[self.pos % len(self.events)] if len(self.events) == self.n else self.events[-1]
+        self.pos += 1
+        ev.record()
+        _READY_SEQ[0] += 1
+        return ev, _READY_SEQ[0]
+
+
+def mark_ready(batch: "IndexBatch", ring: Optional["_ReadyRing"] = None) -> "IndexBatch":
+    """Record 'idx is valid from here on' on the current stream for a batch whose indices were just written there."""
+    ring = ring or _DEFAULT_RING
+    batch.ready, batch.ready_seq = ring.mark()
+    return batch
+
+
+_DEFAULT_RING = _ReadyRing(64)
 
 
 def shard_bank(features: torch.Tensor, labels: torch.Tensor, rank: int, world: int, device="cuda") -> "FeatureBank":
@@ -344,6 +381,7 @@ class BankLoader:
         self._live = None   # the iterator whose permutation currently occupies the ring's buffer
         self.async_min_rows = 65536  # permutations at least this long are produced by a sampler thread
         self._prepared = None        # shard mode: the next epoch's permutation, already being generated
+        self._ready_ring = _ReadyRing()    # events after the index uploads (IndexBatch.ready)
         self._shard_base, self._shard_epoch = 0, 0
 
     def _upload(self, host):
@@ -378,6 +416,7 @@ class _BankIter:
         self.perm_dev = None
         self.perm = None
         self.uploaded = 0
+        self.mark = (None, 0)  # event + order of the last upload into perm_dev (IndexBatch.ready)
         self.tail_drawn = False
         if loader.shard_of is None:
             # base seed (the reference DataLoader's protocol)
@@ -441,6 +480,7 @@ class _BankIter:
                 # wait for every kernel already enqueued and lose its lead over the GPU once per epoch
                 self.perm_dev = self.perm_host.to(l.bank.device, non_blocking=True)
                 self.uploaded = self.n
+                self.mark = l._ready_ring.mark() if self.perm_dev.is_cuda else (None, 0)
 
     def __iter__(self):
         return self
@@ -471,6 +511,7 @@ class _BankIter:
         if self.uploaded < start + total:
             self.perm_dev[self.uploaded:start + total].copy_(self.perm_host[self.uploaded:start + total], non_blocking=True)
             self.uploaded = start + total
+            self.mark = l._ready_ring.mark() if self.perm_dev.is_cuda else (None, 0)
         self.pos = start + total
         return self.perm_dev, start, total
 
@@ -490,11 +531,12 @@ class _BankIter:
             self.perm.wait(start + total)
         host = self.perm_host[start:start + total]
         dev = l._upload(host)
+        ev, seq = l._ready_ring.mark() if dev.is_cuda else (None, 0)
         out, off = [], 0
         while off < total:
             take = min(l.batch_size, total - off)
             gn = take * l.shard_of[1] if l.shard_of is not None else None
-            out.append(IndexBatch(l.bank, dev[off:off + take], take, start + off, host[off:off + take], gn))
+            out.append(IndexBatch(l.bank, dev[off:off + take], take, start + off, host[off:off + take], gn, ev, seq))
             off += take
         self.pos = start + total
         return out
@@ -522,7 +564,10 @@ class _BankIter:
             if self.uploaded < start + take:
                 self.perm_dev[self.uploaded:start + take].copy_(self.perm_host[self.uploaded:start + take], non_blocking=True)
                 self.uploaded = start + take
+                self.mark = l._ready_ring.mark() if self.perm_dev.is_cuda else (None, 0)
             dev = self.perm_dev[start:start + take]
+            ev, seq = self.mark
         else:
             dev = l._upload(host)
-        return IndexBatch(l.bank, dev, take, start, host, gn)
+            ev, seq = l._ready_ring.mark() if dev.is_cuda else (None, 0)
+        return IndexBatch(l.bank, dev, take, start, host, gn, ev, seq)

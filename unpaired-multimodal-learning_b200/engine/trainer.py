@@ -242,6 +242,9 @@ class StepEngine:
         self.slot_modalities[slot] = (n_i > 0, n_t > 0)
         wi, wt = dp_loss_weights(n_i, n_t, alpha, global_img_rows, global_txt_rows)
         bf16 = self._use_bf16(n_i + n_t)
+        if bf16:  # this step writes the operand buffers outside uml_linear_run: its gather pipeline starts cold next time
+            from .._lib import load as _load_lib
+            _load_lib().uml_linear_run_reset()
         if self.adapter and bf16:
             self._step_bf16_adapter(img, txt, n_i, n_t, wi, wt, slot)
         elif self.adapter or not self.single_call:
@@ -379,6 +382,7 @@ class StepEngine:
             # how many following steps share this path (same modalities, same arithmetic)?
             m = j
             steps = []
+            ready, ready_seq, vouched = None, -1, True  # the newest 'indices uploaded' event among the chunk's batches
             while m < n_all:
                 ig, tg = batches[m]
                 if (ig is None) != (img_g is None) or (tg is None) != (txt_g is None):
@@ -396,6 +400,10 @@ class StepEngine:
                         continue
                     rs.idx[kk], rs.n[kk], rs.loss_weight[kk] = b_.idx.data_ptr(), cnt, w_
                     kk += 1
+                    if b_.ready is None:
+                        vouched = False
+                    elif b_.ready_seq > ready_seq:
+                        ready, ready_seq = b_.ready, b_.ready_seq
                 rs.lr = lrs[m]
                 wst["step"] += 1
                 rs.opt_step = wst["step"]
@@ -422,6 +430,8 @@ class StepEngine:
                 self.step(img, txt, alpha, slot0 + j, _global_rows(img_g, self.world), _global_rows(txt_g, self.world))
                 j += 1
                 continue
+            # every index batch vouched for by an upload event: the gather pipeline may run through the call boundary
+            a.idx_ready = ready.cuda_event if (vouched and ready is not None) else None
             arr = (RunStep * len(steps))(*steps)
             check(load().uml_linear_run(C.byref(a), arr, len(steps), torch.cuda.current_stream().cuda_stream))
             LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16) * len(steps) - (0 if self._w16_valid or not bf16 else len(steps) - 1)
