@@ -75,6 +75,24 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
   return 0;
 }
 
+// 3D row-major tensor (d0 contiguous), no swizzle: boxes land in shared memory as dense [box2][box1][box0]
+int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+  encode_tiled_fn enc = get_encode();
+  UML_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  UML_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "tensor map base must be 16B aligned");
+  UML_REQUIRE(pitch1_bytes % 16 == 0 && pitch2_bytes % 16 == 0, "tensor map pitches (%llu, %llu B) must be multiples of 16",
+              (unsigned long long)pitch1_bytes, (unsigned long long)pitch2_bytes);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UML_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3D) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace uml
 
 extern "C" {

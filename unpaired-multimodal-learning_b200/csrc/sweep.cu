@@ -528,6 +528,418 @@ __global__ void __launch_bounds__(256, 2) sweep_dw_update_async_kernel(const __g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tensor-core forms of the two contractions (tcgen05.mma kind::tf32, fp32 accumulators in TMEM) - the default when rows
+// are 16-byte aligned.  The exact path has to stay at fp32 accuracy (the sweep tests hold every head to the oracle's
+// fp32 trajectory), so each operand is split in shared memory into two tf32 terms,
+//     x = hi + lo,   hi = x with the 13 low mantissa bits cleared (exactly what the tf32 datapath reads),
+//                    lo = x - hi (exact in fp32; its own 13 significant bits lose at most two to tf32),
+// and a product is accumulated as  hi*hi + hi*lo + lo*hi  ("3xTF32": relative error 2^-21 per term against 2^-24 for an
+// FFMA, accumulated in fp32).  Three MMAs per k-step still leave the tensor pipe two orders of magnitude ahead of the
+// FFMA loops above; what remains is the operand stream (logits) and the 24 B/parameter of the update (dW).
+// Operands reach shared memory through registers (logits: the split needs them there anyway) or cp.async (dW) in the
+// 128-byte swizzled layouts the MMA descriptors name, bank rows gathered by index on the way; no tensor maps.
+// The order of accumulation is fixed by the instruction stream, so a head's result does not depend on its slot.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: fp32 accumulator, tf32 A and B
+__host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t m, uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// mbarrier wait that cannot hang the GPU: a barrier that does not flip within ~1 s (a bug, never load) traps
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (clock64() - t0 > 2000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+  lo.x = x.x - hi.x;
+  lo.y = x.y - hi.y;
+  lo.z = x.z - hi.z;
+  lo.w = x.w - hi.w;
+}
+// byte offset of 16-byte chunk `ch` of 128-byte row `row` inside a SWIZZLE_128B box (rows 128 B apart, 8-row atoms)
+__device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4)); }
+
+// 1t. raw logits, transposed tile: D[class, row] = W_k[128 classes, :] . X_k[64 rows, :]^T   grid (ceil(C/128), ceil(rows/64), K)
+//     A = weight rows (K-major), B = gathered bank rows (K-major), k-blocks of 32 floats (one swizzle row), two stages:
+//     the loads of block kb + 1 are in registers while block kb is split, stored and multiplied.
+constexpr int kTcLgStage = 48 * 1024;  // W hi 16 KB | W lo 16 KB | X hi 8 KB | X lo 8 KB
+constexpr int kTcLgSmemBytes = 2 * kTcLgStage + 1024 + 64;
+
+__global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_constant__ SweepDev p) {
+  constexpr int BM = 128, BN = 64, BK = 32, S = 2;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* empty_bar = reinterpret_cast<uint64_t*>(smem + S * kTcLgStage);
+  uint64_t* tfull_bar = empty_bar + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  __shared__ const float* rowp[BN];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t R = p.n0 + p.n1;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * BN;
+  const int c0 = blockIdx.x * BM;
+  const int D = p.dim, C = p.n_classes;
+  const float* __restrict__ W = p.W + head * p.head_stride;
+  if (t < BN) rowp[t] = (m0 + t < R) ? row_ptr(p, head, m0 + t) : nullptr;
+  if (t == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&empty_bar[s], 1);
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this thread's 16-byte chunks of a k-block: four of the weight tile, two of the row tile (eight threads per row)
+  const int ch = t & 7;
+  const float* wsrc[4];
+  const float* xsrc[2];
+  uint32_t woff[4], xoff[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = (t >> 3) + 32 * i;
+    wsrc[i] = (c0 + row < C) ? W + static_cast<int64_t>(c0 + row) * D + ch * 4 : nullptr;
+    woff[i] = sw128(row, ch);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int row = (t >> 3) + 32 * i;
+    const float* rp = rowp[row];
+    xsrc[i] = rp ? rp + ch * 4 : nullptr;
+    xoff[i] = sw128(row, ch);
+  }
+  auto load = [&](int kb, float4 (&r)[6]) {
+    const bool kin = kb * BK + ch * 4 < D;  // dim % 4 == 0: a chunk is inside the row or outside, never across its end
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      r[i] = (kin && wsrc[i]) ? __ldg(reinterpret_cast<const float4*>(wsrc[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      r[4 + i] = (kin && xsrc[i]) ? __ldg(reinterpret_cast<const float4*>(xsrc[i] + kb * BK)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+
+  const int nk = (D + BK - 1) / BK;
+  constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+  float4 cur[6], nxt[6];
+  load(0, cur);
+#pragma unroll 1
+  for (int kb = 0; kb < nk; ++kb) {
+    if (kb + 1 < nk) load(kb + 1, nxt);
+    const int s = kb & (S - 1);
+    if (kb >= S) mbar_wait_or_trap(&empty_bar[s], static_cast<uint32_t>((kb / S) - 1) & 1u);  // the MMAs of block kb - S have read it
+    unsigned char* st = smem + s * kTcLgStage;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 hi, lo;
+      split_tf32(cur[i], hi, lo);
+      *reinterpret_cast<float4*>(st + woff[i]) = hi;
+      *reinterpret_cast<float4*>(st + 16384 + woff[i]) = lo;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float4 hi, lo;
+      split_tf32(cur[4 + i], hi, lo);
+      *reinterpret_cast<float4*>(st + 32768 + xoff[i]) = hi;
+      *reinterpret_cast<float4*>(st + 40960 + xoff[i]) = lo;
+    }
+    fence_proxy_async();  // generic-proxy stores -> the tensor core's async-proxy reads
+    __syncthreads();
+    if (t == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + 16384, b_hi = a_hi + 32768, b_lo = a_hi + 40960;
+#pragma unroll
+      for (int k = 0; k < BK / 8; ++k) {  // a k-step of 8 floats = 32 B inside the swizzle row; 8-row atoms 1024 B apart
+        const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 1024, kLayoutSw128);
+        const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 1024, kLayoutSw128);
+        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024, kLayoutSw128);
+        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 1024, kLayoutSw128);
+        umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
+        umma_tf32(tmem_base, dah, dbl, idesc, 1);
+        umma_tf32(tmem_base, dah, dbh, idesc, 1);
+      }
+      umma_commit(&empty_bar[s]);
+      if (kb == nk - 1) umma_commit(tfull_bar);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
+  }
+
+  // epilogue: TMEM lane = class, column = row; warp w reads lane quadrant w % 4, column half w / 4
+  mbar_wait_or_trap(tfull_bar, 0);
+  tc_fence_after();
+  {
+    const int q = warp & 3, h = warp >> 2;
+    uint32_t v[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, v);
+    tmem_ld_wait();
+    const int c = c0 + q * 32 + lane;
+    float* __restrict__ G = p.G + head * p.g_stride;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int64_t r = m0 + h * 32 + i;
+        if (r < R) G[r * p.ldg + c] = __uint_as_float(v[i]);  // a warp stores 32 consecutive classes of one row
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 64);
+}
+
+// 3t. dW^T strip with the optimizer update: D[dim, class] = X_k[rows, 128 dims]^T . G_k[rows, 64 classes] for up to four
+//     consecutive 64-class tiles of one head            grid (ceil(D/128), ceil(C/256), K), steps of at most 64 rows
+//     Both operands are stored rows-by-something, i.e. MN-major for this product; 32-bit MN-major operands take the
+//     SWIZZLE_128B_BASE32B layout (128-byte rows of 32 floats, the four 32-byte units of a row permuted by row & 3,
+//     4-row atoms 512 B apart; the next 32 dims / classes one 8 KB box further).  The feature tile is loaded and split
+//     once per CTA; the accumulators alternate between two TMEM regions, so the MMAs of tile j + 1 are issued before
+//     tile j is read back.
+//     The launch is bound by the 24 B/parameter of the update, and what a thread can hold in registers is not enough
+//     to keep HBM busy (a register-staged epilogue ran at 0.3 of the copy peak): W, m and v stream through a ring of
+//     shared-memory slots instead - TMA loads of [16 classes x 128 dims] boxes three slots ahead, the update in place
+//     (TMEM lane = dim, column = class: a warp touches 32 consecutive floats of a slot row), TMA stores behind - so the
+//     bytes in flight are bounded by shared memory, not by the register file.  Boxes that overhang the head's C x D
+//     slab are clipped by the tensor map on both ways, so the epilogue carries no predicates.
+constexpr int kTcDwTiles = 4;
+constexpr int kTcDwSlots = 4;
+constexpr int kTcDwSlotBytes = 3 * 8192;  // W | m | v boxes of 16 classes x 128 dims
+constexpr int kTcDwSmemBytes = 96 * 1024 + kTcDwSlots * kTcDwSlotBytes + 1024 + 128;  // X hi | X lo (32 KB each) | G hi | G lo (16 KB each) | slots
+constexpr uint32_t kLayoutSw128Base32 = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B
+
+__device__ __forceinline__ uint32_t sw128_b32(int row, int ch) {
+  return static_cast<uint32_t>(row * 128 + ((((ch >> 1) ^ (row & 3)) << 5) | ((ch & 1) << 4)));
+}
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// kNT threads per CTA: the update costs ~50 instructions per parameter (IEEE sqrt and division), so the epilogue needs warps to
+// hide its dependency chains as much as it needs bytes in flight - 8 warps per SM left the slots waiting for arithmetic
+template <int kNT>
+__global__ void __launch_bounds__(kNT, 1)
+    sweep_dw_update_tc_kernel(const __grid_constant__ SweepDev p, const __grid_constant__ CUtensorMap tm_w,
+                              const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_v) {
+  constexpr int BM = 128, BN = 64, kR = 64, NS = kTcDwSlots;
+  const int head = blockIdx.z;
+  if (!head_active(p, head)) return;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* slots = smem + 96 * 1024;
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(slots + NS * kTcDwSlotBytes);  // [2]
+  uint64_t* full_bar = mma_bar + 2;                                             // [NS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + NS);
+  __shared__ const float* rowp[kR];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int64_t R = p.n0 + p.n1;  // <= 64 (launcher)
+  const int d0 = blockIdx.x * BM, c_strip = blockIdx.y * (BN * kTcDwTiles);
+  const int D = p.dim, C = p.n_classes;
+  const int n_cls = min(BN * kTcDwTiles, C - c_strip);
+  const int n_tiles = (n_cls + BN - 1) / BN, n_stages = (n_cls + 15) / 16;
+  const bool has_v = p.kind != 3;
+  const uint32_t stage_tx = has_v ? 3 * 8192 : 2 * 8192;
+  const float* __restrict__ G = p.G + head * p.g_stride;
+  static_assert(kNT == 256 || kNT == 512 || kNT == 1024, "8, 4 or 2 classes of a stage per thread");
+  if (t < kR) rowp[t] = (t < R) ? row_ptr(p, head, t) : nullptr;
+  if (t == 0) {
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_m);
+    if (has_v) tma_prefetch_desc(&tm_v);
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto slot_load = [&](int g) {  // one thread: stage g -> slot g % NS
+    unsigned char* sl = slots + (g % NS) * kTcDwSlotBytes;
+    uint64_t* bar = &full_bar[g % NS];
+    const int c = c_strip + g * 16;
+    mbar_arrive_expect_tx(bar, stage_tx);
+    tma_load_3d(sl, &tm_w, bar, d0, c, head);
+    tma_load_3d(sl + 8192, &tm_m, bar, d0, c, head);
+    if (has_v) tma_load_3d(sl + 16384, &tm_v, bar, d0, c, head);
+  };
+  if (t == 0) {
+    for (int g = 0; g < NS - 1 && g < n_stages; ++g) slot_load(g);  // W, m, v are on their way while the operand tiles land
+  }
+
+  // G tile: 64 rows x 16 chunks
+  auto g_issue = [&](int tile) {
+    unsigned char* gb = smem + 65536;
+    const int c0 = c_strip + tile * BN;
+#pragma unroll
+    for (int i = 0; i < 1024 / kNT; ++i) {
+      const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
+      const bool ok = row < R && c0 + chg * 4 < C;  // ldg % 4 == 0 and ldg >= C: the 16 bytes stay inside the row
+      cp_async16(gb + box * 8192 + sw128_b32(row, chg & 7), ok ? G + row * p.ldg + c0 + chg * 4 : G, ok);
+    }
+    cp_async_commit();
+  };
+  // split this thread's own chunks (its cp.async writes are visible to it after the wait)
+  auto g_split = [&]() {
+    unsigned char* gb = smem + 65536;
+#pragma unroll
+    for (int i = 0; i < 1024 / kNT; ++i) {
+      const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
+      unsigned char* b = gb + box * 8192 + sw128_b32(row, chg & 7);
+      float4 hi, lo;
+      split_tf32(*reinterpret_cast<const float4*>(b), hi, lo);
+      *reinterpret_cast<float4*>(b) = hi;
+      *reinterpret_cast<float4*>(b + 16384) = lo;
+    }
+  };
+  constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 1, 1);
+  const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + 32768, b_hi = a_hi + 65536, b_lo = b_hi + 16384;
+  auto mma_tile = [&](int tile) {  // one thread
+    const uint32_t acc = tmem_base + (tile & 1) * BN;
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < kR / 8; ++k) {  // 8 rows = two 4-row atoms (SBO 512 B); the next 32 dims / classes 8 KB further (LBO)
+      const uint64_t dah = make_smem_desc(a_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
+      const uint64_t dal = make_smem_desc(a_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
+      const uint64_t dbh = make_smem_desc(b_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
+      const uint64_t dbl = make_smem_desc(b_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
+      umma_tf32(acc, dal, dbh, idesc, k != 0);
+      umma_tf32(acc, dah, dbl, idesc, 1);
+      umma_tf32(acc, dah, dbh, idesc, 1);
+    }
+    umma_commit(&mma_bar[tile & 1]);
+  };
+
+  // prologue: feature tile (64 rows x 32 chunks, a warp per row) and G tile 0
+  constexpr int kWarps = kNT / 32;
+#pragma unroll
+  for (int i = 0; i < kR / kWarps; ++i) {
+    const int row = warp + kWarps * i, box = lane >> 3;
+    const float* rp = rowp[row];
+    const bool ok = rp != nullptr && d0 + lane * 4 < D;
+    cp_async16(smem + box * 8192 + sw128_b32(row, lane & 7), ok ? rp + d0 + lane * 4 : G, ok);
+  }
+  g_issue(0);
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < kR / kWarps; ++i) {
+    const int row = warp + kWarps * i, box = lane >> 3;
+    unsigned char* a = smem + box * 8192 + sw128_b32(row, lane & 7);
+    float4 hi, lo;
+    split_tf32(*reinterpret_cast<const float4*>(a), hi, lo);
+    *reinterpret_cast<float4*>(a) = hi;
+    *reinterpret_cast<float4*>(a + 32768) = lo;
+  }
+  g_split();
+  fence_proxy_async();
+  __syncthreads();
+  if (t == 0) mma_tile(0);
+
+  const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
+  constexpr int kCpt = 16 / (kNT / 128);  // classes of a stage per thread
+  const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant (dims 32 q + lane), classes kCpt h + [0, kCpt) of a stage
+  const int dl = q * 32 + lane;
+#pragma unroll 1
+  for (int g = 0; g < n_stages; ++g) {
+    const int j = g >> 2, u = g & 3;
+    if (u == 0) {
+      mbar_wait_or_trap(&mma_bar[j & 1], static_cast<uint32_t>(j >> 1) & 1u);  // tile j is in TMEM, the G tile has been read
+      tc_fence_after();
+      if (j + 1 < n_tiles) {  // stage and issue tile j + 1 (its TMEM region was last read by this CTA's loads of tile j - 1)
+        g_issue(j + 1);
+        cp_async_wait<0>();
+        g_split();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) mma_tile(j + 1);
+      }
+    }
+    unsigned char* sl = slots + (g % NS) * kTcDwSlotBytes;
+    mbar_wait_or_trap(&full_bar[g % NS], static_cast<uint32_t>(g / NS) & 1u);
+    uint32_t acc[kCpt];
+    tmem_ldn(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (j & 1) * BN + u * 16 + h * kCpt, acc);
+    tmem_ld_wait();
+    float* ws = reinterpret_cast<float*>(sl) + (h * kCpt) * BM + dl;
+    float* ms = ws + 2048;
+    float* vs = ws + 4096;
+#pragma unroll
+    for (int i = 0; i < kCpt; ++i) {
+      float w = ws[i * BM], mo = ms[i * BM], vo = has_v ? vs[i * BM] : 0.f;
+      update_one(p, lr, step_size, decay, wd, w, mo, vo, __uint_as_float(acc[i]));
+      ws[i * BM] = w;
+      ms[i * BM] = mo;
+      if (has_v) vs[i * BM] = vo;
+    }
+    fence_proxy_async();  // generic-proxy stores -> the TMA stores' async-proxy reads
+    __syncthreads();
+    if (t == 0) {
+      const int c = c_strip + g * 16;
+      tma_store_3d(&tm_w, sl, d0, c, head);
+      tma_store_3d(&tm_m, sl + 8192, d0, c, head);
+      if (has_v) tma_store_3d(&tm_v, sl + 16384, d0, c, head);
+      bulk_commit();
+      if (g + NS - 1 < n_stages) {
+        bulk_wait_read<1>();  // every store group but this one has read its slot: the slot of stage g - 1 is free again
+        slot_load(g + NS - 1);
+      }
+    }
+  }
+  if (t == 0) bulk_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 4. per-head, per-run {mean loss, hits, rows} in a fixed summation order   grid (2, K)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sweep_stats_kernel(const __grid_constant__ SweepDev p) {
@@ -619,6 +1031,48 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
                                                          kLogitsSmemBytes);
     UML_CUDA(attr);
   }
+  // tensor-core forms (3xTF32, see above) whenever the async forms' alignment contract holds; UML_SWEEP_TC=0 keeps the FFMA kernels
+  static const bool want_tc = [] {
+    const char* e = getenv("UML_SWEEP_TC");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool use_tc = want_tc && use_async;
+  if (use_tc) {
+    static const cudaError_t attr1 = cudaFuncSetAttribute(sweep_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          kTcLgSmemBytes);
+    UML_CUDA(attr1);
+    static const cudaError_t attr2 = [] {
+      cudaError_t e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
+      return e;
+    }();
+    UML_CUDA(attr2);
+  }
+  // UML_SWEEP_TC_DW=0 keeps the FFMA dW + update launch next to the tensor-core logits; UML_SWEEP_DW_THREADS its CTA size
+  static const bool want_tc_dw = [] {
+    const char* e = getenv("UML_SWEEP_TC_DW");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  static const int dw_threads = [] {
+    const char* e = getenv("UML_SWEEP_DW_THREADS");
+    const int v = e ? atoi(e) : 512;  // measured, 30 heads of 1000 x 512: 0.148 / 0.109 / 0.113 ms with 256 / 512 / 1024
+    return (v == 256 || v == 1024) ? v : 512;
+  }();
+  const bool use_tc_dw = use_tc && want_tc_dw;
+  CUtensorMap tm_w, tm_m, tm_v;  // [K][C][D] views of the W, m, v slabs for the dW kernel's slot ring
+  memset(&tm_w, 0, sizeof(tm_w));
+  memset(&tm_m, 0, sizeof(tm_m));
+  memset(&tm_v, 0, sizeof(tm_v));
+  if (use_tc) {
+    const uint64_t d = static_cast<uint64_t>(a->dim), c = static_cast<uint64_t>(a->n_classes), k = static_cast<uint64_t>(K);
+    const uint64_t hs = static_cast<uint64_t>(a->head_stride) * 4;
+    if (make_tmap_3d(&tm_w, a->W, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d, c, k, d * 4, hs, 128, 16, 1)) return 1;
+    if (make_tmap_3d(&tm_m, a->m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d, c, k, d * 4, hs, 128, 16, 1)) return 1;
+    if (a->kind != 3 && make_tmap_3d(&tm_v, a->v, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d, c, k, d * 4, hs, 128, 16, 1)) return 1;
+  }
   p.kind = a->kind;
   p.beta1 = a->beta1;
   p.beta2 = a->beta2;
@@ -662,7 +1116,9 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       return 0;
     };
     if (mark(0)) return 1;
-    if (use_async)
+    if (use_tc)
+      sweep_logits_tc_kernel<<<dim3((a->n_classes + 127) / 128, rt, K), 256, kTcLgSmemBytes, st>>>(p);
+    else if (use_async)
       sweep_logits_async_kernel<<<dim3(ct, rt, K), 256, kLogitsSmemBytes, st>>>(p);
     else
       sweep_logits_kernel<<<dim3(ct, rt, K), 256, 0, st>>>(p);
@@ -671,7 +1127,13 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
     if (mark(3) || mark(4)) return 1;
-    if (use_async)
+    if (use_tc_dw && R <= 64) {  // (larger steps: the feature tile of the tensor-core form holds 64 rows)
+      const dim3 g((a->dim + 127) / 128, (a->n_classes + 64 * kTcDwTiles - 1) / (64 * kTcDwTiles), K);
+      if (dw_threads == 256) sweep_dw_update_tc_kernel<256><<<g, 256, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      else if (dw_threads == 512) sweep_dw_update_tc_kernel<512><<<g, 512, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      else sweep_dw_update_tc_kernel<1024><<<g, 1024, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+    }
+    else if (use_async)
       sweep_dw_update_async_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
     else
       sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
