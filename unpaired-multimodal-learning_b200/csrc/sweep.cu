@@ -16,6 +16,7 @@
 // (16-byte aligned rows; the default - double-buffered k-tiles for the logits, all rows of the step plus the thread's
 // W, m, v requested up front for dW).  Measured on B200 with K = 30 heads of 1000 x 512: 0.219 ms per step of all heads
 // (logits 73 us, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7); register-staged 0.268 ms.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -760,40 +761,87 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-// kNT threads per CTA: the update costs ~50 instructions per parameter (IEEE sqrt and division), so the epilogue needs warps to
-// hide its dependency chains as much as it needs bytes in flight - 8 warps per SM left the slots waiting for arithmetic
+// kNT update threads per CTA plus one TMA warp.  The update costs ~50 instructions per parameter (IEEE sqrt and division),
+// so the read-back needs warps to hide its dependency chains as much as it needs bytes in flight (8 warps per SM left the
+// slots waiting for arithmetic), and nothing in it may wait for anything but its own data: an update warp waits for a
+// slot's loads, updates its share in place and arrives on the slot's `done` barrier; the TMA warp waits for that
+// barrier, stores the slot and refills the one before it - no CTA-wide barrier per slot.
+// Persistent: the (head, 128-dim tile, 64-class tile) units of all running heads are dealt out in equal contiguous
+// ranges to one CTA per SM (no tail wave; the feature tile changes at most twice per CTA), the next unit's tiles are
+// requested at the start of a unit's read-back and split / multiplied one slot later, and the W / m / v ring runs
+// across unit boundaries.
+struct DwUnit {
+  int unit;     // position in the CTA-independent unit order: running head (ascending), dim tile, class tile
+  int st, nst;  // stage (16 classes) inside the unit, stages of the unit
+  int head, dt, ct;
+};
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 template <int kNT>
-__global__ void __launch_bounds__(kNT, 1)
+__global__ void __launch_bounds__(kNT + 32, 1)
     sweep_dw_update_tc_kernel(const __grid_constant__ SweepDev p, const __grid_constant__ CUtensorMap tm_w,
                               const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_v) {
-  constexpr int BM = 128, BN = 64, kR = 64, NS = kTcDwSlots;
-  const int head = blockIdx.z;
-  if (!head_active(p, head)) return;
+  static_assert(kNT == 256 || kNT == 512, "8 or 4 classes of a stage per thread");
+  constexpr int BM = 128, BN = 64, kR = 64, NS = kTcDwSlots, kWarps = kNT / 32;
+  const int D = p.dim, C = p.n_classes;
+  const int n_dt = (D + BM - 1) / BM, n_ct = (C + BN - 1) / BN, per_head = n_dt * n_ct;
+  const int n_units = __popc(p.active_mask) * per_head;
+  const int u_lo = static_cast<int>(static_cast<int64_t>(n_units) * blockIdx.x / gridDim.x);
+  const int u_hi = static_cast<int>(static_cast<int64_t>(n_units) * (blockIdx.x + 1) / gridDim.x);
+  if (u_lo >= u_hi) return;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* slots = smem + 96 * 1024;
   uint64_t* mma_bar = reinterpret_cast<uint64_t*>(slots + NS * kTcDwSlotBytes);  // [2]
-  uint64_t* full_bar = mma_bar + 2;                                             // [NS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + NS);
+  uint64_t* full_bar = mma_bar + 2;                                             // [NS] slot loaded
+  uint64_t* done_bar = full_bar + NS;                                           // [NS] slot updated by every update warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + NS);
   __shared__ const float* rowp[kR];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int64_t R = p.n0 + p.n1;  // <= 64 (launcher)
-  const int d0 = blockIdx.x * BM, c_strip = blockIdx.y * (BN * kTcDwTiles);
-  const int D = p.dim, C = p.n_classes;
-  const int n_cls = min(BN * kTcDwTiles, C - c_strip);
-  const int n_tiles = (n_cls + BN - 1) / BN, n_stages = (n_cls + 15) / 16;
   const bool has_v = p.kind != 3;
   const uint32_t stage_tx = has_v ? 3 * 8192 : 2 * 8192;
-  const float* __restrict__ G = p.G + head * p.g_stride;
-  static_assert(kNT == 256 || kNT == 512 || kNT == 1024, "8, 4 or 2 classes of a stage per thread");
-  if (t < kR) rowp[t] = (t < R) ? row_ptr(p, head, t) : nullptr;
+
+  auto first_unit = [&](DwUnit& c) {
+    const int a = u_lo / per_head, r = u_lo - a * per_head;
+    c.unit = u_lo;
+    c.st = 0;
+    c.head = __fns(p.active_mask, 0, a + 1);  // the a-th running head
+    c.dt = r / n_ct;
+    c.ct = r - c.dt * n_ct;
+    c.nst = (min(BN, C - c.ct * BN) + 15) >> 4;
+  };
+  auto next_unit = [&](DwUnit& c) {  // (no divisions: the cursors move one unit at a time)
+    ++c.unit;
+    c.st = 0;
+    if (++c.ct == n_ct) {
+      c.ct = 0;
+      if (++c.dt == n_dt) {
+        c.dt = 0;
+        if (c.unit < u_hi) c.head = __ffs(p.active_mask >> (c.head + 1)) + c.head;  // the next running head
+      }
+    }
+    c.nst = (min(BN, C - c.ct * BN) + 15) >> 4;
+  };
+  DwUnit cur;
+  first_unit(cur);
+
+  if (t < kR) rowp[t] = (t < R) ? row_ptr(p, cur.head, t) : nullptr;
   if (t == 0) {
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_m);
     if (has_v) tma_prefetch_desc(&tm_v);
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
-    for (int s = 0; s < NS; ++s) mbar_init(&full_bar[s], 1);
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&done_bar[s], kWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 128);
@@ -802,138 +850,175 @@ __global__ void __launch_bounds__(kNT, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto slot_load = [&](int g) {  // one thread: stage g -> slot g % NS
-    unsigned char* sl = slots + (g % NS) * kTcDwSlotBytes;
-    uint64_t* bar = &full_bar[g % NS];
-    const int c = c_strip + g * 16;
-    mbar_arrive_expect_tx(bar, stage_tx);
-    tma_load_3d(sl, &tm_w, bar, d0, c, head);
-    tma_load_3d(sl + 8192, &tm_m, bar, d0, c, head);
-    if (has_v) tma_load_3d(sl + 16384, &tm_v, bar, d0, c, head);
-  };
-  if (t == 0) {
-    for (int g = 0; g < NS - 1 && g < n_stages; ++g) slot_load(g);  // W, m, v are on their way while the operand tiles land
-  }
-
-  // G tile: 64 rows x 16 chunks
-  auto g_issue = [&](int tile) {
-    unsigned char* gb = smem + 65536;
-    const int c0 = c_strip + tile * BN;
-#pragma unroll
-    for (int i = 0; i < 1024 / kNT; ++i) {
-      const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
-      const bool ok = row < R && c0 + chg * 4 < C;  // ldg % 4 == 0 and ldg >= C: the 16 bytes stay inside the row
-      cp_async16(gb + box * 8192 + sw128_b32(row, chg & 7), ok ? G + row * p.ldg + c0 + chg * 4 : G, ok);
+  if (warp == kWarps) {
+    // ------------------------------------------------ TMA warp: slot ring of W, m, v ---------------------------------
+    if (lane == 0) {
+      DwUnit prod = cur, stc = cur;  // load cursor (NS - 1 stages ahead), store cursor
+      auto prod_issue = [&](int gs) {
+        unsigned char* sl = slots + (gs % NS) * kTcDwSlotBytes;
+        uint64_t* bar = &full_bar[gs % NS];
+        const int c = prod.ct * BN + prod.st * 16, d0 = prod.dt * BM;
+        mbar_arrive_expect_tx(bar, stage_tx);
+        tma_load_3d(sl, &tm_w, bar, d0, c, prod.head);
+        tma_load_3d(sl + 8192, &tm_m, bar, d0, c, prod.head);
+        if (has_v) tma_load_3d(sl + 16384, &tm_v, bar, d0, c, prod.head);
+        if (++prod.st == prod.nst) next_unit(prod);
+      };
+      for (int g = 0; g < NS - 1 && prod.unit < u_hi; ++g) prod_issue(g);  // on their way while the operand tiles land
+      for (int gs = 0; stc.unit < u_hi; ++gs) {
+        unsigned char* sl = slots + (gs % NS) * kTcDwSlotBytes;
+        mbar_wait_or_trap(&done_bar[gs % NS], static_cast<uint32_t>(gs / NS) & 1u);  // (the update warps fenced their stores)
+        const int c = stc.ct * BN + stc.st * 16, d0 = stc.dt * BM;
+        tma_store_3d(&tm_w, sl, d0, c, stc.head);
+        tma_store_3d(&tm_m, sl + 8192, d0, c, stc.head);
+        if (has_v) tma_store_3d(&tm_v, sl + 16384, d0, c, stc.head);
+        bulk_commit();
+        if (++stc.st == stc.nst) next_unit(stc);
+        if (prod.unit < u_hi) {
+          bulk_wait_read<1>();  // every store group but this one has read its slot: the slot of the previous stage is free again
+          prod_issue(gs + NS - 1);
+        }
+      }
+      bulk_wait<0>();
     }
-    cp_async_commit();
-  };
-  // split this thread's own chunks (its cp.async writes are visible to it after the wait)
-  auto g_split = [&]() {
-    unsigned char* gb = smem + 65536;
+  } else {
+    // ------------------------------------------------ update warps: operand staging, MMA issue, read-back --------------
+    auto sync_update_warps = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kNT) : "memory"); };
+    // feature tile: 64 rows x 32 chunks (a warp per row); G tile: 64 rows x 16 chunks
+    auto x_issue = [&](int d0) {
 #pragma unroll
-    for (int i = 0; i < 1024 / kNT; ++i) {
-      const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
-      unsigned char* b = gb + box * 8192 + sw128_b32(row, chg & 7);
-      float4 hi, lo;
-      split_tf32(*reinterpret_cast<const float4*>(b), hi, lo);
-      *reinterpret_cast<float4*>(b) = hi;
-      *reinterpret_cast<float4*>(b + 16384) = lo;
-    }
-  };
-  constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 1, 1);
-  const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + 32768, b_hi = a_hi + 65536, b_lo = b_hi + 16384;
-  auto mma_tile = [&](int tile) {  // one thread
-    const uint32_t acc = tmem_base + (tile & 1) * BN;
-    tc_fence_after();
+      for (int i = 0; i < kR / kWarps; ++i) {
+        const int row = warp + kWarps * i, box = lane >> 3;
+        const float* rp = rowp[row];
+        const bool ok = rp != nullptr && d0 + lane * 4 < D;
+        cp_async16(smem + box * 8192 + sw128_b32(row, lane & 7), ok ? rp + d0 + lane * 4 : p.G, ok);
+      }
+    };
+    auto x_split = [&]() {  // a thread splits its own chunks (its cp.async writes are visible to it after the wait)
 #pragma unroll
-    for (int k = 0; k < kR / 8; ++k) {  // 8 rows = two 4-row atoms (SBO 512 B); the next 32 dims / classes 8 KB further (LBO)
-      const uint64_t dah = make_smem_desc(a_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
-      const uint64_t dal = make_smem_desc(a_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
-      const uint64_t dbh = make_smem_desc(b_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
-      const uint64_t dbl = make_smem_desc(b_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
-      umma_tf32(acc, dal, dbh, idesc, k != 0);
-      umma_tf32(acc, dah, dbl, idesc, 1);
-      umma_tf32(acc, dah, dbh, idesc, 1);
-    }
-    umma_commit(&mma_bar[tile & 1]);
-  };
-
-  // prologue: feature tile (64 rows x 32 chunks, a warp per row) and G tile 0
-  constexpr int kWarps = kNT / 32;
+      for (int i = 0; i < kR / kWarps; ++i) {
+        const int row = warp + kWarps * i, box = lane >> 3;
+        unsigned char* a = smem + box * 8192 + sw128_b32(row, lane & 7);
+        float4 hi, lo;
+        split_tf32(*reinterpret_cast<const float4*>(a), hi, lo);
+        *reinterpret_cast<float4*>(a) = hi;
+        *reinterpret_cast<float4*>(a + 32768) = lo;
+      }
+    };
+    auto g_issue = [&](const DwUnit& un) {
+      unsigned char* gb = smem + 65536;
+      const float* __restrict__ G = p.G + un.head * p.g_stride;
+      const int c0 = un.ct * BN;
 #pragma unroll
-  for (int i = 0; i < kR / kWarps; ++i) {
-    const int row = warp + kWarps * i, box = lane >> 3;
-    const float* rp = rowp[row];
-    const bool ok = rp != nullptr && d0 + lane * 4 < D;
-    cp_async16(smem + box * 8192 + sw128_b32(row, lane & 7), ok ? rp + d0 + lane * 4 : G, ok);
-  }
-  g_issue(0);
-  cp_async_wait<0>();
+      for (int i = 0; i < 1024 / kNT; ++i) {
+        const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
+        const bool ok = row < R && c0 + chg * 4 < C;  // ldg % 4 == 0 and ldg >= C: the 16 bytes stay inside the row
+        cp_async16(gb + box * 8192 + sw128_b32(row, chg & 7), ok ? G + row * p.ldg + c0 + chg * 4 : G, ok);
+      }
+    };
+    auto g_split = [&]() {
+      unsigned char* gb = smem + 65536;
 #pragma unroll
-  for (int i = 0; i < kR / kWarps; ++i) {
-    const int row = warp + kWarps * i, box = lane >> 3;
-    unsigned char* a = smem + box * 8192 + sw128_b32(row, lane & 7);
-    float4 hi, lo;
-    split_tf32(*reinterpret_cast<const float4*>(a), hi, lo);
-    *reinterpret_cast<float4*>(a) = hi;
-    *reinterpret_cast<float4*>(a + 32768) = lo;
-  }
-  g_split();
-  fence_proxy_async();
-  __syncthreads();
-  if (t == 0) mma_tile(0);
-
-  const float lr = p.lr[head], step_size = p.step_size[head], decay = p.decay[head], wd = p.wd[head];
-  constexpr int kCpt = 16 / (kNT / 128);  // classes of a stage per thread
-  const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant (dims 32 q + lane), classes kCpt h + [0, kCpt) of a stage
-  const int dl = q * 32 + lane;
-#pragma unroll 1
-  for (int g = 0; g < n_stages; ++g) {
-    const int j = g >> 2, u = g & 3;
-    if (u == 0) {
-      mbar_wait_or_trap(&mma_bar[j & 1], static_cast<uint32_t>(j >> 1) & 1u);  // tile j is in TMEM, the G tile has been read
+      for (int i = 0; i < 1024 / kNT; ++i) {
+        const int f = t + kNT * i, row = f >> 4, chg = f & 15, box = chg >> 3;
+        unsigned char* b = gb + box * 8192 + sw128_b32(row, chg & 7);
+        float4 hi, lo;
+        split_tf32(*reinterpret_cast<const float4*>(b), hi, lo);
+        *reinterpret_cast<float4*>(b) = hi;
+        *reinterpret_cast<float4*>(b + 16384) = lo;
+      }
+    };
+    constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 1, 1);
+    const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + 32768, b_hi = a_hi + 65536, b_lo = b_hi + 16384;
+    auto mma_unit = [&](int n) {  // one thread; accumulators of local unit n in TMEM region n & 1
+      const uint32_t acc = tmem_base + (n & 1) * BN;
       tc_fence_after();
-      if (j + 1 < n_tiles) {  // stage and issue tile j + 1 (its TMEM region was last read by this CTA's loads of tile j - 1)
-        g_issue(j + 1);
-        cp_async_wait<0>();
-        g_split();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (t == 0) mma_tile(j + 1);
-      }
-    }
-    unsigned char* sl = slots + (g % NS) * kTcDwSlotBytes;
-    mbar_wait_or_trap(&full_bar[g % NS], static_cast<uint32_t>(g / NS) & 1u);
-    uint32_t acc[kCpt];
-    tmem_ldn(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (j & 1) * BN + u * 16 + h * kCpt, acc);
-    tmem_ld_wait();
-    float* ws = reinterpret_cast<float*>(sl) + (h * kCpt) * BM + dl;
-    float* ms = ws + 2048;
-    float* vs = ws + 4096;
 #pragma unroll
-    for (int i = 0; i < kCpt; ++i) {
-      float w = ws[i * BM], mo = ms[i * BM], vo = has_v ? vs[i * BM] : 0.f;
-      update_one(p, lr, step_size, decay, wd, w, mo, vo, __uint_as_float(acc[i]));
-      ws[i * BM] = w;
-      ms[i * BM] = mo;
-      if (has_v) vs[i * BM] = vo;
-    }
-    fence_proxy_async();  // generic-proxy stores -> the TMA stores' async-proxy reads
-    __syncthreads();
-    if (t == 0) {
-      const int c = c_strip + g * 16;
-      tma_store_3d(&tm_w, sl, d0, c, head);
-      tma_store_3d(&tm_m, sl + 8192, d0, c, head);
-      if (has_v) tma_store_3d(&tm_v, sl + 16384, d0, c, head);
-      bulk_commit();
-      if (g + NS - 1 < n_stages) {
-        bulk_wait_read<1>();  // every store group but this one has read its slot: the slot of stage g - 1 is free again
-        slot_load(g + NS - 1);
+      for (int k = 0; k < kR / 8; ++k) {  // 8 rows = two 4-row atoms (SBO 512 B); the next 32 dims / classes 8 KB further (LBO)
+        const uint64_t dah = make_smem_desc(a_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
+        const uint64_t dal = make_smem_desc(a_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
+        const uint64_t dbh = make_smem_desc(b_hi + k * 1024, 8192, 512, kLayoutSw128Base32);
+        const uint64_t dbl = make_smem_desc(b_lo + k * 1024, 8192, 512, kLayoutSw128Base32);
+        umma_tf32(acc, dal, dbh, idesc, k != 0);
+        umma_tf32(acc, dah, dbl, idesc, 1);
+        umma_tf32(acc, dah, dbh, idesc, 1);
       }
+      umma_commit(&mma_bar[n & 1]);
+    };
+
+    // prologue: the first unit's tiles
+    x_issue(cur.dt * BM);
+    g_issue(cur);
+    cp_async_commit();
+    cp_async_wait<0>();
+    x_split();
+    g_split();
+    fence_proxy_async();
+    sync_update_warps();
+    if (t == 0) mma_unit(0);
+
+    constexpr int kCpt = 16 / (kNT / 128);  // classes of a stage per thread
+    const int q = warp & 3, h = warp >> 2;  // TMEM lane quadrant (dims 32 q + lane), classes kCpt h + [0, kCpt) of a stage
+    const uint32_t slot0 = smem_u32(slots) + static_cast<uint32_t>(((h * kCpt) * BM + q * 32 + lane) * 4);
+    int gs = 0;  // stages read back so far (slot ring position)
+#pragma unroll 1
+    for (int n = 0; cur.unit < u_hi; ++n) {
+      DwUnit nxt = cur;
+      next_unit(nxt);
+      const bool have_next = nxt.unit < u_hi;
+      const bool new_x = have_next && (nxt.head != cur.head || nxt.dt != cur.dt);
+      const float lr = p.lr[cur.head], step_size = p.step_size[cur.head], decay = p.decay[cur.head], wd = p.wd[cur.head];
+      const int fin = min(1, cur.nst - 1);  // the stage before which the next unit is split and multiplied
+      mbar_wait_or_trap(&mma_bar[n & 1], static_cast<uint32_t>(n >> 1) & 1u);  // unit n is in TMEM, its tiles have been read
+      tc_fence_after();
+      if (have_next) {
+        if (nxt.head != cur.head) {
+          if (t < kR) rowp[t] = (t < R) ? row_ptr(p, nxt.head, t) : nullptr;
+          sync_update_warps();
+        }
+        if (new_x) x_issue(nxt.dt * BM);
+        g_issue(nxt);
+        cp_async_commit();
+      }
+#pragma unroll 1
+      for (int u = 0; u < cur.nst; ++u, ++gs) {
+        if (have_next && u == fin) {
+          // (the other TMEM region was last read by this CTA's loads of unit n - 1, a full unit ago)
+          cp_async_wait<0>();
+          if (new_x) x_split();
+          g_split();
+          fence_proxy_async();
+          tc_fence_before();
+          sync_update_warps();
+          if (t == 0) mma_unit(n + 1);
+        }
+        const uint32_t sa = slot0 + (gs % NS) * kTcDwSlotBytes;
+        mbar_wait_or_trap(&full_bar[gs % NS], static_cast<uint32_t>(gs / NS) & 1u);
+        float w[kCpt], mo[kCpt], vo[kCpt];
+#pragma unroll
+        for (int i = 0; i < kCpt; ++i) {  // every load first: kCpt independent chains of sqrt and division follow
+          w[i] = lds_f32(sa + i * (BM * 4));
+          mo[i] = lds_f32(sa + 8192 + i * (BM * 4));
+          vo[i] = has_v ? lds_f32(sa + 16384 + i * (BM * 4)) : 0.f;
+        }
+        uint32_t acc[kCpt];
+        tmem_ldn(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (n & 1) * BN + u * 16 + h * kCpt, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < kCpt; ++i) update_one(p, lr, step_size, decay, wd, w[i], mo[i], vo[i], __uint_as_float(acc[i]));
+#pragma unroll
+        for (int i = 0; i < kCpt; ++i) {
+          sts_f32(sa + i * (BM * 4), w[i]);
+          sts_f32(sa + 8192 + i * (BM * 4), mo[i]);
+          if (has_v) sts_f32(sa + 16384 + i * (BM * 4), vo[i]);
+        }
+        fence_proxy_async();  // generic-proxy stores -> the TMA stores' async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done_bar[gs % NS]);
+      }
+      cur = nxt;
     }
   }
-  if (t == 0) bulk_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 128);
@@ -1045,8 +1130,6 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       cudaError_t e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
       return e;
     }();
     UML_CUDA(attr2);
@@ -1058,8 +1141,7 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
   }();
   static const int dw_threads = [] {
     const char* e = getenv("UML_SWEEP_DW_THREADS");
-    const int v = e ? atoi(e) : 512;  // measured, 30 heads of 1000 x 512: 0.148 / 0.109 / 0.113 ms with 256 / 512 / 1024
-    return (v == 256 || v == 1024) ? v : 512;
+    return (e && atoi(e) == 256) ? 256 : 512;
   }();
   const bool use_tc_dw = use_tc && want_tc_dw;
   CUtensorMap tm_w, tm_m, tm_v;  // [K][C][D] views of the W, m, v slabs for the dW kernel's slot ring
@@ -1128,10 +1210,10 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     UML_CUDA(cudaGetLastError());
     if (mark(3) || mark(4)) return 1;
     if (use_tc_dw && R <= 64) {  // (larger steps: the feature tile of the tensor-core form holds 64 rows)
-      const dim3 g((a->dim + 127) / 128, (a->n_classes + 64 * kTcDwTiles - 1) / (64 * kTcDwTiles), K);
-      if (dw_threads == 256) sweep_dw_update_tc_kernel<256><<<g, 256, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
-      else if (dw_threads == 512) sweep_dw_update_tc_kernel<512><<<g, 512, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
-      else sweep_dw_update_tc_kernel<1024><<<g, 1024, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      const int64_t units = static_cast<int64_t>(__builtin_popcount(mask)) * ((a->dim + 127) / 128) * ((a->n_classes + 63) / 64);
+      const unsigned g = static_cast<unsigned>(std::min<int64_t>(units, sm_count()));
+      if (dw_threads == 256) sweep_dw_update_tc_kernel<256><<<g, 256 + 32, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      else sweep_dw_update_tc_kernel<512><<<g, 512 + 32, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
     }
     else if (use_async)
       sweep_dw_update_async_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
