@@ -595,6 +595,9 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<
 // 1t. raw logits, transposed tile: D[class, row] = W_k[128 classes, :] . X_k[64 rows, :]^T   grid (ceil(C/128), ceil(rows/64), K)
 //     A = weight rows (K-major), B = gathered bank rows (K-major), k-blocks of 32 floats (one swizzle row), two stages:
 //     the loads of block kb + 1 are in registers while block kb is split, stored and multiplied.
+//     (Measured alternatives, 30 heads of 1000 x 512: a five-stage cp.async ring three blocks ahead with one CTA per SM took
+//     47 us, the same with the weight tile requested from L2 up front by cp.async.bulk.prefetch 51 us, against 37 us for
+//     this form - two CTAs per SM, every tile of the launch resident at once.)
 constexpr int kTcLgStage = 48 * 1024;  // W hi 16 KB | W lo 16 KB | X hi 8 KB | X lo 8 KB
 constexpr int kTcLgSmemBytes = 2 * kTcLgStage + 1024 + 64;
 
@@ -736,8 +739,10 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
 //     (TMEM lane = dim, column = class: a warp touches 32 consecutive floats of a slot row), TMA stores behind - so the
 //     bytes in flight are bounded by shared memory, not by the register file.  Boxes that overhang the head's C x D
 //     slab are clipped by the tensor map on both ways, so the epilogue carries no predicates.
-constexpr int kTcDwTiles = 4;
-constexpr int kTcDwSlots = 4;
+#ifndef UML_DW_SLOTS
+#define UML_DW_SLOTS 5  // measured, 30 heads of 1000 x 512: 82 us with 4 slots, 76 us with 5 (0.76 of the HBM copy peak)
+#endif
+constexpr int kTcDwSlots = UML_DW_SLOTS;
 constexpr int kTcDwSlotBytes = 3 * 8192;  // W | m | v boxes of 16 classes x 128 dims
 constexpr int kTcDwSmemBytes = 96 * 1024 + kTcDwSlots * kTcDwSlotBytes + 1024 + 128;  // X hi | X lo (32 KB each) | G hi | G lo (16 KB each) | slots
 constexpr uint32_t kLayoutSw128Base32 = 1;  // UMMA::LayoutType::SWIZZLE_128B_BASE32B
