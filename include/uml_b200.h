@@ -106,6 +106,18 @@ int uml_head_bwd_dw_f32(const uml_segment* segs /*host*/, int32_t nseg, int32_t 
                         float* W, float* dW /*may be NULL when fused*/, const uml_update* upd /*host*/,
                         void* stream);
 
+/* ---- the whole exact step of the reference's own batch sizes (8..64 rows per modality, engine/optimizer/default.py:8,24,39)
+ *      in ONE cooperative launch: K2+K3 (head.py:131-137, finetune.py:186-188), K4 (autograd of the head, finetune.py:190-193)
+ *      and the optimizer (optim.py:42-70), i.e. uml_head_fwd_ce_f32 followed by uml_head_bwd_dw_f32 with a fused update.
+ *      *launched = 1 when the step ran; 0 (and nothing was launched) when the shape does not fit the kernel's contract -
+ *      16-byte aligned rows, dim % 4 == 0, rows x dim floats of shared memory - and the caller takes the separate launches. */
+int uml_head_step_fused_f32(const uml_segment* segs /*host*/, int32_t nseg, int32_t dim, float* W, int32_t n_classes,
+                            float* G, int64_t ldg, float* row_loss, int32_t* row_correct, float* row_dscale,
+                            uml_seg_stats* stats, const uml_update* upd /*host*/, int32_t* launched /*host*/, void* stream);
+/* fused-step launches of this process so far (modulo 2^31): lets a caller that goes through uml_linear_step / uml_linear_run
+ * count the kernels it launched (one per step instead of four when the fused kernel took the step) */
+int uml_head_step_fused_count(void);
+
 /* ---- K5  adapter GEMMs in fp32 (head.py:65,79 and their autograd) ---------------------------- */
 /* C[m,n] = alpha * sum_k A[m,k] * B[n,k]        (both operands K-contiguous: nn.Linear forward)   */
 int uml_gemm_nt_f32(const float* A, int64_t lda, const int64_t* a_row_idx, const float* B, int64_t ldb,

@@ -497,3 +497,60 @@ def test_full_size_step_properties():
         ops.head_fwd_ce_bf16(x16, w16, y, ops.tc_segments([n0, n1], [100.0, 100.0], [1.0, 0.5]), None, row_loss, n_rows=n0 + n1)
         got = row_loss[rows]
         torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("case", HEAD_CASES[:4] + [(300, 200, 36, 12, 8, 8, 100.0, 0.5)])
+@pytest.mark.parametrize("optim", ["adamw", "sgd"])
+def test_fused_step_f32_matches_the_separate_launches_and_the_oracle(case, optim):
+    """uml_head_step_fused_f32 (one cooperative launch: logits, softmax CE, dW, optimizer update, statistics) against
+    uml_head_fwd_ce_f32 + uml_head_bwd_dw_f32 on the same rows - G, per-row results and statistics to summation-order
+    noise, the updated weights and moments - and the statistics against the oracle.  Two consecutive steps, so that
+    the second one starts from moments the kernel wrote itself."""
+    nib, ntb, d, c, bi, bt, scale, alpha = case
+    xi, yi, xt, yt, w, g = _mk(sum(case[:6]) + 1, nib, ntb, d, d, c)
+    dev = [t.to(DEV) for t in (xi, yi, xt, yt)]
+    Wa, Wb = w.to(DEV), w.to(DEV)
+    ma, va, mb, vb = (torch.zeros_like(Wa) for _ in range(4))
+    wsa, wsb = ops.HeadWorkspace(bi + bt, c, DEV), ops.HeadWorkspace(bi + bt, c, DEV)
+    st = O.HeadState(head=w.clone(), img_scale=scale, txt_scale=scale * 0.5)
+    for step in (1, 2):
+        ii = torch.randint(0, nib, (bi,), generator=g)
+        it = torch.randint(0, ntb, (bt,), generator=g)
+        runs = _runs(*dev, ii.to(DEV), it.to(DEV), scale, scale * 0.5, alpha)
+        kw = dict(weight_decay=0.01) if optim == "adamw" else dict(weight_decay=0.01, momentum=0.9)
+        ua = ops.make_update(optim, 2e-4, step, ma, va if optim == "adamw" else None, **kw)
+        ub = ops.make_update(optim, 2e-4, step, mb, vb if optim == "adamw" else None, **kw)
+        launched = ops.head_step_fused_f32(runs, Wa, wsa, ua)
+        if (bi + bt) * (d + 4) * 4 > 200 * 1024:
+            assert not launched, "the step's rows do not fit shared memory: the caller takes the separate launches"
+            return
+        assert launched, "these shapes fit the fused kernel's contract"
+        ops.head_fwd_ce_f32(runs, Wb, wsb)
+        Gb = wsb.G[: bi + bt, :c].clone()
+        ops.head_bwd_dw_f32(runs, Wb, wsb, update=ub)
+        torch.cuda.synchronize()
+        n = bi + bt
+        np.testing.assert_allclose(wsa.row_loss[:n].cpu().numpy(), wsb.row_loss[:n].cpu().numpy(), rtol=2e-5, atol=2e-5)
+        assert torch.equal(wsa.row_correct[:n], wsb.row_correct[:n])
+        ga, gb = wsa.G[:n, :c].cpu(), Gb.cpu()
+        # (a logit's rounding noise is multiplied by the logit scale before the exponential: 1e-4 of the largest |G|)
+        assert float((ga - gb).abs().max()) <= 1e-4 * max(1e-6, float(gb.abs().max()))
+        sa, sb = wsa.read_stats(), wsb.read_stats()
+        for k in range(len(runs)):
+            assert math.isclose(sa[k]["loss_mean"], sb[k]["loss_mean"], rel_tol=2e-5, abs_tol=1e-5)
+            assert sa[k]["correct"] == sb[k]["correct"] and sa[k]["n"] == sb[k]["n"]
+            assert math.isclose(sa[k]["dscale"], sb[k]["dscale"], rel_tol=1e-4, abs_tol=1e-5)
+        stats, _ = O.uml_step_grads(st, xi[ii] if bi else None, yi[ii] if bi else None, xt[it] if bt else None,
+                                    yt[it] if bt else None, alpha)
+        if step == 1:
+            k = 0
+            if bi:
+                assert math.isclose(sa[k]["loss_mean"], stats["image_loss"], rel_tol=2e-5, abs_tol=1e-5)
+                k += 1
+            if bt:
+                assert math.isclose(sa[k]["loss_mean"], stats["text_loss"], rel_tol=2e-5, abs_tol=1e-5)
+        # Adam's first step is lr * sign(g): an element whose gradient is ~0 may flip between two summation orders
+        diff = (Wa - Wb).abs()
+        assert float(diff.max()) <= 2 * 2e-4 + 1e-7 and float((diff > 1e-6).float().mean()) < 1e-3
+        assert float((ma - mb).abs().max()) <= 1e-4 * max(1e-6, float(mb.abs().max()))
+        Wb.copy_(Wa); mb.copy_(ma); vb.copy_(va)   # the next step compares one step, not a drifting trajectory

@@ -5,7 +5,10 @@
 //   2. per-row softmax / CE / argmax, L <- G = w*s/n (softmax - onehot)
 //   3. dW = G^T [X_img ; X_txt] with the AdamW/Adam/SGD update applied in the GEMM epilogue
 // plus the adapter GEMMs (K5) and the streaming eval kernel (K7).
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -69,24 +72,27 @@ static DeviceUpdate make_update(const uml_update* u) {
 }
 
 // One parameter element; the same arithmetic order as torch.optim's single-tensor rules.
-__device__ __forceinline__ void apply_update(const DeviceUpdate& u, float* p, int64_t i, float g) {
-  float w = p[i];
+__device__ __forceinline__ void update_value(const DeviceUpdate& u, float& w, float& m, float& v, float g) {
   if (u.kind == 3) {  // SGD momentum, L2 decay folded into the gradient
     g = fmaf(u.wd, w, g);
-    float b = u.first_step ? g : fmaf(u.momentum, u.m[i], g);
-    u.m[i] = b;
-    p[i] = w - u.lr * b;
+    const float b = u.first_step ? g : fmaf(u.momentum, m, g);
+    m = b;
+    w = w - u.lr * b;
     return;
   }
   if (u.kind == 1) w *= u.decay;            // AdamW: decoupled decay
   else if (u.wd != 0.f) g = fmaf(u.wd, w, g);  // Adam: L2
-  float m = u.m[i], v = u.v[i];
   m = m + (g - m) * (1.f - u.beta1);
   v = v * u.beta2 + (1.f - u.beta2) * g * g;
-  u.m[i] = m;
-  u.v[i] = v;
   const float denom = sqrtf(v) * u.bc2_sqrt_inv + u.eps;
-  p[i] = w - u.step_size * (m / denom);
+  w = w - u.step_size * (m / denom);
+}
+__device__ __forceinline__ void apply_update(const DeviceUpdate& u, float* p, int64_t i, float g) {
+  float w = p[i], m = u.m[i], v = u.kind == 3 ? 0.f : u.v[i];
+  update_value(u, w, m, v, g);
+  p[i] = w;
+  u.m[i] = m;
+  if (u.kind != 3) u.v[i] = v;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -229,20 +235,10 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
   return r;
 }
 
-__global__ void __launch_bounds__(256)
-    softmax_ce_grad_kernel(float* __restrict__ L, int64_t ldl, int C, SegInfo seg, float* __restrict__ row_loss,
-                           int32_t* __restrict__ row_correct, float* __restrict__ row_dscale, int planes, int64_t plane) {
-  __shared__ float sh[8];
-  __shared__ int sh_arg;
-  const int64_t r = blockIdx.x;
-  if (planes > 1) {  // split-K forward: raw logits = sum of the planes, in plane order
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float x = L[r * ldl + c];
-      for (int z = 1; z < planes; ++z) x += L[z * plane + r * ldl + c];
-      L[r * ldl + c] = x;
-    }
-    __syncthreads();
-  }
+// one row by one CTA of 256 threads: raw logits row -> G row, row loss / hit / d loss / d scale
+__device__ __forceinline__ void softmax_ce_grad_row(int64_t r, float* __restrict__ L, int64_t ldl, int C, const SegInfo& seg,
+                                                    float* __restrict__ row_loss, int32_t* __restrict__ row_correct,
+                                                    float* __restrict__ row_dscale, float* sh, int& sh_arg) {
   const bool s = r >= seg.n0;
   const int64_t l = s ? r - seg.n0 : r;
   const int64_t n_seg = s ? seg.n1 : seg.n0;
@@ -283,6 +279,160 @@ __global__ void __launch_bounds__(256)
     row_loss[r] = logf(sum) - (label_raw * scale - bmax);  // log_softmax form: exact 0 for a dominant label
     row_correct[r] = (sh_arg == label) ? 1 : 0;
     row_dscale[r] = dsum * weight / static_cast<float>(n_seg);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    softmax_ce_grad_kernel(float* __restrict__ L, int64_t ldl, int C, SegInfo seg, float* __restrict__ row_loss,
+                           int32_t* __restrict__ row_correct, float* __restrict__ row_dscale, int planes, int64_t plane) {
+  __shared__ float sh[8];
+  __shared__ int sh_arg;
+  const int64_t r = blockIdx.x;
+  if (planes > 1) {  // split-K forward: raw logits = sum of the planes, in plane order
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float x = L[r * ldl + c];
+      for (int z = 1; z < planes; ++z) x += L[z * plane + r * ldl + c];
+      L[r * ldl + c] = x;
+    }
+    __syncthreads();
+  }
+  softmax_ce_grad_row(r, L, ldl, C, seg, row_loss, row_correct, row_dscale, sh, sh_arg);
+}
+
+// -------------------------------------------------------------------------------------------------
+// The whole step of the reference's own batch sizes in ONE cooperative launch (one CTA per SM):
+// at 32 + 32 rows the four launches above spend their time starting, draining and re-reading
+// (56 us per step); here the step's rows stay in shared memory from the logits to the gradient,
+// every CTA owns a contiguous range of classes for both contractions, and the three phases are
+// separated by two grid-wide barriers:
+//   1. raw logits of the CTA's classes for all rows            (weight rows streamed once)
+//   2. softmax / CE / argmax, one row per CTA, G written back  (the row kernel's arithmetic)
+//   3. dW of the CTA's classes (rows summed in order, like the GEMM) + optimizer update, and the
+//      per-run statistics by CTA 0
+// Needs 16-byte aligned rows and R x D floats of shared memory; anything else takes the launches above.
+// -------------------------------------------------------------------------------------------------
+constexpr int kFusedMaxRows = 128;
+struct FusedStepArgs {
+  RowSrc X;
+  SegInfo seg;
+  float* W;
+  DeviceUpdate upd;
+  float* G;
+  int64_t ldg;
+  int C, D, R, nseg;
+  float* row_loss;
+  int32_t* row_correct;
+  float* row_dscale;
+  uml_seg_stats* stats;
+};
+
+__global__ void __launch_bounds__(256, 1) head_step_fused_kernel(const __grid_constant__ FusedStepArgs a) {
+  extern __shared__ __align__(16) float fused_smem[];
+  __shared__ float sh[8];
+  __shared__ int sh_arg;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int C = a.C, D = a.D, R = a.R, D4 = D >> 2;
+  const int c_lo = static_cast<int>(static_cast<int64_t>(C) * blockIdx.x / gridDim.x);
+  const int c_hi = static_cast<int>(static_cast<int64_t>(C) * (blockIdx.x + 1) / gridDim.x);
+  const int nc = c_hi - c_lo;
+  // rows of the step, gathered from the banks by index: row stride D4 + 1 float4, so that threads that walk different rows
+  // in step (phase 1) hit different banks; every thread has eight 16-byte loads in flight
+  const int XS = D4 + 1;
+  float4* xs = reinterpret_cast<float4*>(fused_smem);  // [R][XS]
+  __shared__ const float4* rowp[kFusedMaxRows];
+  for (int r = t; r < R; r += 256) rowp[r] = reinterpret_cast<const float4*>(a.X.row(r));
+  __syncthreads();
+  // the CTA's weight rows (contiguous in HBM) come along: read from HBM exactly once, by all threads at once - a thread
+  // walking its row 16 bytes at a time straight from HBM made phase 1 a 30 us pointer chase
+  float4* wsm = xs + static_cast<size_t>(R) * XS;  // [nc][D4]
+  {
+    const float4* wsrc = reinterpret_cast<const float4*>(a.W + static_cast<int64_t>(c_lo) * D);
+    const int nw = nc * D4;
+#pragma unroll 4
+    for (int e = t; e < nw; e += 256) wsm[e] = wsrc[e];  // (plain loads: W is written later in this launch)
+    const int n = R * D4;
+#pragma unroll 8
+    for (int e = t; e < n; e += 256) {
+      const int r = e / D4, q = e - r * D4;
+      xs[r * XS + q] = __ldg(rowp[r] + q);
+    }
+  }
+  __syncthreads();
+  // ---- 1. raw logits: thread = (row, class group); the sum runs over the dim in order, one FFMA per term, like the GEMM ----
+  for (int r = t & 63; r < R; r += 64) {
+    for (int j = t >> 6; j < nc; j += 4) {  // (a warp shares j: its weight loads are one broadcast address)
+      const float4* wrow = wsm + j * D4;
+      const float4* xrow = xs + r * XS;
+      float acc = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < D4; ++q) {
+        const float4 w = wrow[q], x = xrow[q];
+        acc = fmaf(x.x, w.x, acc);
+        acc = fmaf(x.y, w.y, acc);
+        acc = fmaf(x.z, w.z, acc);
+        acc = fmaf(x.w, w.w, acc);
+      }
+      a.G[static_cast<int64_t>(r) * a.ldg + c_lo + j] = acc;
+    }
+  }
+  grid.sync();
+  // ---- 2. rows -------------------------------------------------------------------------------------
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    softmax_ce_grad_row(r, a.G, a.ldg, C, a.seg, a.row_loss, a.row_correct, a.row_dscale, sh, sh_arg);
+    __syncthreads();
+  }
+  grid.sync();
+  // ---- 3. dW of this CTA's classes + update -----------------------------------------------------
+  float* gs = reinterpret_cast<float*>(wsm + static_cast<size_t>(nc) * D4);  // [R][nc] the CTA's columns of G
+  for (int e = t; e < R * nc; e += 256) {
+    const int r = e / nc, j = e - r * nc;
+    gs[e] = __ldcg(a.G + static_cast<int64_t>(r) * a.ldg + c_lo + j);  // (written by other CTAs: not through the read-only path)
+  }
+  __syncthreads();
+  for (int it = t; it < nc * D4; it += 256) {
+    const int j = it / D4, q = it - j * D4;
+    const int64_t off = (static_cast<int64_t>(c_lo + j) * D) + 4 * q;
+    float4 w = wsm[it];  // (= W[c_lo + j][4 q ..]: nobody has written it since phase 1)
+    float4 m = *reinterpret_cast<const float4*>(a.upd.m + off);
+    float4 v = a.upd.kind == 3 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(a.upd.v + off);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int r = 0; r < R; ++r) {
+      const float g = gs[r * nc + j];
+      const float4 x = xs[r * XS + q];
+      acc.x = fmaf(g, x.x, acc.x);
+      acc.y = fmaf(g, x.y, acc.y);
+      acc.z = fmaf(g, x.z, acc.z);
+      acc.w = fmaf(g, x.w, acc.w);
+    }
+    update_value(a.upd, w.x, m.x, v.x, acc.x);
+    update_value(a.upd, w.y, m.y, v.y, acc.y);
+    update_value(a.upd, w.z, m.z, v.z, acc.z);
+    update_value(a.upd, w.w, m.w, v.w, acc.w);
+    *reinterpret_cast<float4*>(a.W + off) = w;
+    *reinterpret_cast<float4*>(a.upd.m + off) = m;
+    if (a.upd.kind != 3) *reinterpret_cast<float4*>(a.upd.v + off) = v;
+  }
+  // per-run statistics, fixed order: warp s of CTA 0 sums run s (lanes stride over the rows, shuffle tree)
+  if (blockIdx.x == 0 && warp < a.nseg) {
+    const int64_t beg = warp ? a.seg.n0 : 0, n = warp ? a.seg.n1 : a.seg.n0;
+    float ls = 0.f, ds = 0.f;
+    int hits = 0;
+    for (int64_t i = lane; i < n; i += 32) {
+      ls += __ldcg(a.row_loss + beg + i);
+      ds += __ldcg(a.row_dscale + beg + i);
+      hits += __ldcg(a.row_correct + beg + i);
+    }
+    ls = warp_sum(ls);
+    ds = warp_sum(ds);
+    hits = warp_sum_i(hits);
+    if (lane == 0) {
+      a.stats[warp].loss_mean = n > 0 ? ls / static_cast<float>(n) : 0.f;
+      a.stats[warp].dscale = ds;
+      a.stats[warp].correct = hits;
+      a.stats[warp].n = static_cast<int32_t>(n);
+    }
   }
 }
 
@@ -528,6 +678,8 @@ static RowSrc seg_src(const uml_segment* segs, int32_t nseg) {
 
 }  // namespace uml
 
+static long long g_fused_steps = 0;  // fused-step launches of this process (launch accounting of the callers)
+
 extern "C" {
 
 int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, const float* W, int32_t n_classes,
@@ -573,6 +725,69 @@ int uml_head_fwd_ce_f32(const uml_segment* segs, int32_t nseg, int32_t dim, cons
   UML_CUDA(cudaGetLastError());
   return 0;
 }
+
+int uml_head_step_fused_f32(const uml_segment* segs, int32_t nseg, int32_t dim, float* W, int32_t n_classes, float* G,
+                            int64_t ldg, float* row_loss, int32_t* row_correct, float* row_dscale, uml_seg_stats* stats,
+                            const uml_update* upd, int32_t* launched, void* stream) {
+  using namespace uml;
+  UML_REQUIRE(launched != nullptr, "head_step_fused_f32: null launched");
+  *launched = 0;
+  if (check_segs(segs, nseg)) return 1;
+  UML_REQUIRE(W && G && row_loss && row_correct && row_dscale && stats && dim > 0 && n_classes > 0 && ldg >= n_classes,
+              "head_step_fused_f32: bad arguments");
+  static const bool enabled = [] {
+    const char* e = getenv("UML_FUSED_STEP");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (!enabled || !upd || upd->kind < 1 || upd->kind > 3 || !upd->m || (upd->kind != 3 && !upd->v)) return 0;
+  const int64_t n0 = segs[0].n, n1 = nseg > 1 ? segs[1].n : 0, total = n0 + n1;
+  if (total <= 0 || total > kFusedMaxRows || dim % 4 != 0) return 0;
+  auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!aligned(W) || !aligned(upd->m) || (upd->kind != 3 && !aligned(upd->v))) return 0;
+  for (int i = 0; i < nseg; ++i)
+    if (segs[i].n > 0 && (!aligned(segs[i].rows) || segs[i].ld % 4 != 0)) return 0;
+  const int grid = sm_count();
+  const int64_t nc_max = (n_classes + grid - 1) / grid + 1;
+  const size_t smem = static_cast<size_t>(total) * (dim + 4) * 4 + static_cast<size_t>(nc_max) * dim * 4 +
+                      static_cast<size_t>(total) * nc_max * 4;
+  if (smem > 224 * 1024) return 0;
+  static const cudaError_t attr =
+      cudaFuncSetAttribute(head_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+  UML_CUDA(attr);
+  FusedStepArgs fa;
+  memset(&fa, 0, sizeof(fa));
+  fa.X = seg_src(segs, nseg);
+  fa.seg.n0 = n0;
+  fa.seg.n1 = n1;
+  for (int i = 0; i < 2; ++i) {
+    const uml_segment& sg = segs[i < nseg ? i : 0];
+    fa.seg.idx[i] = sg.label_idx ? sg.label_idx : sg.idx;
+    fa.seg.labels[i] = sg.labels;
+    fa.seg.scale_dev[i] = sg.scale_dev;
+    fa.seg.scale[i] = sg.scale;
+    fa.seg.weight[i] = sg.loss_weight;
+  }
+  fa.W = W;
+  fa.upd = make_update(upd);
+  fa.G = G;
+  fa.ldg = ldg;
+  fa.C = n_classes;
+  fa.D = dim;
+  fa.R = static_cast<int>(total);
+  fa.nseg = nseg;
+  fa.row_loss = row_loss;
+  fa.row_correct = row_correct;
+  fa.row_dscale = row_dscale;
+  fa.stats = stats;
+  void* kargs[] = {&fa};
+  UML_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(head_step_fused_kernel), dim3(grid), dim3(256), kargs, smem,
+                                       as_stream(stream)));
+  *launched = 1;
+  ++g_fused_steps;
+  return 0;
+}
+
+int uml_head_step_fused_count(void) { return static_cast<int>(g_fused_steps & 0x7fffffff); }
 
 int uml_head_bwd_dw_f32(const uml_segment* segs, int32_t nseg, int32_t dim, const float* G, int64_t ldg,
                         int32_t n_classes, float* W, float* dW, const uml_update* upd, void* stream) {

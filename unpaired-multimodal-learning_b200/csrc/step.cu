@@ -536,6 +536,18 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
     // ------------------------------------------------------------------ fp32 exact path (3 launches)
     UML_REQUIRE(a->row_dscale, "linear_step: fp32 path needs row_dscale");
     rec(a->ev[2], stream);
+    if (fused && !dp && total > 0) {  // the reference's batch sizes: forward, gradient and update in one cooperative launch
+      int32_t launched = 0;
+      rc = uml_head_step_fused_f32(a->seg, a->nseg, a->dim, a->W, a->n_classes, static_cast<float*>(a->G), a->ldg, a->row_loss,
+                                   a->row_correct, a->row_dscale, a->stats, &a->upd, &launched, stream);
+      if (rc) return rc;
+      if (launched) {
+        rec(a->ev[3], stream);
+        rec(a->ev[4], stream);
+        rec(a->ev[5], stream);
+        return 0;
+      }
+    }
     rc = uml_head_fwd_ce_f32(a->seg, a->nseg, a->dim, a->W, a->n_classes, static_cast<float*>(a->G), a->ldg,
                              a->row_loss, a->row_correct, a->row_dscale, a->stats, a->g_capacity_rows, stream);
     if (rc) return rc;

@@ -766,7 +766,7 @@ __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-// kNT update threads per CTA plus one TMA warp.  The update costs ~50 instructions per parameter (IEEE sqrt and division),
+// kNT update threads per CTA plus one TMA warp and one statistics warp.  The update costs ~50 instructions per parameter (IEEE sqrt and division),
 // so the read-back needs warps to hide its dependency chains as much as it needs bytes in flight (8 warps per SM left the
 // slots waiting for arithmetic), and nothing in it may wait for anything but its own data: an update warp waits for a
 // slot's loads, updates its share in place and arrives on the slot's `done` barrier; the TMA warp waits for that
@@ -788,7 +788,7 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 template <int kNT>
-__global__ void __launch_bounds__(kNT + 32, 1)
+__global__ void __launch_bounds__(kNT + 64, 1)
     sweep_dw_update_tc_kernel(const __grid_constant__ SweepDev p, const __grid_constant__ CUtensorMap tm_w,
                               const __grid_constant__ CUtensorMap tm_m, const __grid_constant__ CUtensorMap tm_v) {
   static_assert(kNT == 256 || kNT == 512, "8 or 4 classes of a stage per thread");
@@ -855,7 +855,34 @@ __global__ void __launch_bounds__(kNT + 32, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == kWarps) {
+  if (warp == kWarps + 1) {
+    // ------------------------------------------------ statistics warp: what sweep_stats_kernel computes, in a warp that
+    // would otherwise not exist (running head a belongs to CTA a mod gridDim.x; lanes stride over the rows, shuffle tree)
+    const int n_act = __popc(p.active_mask);
+    for (int a = blockIdx.x; a < n_act; a += gridDim.x) {
+      const int hd = __fns(p.active_mask, 0, a + 1);
+      for (int sg = 0; sg < 2; ++sg) {
+        const int64_t beg = sg ? p.n0 : 0, n = sg ? p.n1 : p.n0;
+        const float* rl = p.row_loss + hd * p.row_stride + beg;
+        const int32_t* rc = p.row_correct + hd * p.row_stride + beg;
+        float ls = 0.f;
+        int hits = 0;
+        for (int64_t i = lane; i < n; i += 32) {
+          ls += rl[i];
+          hits += rc[i];
+        }
+        ls = warp_sum(ls);
+        hits = warp_sum_i(hits);
+        if (lane == 0) {
+          uml_seg_stats& o = p.stats[hd * 2 + sg];
+          o.loss_mean = n > 0 ? ls / static_cast<float>(n) : 0.f;
+          o.dscale = 0.f;
+          o.correct = hits;
+          o.n = static_cast<int32_t>(n);
+        }
+      }
+    }
+  } else if (warp == kWarps) {
     // ------------------------------------------------ TMA warp: slot ring of W, m, v ---------------------------------
     if (lane == 0) {
       DwUnit prod = cur, stc = cur;  // load cursor (NS - 1 stages ahead), store cursor
@@ -1217,8 +1244,8 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     if (use_tc_dw && R <= 64) {  // (larger steps: the feature tile of the tensor-core form holds 64 rows)
       const int64_t units = static_cast<int64_t>(__builtin_popcount(mask)) * ((a->dim + 127) / 128) * ((a->n_classes + 63) / 64);
       const unsigned g = static_cast<unsigned>(std::min<int64_t>(units, sm_count()));
-      if (dw_threads == 256) sweep_dw_update_tc_kernel<256><<<g, 256 + 32, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
-      else sweep_dw_update_tc_kernel<512><<<g, 512 + 32, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      if (dw_threads == 256) sweep_dw_update_tc_kernel<256><<<g, 256 + 64, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
+      else sweep_dw_update_tc_kernel<512><<<g, 512 + 64, kTcDwSmemBytes, st>>>(p, tm_w, tm_m, tm_v);
     }
     else if (use_async)
       sweep_dw_update_async_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
@@ -1226,8 +1253,10 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
     if (mark(5) || mark(6)) return 1;
-    sweep_stats_kernel<<<dim3(2, K), 256, 0, st>>>(p);
-    UML_CUDA(cudaGetLastError());
+    if (!(use_tc_dw && R <= 64)) {  // (the tensor-core dW launch carries a statistics warp)
+      sweep_stats_kernel<<<dim3(2, K), 256, 0, st>>>(p);
+      UML_CUDA(cudaGetLastError());
+    }
     if (mark(7)) return 1;
     pos[0] += n0;
     pos[1] += n1;

@@ -345,8 +345,10 @@ class StepEngine:
                 e0, e1 = self._event_pool.pop() if self._event_pool else self._new_event_pair()
                 a.ev[2 * j], a.ev[2 * j + 1] = e0.cuda_event, e1.cuda_event
                 self.profile.setdefault(nm, []).append((e0, e1))
+        f0 = load().uml_head_step_fused_count()
         check(load().uml_linear_step(C.byref(a), torch.cuda.current_stream().cuda_stream))
-        LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16)
+        # (a step the fused exact-path kernel took is one launch instead of four)
+        LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16) - 3 * ((load().uml_head_step_fused_count() - f0) & 0x7fffffff)
         self._w16_valid = bf16
 
     def run(self, batches, alpha, lrs, slot0):
@@ -433,8 +435,10 @@ class StepEngine:
             # every index batch vouched for by an upload event: the gather pipeline may run through the call boundary
             a.idx_ready = ready.cuda_event if (vouched and ready is not None) else None
             arr = (RunStep * len(steps))(*steps)
+            f0 = load().uml_head_step_fused_count()
             check(load().uml_linear_run(C.byref(a), arr, len(steps), torch.cuda.current_stream().cuda_stream))
             LAUNCH_COUNT[0] += self._kernels_per_step(k, bf16) * len(steps) - (0 if self._w16_valid or not bf16 else len(steps) - 1)
+            LAUNCH_COUNT[0] -= 3 * ((load().uml_head_step_fused_count() - f0) & 0x7fffffff)
             self._w16_valid = bf16
             j = m
 

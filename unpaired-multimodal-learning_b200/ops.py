@@ -196,6 +196,25 @@ def head_bwd_dw_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, dW:
                                           _ptr(dW), C.byref(update) if update is not None else None, _stream()))
 
 
+def head_step_fused_f32(runs: Sequence[Run], W: torch.Tensor, ws: HeadWorkspace, update: Update,
+                        stats: Optional[torch.Tensor] = None) -> bool:
+    """The whole exact step (logits, softmax CE, dW, optimizer update, per-run stats) in one cooperative launch.
+    Returns False - and launches nothing - when the shape does not fit the kernel's contract; the caller then takes
+    head_fwd_ce_f32 + head_bwd_dw_f32.  finetune.py:181-195."""
+    _need(W, torch.float32, "W")
+    arr, n = _segs(runs)
+    if sum(r.n for r in runs) > ws.max_rows:
+        raise ValueError("workspace too small")
+    stats = ws.stats if stats is None else stats
+    launched = C.c_int32(0)
+    check(_lib.load().uml_head_step_fused_f32(arr, n, W.shape[1], W.data_ptr(), W.shape[0], ws.G.data_ptr(), ws.ldg,
+                                              ws.row_loss.data_ptr(), ws.row_correct.data_ptr(), ws.row_dscale.data_ptr(),
+                                              stats.data_ptr(), C.byref(update), C.byref(launched), _stream()))
+    if launched.value:
+        _lib.LAUNCH_COUNT[0] += 1
+    return bool(launched.value)
+
+
 def gemm_nt(A: torch.Tensor, B: torch.Tensor, out: torch.Tensor, alpha: float = 1.0,
             a_row_idx: Optional[torch.Tensor] = None, m: Optional[int] = None):
     """out[m,n] = alpha * sum_k A[row(m),k] B[n,k]"""
