@@ -312,6 +312,10 @@ __global__ void __launch_bounds__(256)
 // Needs 16-byte aligned rows and R x D floats of shared memory; anything else takes the launches above.
 // -------------------------------------------------------------------------------------------------
 constexpr int kFusedMaxRows = 128;
+// 16-byte asynchronous global -> shared copy (LDGSTS)
+__device__ __forceinline__ void ldgsts16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 struct FusedStepArgs {
   RowSrc X;
   SegInfo seg;
@@ -336,9 +340,9 @@ __global__ void __launch_bounds__(256, 1) head_step_fused_kernel(const __grid_co
   const int c_lo = static_cast<int>(static_cast<int64_t>(C) * blockIdx.x / gridDim.x);
   const int c_hi = static_cast<int>(static_cast<int64_t>(C) * (blockIdx.x + 1) / gridDim.x);
   const int nc = c_hi - c_lo;
-  // rows of the step, gathered from the banks by index: row stride D4 + 1 float4, so that threads that walk different rows
-  // in step (phase 1) hit different banks; every thread has eight 16-byte loads in flight
-  const int XS = D4 + 1;
+  // rows of the step, gathered from the banks by index; row stride D4 + 4 float4: the eight lanes of a quarter warp in
+  // phase 1 - two rows x four interleaved k-lanes - then cover all 32 banks exactly once
+  const int XS = D4 + 4;
   float4* xs = reinterpret_cast<float4*>(fused_smem);  // [R][XS]
   __shared__ const float4* rowp[kFusedMaxRows];
   for (int r = t; r < R; r += 256) rowp[r] = reinterpret_cast<const float4*>(a.X.row(r));
@@ -347,33 +351,67 @@ __global__ void __launch_bounds__(256, 1) head_step_fused_kernel(const __grid_co
   // walking its row 16 bytes at a time straight from HBM made phase 1 a 30 us pointer chase
   float4* wsm = xs + static_cast<size_t>(R) * XS;  // [nc][D4]
   {
+    // the optimizer state of the CTA's classes (contiguous, first touched in phase 3) is asked into L2 now
+    if (t < 2 && nc > 0) {
+      const float* st = t == 0 ? a.upd.m : a.upd.v;
+      if (st != nullptr)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(st + static_cast<int64_t>(c_lo) * D),
+                     "r"(static_cast<uint32_t>(nc) * static_cast<uint32_t>(D) * 4u)
+                     : "memory");
+    }
+    // both tiles go global -> shared without passing through registers (cp.async): every 16-byte piece of the CTA's share is
+    // in flight at once instead of eight per thread
     const float4* wsrc = reinterpret_cast<const float4*>(a.W + static_cast<int64_t>(c_lo) * D);
     const int nw = nc * D4;
-#pragma unroll 4
-    for (int e = t; e < nw; e += 256) wsm[e] = wsrc[e];  // (plain loads: W is written later in this launch)
+    for (int e = t; e < nw; e += 256) ldgsts16(wsm + e, wsrc + e);
+    // every CTA needs the same R rows: each starts somewhere else in them, or all SMs would ask the same L2 lines at the
+    // same moment (measured: the in-step walk took 15 us for 128 KB per CTA, 10 us staggered)
     const int n = R * D4;
-#pragma unroll 8
-    for (int e = t; e < n; e += 256) {
+    const int rot = static_cast<int>(static_cast<int64_t>(n) * blockIdx.x / gridDim.x);
+    for (int e0 = t; e0 < n; e0 += 256) {
+      int e = e0 + rot;
+      if (e >= n) e -= n;
       const int r = e / D4, q = e - r * D4;
-      xs[r * XS + q] = __ldg(rowp[r] + q);
+      ldgsts16(xs + r * XS + q, rowp[r] + q);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  // ---- 1. raw logits: thread = (row, class group); the sum runs over the dim in order, one FFMA per term, like the GEMM ----
-  for (int r = t & 63; r < R; r += 64) {
-    for (int j = t >> 6; j < nc; j += 4) {  // (a warp shares j: its weight loads are one broadcast address)
-      const float4* wrow = wsm + j * D4;
-      const float4* xrow = xs + r * XS;
-      float acc = 0.f;
-#pragma unroll 4
-      for (int q = 0; q < D4; ++q) {
-        const float4 w = wrow[q], x = xrow[q];
-        acc = fmaf(x.x, w.x, acc);
-        acc = fmaf(x.y, w.y, acc);
-        acc = fmaf(x.z, w.z, acc);
-        acc = fmaf(x.w, w.w, acc);
+  // ---- 1. raw logits: thread = (row, k-lane g); lane g walks the 16-byte chunks q = g (mod 4) of the row for up to eight
+  //         classes at a time (x from shared memory once per eight classes), the four lanes of a row meet by shuffle ----
+  {
+    const int g = t & 3;
+    for (int r = t >> 2; r < ((R + 63) & ~63); r += 64) {  // (whole warps stay in the loop: the shuffles below need them)
+      const float4* xrow = xs + min(r, R - 1) * XS;
+      for (int j0 = 0; j0 < nc; j0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+        for (int q = g; q < D4; q += 4) {
+          const float4 x = xrow[q];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 w = wsm[min(j0 + k, nc - 1) * D4 + q];  // (a class past the CTA's range repeats the last one, unused)
+            float c = acc[k];
+            c = fmaf(x.x, w.x, c);
+            c = fmaf(x.y, w.y, c);
+            c = fmaf(x.z, w.z, c);
+            c = fmaf(x.w, w.w, c);
+            acc[k] = c;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+          acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+        }
+        if (r < R) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if ((k & 3) == g && j0 + k < nc) a.G[static_cast<int64_t>(r) * a.ldg + c_lo + j0 + k] = acc[k];
+        }
       }
-      a.G[static_cast<int64_t>(r) * a.ldg + c_lo + j] = acc;
     }
   }
   grid.sync();
@@ -383,36 +421,54 @@ __global__ void __launch_bounds__(256, 1) head_step_fused_kernel(const __grid_co
     __syncthreads();
   }
   grid.sync();
-  // ---- 3. dW of this CTA's classes + update -----------------------------------------------------
-  float* gs = reinterpret_cast<float*>(wsm + static_cast<size_t>(nc) * D4);  // [R][nc] the CTA's columns of G
-  for (int e = t; e < R * nc; e += 256) {
-    const int r = e / nc, j = e - r * nc;
-    gs[e] = __ldcg(a.G + static_cast<int64_t>(r) * a.ldg + c_lo + j);  // (written by other CTAs: not through the read-only path)
+  // ---- 3. dW of this CTA's classes + update: thread = (four classes, one 16-byte chunk of the dim); the rows are summed
+  //         in order, one FFMA per term, like the GEMM -----------------------------------------------------
+  const int NCP = (nc + 3) & ~3;
+  float* gs = reinterpret_cast<float*>(wsm + static_cast<size_t>(nc) * D4);  // [R][NCP] the CTA's columns of G
+  for (int e = t; e < R * NCP; e += 256) {
+    const int r = e / NCP, j = e - r * NCP;
+    // (written by other CTAs in this launch: not through the read-only path)
+    gs[e] = j < nc ? __ldcg(a.G + static_cast<int64_t>(r) * a.ldg + c_lo + j) : 0.f;
   }
   __syncthreads();
-  for (int it = t; it < nc * D4; it += 256) {
-    const int j = it / D4, q = it - j * D4;
-    const int64_t off = (static_cast<int64_t>(c_lo + j) * D) + 4 * q;
-    float4 w = wsm[it];  // (= W[c_lo + j][4 q ..]: nobody has written it since phase 1)
-    float4 m = *reinterpret_cast<const float4*>(a.upd.m + off);
-    float4 v = a.upd.kind == 3 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(a.upd.v + off);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = t; it < (NCP >> 2) * D4; it += 256) {
+    const int jb = (it / D4) << 2, q = it % D4;
+    float4 w[4], m[4], v[4], acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc[k] = w[k] = m[k] = v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (jb + k < nc) {
+        const int64_t off = (static_cast<int64_t>(c_lo + jb + k) * D) + 4 * q;
+        w[k] = wsm[(jb + k) * D4 + q];  // (= W[c_lo + j][4 q ..]: nobody has written it since phase 1)
+        m[k] = *reinterpret_cast<const float4*>(a.upd.m + off);
+        if (a.upd.kind != 3) v[k] = *reinterpret_cast<const float4*>(a.upd.v + off);
+      }
+    }
 #pragma unroll 4
     for (int r = 0; r < R; ++r) {
-      const float g = gs[r * nc + j];
+      const float4 g4 = *reinterpret_cast<const float4*>(gs + r * NCP + jb);
       const float4 x = xs[r * XS + q];
-      acc.x = fmaf(g, x.x, acc.x);
-      acc.y = fmaf(g, x.y, acc.y);
-      acc.z = fmaf(g, x.z, acc.z);
-      acc.w = fmaf(g, x.w, acc.w);
+      const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[k].x = fmaf(g[k], x.x, acc[k].x);
+        acc[k].y = fmaf(g[k], x.y, acc[k].y);
+        acc[k].z = fmaf(g[k], x.z, acc[k].z);
+        acc[k].w = fmaf(g[k], x.w, acc[k].w);
+      }
     }
-    update_value(a.upd, w.x, m.x, v.x, acc.x);
-    update_value(a.upd, w.y, m.y, v.y, acc.y);
-    update_value(a.upd, w.z, m.z, v.z, acc.z);
-    update_value(a.upd, w.w, m.w, v.w, acc.w);
-    *reinterpret_cast<float4*>(a.W + off) = w;
-    *reinterpret_cast<float4*>(a.upd.m + off) = m;
-    if (a.upd.kind != 3) *reinterpret_cast<float4*>(a.upd.v + off) = v;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (jb + k >= nc) continue;
+      const int64_t off = (static_cast<int64_t>(c_lo + jb + k) * D) + 4 * q;
+      update_value(a.upd, w[k].x, m[k].x, v[k].x, acc[k].x);
+      update_value(a.upd, w[k].y, m[k].y, v[k].y, acc[k].y);
+      update_value(a.upd, w[k].z, m[k].z, v[k].z, acc[k].z);
+      update_value(a.upd, w[k].w, m[k].w, v[k].w, acc[k].w);
+      *reinterpret_cast<float4*>(a.W + off) = w[k];
+      *reinterpret_cast<float4*>(a.upd.m + off) = m[k];
+      if (a.upd.kind != 3) *reinterpret_cast<float4*>(a.upd.v + off) = v[k];
+    }
   }
   // per-run statistics, fixed order: warp s of CTA 0 sums run s (lanes stride over the rows, shuffle tree)
   if (blockIdx.x == 0 && warp < a.nseg) {
@@ -748,8 +804,8 @@ int uml_head_step_fused_f32(const uml_segment* segs, int32_t nseg, int32_t dim, 
     if (segs[i].n > 0 && (!aligned(segs[i].rows) || segs[i].ld % 4 != 0)) return 0;
   const int grid = sm_count();
   const int64_t nc_max = (n_classes + grid - 1) / grid + 1;
-  const size_t smem = static_cast<size_t>(total) * (dim + 4) * 4 + static_cast<size_t>(nc_max) * dim * 4 +
-                      static_cast<size_t>(total) * nc_max * 4;
+  const size_t smem = static_cast<size_t>(total) * (dim + 16) * 4 + static_cast<size_t>(nc_max) * dim * 4 +
+                      static_cast<size_t>(total) * (nc_max + 3) * 4;
   if (smem > 224 * 1024) return 0;
   static const cudaError_t attr =
       cudaFuncSetAttribute(head_step_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
