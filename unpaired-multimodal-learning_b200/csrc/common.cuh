@@ -89,7 +89,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
                  uint32_t box_outer, CUtensorMapSwizzle swizzle);
 
 int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2);
+                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE);
 
 // ---------------------------------------------------------------------------------------------
 // device-side PTX wrappers

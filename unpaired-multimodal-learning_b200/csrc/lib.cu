@@ -75,9 +75,10 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
   return 0;
 }
 
-// 3D row-major tensor (d0 contiguous), no swizzle: boxes land in shared memory as dense [box2][box1][box0]
+// 3D row-major tensor (d0 contiguous): boxes land in shared memory as [box2][box1][box0], rows swizzled as asked
 int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, uint64_t d0, uint64_t d1, uint64_t d2,
-                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2) {
+                 uint64_t pitch1_bytes, uint64_t pitch2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 CUtensorMapSwizzle swizzle) {
   encode_tiled_fn enc = get_encode();
   UML_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   UML_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15u) == 0, "tensor map base must be 16B aligned");
@@ -88,7 +89,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, CUtensorMapDataType dtype, 
   cuuint32_t box[3] = {box0, box1, box2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UML_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3D) failed with CUresult %d", (int)r);
   return 0;
 }

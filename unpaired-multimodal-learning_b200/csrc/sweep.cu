@@ -595,9 +595,13 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<
 // 1t. raw logits, transposed tile: D[class, row] = W_k[128 classes, :] . X_k[64 rows, :]^T   grid (ceil(C/128), ceil(rows/64), K)
 //     A = weight rows (K-major), B = gathered bank rows (K-major), k-blocks of 32 floats (one swizzle row), two stages:
 //     the loads of block kb + 1 are in registers while block kb is split, stored and multiplied.
-//     (Measured alternatives, 30 heads of 1000 x 512: a five-stage cp.async ring three blocks ahead with one CTA per SM took
-//     47 us, the same with the weight tile requested from L2 up front by cp.async.bulk.prefetch 51 us, against 37 us for
-//     this form - two CTAs per SM, every tile of the launch resident at once.)
+//     (Measured alternatives, 30 heads of 1000 x 512, against 37 us for this form - two CTAs per SM, every tile of the
+//     launch resident at once: register buffers two blocks ahead 38 us; a five-stage cp.async ring three blocks ahead, one
+//     CTA per SM, 47 us, with the weight tile asked into L2 up front 51 us; a TMA warp for the weight boxes with four
+//     row-loader warps 51 us, with one 128-byte bulk copy per row instead 88 us.  None of it is a load-latency problem:
+//     a k-block moves 48 KB of split stores, 24 KB of loads and 72 KB of operand reads for its 12 MMAs through shared
+//     memory - about 0.6 us of its bandwidth, 15 us for the launch - and the rest is the split -> fence.proxy.async ->
+//     barrier -> issue chain of each block, which only more resident CTAs hide.)
 constexpr int kTcLgStage = 48 * 1024;  // W hi 16 KB | W lo 16 KB | X hi 8 KB | X lo 8 KB
 constexpr int kTcLgSmemBytes = 2 * kTcLgStage + 1024 + 64;
 
