@@ -696,7 +696,7 @@ def run_eval(args):
 def run_sweep(args):
     """--workload cfg2_sweep: the reference's real few-shot workload - the hyper-parameter sweep of preset `clip_linear`
     (lr x weight decay, engine/optimizer/default.py:17-31) times its alpha sweep over the SAME cfg2 banks - with
-    --heads combinations trained in lock step (finetune.train_group / uml_sweep_run: four launches per step of all
+    --heads combinations trained in lock step (finetune.train_group / uml_sweep_run: three launches per step of all
     heads).  value: device-resident (every head's epoch permutation in HBM before the clock starts); e2e: ONE public
     train_group() call; `sequential`: the same banks through the single-head engine (finetune.train), which is what
     the sweep costs one combination at a time."""
@@ -808,7 +808,7 @@ def run_sweep(args):
     # algorithmic bytes of the dW + optimizer launch: W, m, v read and written once per head (24 B/parameter; the
     # gradient itself never reaches HBM) plus the step's G and feature rows read once
     bytes_ = H * (24.0 * C * D + 4.0 * (B + BT) * (C + D))
-    roof = {"bound": "hbm", "kernel": "sweep_dw_update_kernel", "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
+    roof = {"bound": "hbm", "kernel": "sweep_dw_update_tc_kernel", "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
             "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
             "algorithmic_bytes_per_launch": bytes_, "kernel_ms": {k: round(v, 5) for k, v in ktimes.items()}}
     roof["frac"] = roof["achieved"] / roof["peak"]
@@ -1039,11 +1039,25 @@ def main():
                     "peak_source": f"{peaks['src']} bf16 burst (the timed region is {res['ms']:.1f} ms long)",
                     "frac_of_sustained_peak": flops / (kms * 1e-3) / 1e12 / peaks["tf_sustained"]}
         else:
-            kname = "head_bwd_dw_f32"
-            kms = res["ktimes"].get(kname, float("nan"))
-            bytes_ = 28.0 * C * D  # AdamW pass fused in the dW epilogue: p,g,m,v read + p,m,v written
+            from uml_b200 import _lib as _l
+            if _l.load().uml_head_step_fused_count() > 0:
+                # the whole exact step ran as ONE cooperative launch (csrc/simt.cu head_step_fused_kernel); the C launcher's
+                # forward events bracket it.  Algorithmic bytes: W, m, v read and written once (24 B/parameter - neither the
+                # logits' gradient nor dW reach HBM) plus the step's bank rows, labels and indices
+                kname = "head_step_fused_kernel"
+                kms = res["ktimes"].get("head_fwd_ce_f32", float("nan"))
+                bytes_ = 24.0 * C * D + rows_per_gpu * (4.0 * D + 16.0)
+                note = "one launch per step; a 12 MB working set at a 32 + 32-row step is latency bound, not bandwidth bound"
+            else:
+                kname = "head_bwd_dw_f32"
+                kms = res["ktimes"].get(kname, float("nan"))
+                bytes_ = 28.0 * C * D  # AdamW pass fused in the dW epilogue: p,g,m,v read + p,m,v written
+                note = None
             roof = {"bound": "hbm", "kernel": kname, "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
-                    "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy"}
+                    "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
+                    "algorithmic_bytes_per_launch": bytes_}
+            if note:
+                roof["note"] = note
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel_ms"] = {k: round(v, 5) for k, v in res["ktimes"].items()}
         roof["step_breakdown_ms"] = {k: round(v, 5) for k, v in res["breakdown"].items()}

@@ -396,6 +396,9 @@ typedef struct {
  * the last batch of an epoch is short) with learning rates lr[i*n_heads + k] (host array).                      */
 int uml_sweep_run(const uml_sweep_args* args /*host*/, int32_t n_steps, const int64_t* rows /*host*/,
                   const float* lr /*host*/, void* stream);
+/* kernels launched by uml_sweep_run in this process so far (modulo 2^31): three per step when the tensor-core dW launch
+ * carries the statistics warp, four otherwise */
+int uml_sweep_launch_count(void);
 
 /* ---- sampler: the epoch permutation on the host, bit-exact with torch.randperm(n, generator=
  * torch.Generator().manual_seed(seed)) on the CPU - what RandomSampler draws once per epoch for the

@@ -83,6 +83,7 @@ PROTOTYPES = {
     "uml_head_fwd_ce_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp],
     "uml_head_bwd_dw_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i64, c_i32, c_vp, c_vp, C.POINTER(Update), c_vp],
     "uml_head_step_fused_count": [],
+    "uml_sweep_launch_count": [],
     "uml_head_step_fused_f32": [C.POINTER(Segment), c_i32, c_i32, c_vp, c_i32, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
                                 C.POINTER(Update), C.POINTER(c_i32), c_vp],
     "uml_gemm_nt_f32": [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_f32, c_vp],

@@ -1090,7 +1090,11 @@ __global__ void __launch_bounds__(256) sweep_stats_kernel(const __grid_constant_
 }  // namespace sweep
 }  // namespace uml
 
+static long long g_sweep_launches = 0;  // kernels launched by uml_sweep_run in this process (launch accounting of the callers)
+
 extern "C" {
+
+int uml_sweep_launch_count(void) { return static_cast<int>(g_sweep_launches & 0x7fffffff); }
 
 int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows, const float* lr, void* stream) {
   using namespace uml;
@@ -1241,9 +1245,11 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     else
       sweep_logits_kernel<<<dim3(ct, rt, K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
+    ++g_sweep_launches;
     if (mark(1) || mark(2)) return 1;
     sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
+    ++g_sweep_launches;
     if (mark(3) || mark(4)) return 1;
     if (use_tc_dw && R <= 64) {  // (larger steps: the feature tile of the tensor-core form holds 64 rows)
       const int64_t units = static_cast<int64_t>(__builtin_popcount(mask)) * ((a->dim + 127) / 128) * ((a->n_classes + 63) / 64);
@@ -1256,10 +1262,12 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     else
       sweep_dw_update_kernel<<<dim3((a->dim + 63) / 64, (a->n_classes + 63) / 64, K), 256, 0, st>>>(p);
     UML_CUDA(cudaGetLastError());
+    ++g_sweep_launches;
     if (mark(5) || mark(6)) return 1;
     if (!(use_tc_dw && R <= 64)) {  // (the tensor-core dW launch carries a statistics warp)
       sweep_stats_kernel<<<dim3(2, K), 256, 0, st>>>(p);
       UML_CUDA(cudaGetLastError());
+      ++g_sweep_launches;
     }
     if (mark(7)) return 1;
     pos[0] += n0;
