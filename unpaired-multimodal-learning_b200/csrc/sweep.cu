@@ -3,19 +3,25 @@
 //
 // The reference trains the lr x weight-decay (x alpha) combinations of a sweep one after the other over the SAME
 // feature banks, each a 32-row step that cannot fill one SM.  Here K heads (own weights, optimizer state, sampler
-// stream, lr, weight decay and alpha) advance in lock step: every launch carries a head index in gridDim.z / .y, so
-// one step of all K heads is four launches and the dW + optimizer kernel streams K x 24 B/parameter from HBM with the
-// whole machine.  Per head the arithmetic is the single-head fp32 path's (simt.cu): sequential-k FFMA logits, the same
-// softmax / CE / argmax row kernel, dW summed over rows in order, torch.optim's update rules in the epilogue.
+// stream, lr, weight decay and alpha) advance in lock step: every launch covers all heads, so one step of all K heads
+// is three launches - logits, softmax / CE, dW + optimizer update (+ statistics) - and the last one streams
+// K x 24 B/parameter from HBM with the whole machine.
 //
 // Layout in HBM: W, m, v are [K][C*D] slabs (head_stride apart); G is [K][rows][ldg] scratch; every head reads its
 // own epoch permutation (device int64) at the common position `pos` - the heads share bank and batch sizes, so their
 // epochs turn over on the same steps.
 //
-// Two GEMM-shaped launches exist in two forms with identical arithmetic: register-staged (any alignment) and cp.async
-// (16-byte aligned rows; the default - double-buffered k-tiles for the logits, all rows of the step plus the thread's
-// W, m, v requested up front for dW).  Measured on B200 with K = 30 heads of 1000 x 512: 0.219 ms per step of all heads
-// (logits 73 us, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7); register-staged 0.268 ms.
+// The two contractions exist in three forms:
+//   * tensor cores (default when rows are 16-byte aligned): tcgen05.mma kind::tf32 with every operand split into two tf32
+//     terms, i.e. fp32-level accuracy (section "Tensor-core forms" below); W, m, v of the update move through a TMA
+//     slot ring.  Measured on B200 with K = 30 heads of 1000 x 512: 0.138 ms per step of all heads (logits 37 us,
+//     softmax/CE 15, dW + update + statistics 76 = 0.76 of the HBM copy peak);
+//   * FFMA with cp.async staging (UML_SWEEP_TC=0, and the dW + update of steps with more than 64 rows): 0.219 ms
+//     (logits 73, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7);
+//   * FFMA, register-staged (any alignment; UML_SWEEP_ASYNC=0): 0.268 ms.
+// Per head the arithmetic of the FFMA forms is the single-head fp32 path's (simt.cu): sequential-k FFMA logits, the
+// same softmax / CE / argmax row kernel, dW summed over rows in order, torch.optim's update rules in the epilogue.  In
+// every form a head's result depends neither on its slot in the group nor on its neighbours.
 #include <algorithm>
 #include <cstdlib>
 
