@@ -696,7 +696,7 @@ def run_eval(args):
 def run_sweep(args):
     """--workload cfg2_sweep: the reference's real few-shot workload - the hyper-parameter sweep of preset `clip_linear`
     (lr x weight decay, engine/optimizer/default.py:17-31) times its alpha sweep over the SAME cfg2 banks - with
-    --heads combinations trained in lock step (finetune.train_group / uml_sweep_run: three launches per step of all
+    --heads combinations trained in lock step (finetune.train_group / uml_sweep_run: two launches per step of all
     heads).  value: device-resident (every head's epoch permutation in HBM before the clock starts); e2e: ONE public
     train_group() call; `sequential`: the same banks through the single-head engine (finetune.train), which is what
     the sweep costs one combination at a time."""
@@ -909,7 +909,7 @@ def run_ratio(args):
     value = rows_total / secs_total
     # whole-step algorithmic HBM bytes of a head-step: W, m, v read and written (24 B / parameter) + G and rows once
     bytes_total = sum(p["heads"] * K * (24.0 * p["classes"] * D + 4.0 * (B + (B if p["text_shot"] else 0)) * (p["classes"] + D)) for p in points)
-    roof = {"bound": "hbm", "kernel": "whole step (3 launches per step of a group)", "achieved": bytes_total / secs_total / 1e9,
+    roof = {"bound": "hbm", "kernel": "whole step (2 launches per step of a group)", "achieved": bytes_total / secs_total / 1e9,
             "peak": peaks["hbm"], "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
             "note": "six 0.2-0.8 MB heads per group: the whole working set sits in L2 and a step is launch-latency bound"}
     roof["frac"] = roof["achieved"] / roof["peak"]

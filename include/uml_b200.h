@@ -361,7 +361,8 @@ int uml_gauss_embed(const float* params, int32_t dim_obs, int32_t dim_common, in
 /* ---- sweep-level batching: the lr x weight-decay (x alpha) combinations that
  * finetune.py:406-448 (`sweep`) and engine/optimizer/default.py:17-31 (`HYPER_DICT`) train one after the other over the
  * SAME banks advance here in lock step - K heads with their own weights, optimizer state, sampler stream, lr, weight
- * decay and alpha; one step of all K heads is three launches (four when rows are not 16-byte aligned).  fp32-level
+ * decay and alpha; one step of all K heads is two launches (three with more than 1024 classes, four when rows are not
+ * 16-byte aligned).  fp32-level
  * arithmetic per head: the two contractions run on the tensor cores as tf32 products of operands split into two terms
  * each (hi * hi + hi * lo + lo * hi, fp32 accumulation) when rows are 16-byte aligned, else as FFMA loops; linear
  * head without adapter and with fixed logit scales (UMLClip, head.py:131-137).  All heads share bank sizes and batch

@@ -499,7 +499,8 @@ def test_full_size_step_properties():
         torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.parametrize("case", HEAD_CASES[:4] + [(300, 200, 36, 12, 8, 8, 100.0, 0.5)])
+@pytest.mark.parametrize("case", HEAD_CASES[:4] + [(300, 200, 36, 12, 8, 8, 100.0, 0.5),
+                                                  (2000, 1000, 768, 1000, 32, 32, 100.0, 0.5)])  # cfg3 at the reference batch: the largest footprint that fits
 @pytest.mark.parametrize("optim", ["adamw", "sgd"])
 def test_fused_step_f32_matches_the_separate_launches_and_the_oracle(case, optim):
     """uml_head_step_fused_f32 (one cooperative launch: logits, softmax CE, dW, optimizer update, statistics) against

@@ -4,8 +4,8 @@
 // The reference trains the lr x weight-decay (x alpha) combinations of a sweep one after the other over the SAME
 // feature banks, each a 32-row step that cannot fill one SM.  Here K heads (own weights, optimizer state, sampler
 // stream, lr, weight decay and alpha) advance in lock step: every launch covers all heads, so one step of all K heads
-// is three launches - logits, softmax / CE, dW + optimizer update (+ statistics) - and the last one streams
-// K x 24 B/parameter from HBM with the whole machine.
+// is two launches - logits with softmax / CE in the epilogue (the class tiles of a head form a cluster), dW + optimizer
+// update (+ statistics) - and the last one streams K x 24 B/parameter from HBM with the whole machine.
 //
 // Layout in HBM: W, m, v are [K][C*D] slabs (head_stride apart); G is [K][rows][ldg] scratch; every head reads its
 // own epoch permutation (device int64) at the common position `pos` - the heads share bank and batch sizes, so their
@@ -14,8 +14,9 @@
 // The two contractions exist in three forms:
 //   * tensor cores (default when rows are 16-byte aligned): tcgen05.mma kind::tf32 with every operand split into two tf32
 //     terms, i.e. fp32-level accuracy (section "Tensor-core forms" below); W, m, v of the update move through a TMA
-//     slot ring.  Measured on B200 with K = 30 heads of 1000 x 512: 0.138 ms per step of all heads (logits 37 us,
-//     softmax/CE 15, dW + update + statistics 76 = 0.76 of the HBM copy peak);
+//     slot ring; softmax / CE in the logits epilogue when a head has at most eight class tiles (a cluster).  Measured on
+//     B200 with K = 30 heads of 1000 x 512: 0.136 ms per step of all heads (logits + softmax/CE 44 us, dW + update +
+//     statistics 76 = 0.76 of the HBM copy peak); with the separate softmax launch 0.139 ms (logits 36, softmax/CE 15);
 //   * FFMA with cp.async staging (UML_SWEEP_TC=0, and the dW + update of steps with more than 64 rows): 0.219 ms
 //     (logits 73, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7);
 //   * FFMA, register-staged (any alignment; UML_SWEEP_ASYNC=0): 0.268 ms.
@@ -611,6 +612,15 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<
 constexpr int kTcLgStage = 48 * 1024;  // W hi 16 KB | W lo 16 KB | X hi 8 KB | X lo 8 KB
 constexpr int kTcLgSmemBytes = 2 * kTcLgStage + 1024 + 64;
 
+// kSoftmax: the (up to eight) class tiles of a head form a thread-block cluster and finish the rows together - softmax / CE /
+// argmax in the epilogue, the row maxima and sums exchanged through distributed shared memory - so G leaves the kernel
+// final and the softmax launch (one read and one write of the logits) disappears.
+__device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
+  return v;
+}
+template <bool kSoftmax>
 __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_constant__ SweepDev p) {
   constexpr int BM = 128, BN = 64, BK = 32, S = 2;
   const int head = blockIdx.z;
@@ -716,13 +726,13 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
   // epilogue: TMEM lane = class, column = row; warp w reads lane quadrant w % 4, column half w / 4
   mbar_wait_or_trap(tfull_bar, 0);
   tc_fence_after();
-  {
-    const int q = warp & 3, h = warp >> 2;
-    uint32_t v[32];
-    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, v);
-    tmem_ld_wait();
+  const int q = warp & 3, h = warp >> 2;
+  uint32_t v[32];
+  tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, v);
+  tmem_ld_wait();
+  float* __restrict__ G = p.G + head * p.g_stride;
+  if (!kSoftmax) {
     const int c = c0 + q * 32 + lane;
-    float* __restrict__ G = p.G + head * p.g_stride;
     if (c < C) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -730,6 +740,150 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
         if (r < R) G[r * p.ldg + c] = __uint_as_float(v[i]);  // a warp stores 32 consecutive classes of one row
       }
     }
+  } else {
+    // The tile goes to shared memory as [row][class] (the operand stages are free: every MMA has completed), then a warp
+    // owns eight rows: lane = four consecutive classes.  Arithmetic per element as in sweep_softmax_kernel; the sum of a
+    // row is per lane, then a shuffle tree, then the tiles in class order.
+    __shared__ float pub_max[BN], pub_sum[BN];  // published to the cluster: tile maximum, tile sum of exponentials
+    __shared__ int pub_arg[BN];                 //                            first maximal class of the tile
+    __shared__ float row_scale[BN], row_gcoef[BN], row_lab[BN];
+    __shared__ int row_label[BN], row_arg[BN];
+    float* tile = reinterpret_cast<float*>(smem);  // [BN][BM]
+    if (t < BN) {
+      const int64_t r = m0 + t;
+      row_label[t] = -1;
+      row_scale[t] = 1.f;
+      row_gcoef[t] = 0.f;
+      if (r < R) {
+        bool is_txt;
+        const int64_t src = bank_row(p, head, r, is_txt);
+        row_label[t] = static_cast<int>((is_txt ? p.labels[1] : p.labels[0])[src]);
+        const float sc = is_txt ? p.scale[1] : p.scale[0];
+        row_scale[t] = sc;
+        row_gcoef[t] = (is_txt ? p.alpha[head] : 1.f) * sc / static_cast<float>(is_txt ? p.n1 : p.n0);
+      }
+    }
+    __syncthreads();
+    {
+      const int cl = q * 32 + lane;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int rl = h * 32 + i;
+        tile[rl * BM + cl] = (c0 + cl < C) ? __uint_as_float(v[i]) * row_scale[rl] : -INFINITY;
+      }
+    }
+    __syncthreads();
+    const uint32_t n_tiles = gridDim.x;  // (cluster = the head's class tiles: rank == blockIdx.x)
+    // ---- tile maximum and first maximal class of every row ----
+    for (int rl = warp * 8; rl < warp * 8 + 8; ++rl) {
+      const float4 x4 = *reinterpret_cast<const float4*>(tile + rl * BM + 4 * lane);
+      float mx = x4.x;
+      int arg = 0;
+      if (x4.y > mx) { mx = x4.y; arg = 1; }
+      if (x4.z > mx) { mx = x4.z; arg = 2; }
+      if (x4.w > mx) { mx = x4.w; arg = 3; }
+      arg += c0 + 4 * lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+        if (om > mx || (om == mx && oa < arg)) { mx = om; arg = oa; }
+      }
+      if (lane == 0) {
+        pub_max[rl] = mx;
+        pub_arg[rl] = arg;
+      }
+    }
+    cluster_sync_all();
+    // ---- row maximum over the tiles (lower class wins a tie: first maximal index, like torch.argmax), exponentials ----
+    // A lane fetches the published values of ONE tile for two of the warp's eight rows (rows rs and rs + 4 of the group,
+    // tile = lane & 7): the remote loads are independent, and the eight tiles of a row meet by three shuffles.  (Every
+    // lane walking the eight tiles of a row in turn cost a remote round trip per tile and row: 15 us per launch.)
+    const uint32_t tl = lane & 7, rs = lane >> 3;
+    float gm[2];
+    int ga[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int rl = warp * 8 + rs + 4 * k;
+      gm[k] = -INFINITY;
+      ga[k] = INT_MAX;
+      if (tl < n_tiles) {
+        gm[k] = ld_cluster_f32(mapa_cta(smem_u32(&pub_max[rl]), tl));
+        ga[k] = __float_as_int(ld_cluster_f32(mapa_cta(smem_u32(&pub_arg[rl]), tl)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, gm[k], o);
+        const int oa = __shfl_xor_sync(0xffffffffu, ga[k], o);
+        if (om > gm[k] || (om == gm[k] && oa < ga[k])) { gm[k] = om; ga[k] = oa; }
+      }
+    }
+    for (int i = 0; i < 8; ++i) {
+      const int rl = warp * 8 + i;
+      const float bmax = __shfl_sync(0xffffffffu, (i >> 2) ? gm[1] : gm[0], (i & 3) * 8);
+      const int barg = __shfl_sync(0xffffffffu, (i >> 2) ? ga[1] : ga[0], (i & 3) * 8);
+      float4 x4 = *reinterpret_cast<const float4*>(tile + rl * BM + 4 * lane);
+      {  // the lane that holds the label's class keeps x_label - max for the loss (exact 0 for a dominant label)
+        const int lk = row_label[rl] - (c0 + 4 * lane);
+        if (lk >= 0 && lk < 4) row_lab[rl] = (lk == 0 ? x4.x : lk == 1 ? x4.y : lk == 2 ? x4.z : x4.w) - bmax;
+      }
+      x4.x = expf(x4.x - bmax);
+      x4.y = expf(x4.y - bmax);
+      x4.z = expf(x4.z - bmax);
+      x4.w = expf(x4.w - bmax);
+      *reinterpret_cast<float4*>(tile + rl * BM + 4 * lane) = x4;
+      const float se = warp_sum((x4.x + x4.y) + (x4.z + x4.w));
+      if (lane == 0) {
+        pub_sum[rl] = se;
+        row_arg[rl] = barg;
+      }
+    }
+    cluster_sync_all();
+    // ---- row sum over the tiles (fixed shuffle tree over the tile index), G, loss and hit ----
+    float gsum[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int rl = warp * 8 + rs + 4 * k;
+      gsum[k] = tl < n_tiles ? ld_cluster_f32(mapa_cta(smem_u32(&pub_sum[rl]), tl)) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) gsum[k] += __shfl_xor_sync(0xffffffffu, gsum[k], o);
+    }
+    for (int i = 0; i < 8; ++i) {
+      const int rl = warp * 8 + i;
+      const float sum = __shfl_sync(0xffffffffu, (i >> 2) ? gsum[1] : gsum[0], (i & 3) * 8);
+      const int64_t r = m0 + rl;
+      if (r >= R) continue;  // (warp-uniform)
+      const float inv = 1.f / sum, gcoef = row_gcoef[rl];
+      const int label = row_label[rl];
+      const float4 e4 = *reinterpret_cast<const float4*>(tile + rl * BM + 4 * lane);
+      float pr[4] = {e4.x * inv, e4.y * inv, e4.z * inv, e4.w * inv};
+      const int cb = c0 + 4 * lane;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (cb + k == label) pr[k] -= 1.f;
+        pr[k] *= gcoef;
+      }
+      float* grow = G + r * p.ldg + cb;
+      if (cb + 3 < C) {
+        *reinterpret_cast<float4*>(grow) = make_float4(pr[0], pr[1], pr[2], pr[3]);  // (ldg % 4 == 0, G 16-byte aligned)
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (cb + k < C) grow[k] = pr[k];
+      }
+      // the lane that holds the label's class writes the row's loss (log_softmax form) and hit flag
+      if (label >= cb && label < cb + 4) {
+        p.row_loss[head * p.row_stride + r] = logf(sum) - row_lab[rl];
+        p.row_correct[head * p.row_stride + r] = (row_arg[rl] == label) ? 1 : 0;
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a neighbour may still read its published values
   }
   tc_fence_before();
   __syncthreads();
@@ -1169,8 +1323,12 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
   }();
   const bool use_tc = want_tc && use_async;
   if (use_tc) {
-    static const cudaError_t attr1 = cudaFuncSetAttribute(sweep_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                          kTcLgSmemBytes);
+    static const cudaError_t attr1 = [] {
+      cudaError_t e = cudaFuncSetAttribute(sweep_logits_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcLgSmemBytes);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(sweep_logits_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcLgSmemBytes);
+      return e;
+    }();
     UML_CUDA(attr1);
     static const cudaError_t attr2 = [] {
       cudaError_t e = cudaFuncSetAttribute(sweep_dw_update_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcDwSmemBytes);
@@ -1190,6 +1348,10 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     return (e && atoi(e) == 256) ? 256 : 512;
   }();
   const bool use_tc_dw = use_tc && want_tc_dw;
+  static const bool want_fused_softmax = [] {  // UML_SWEEP_FUSED_SOFTMAX=0 keeps the separate softmax / CE launch
+    const char* e = getenv("UML_SWEEP_FUSED_SOFTMAX");
+    return !(e != nullptr && e[0] == '0');
+  }();
   CUtensorMap tm_w, tm_m, tm_v;  // [K][C][D] views of the W, m, v slabs for the dW kernel's slot ring
   memset(&tm_w, 0, sizeof(tm_w));
   memset(&tm_m, 0, sizeof(tm_m));
@@ -1244,8 +1406,14 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
       return 0;
     };
     if (mark(0)) return 1;
-    if (use_tc)
-      sweep_logits_tc_kernel<<<dim3((a->n_classes + 127) / 128, rt, K), 256, kTcLgSmemBytes, st>>>(p);
+    // up to eight class tiles per head: they form a cluster and finish the rows (softmax / CE) in the logits epilogue
+    const unsigned n_ctile = static_cast<unsigned>((a->n_classes + 127) / 128);
+    const bool fuse_softmax = use_tc && want_fused_softmax && n_ctile <= 8;
+    if (fuse_softmax)
+      UML_CUDA(launch_kernel(sweep_logits_tc_kernel<true>, dim3(n_ctile, rt, K), dim3(256), kTcLgSmemBytes, st,
+                             static_cast<int>(n_ctile), 0, p));
+    else if (use_tc)
+      sweep_logits_tc_kernel<false><<<dim3(n_ctile, rt, K), 256, kTcLgSmemBytes, st>>>(p);
     else if (use_async)
       sweep_logits_async_kernel<<<dim3(ct, rt, K), 256, kLogitsSmemBytes, st>>>(p);
     else
@@ -1253,9 +1421,11 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     UML_CUDA(cudaGetLastError());
     ++g_sweep_launches;
     if (mark(1) || mark(2)) return 1;
-    sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
-    UML_CUDA(cudaGetLastError());
-    ++g_sweep_launches;
+    if (!fuse_softmax) {
+      sweep_softmax_kernel<<<dim3(static_cast<unsigned>(R), K), 256, 0, st>>>(p);
+      UML_CUDA(cudaGetLastError());
+      ++g_sweep_launches;
+    }
     if (mark(3) || mark(4)) return 1;
     if (use_tc_dw && R <= 64) {  // (larger steps: the feature tile of the tensor-core form holds 64 rows)
       const int64_t units = static_cast<int64_t>(__builtin_popcount(mask)) * ((a->dim + 127) / 128) * ((a->n_classes + 63) / 64);

@@ -3,7 +3,7 @@
 The reference's ``sweep`` (finetune.py:406-448) trains every lr x weight-decay combination of ``HYPER_DICT``
 (engine/optimizer/default.py) one after the other over the same banks; at its batch size of 32 a step cannot fill one
 SM.  ``HeadGroup`` keeps the K heads' weights and optimizer state in three ``[K, C*D]`` slabs and runs one step of all
-of them with three launches - logits and dW + update on the tensor cores (``uml_sweep_run``, csrc/sweep.cu).  Each head keeps its own sampler stream, learning-rate
+of them with two launches - logits + softmax / CE and dW + update, both on the tensor cores (``uml_sweep_run``, csrc/sweep.cu).  Each head keeps its own sampler stream, learning-rate
 schedule, weight decay, alpha and early-stopping state; a stopped head is masked out of the launches.
 """
 from __future__ import annotations
@@ -152,7 +152,7 @@ class HeadGroup:
         lr_c = (C.c_float * (n * K))(*[float(x) for l in lrs for x in l])
         l0 = _lib.load().uml_sweep_launch_count()
         check(_lib.load().uml_sweep_run(C.byref(a), n, rows_c, lr_c, torch.cuda.current_stream().cuda_stream))
-        launched = (_lib.load().uml_sweep_launch_count() - l0) & 0x7FFFFFFF  # three or four kernels per step (csrc/sweep.cu)
+        launched = (_lib.load().uml_sweep_launch_count() - l0) & 0x7FFFFFFF  # two to four kernels per step (csrc/sweep.cu)
         self.launches += launched
         _lib.LAUNCH_COUNT[0] += launched
         for k in range(K):
