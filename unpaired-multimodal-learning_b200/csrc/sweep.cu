@@ -601,7 +601,8 @@ __device__ __forceinline__ uint32_t sw128(int row, int ch) { return static_cast<
 
 // 1t. raw logits, transposed tile: D[class, row] = W_k[128 classes, :] . X_k[64 rows, :]^T   grid (ceil(C/128), ceil(rows/64), K)
 //     A = weight rows (K-major), B = gathered bank rows (K-major), k-blocks of 32 floats (one swizzle row), two stages:
-//     the loads of block kb + 1 are in registers while block kb is split, stored and multiplied.
+//     the loads of block kb + 1 are in registers while block kb is split, stored and multiplied (8 MMAs per block: see
+//     idesc2 below).
 //     (Measured alternatives, 30 heads of 1000 x 512, against 37 us for this form - two CTAs per SM, every tile of the
 //     launch resident at once: register buffers two blocks ahead 38 us; a five-stage cp.async ring three blocks ahead, one
 //     CTA per SM, 47 us, with the weight tile asked into L2 up front 51 us; a TMA warp for the weight boxes with four
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 64);
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -678,7 +679,10 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
   };
 
   const int nk = (D + BK - 1) / BK;
-  constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0);
+  // The row tile's hi and lo terms lie back to back (64 + 64 rows of one K-major tile), so  W_hi . [X_hi | X_lo]^T  is ONE
+  // MMA with N = 128 whose halves land in TMEM columns [0, 64) and [64, 128); W_lo . X_hi^T adds to the first half and the
+  // epilogue adds the halves: 8 MMAs and 56 KB of operand reads per k-block instead of 12 and 72 KB.
+  constexpr uint32_t idesc = make_idesc_tf32(BM, BN, 0, 0), idesc2 = make_idesc_tf32(BM, 2 * BN, 0, 0);
   float4 cur[6], nxt[6];
   load(0, cur);
 #pragma unroll 1
@@ -705,16 +709,14 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
     __syncthreads();
     if (t == 0) {
       tc_fence_after();
-      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + 16384, b_hi = a_hi + 32768, b_lo = a_hi + 40960;
+      const uint32_t a_hi = smem_u32(st), a_lo = a_hi + 16384, b_hi = a_hi + 32768;
 #pragma unroll
       for (int k = 0; k < BK / 8; ++k) {  // a k-step of 8 floats = 32 B inside the swizzle row; 8-row atoms 1024 B apart
         const uint64_t dah = make_smem_desc(a_hi + k * 32, 16, 1024, kLayoutSw128);
         const uint64_t dal = make_smem_desc(a_lo + k * 32, 16, 1024, kLayoutSw128);
-        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024, kLayoutSw128);
-        const uint64_t dbl = make_smem_desc(b_lo + k * 32, 16, 1024, kLayoutSw128);
-        umma_tf32(tmem_base, dal, dbh, idesc, (kb | k) != 0);
-        umma_tf32(tmem_base, dah, dbl, idesc, 1);
-        umma_tf32(tmem_base, dah, dbh, idesc, 1);
+        const uint64_t dbh = make_smem_desc(b_hi + k * 32, 16, 1024, kLayoutSw128);  // (b_lo = b_hi + 8 KB: rows 64 .. 127)
+        umma_tf32(tmem_base, dah, dbh, idesc2, (kb | k) != 0);
+        umma_tf32(tmem_base, dal, dbh, idesc, 1);
       }
       umma_commit(&empty_bar[s]);
       if (kb == nk - 1) umma_commit(tfull_bar);
@@ -728,8 +730,14 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
   tc_fence_after();
   const int q = warp & 3, h = warp >> 2;
   uint32_t v[32];
-  tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, v);
-  tmem_ld_wait();
+  {
+    uint32_t v2[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 32, v);
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + BN + h * 32, v2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+  }
   float* __restrict__ G = p.G + head * p.g_stride;
   if (!kSoftmax) {
     const int c = c0 + q * 32 + lane;
@@ -887,7 +895,7 @@ __global__ void __launch_bounds__(256, 2) sweep_logits_tc_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 64);
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
 // 3t. dW^T strip with the optimizer update: D[dim, class] = X_k[rows, 128 dims]^T . G_k[rows, 64 classes] for up to four
