@@ -35,7 +35,9 @@ def test_train_group_adam_text_only():
     run_group_case(ft, DEV, optim="adam", modality="text")
 
 
-@pytest.mark.parametrize("C,D,optim", [(37, 50, "adamw"), (64, 128, "adamw"), (100, 36, "sgd"), (1000, 512, "adam")])
+@pytest.mark.parametrize("C,D,optim", [(37, 50, "adamw"), (64, 128, "adamw"), (100, 36, "sgd"), (1000, 512, "adam"),
+                                       (300, 32, "sgd"), (650, 64, "adamw"), (800, 64, "adamw"),   # clusters of 3, 6 and 7 class tiles
+                                       (1100, 32, "adamw")])                                        # 9 tiles: separate softmax launch
 def test_sweep_run_against_oracle(C, D, optim):
     """K heads (one of them switched off) x 3 steps with ragged batches through uml_sweep_run; every head against the
     oracle's step + optimizer on the same rows.  Shapes cover the vector (dim % 4 == 0) and scalar epilogues and tiles

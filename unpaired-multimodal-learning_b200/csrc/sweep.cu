@@ -569,7 +569,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
-// mbarrier wait that cannot hang the GPU: a barrier that does not flip within ~1 s (a bug, never load) traps
+// mbarrier wait that cannot hang the GPU: a barrier that does not flip within ~10 s (a bug, never load) traps
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   const long long t0 = clock64();
@@ -583,7 +583,7 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 2000000000ll) __trap();
+    if (clock64() - t0 > 20000000000ll) __trap();
   }
 }
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
@@ -1416,7 +1416,12 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     if (mark(0)) return 1;
     // up to eight class tiles per head: they form a cluster and finish the rows (softmax / CE) in the logits epilogue
     const unsigned n_ctile = static_cast<unsigned>((a->n_classes + 127) / 128);
-    const bool fuse_softmax = use_tc && want_fused_softmax && n_ctile <= 8;
+    // (cluster sizes that are not a power of two are legal but were not measured here: UML_SWEEP_ANY_CLUSTER=1 admits them)
+    static const bool any_cluster = [] {
+      const char* e = getenv("UML_SWEEP_ANY_CLUSTER");
+      return e != nullptr && e[0] == '1';
+    }();
+    const bool fuse_softmax = use_tc && want_fused_softmax && n_ctile <= 8 && (any_cluster || (n_ctile & (n_ctile - 1)) == 0);
     if (fuse_softmax)
       UML_CUDA(launch_kernel(sweep_logits_tc_kernel<true>, dim3(n_ctile, rt, K), dim3(256), kTcLgSmemBytes, st,
                              static_cast<int>(n_ctile), 0, p));
