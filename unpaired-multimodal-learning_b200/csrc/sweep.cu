@@ -1416,12 +1416,8 @@ int uml_sweep_run(const uml_sweep_args* a, int32_t n_steps, const int64_t* rows,
     if (mark(0)) return 1;
     // up to eight class tiles per head: they form a cluster and finish the rows (softmax / CE) in the logits epilogue
     const unsigned n_ctile = static_cast<unsigned>((a->n_classes + 127) / 128);
-    // (cluster sizes that are not a power of two are legal but were not measured here: UML_SWEEP_ANY_CLUSTER=1 admits them)
-    static const bool any_cluster = [] {
-      const char* e = getenv("UML_SWEEP_ANY_CLUSTER");
-      return e != nullptr && e[0] == '1';
-    }();
-    const bool fuse_softmax = use_tc && want_fused_softmax && n_ctile <= 8 && (any_cluster || (n_ctile & (n_ctile - 1)) == 0);
+    // (any tile count up to eight: clusters of 3, 6 and 7 are covered by tests/test_sweep_gpu.py)
+    const bool fuse_softmax = use_tc && want_fused_softmax && n_ctile <= 8;
     if (fuse_softmax)
       UML_CUDA(launch_kernel(sweep_logits_tc_kernel<true>, dim3(n_ctile, rt, K), dim3(256), kTcLgSmemBytes, st,
                              static_cast<int>(n_ctile), 0, p));
