@@ -15,7 +15,7 @@
 //   * tensor cores (default when rows are 16-byte aligned): tcgen05.mma kind::tf32 with every operand split into two tf32
 //     terms, i.e. fp32-level accuracy (section "Tensor-core forms" below); W, m, v of the update move through a TMA
 //     slot ring; softmax / CE in the logits epilogue when a head has at most eight class tiles (a cluster).  Measured on
-//     B200 with K = 30 heads of 1000 x 512: 0.136 ms per step of all heads (logits + softmax/CE 44 us, dW + update +
+//     B200 with K = 30 heads of 1000 x 512: 0.134 ms per step of all heads (logits + softmax/CE 44 us, dW + update +
 //     statistics 76 = 0.76 of the HBM copy peak); with the separate softmax launch 0.139 ms (logits 36, softmax/CE 15);
 //   * FFMA with cp.async staging (UML_SWEEP_TC=0, and the dW + update of steps with more than 64 rows): 0.219 ms
 //     (logits 73, softmax/CE 15, dW + update 123 = 0.47 of the HBM peak, stats 7);
