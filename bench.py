@@ -809,7 +809,12 @@ def run_sweep(args):
     # gradient itself never reaches HBM) plus the step's G and feature rows read once
     bytes_ = H * (24.0 * C * D + 4.0 * (B + BT) * (C + D))
     roof = {"bound": "hbm", "kernel": "sweep_dw_update_tc_kernel", "achieved": bytes_ / (kms * 1e-3) / 1e9, "peak": peaks["hbm"],
-            "unit": "GB/s", "traffic": None, "peak_source": f"{peaks['src']} HBM copy",
+            "unit": "GB/s",
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per launch from the committed `ncu --set full` capture
+            # (profiles/r02_sweep_tc.md: 200.3 MB + 126.2 MB at 30 heads of 1000 x 512; part of the writes is still in L2 when
+            # the kernel ends), scaled by the parameters of the group
+            "traffic": 3.266e8 * (H * C * D) / (30.0 * 1000 * 512), "traffic_unit": "bytes per launch",
+            "peak_source": f"{peaks['src']} HBM copy",
             "algorithmic_bytes_per_launch": bytes_, "kernel_ms": {k: round(v, 5) for k, v in ktimes.items()}}
     roof["frac"] = roof["achieved"] / roof["peak"]
     line = {"metric": "UML train samples/sec (img+text)", "value": rows / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
@@ -1047,7 +1052,8 @@ def main():
                 kname = "head_step_fused_kernel"
                 kms = res["ktimes"].get("head_fwd_ce_f32", res["breakdown"].get("head_fwd_ce_f32", float("nan")))
                 bytes_ = 24.0 * C * D + rows_per_gpu * (4.0 * D + 16.0)
-                note = "one launch per step; a 12 MB working set at a 32 + 32-row step is latency bound, not bandwidth bound"
+                note = ("one launch per step; a 12 MB working set at a 32 + 32-row step is latency bound, not bandwidth bound; "
+                        "ncu (profiles/r02_fused_step.md): 6.36 MB read from DRAM per launch at cfg2, the updated state stays in L2")
             else:
                 kname = "head_bwd_dw_f32"
                 kms = res["ktimes"].get(kname, float("nan"))
