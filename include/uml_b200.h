@@ -392,8 +392,9 @@ typedef struct {
   float          weight_decay[UML_SWEEP_MAX_HEADS];
   float          alpha[UML_SWEEP_MAX_HEADS];       /* text-loss weight per head (finetune.py:188)               */
   uint8_t        active[UML_SWEEP_MAX_HEADS];      /* 0: the head stopped early, nothing of it is touched       */
-  void*          ev[8];           /* optional cudaEvent_t pairs recorded around the four launches of the LAST step:
-                                     logits, softmax/CE, dW + update, stats (NULL = not timed)                    */
+  void*          ev[8];           /* optional cudaEvent_t pairs recorded around the four launch sites of the LAST
+                                     step: logits (+ softmax/CE when fused), softmax/CE, dW + update (+ stats when
+                                     fused), stats (NULL = not timed; a pair around a fused-away site spans nothing) */
 } uml_sweep_args;
 /* n_steps consecutive steps: step i consumes rows[2i] image rows and rows[2i+1] text rows per head (host array;
  * the last batch of an epoch is short) with learning rates lr[i*n_heads + k] (host array).                      */

@@ -533,7 +533,7 @@ static int linear_step_impl(const uml_linear_step_args* a, void* stream, const S
   int rc;
 
   if (a->precision == 0) {
-    // ------------------------------------------------------------------ fp32 exact path (3 launches)
+    // ------------------------------------------------------------------ fp32 exact path (one fused launch, else 3 + 1)
     UML_REQUIRE(a->row_dscale, "linear_step: fp32 path needs row_dscale");
     rec(a->ev[2], stream);
     if (fused && !dp && total > 0) {  // the reference's batch sizes: forward, gradient and update in one cooperative launch

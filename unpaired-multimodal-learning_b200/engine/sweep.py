@@ -162,7 +162,8 @@ class HeadGroup:
     KERNELS = ("sweep_logits", "sweep_softmax_ce", "sweep_dw_update", "sweep_stats")
 
     def time_last_step(self, enable: bool = True):
-        """Bracket the four launches of the LAST step of every following ``run`` with CUDA events."""
+        """Bracket the four launch sites of the LAST step of every following ``run`` with CUDA events (a site whose work was
+        fused into its neighbour spans nothing)."""
         self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)] if enable else []
         for i in range(8):
             if enable:

@@ -8,7 +8,8 @@ log that the caller reads at evaluation cadence.
 
 Two arithmetic paths (chosen per step from the row count unless forced):
   fp32  SIMT kernels, exact like the reference; rows are gathered inside the GEMMs by index and the
-        optimizer update runs in the dW epilogue: 4 launches for the linear head.
+        optimizer update runs in the dW epilogue: 4 launches for the linear head - or ONE cooperative
+        launch for the whole step at the reference's batch sizes (csrc/simt.cu head_step_fused_kernel).
   bf16  tcgen05 kernels: row gather from the bf16 shadow banks (prefetched one step ahead on a side stream)
         -> fused forward/CE/G -> fix-up -> split-K dW -> optimizer update that also sums the split-K
         partials and refreshes the bf16 weight shadow: 5 launches, enqueued by one C call per chunk of steps.

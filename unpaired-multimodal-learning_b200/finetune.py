@@ -398,7 +398,7 @@ def train(model, image_loader, text_loader, val_loader, test_loader, optimizer, 
 def train_group(models, image_loaders, text_loaders, val_loaders, test_loaders, optimizers, schedulers, device="cuda",
                 max_iters=1000, alphas=1.0, eval_freq=EVAL_FREQ, patience=5, loggers=None, traces=None, tags=None):
     """K runs of ``train`` advanced in lock step over shared banks (sweep-level batching): one step of all
-    K heads is four launches (``engine/sweep.py``, ``csrc/sweep.cu``) instead of K latency-bound steps.
+    K heads is two launches (``engine/sweep.py``, ``csrc/sweep.cu``) instead of K latency-bound steps.
 
     Every argument that ``train`` takes once is a list with one entry per head (``max_iters``, ``alphas`` and
     ``patience`` may be scalars); returns the list of ``train``'s result dicts.  Head k follows exactly the loop of
